@@ -1,0 +1,202 @@
+// Shared device/host helpers for libdgp_b200 (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <math.h>
+#include "../../include/dgp_b200.h"
+
+namespace dgp {
+
+// ------------------------------------------------------------------------------------------------ launch counter
+extern long long g_launches;  // bench.py's gpu_launches (host-side count of our kernel launches)
+#define DGP_COUNT_LAUNCH() (++::dgp::g_launches)
+
+#define DGP_CHECK_LAUNCH()                                   \
+    do {                                                     \
+        if (cudaGetLastError() != cudaSuccess) return DGP_ERR_LAUNCH; \
+    } while (0)
+
+static inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
+static inline size_t align256(size_t x) { return (x + 255) & ~size_t(255); }
+
+// ------------------------------------------------------------------------------------------------ workspace layout
+// One conditional's workspace.  All offsets in bytes from the workspace base; computed identically by
+// dgp_cond_ws_bytes and every entry point (pure function of the descriptor, n_rows and need_bwd).
+struct WsLayout {
+    int Mpad, Dp, ncta, nsplit, npart;
+    size_t status;     // int32[64]
+    size_t scal;       // double[256] small reductions (KL partials, ...)
+    size_t Zs;         // [Mpad][Dp]   z / lengthscale(task(z)); pad rows / cols zero
+    size_t zn;         // [Mpad]       |Zs row|^2
+    size_t ztask;      // int32[Mpad]  task id of each inducing point (-1 on pad rows; 0 when T == 1)
+    size_t Lm;         // [Mpad][Mpad] Kuu(+jitter) -> Cholesky factor in place (pad = identity)
+    size_t Linv;       // [Mpad][Mpad] Lm^-1 (lower)
+    size_t LqT;        // [R][Mpad][Mpad] tril(q_sqrt_r)^T (upper), pad zero
+    // backward only
+    size_t LinvT;      // [Mpad][Mpad]
+    size_t SmI;        // [R][Mpad][Mpad] tril(q_sqrt_r) tril(q_sqrt_r)^T - I
+    size_t dKuf;       // [n_rows][Mpad]
+    size_t gmv;        // [n_rows][2R] combined g_mean | g_var of this conditional
+    size_t gram;       // [nsplit][R+1][Mpad][Mpad]  split-K partials of G_r (r<R) and P (r==R)
+    size_t part;       // [ncta][npart] per-CTA partials: T2z[Mpad][Dp], cs[Mpad], dq_mu[Mpad][R], th[T][2+Dp]
+    size_t tail;       // [R+4][Mpad][Mpad] scratch of the parameter tail
+    size_t total;
+};
+
+int device_sm_count();
+
+static inline WsLayout ws_layout(const dgp_cond_desc& d, int64_t n_rows, int need_bwd) {
+    WsLayout w{};
+    w.Mpad = dgp_mpad(d.M);
+    w.Dp = round_up(d.D, 4);
+    w.ncta = device_sm_count();
+    const size_t mm = size_t(w.Mpad) * w.Mpad * sizeof(double);
+    size_t o = 0;
+    w.status = o; o += align256(64 * sizeof(int32_t));
+    w.scal = o;   o += align256(256 * sizeof(double));
+    w.Zs = o;     o += align256(size_t(w.Mpad) * w.Dp * sizeof(double));
+    w.zn = o;     o += align256(size_t(w.Mpad) * sizeof(double));
+    w.ztask = o;  o += align256(size_t(w.Mpad) * sizeof(int32_t));
+    w.Lm = o;     o += align256(mm);
+    w.Linv = o;   o += align256(mm);
+    w.LqT = o;    o += align256(mm * d.R);
+    if (need_bwd) {
+        // split-K factor of the Gram kernel: enough CTAs to fill the machine ~3x (independent of n_rows so that every
+        // offset except the two row-sized buffers at the end is a function of the descriptor only)
+        const int nb = w.Mpad / 64;
+        const int tiles = (d.R + 1) * nb * (nb + 1) / 2;
+        int ns = (3 * w.ncta + tiles - 1) / tiles;
+        if (ns < 1) ns = 1;
+        if (ns > 64) ns = 64;
+        w.nsplit = ns;
+        w.npart = round_up(w.Mpad * w.Dp + w.Mpad + w.Mpad * d.R + d.T * (2 + w.Dp), 32);
+        w.LinvT = o; o += align256(mm);
+        w.SmI = o;   o += align256(mm * d.R);
+        w.gram = o;  o += align256(mm * (d.R + 1) * w.nsplit);
+        w.part = o;  o += align256(size_t(w.ncta) * w.npart * sizeof(double));
+        w.tail = o;  o += align256(mm * (d.R + 4));
+        w.gmv = o;   o += align256(size_t(n_rows) * 2 * d.R * sizeof(double));
+        w.dKuf = o;  o += align256(size_t(n_rows) * w.Mpad * sizeof(double));
+    }
+    w.total = o;
+    return w;
+}
+
+template <typename T>
+static inline T* ws_ptr(void* ws, size_t off) { return reinterpret_cast<T*>(static_cast<char*>(ws) + off); }
+template <typename T>
+static inline const T* ws_ptr(const void* ws, size_t off) { return reinterpret_cast<const T*>(static_cast<const char*>(ws) + off); }
+
+int check_desc(const dgp_cond_desc* d);
+
+#ifdef __CUDACC__
+// ------------------------------------------------------------------------------------------------ PTX wrappers
+// fp64 tensor-core MMA, m8n8k4 (SASS: DMMA.8x8x4).  Fragment layout (g = lane>>2, t = lane&3):
+//   a = A[g][t]     b = B[t][g]     c[i] = C[g][2t+i]
+__device__ __forceinline__ void dmma884(double (&c)[2], double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                 : "+d"(c[0]), "+d"(c[1]) : "d"(a), "d"(b));
+}
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" :: "r"(smem_u32(smem)), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" :: "n"(N) : "memory"); }
+
+// ---- bulk async copies (TMA engine, SASS UBLKCP): 16-byte aligned addresses, size multiple of 16
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" :: "r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" :: "r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "DGP_WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DGP_DONE_%=;\n"
+        "bra DGP_WAIT_%=;\n"
+        "DGP_DONE_%=:\n"
+        "}\n" :: "r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n"
+                 :: "r"(smem_u32(smem_dst)), "l"(gsrc), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void bulk_s2g(void* gdst, const void* smem_src, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;\n"
+                 :: "l"(gdst), "r"(smem_u32(smem_src)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;\n" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;\n" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory"); }
+
+// ------------------------------------------------------------------------------------------------ covariance functions
+// value k(r2)/variance and d k/d r2 / variance  (gpflow RBF / Matern52)
+__device__ __forceinline__ double kern_val(int kind, double r2) {
+    if (kind == DGP_KIND_RBF) return exp(-0.5 * r2);
+    const double s5 = 2.23606797749978969641;
+    const double r = sqrt(r2 + 1e-12);
+    return (1.0 + s5 * r + (5.0 / 3.0) * r * r) * exp(-s5 * r);
+}
+__device__ __forceinline__ void kern_val_grad(int kind, double r2, double& k, double& dk_dr2) {
+    if (kind == DGP_KIND_RBF) {
+        k = exp(-0.5 * r2);
+        dk_dr2 = -0.5 * k;
+        return;
+    }
+    const double s5 = 2.23606797749978969641;
+    const double r = sqrt(r2 + 1e-12);
+    const double e = exp(-s5 * r);
+    k = (1.0 + s5 * r + (5.0 / 3.0) * r * r) * e;
+    dk_dr2 = -(5.0 / 6.0) * (1.0 + s5 * r) * e;  // (dk/dr) / (2 r); finite at r -> 0
+}
+
+// ------------------------------------------------------------------------------------------------ Philox4x32-10
+__device__ __forceinline__ void philox4x32_10(uint32_t (&c)[4], uint32_t k0, uint32_t k1) {
+#pragma unroll
+    for (int i = 0; i < 10; ++i) {
+        const uint32_t hi0 = __umulhi(0xD2511F53u, c[0]), lo0 = 0xD2511F53u * c[0];
+        const uint32_t hi1 = __umulhi(0xCD9E8D57u, c[2]), lo1 = 0xCD9E8D57u * c[2];
+        const uint32_t n0 = hi1 ^ c[1] ^ k0, n1 = lo1, n2 = hi0 ^ c[3] ^ k1, n3 = lo0;
+        c[0] = n0; c[1] = n1; c[2] = n2; c[3] = n3;
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+}
+// One N(0,1) draw per (global row, output column): counter = (row, col), key = seed.  Independent of how rows are
+// sharded over GPUs or tiles, so 1/2/4/8-GPU runs see the same noise.
+__device__ __forceinline__ double philox_normal(uint64_t seed, uint64_t row, uint32_t col) {
+    uint32_t c[4] = {(uint32_t)row, (uint32_t)(row >> 32), col, 0x44475042u};
+    philox4x32_10(c, (uint32_t)seed, (uint32_t)(seed >> 32));
+    const double u1 = ((double)(((uint64_t)c[0] << 21) | (c[1] >> 11)) + 0.5) * (1.0 / 9007199254740992.0);
+    const double u2 = ((double)(((uint64_t)c[2] << 21) | (c[3] >> 11)) + 0.5) * (1.0 / 9007199254740992.0);
+    return sqrt(-2.0 * log(u1)) * cospi(2.0 * u2);
+}
+
+// ------------------------------------------------------------------------------------------------ block reduce
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+// deterministic block sum; `red` is shared scratch of >= 32 doubles; result valid in every thread
+__device__ __forceinline__ double block_sum(double v, double* red) {
+    v = warp_sum(v);
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+    __syncthreads();
+    if (lane == 0) red[w] = v;
+    __syncthreads();
+    double s = 0.0;
+    for (int i = 0; i < nw; ++i) s += red[i];
+    return s;
+}
+#endif  // __CUDACC__
+
+}  // namespace dgp

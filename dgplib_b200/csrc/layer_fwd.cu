@@ -1,0 +1,311 @@
+// Fused forward row-tile kernel of one whitened conditional (the per-row hot path).
+//
+// For a tile of NT rows x_n of the flattened [S*B] batch, entirely on chip:
+//   K   Kuf tile   k(z_m, x_n)                  cross term on fp64 tensor cores (DMMA), norms + exp epilogue
+//   T   A = Lm^-1 Kuf                           streamed lower-triangular GEMM, in place in shared memory
+//   E1  mean = A^T q_mu + mean_fn(x), sum_m A^2 ; A tile -> HBM (bulk async store) for the backward pass
+//   U   sum_m (tril(q_sqrt_r)^T A)^2, r < R     streamed upper-triangular GEMMs, squared-column-sum epilogue;
+//                                               the reference's [R, M, N'] LTA tensor is never materialised
+//   E2  var = Kdiag - sum A^2 + sum U^2 ; F = mean + eps sqrt(var)   (eps given, or Philox4x32-10)
+// Replaces the TF sub-graph of gpflow's base_conditional(white=True) as called from dgplib/layers.py:65-71 on the
+// flattened samples (dgplib/layers.py:84-87), and normal_sample's diag branch (dgplib/utils.py:25-27).
+#include "stream_gemm.cuh"
+
+namespace dgp {
+
+struct FwdArgs {
+    dgp_cond_desc d;
+    int Mpad, Dp;
+    const double* Zs; const double* zn; const int32_t* ztask;
+    const double* Linv; const double* LqT;
+    const double* X; long long x_rows, n_rows;
+    const double* eps; unsigned long long seed, row_offset; long long rows_per_sample, sample_stride;
+    double* mean; double* var; double* F; int ldf; double* A_save;
+    int ntiles;
+};
+
+template <class C>
+struct FwdSmem {
+    // offsets in doubles inside the dynamic shared memory block
+    int ldb, xld;
+    int Bt, Wst, xs, xn, kd, sumsq, usqp, xtask, total_doubles;
+    __host__ __device__ FwdSmem(int Mpad, int Dp) {
+        ldb = Mpad + 4;
+        xld = Dp + 4;
+        int o = 0;
+        Bt = o; o += C::NT * ldb;
+        Wst = o; o += C::STAGES * C::STAGE_DOUBLES;
+        xs = o; o += C::NT * xld;
+        xn = o; o += C::NT;
+        kd = o; o += C::NT;
+        sumsq = o; o += C::NT;
+        usqp = o; o += 2 * C::WM * C::NT;
+        xtask = o; o += C::NT / 2 + 1;  // int32[NT]
+        total_doubles = o;
+    }
+};
+
+template <class C>
+__global__ void __launch_bounds__(C::NTHREADS, 1) k_cond_fwd(FwdArgs a) {
+    extern __shared__ __align__(128) double smem[];
+    const FwdSmem<C> L(a.Mpad, a.Dp);
+    double* Bt = smem + L.Bt;
+    double* Wst = smem + L.Wst;
+    double* xs = smem + L.xs;
+    double* xn = smem + L.xn;
+    double* kd = smem + L.kd;
+    double* sumsq = smem + L.sumsq;
+    double* usqp = smem + L.usqp;
+    int32_t* xtask = reinterpret_cast<int32_t*>(smem + L.xtask);
+
+    const dgp_cond_desc& d = a.d;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
+    const int wm = warp / C::WN;
+    const int Mpad = a.Mpad, Dp = a.Dp, ldb = L.ldb, xld = L.xld;
+    const int nb = (Mpad + C::MB - 1) / C::MB;
+    const int thd = 2 + d.D;
+
+    for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
+        const long long n0 = (long long)tile * C::NT;
+        // the previous tile's bulk store of Bt must have finished reading shared memory, and every warp must be done
+        // with the previous tile, before Bt / xs are overwritten
+        bulk_wait_read0();
+        __syncthreads();
+
+        // ---- tile setup: scaled inputs, norms, task ids, Kdiag
+        for (int n = tid; n < C::NT; n += C::NTHREADS) {
+            long long gn = n0 + n;
+            if (gn >= a.n_rows) gn = a.n_rows - 1;  // ragged last tile: compute on a valid row, never store it
+            const double* xr = a.X + (size_t)(gn % a.x_rows) * d.Dx;
+            int tk = 0;
+            if (d.T > 1) {
+                tk = (int)xr[d.Dx - 1];
+                if (tk < 0 || tk >= d.T) tk = -1;
+            }
+            xtask[n] = tk;
+            const double* th = d.theta + (size_t)(tk < 0 ? 0 : tk) * thd;
+            double s = 0.0;
+            for (int k = 0; k < Dp; ++k) {
+                double v = 0.0;
+                if (k < d.D) v = xr[k] / th[2 + k];
+                xs[n * xld + k] = v;
+                s = fma(v, v, s);
+            }
+            xn[n] = s;
+            kd[n] = (tk < 0) ? 0.0 : th[0] + th[1];  // Stationary.Kdiag + White.Kdiag
+        }
+        __syncthreads();
+
+        // ---- phase K: Bt[n][m] = k(z_m, x_n); cross term z.x on the tensor cores
+        for (int mt = warp; mt < Mpad / 8; mt += C::NWARPS) {
+            const int m = mt * 8 + g;
+            const double znm = a.zn[m];
+            const int ztm = a.ztask[m];
+            const double* zrow = a.Zs + (size_t)m * Dp;
+            for (int nt = 0; nt < C::NT / 8; ++nt) {
+                double c[2] = {0.0, 0.0};
+                for (int kk = 0; kk < Dp / 4; ++kk) dmma884(c, zrow[kk * 4 + t], xs[(nt * 8 + g) * xld + kk * 4 + t]);
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    const int n = nt * 8 + 2 * t + e;
+                    double val = 0.0;
+                    const int tx = xtask[n];
+                    if (m < d.M && ztm == tx && tx >= 0) {
+                        const double r2 = znm + xn[n] - 2.0 * c[e];
+                        val = d.theta[(size_t)tx * thd] * kern_val(d.kind[tx], r2);
+                    }
+                    Bt[n * ldb + m] = val;
+                }
+            }
+        }
+        // (run_phase starts with a __syncthreads)
+
+        // ---- phase T: A = Linv * Kuf, block rows bottom-up so the tile is updated in place
+        {
+            auto segfn = [&](int s) {
+                Seg sg;
+                sg.W = a.Linv;
+                sg.i = nb - 1 - s;
+                sg.kc0 = 0;
+                int kend = (sg.i + 1) * C::MB;
+                if (kend > Mpad) kend = Mpad;
+                sg.kc1 = kend / C::KC;
+                sg.r = 0;
+                sg.flush = true;
+                return sg;
+            };
+            auto epi = [&](Acc<C>& acc, const Seg& sg) {
+                __syncthreads();  // all warps finished reading this block row's k-range of Bt
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const int row = acc_row<C>(sg.i, q);
+                    if (row < Mpad) {
+#pragma unroll
+                        for (int j = 0; j < C::NJ; ++j) {
+                            Bt[acc_col<C>(j, 0) * ldb + row] = acc.v[q][j][0];
+                            Bt[acc_col<C>(j, 1) * ldb + row] = acc.v[q][j][1];
+                        }
+                    }
+                }
+            };
+            run_phase<C, MASK_LOWER, false>(nb, segfn, epi, Wst, Bt, ldb, Mpad, nullptr, 0);
+        }
+        __syncthreads();
+
+        // ---- E1: A tile -> HBM; mean = A^T q_mu + mean_fn(x); sumsq = sum_m A^2
+        if (a.A_save) {
+            fence_async_smem();
+            if (tid < C::NT && n0 + tid < a.n_rows) {
+                bulk_s2g(a.A_save + (size_t)(n0 + tid) * Mpad, Bt + tid * ldb, (uint32_t)(Mpad * sizeof(double)));
+                bulk_commit();
+            }
+        }
+        for (int idx = tid; idx < C::NT * d.R; idx += C::NTHREADS) {
+            const int n = idx / d.R, r = idx % d.R;
+            const double* arow = Bt + n * ldb;
+            const double* qm = d.q_mu + d.col0 + r;
+            double s = 0.0, a2 = 0.0;
+            for (int m = 0; m < d.M; ++m) {
+                const double av = arow[m];
+                s = fma(av, qm[(size_t)m * d.ldr], s);
+                a2 = fma(av, av, a2);
+            }
+            const long long gn = n0 + n;
+            if (r == 0) sumsq[n] = a2;
+            if (gn < a.n_rows) {
+                if (d.mean_A) {
+                    const double* xr = a.X + (size_t)(gn % a.x_rows) * d.Dx;
+                    for (int k = 0; k < d.Dx; ++k) s = fma(xr[k], d.mean_A[(size_t)k * d.ldr + d.col0 + r], s);
+                    if (d.mean_b) s += d.mean_b[d.col0 + r];
+                }
+                a.mean[(size_t)gn * d.ldr + d.col0 + r] = s;
+            }
+        }
+        // (run_phase starts with a __syncthreads: sumsq and the mean stores are ordered before E2)
+
+        // ---- phase U + E2
+        {
+            double colsq[C::NJ][2];
+#pragma unroll
+            for (int j = 0; j < C::NJ; ++j) { colsq[j][0] = 0.0; colsq[j][1] = 0.0; }
+            auto segfn = [&](int s) {
+                Seg sg;
+                sg.r = s / nb;
+                sg.i = s % nb;
+                sg.W = a.LqT + (size_t)sg.r * Mpad * Mpad;
+                sg.kc0 = sg.i * C::MB / C::KC;
+                sg.kc1 = Mpad / C::KC;
+                sg.flush = true;
+                return sg;
+            };
+            auto epi = [&](Acc<C>& acc, const Seg& sg) {
+#pragma unroll
+                for (int q = 0; q < 4; ++q)
+#pragma unroll
+                    for (int j = 0; j < C::NJ; ++j) {
+                        colsq[j][0] = fma(acc.v[q][j][0], acc.v[q][j][0], colsq[j][0]);
+                        colsq[j][1] = fma(acc.v[q][j][1], acc.v[q][j][1], colsq[j][1]);
+                    }
+                if (sg.i != nb - 1) return;
+                // ---- E2 for output r: reduce the column sums over the 8 row groups of the warp, then over warps
+                double* part = usqp + (sg.r & 1) * C::WM * C::NT;
+#pragma unroll
+                for (int j = 0; j < C::NJ; ++j)
+#pragma unroll
+                    for (int e = 0; e < 2; ++e) {
+                        double v = colsq[j][e];
+                        v += __shfl_xor_sync(0xffffffffu, v, 4);
+                        v += __shfl_xor_sync(0xffffffffu, v, 8);
+                        v += __shfl_xor_sync(0xffffffffu, v, 16);
+                        if (g == 0) part[wm * C::NT + acc_col<C>(j, e)] = v;
+                        colsq[j][e] = 0.0;
+                    }
+                __syncthreads();
+                if (tid < C::NT) {
+                    const int n = tid;
+                    const long long gn = n0 + n;
+                    if (gn < a.n_rows) {
+                        double u = 0.0;
+#pragma unroll
+                        for (int w = 0; w < C::WM; ++w) u += part[w * C::NT + n];
+                        const int col = d.col0 + sg.r;
+                        const double v = kd[n] - sumsq[n] + u;
+                        a.var[(size_t)gn * d.ldr + col] = v;
+                        if (a.F) {
+                            const double mu = a.mean[(size_t)gn * d.ldr + col];
+                            double z;
+                            if (a.eps) {
+                                z = a.eps[(size_t)gn * d.ldr + col];
+                            } else {
+                                const unsigned long long rid = a.row_offset +
+                                    (unsigned long long)(gn / a.rows_per_sample) * a.sample_stride + (gn % a.rows_per_sample);
+                                z = philox_normal(a.seed, rid, (uint32_t)col);
+                            }
+                            a.F[(size_t)gn * a.ldf + col] = mu + z * sqrt(v);  // var ** 0.5, no clamp (dgplib/utils.py:27)
+                            if (sg.r == 0 && d.col0 == 0 && a.ldf > d.ldr)
+                                a.F[(size_t)gn * a.ldf + a.ldf - 1] = a.X[(size_t)(gn % a.x_rows) * d.Dx + d.Dx - 1];
+                        }
+                    }
+                }
+            };
+            run_phase<C, MASK_UPPER, false>(nb * d.R, segfn, epi, Wst, Bt, ldb, Mpad, nullptr, 0);
+        }
+    }
+    bulk_wait_read0();
+}
+
+template <class C>
+static int launch_fwd(const FwdArgs& a, cudaStream_t st) {
+    const FwdSmem<C> L(a.Mpad, a.Dp);
+    const size_t bytes = (size_t)L.total_doubles * sizeof(double);
+    if (bytes > 227 * 1024) return DGP_ERR_UNSUPPORTED;
+    static size_t configured = 0;
+    if (bytes > configured) {
+        if (cudaFuncSetAttribute(k_cond_fwd<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes) != cudaSuccess) return DGP_ERR_LAUNCH;
+        configured = bytes;
+    }
+    int grid = a.ntiles < device_sm_count() ? a.ntiles : device_sm_count();
+    k_cond_fwd<C><<<grid, C::NTHREADS, bytes, st>>>(a);
+    DGP_COUNT_LAUNCH();
+    return cudaGetLastError() == cudaSuccess ? DGP_OK : DGP_ERR_LAUNCH;
+}
+
+}  // namespace dgp
+
+using namespace dgp;
+
+extern "C" int dgp_cond_forward(const dgp_cond_desc* d, const void* ws, const double* X, int64_t x_rows, int64_t n_rows,
+                                const double* eps, uint64_t seed, uint64_t row_offset, int64_t rows_per_sample,
+                                int64_t sample_stride, double* mean, double* var, double* F, int32_t ldf,
+                                double* A_save, void* stream) {
+    int rc = check_desc(d);
+    if (rc != DGP_OK) return rc;
+    if (!ws || !X || !mean || !var || x_rows < 1 || n_rows < 0) return DGP_ERR_ARG;
+    if (F && ldf < d->ldr) return DGP_ERR_ARG;
+    if (n_rows == 0) return DGP_OK;
+    const WsLayout w = ws_layout(*d, 0, 0);
+    FwdArgs a{};
+    a.d = *d;
+    a.Mpad = w.Mpad; a.Dp = w.Dp;
+    a.Zs = ws_ptr<double>(ws, w.Zs); a.zn = ws_ptr<double>(ws, w.zn); a.ztask = ws_ptr<int32_t>(ws, w.ztask);
+    a.Linv = ws_ptr<double>(ws, w.Linv); a.LqT = ws_ptr<double>(ws, w.LqT);
+    a.X = X; a.x_rows = x_rows; a.n_rows = n_rows;
+    a.eps = eps; a.seed = seed; a.row_offset = row_offset;
+    a.rows_per_sample = rows_per_sample > 0 ? rows_per_sample : n_rows;
+    a.sample_stride = sample_stride > 0 ? sample_stride : a.rows_per_sample;
+    a.mean = mean; a.var = var; a.F = F; a.ldf = ldf; a.A_save = A_save;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (w.Mpad <= 256) {
+        using C = TileCfg<4, 2, 64, 3>;
+        a.ntiles = (int)((n_rows + C::NT - 1) / C::NT);
+        return launch_fwd<C>(a, st);
+    } else if (w.Mpad <= 512) {
+        using C = TileCfg<4, 2, 32, 3>;
+        a.ntiles = (int)((n_rows + C::NT - 1) / C::NT);
+        return launch_fwd<C>(a, st);
+    } else {
+        using C = TileCfg<4, 2, 16, 3>;
+        a.ntiles = (int)((n_rows + C::NT - 1) / C::NT);
+        return launch_fwd<C>(a, st);
+    }
+}

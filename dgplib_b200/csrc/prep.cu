@@ -1,0 +1,406 @@
+// Parameter-only stage of one whitened conditional (runs once per ELBO evaluation, independent of the data rows):
+//   Kuu = k(Z,Z) + jitter I  ->  Lm = chol(Kuu)  ->  Linv = Lm^-1,   LqT_r = tril(q_sqrt_r)^T,   KL(q||p) whitened.
+// Replaces features.Kuu / tf.cholesky inside gpflow's base_conditional (called at dgplib/layers.py:66-69) and
+// gauss_kl(q_mu, q_sqrt, K=None) (dgplib/layers.py:58-60).  SURVEY.md Appendix A.
+//
+// Design note: the reference does A = triangular_solve(Lm, Kuf) per evaluation.  Here the solve is turned into a
+// tensor-core GEMM by forming Lm^-1 once (O(M^3), parameter-only) so that the per-row stage is A = Linv * Kuf with
+// block skipping; measured against 50-digit arithmetic the explicit inverse stays within 3x of LAPACK's substitution
+// error on the worst-conditioned reference configuration (D=1, M=50).
+#include "common.cuh"
+#define DGP_GEMM_SMALL_IMPL
+#include "gemm_small.cuh"
+
+namespace dgp {
+
+long long g_launches = 0;
+
+int device_sm_count() {
+    static int n = 0;
+    if (n == 0) {
+        int dev = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0)
+            n = 148;  // B200; also used when cross-checking layouts on a GPU-less host
+    }
+    return n;
+}
+
+int check_desc(const dgp_cond_desc* d) {
+    if (!d) return DGP_ERR_ARG;
+    if (d->M < 1 || d->M > 1024) return DGP_ERR_UNSUPPORTED;
+    if (d->D < 1 || d->D > DGP_MAX_D || d->Dx < d->D) return DGP_ERR_ARG;
+    if (d->R < 1 || d->R > DGP_MAX_R || d->ldr < d->R || d->col0 < 0 || d->col0 + d->R > d->ldr) return DGP_ERR_ARG;
+    if (d->T < 1 || d->T > DGP_MAX_TASKS) return DGP_ERR_ARG;
+    if (d->T > 1 && d->Dx < d->D + 1) return DGP_ERR_ARG;
+    for (int t = 0; t < d->T; ++t)
+        if (d->kind[t] != DGP_KIND_RBF && d->kind[t] != DGP_KIND_MATERN52) return DGP_ERR_UNSUPPORTED;
+    if (!d->Z || !d->theta || !d->q_mu || !d->q_sqrt) return DGP_ERR_ARG;
+    return DGP_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ scaled inducing inputs
+__global__ void k_prep_z(dgp_cond_desc d, int Mpad, int Dp, double* __restrict__ Zs, double* __restrict__ zn,
+                         int32_t* __restrict__ ztask) {
+    const int m = blockIdx.x * blockDim.x + threadIdx.x;
+    if (m >= Mpad) return;
+    if (m >= d.M) {
+        for (int k = 0; k < Dp; ++k) Zs[(size_t)m * Dp + k] = 0.0;
+        zn[m] = 0.0;
+        ztask[m] = -1;
+        return;
+    }
+    int t = 0;
+    if (d.T > 1) {
+        t = (int)d.Z[(size_t)m * d.Dx + d.Dx - 1];
+        if (t < 0 || t >= d.T) t = -1;  // out-of-range id: matches no kernel (row of zeros, like an empty partition)
+    }
+    ztask[m] = t;
+    const double* th = d.theta + (size_t)(t < 0 ? 0 : t) * (2 + d.D);
+    double s = 0.0;
+    for (int k = 0; k < Dp; ++k) {
+        double v = 0.0;
+        if (k < d.D) v = d.Z[(size_t)m * d.Dx + k] / th[2 + k];
+        Zs[(size_t)m * Dp + k] = v;
+        s = fma(v, v, s);
+    }
+    zn[m] = s;
+}
+
+// Kuu(+jitter) into the Lm buffer, padded with the identity.  r2 = |zi|^2 + |zj|^2 - 2 zi.zj on scaled inputs with no
+// clamp, as gpflow's Stationary.scaled_square_dist does.  White enters the symmetric call only (T == 1); inside a
+// SwitchedKernel the sub-kernels are always called with an explicit X2 (dgplib/specialized_kernels.py:47).
+__global__ void k_kuu(dgp_cond_desc d, int Mpad, int Dp, const double* __restrict__ Zs, const double* __restrict__ zn,
+                      const int32_t* __restrict__ ztask, double* __restrict__ K) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    const int i = blockIdx.y;
+    if (j >= Mpad) return;
+    double v;
+    if (i >= d.M || j >= d.M) {
+        v = (i == j) ? 1.0 : 0.0;
+    } else {
+        const int ti = ztask[i], tj = ztask[j];
+        v = 0.0;
+        if (ti == tj && ti >= 0) {
+            const double* th = d.theta + (size_t)ti * (2 + d.D);
+            double c = 0.0;
+            for (int k = 0; k < Dp; ++k) c = fma(Zs[(size_t)i * Dp + k], Zs[(size_t)j * Dp + k], c);
+            const double r2 = zn[i] + zn[j] - 2.0 * c;
+            v = th[0] * kern_val(d.kind[ti], r2);
+        }
+        if (i == j) {
+            v += d.jitter;
+            if (d.T == 1) v += d.theta[1];
+        }
+    }
+    K[(size_t)i * Mpad + j] = v;
+}
+
+// ------------------------------------------------------------------------------------------------ Cholesky (one CTA)
+// Right-looking blocked Cholesky of the Mpad x Mpad matrix in global memory (L2-resident), lower factor in place,
+// strict upper triangle zeroed.  NB = 32 (Mpad <= 512) or 16.  512 threads.
+constexpr int CHOL_THREADS = 512;
+
+__global__ void __launch_bounds__(CHOL_THREADS, 1)
+k_cholesky(double* __restrict__ K, int Mpad, int NB, int32_t* __restrict__ status) {
+    extern __shared__ double sm[];
+    double* sD = sm;                 // [NB][33]
+    double* sDinv = sD + 32 * 33;    // [32]
+    double* sP = sDinv + 32;         // [(Mpad-NB)][NB+1]
+    __shared__ int s_fail;
+    const int tid = threadIdx.x;
+    const int ldp = NB + 1;
+    if (tid == 0) s_fail = 0;
+    __syncthreads();
+
+    for (int j0 = 0; j0 < Mpad; j0 += NB) {
+        // 1. diagonal block -> smem
+        for (int e = tid; e < NB * NB; e += CHOL_THREADS) {
+            const int i = e / NB, j = e % NB;
+            sD[i * 33 + j] = K[(size_t)(j0 + i) * Mpad + j0 + j];
+        }
+        __syncthreads();
+        // 2. unblocked factorisation of the NB x NB block by the whole CTA
+        for (int k = 0; k < NB; ++k) {
+            if (tid == 0) {
+                double p = sD[k * 33 + k];
+                if (!(p > 0.0)) {
+                    if (s_fail == 0) s_fail = j0 + k + 1;
+                    p = 1.0;
+                }
+                const double dk = sqrt(p);
+                sD[k * 33 + k] = dk;
+                sDinv[k] = 1.0 / dk;
+            }
+            __syncthreads();
+            if (tid > k && tid < NB) sD[tid * 33 + k] *= sDinv[k];
+            __syncthreads();
+            for (int e = tid; e < NB * NB; e += CHOL_THREADS) {
+                const int i = e / NB, j = e % NB;
+                if (j > k && j <= i) sD[i * 33 + j] = fma(-sD[i * 33 + k], sD[j * 33 + k], sD[i * 33 + j]);
+            }
+            __syncthreads();
+        }
+        // write the factored block back (upper part zero)
+        for (int e = tid; e < NB * NB; e += CHOL_THREADS) {
+            const int i = e / NB, j = e % NB;
+            K[(size_t)(j0 + i) * Mpad + j0 + j] = (j <= i) ? sD[i * 33 + j] : 0.0;
+        }
+        const int rem = Mpad - j0 - NB;
+        // 3. panel: rows below the block, one thread per row: x = a * Ljj^-T by forward substitution
+        for (int ri = tid; ri < rem; ri += CHOL_THREADS) {
+            const int i = j0 + NB + ri;
+            double x[32];
+#pragma unroll
+            for (int k = 0; k < 32; ++k) {
+                if (k < NB) {
+                    double s = K[(size_t)i * Mpad + j0 + k];
+#pragma unroll
+                    for (int p = 0; p < k; ++p) s = fma(-x[p], sD[k * 33 + p], s);
+                    x[k] = s * sDinv[k];
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < 32; ++k) {
+                if (k < NB) {
+                    K[(size_t)i * Mpad + j0 + k] = x[k];
+                    sP[ri * ldp + k] = x[k];
+                }
+            }
+        }
+        // zero the strict upper part right of the diagonal block
+        for (int e = tid; e < NB * rem; e += CHOL_THREADS) {
+            const int i = e / rem, j = e % rem;
+            K[(size_t)(j0 + i) * Mpad + j0 + NB + j] = 0.0;
+        }
+        __syncthreads();
+        // 4. trailing update (lower part only), 4x4 micro-tiles over the triangular tile set
+        const int nt = rem / 4;
+        const int ntile = nt * (nt + 1) / 2;
+        for (int p = tid; p < ntile; p += CHOL_THREADS) {
+            int ti = (int)((sqrt(8.0 * (double)p + 1.0) - 1.0) * 0.5);
+            while ((ti + 1) * (ti + 2) / 2 <= p) ++ti;
+            while (ti * (ti + 1) / 2 > p) --ti;
+            const int tj = p - ti * (ti + 1) / 2;
+            double acc[4][4];
+#pragma unroll
+            for (int a = 0; a < 4; ++a)
+#pragma unroll
+                for (int b = 0; b < 4; ++b) acc[a][b] = 0.0;
+            for (int k = 0; k < NB; ++k) {
+                double pa[4], pb[4];
+#pragma unroll
+                for (int a = 0; a < 4; ++a) pa[a] = sP[(ti * 4 + a) * ldp + k];
+#pragma unroll
+                for (int b = 0; b < 4; ++b) pb[b] = sP[(tj * 4 + b) * ldp + k];
+#pragma unroll
+                for (int a = 0; a < 4; ++a)
+#pragma unroll
+                    for (int b = 0; b < 4; ++b) acc[a][b] = fma(pa[a], pb[b], acc[a][b]);
+            }
+            const int i0 = j0 + NB + ti * 4, c0 = j0 + NB + tj * 4;
+#pragma unroll
+            for (int a = 0; a < 4; ++a)
+#pragma unroll
+                for (int b = 0; b < 4; ++b)
+                    if (c0 + b <= i0 + a) K[(size_t)(i0 + a) * Mpad + c0 + b] -= acc[a][b];
+        }
+        __syncthreads();
+    }
+    if (tid == 0) status[0] = s_fail;
+}
+
+// ------------------------------------------------------------------------------------------------ triangular inverse
+// (a) inverses of the 32x32 diagonal blocks of Lm, one CTA (32 threads) per block, written into Linv's diagonal blocks;
+//     everything else in Linv's block row is zeroed here.
+__global__ void k_diag_inv(const double* __restrict__ L, double* __restrict__ Linv, int Mpad) {
+    __shared__ double sL[32 * 33];
+    __shared__ double sX[32 * 33];
+    const int b0 = blockIdx.x * 32, lane = threadIdx.x;
+    for (int i = 0; i < 32; ++i) sL[i * 33 + lane] = L[(size_t)(b0 + i) * Mpad + b0 + lane];
+    __syncwarp();
+    // lane = column j of the inverse: forward substitution L x = e_j
+    for (int i = 0; i < 32; ++i) {
+        double s = (i == lane) ? 1.0 : 0.0;
+        for (int k = lane; k < i; ++k) s = fma(-sL[i * 33 + k], sX[k * 33 + lane], s);
+        sX[i * 33 + lane] = (i >= lane) ? s / sL[i * 33 + i] : 0.0;
+    }
+    __syncwarp();
+    for (int i = 0; i < 32; ++i) {
+        for (int j = lane; j < Mpad; j += 32) {
+            const bool in = (j >= b0 && j < b0 + 32);
+            Linv[(size_t)(b0 + i) * Mpad + j] = in ? sX[i * 33 + (j - b0)] : 0.0;
+        }
+    }
+}
+// (b) block forward substitution, one CTA per 32-wide column block c:  X_Ic = -Linv_II * sum_{K=c}^{I-1} L_IK X_Kc.
+__global__ void __launch_bounds__(256)
+k_tri_inv_cols(const double* __restrict__ L, double* __restrict__ Linv, int Mpad) {
+    __shared__ double sT[32 * 33];
+    __shared__ double sDi[32 * 33];
+    const int c = blockIdx.x, nb = Mpad / 32, tid = threadIdx.x;
+    const int c0 = c * 32;
+    for (int I = c + 1; I < nb; ++I) {
+        const int i0 = I * 32;
+        // T = sum_K L[I-block rows][K-block cols] * X[K-block rows][c-block cols], K = c .. I-1
+        // thread -> 4 consecutive columns of one row
+        const int ti = tid >> 3, tj = (tid & 7) * 4;
+        double acc[4] = {0.0, 0.0, 0.0, 0.0};
+        for (int k = c0; k < i0; ++k) {
+            const double l = L[(size_t)(i0 + ti) * Mpad + k];
+            const double* x = Linv + (size_t)k * Mpad + c0 + tj;
+#pragma unroll
+            for (int b = 0; b < 4; ++b) acc[b] = fma(l, x[b], acc[b]);
+        }
+#pragma unroll
+        for (int b = 0; b < 4; ++b) sT[ti * 33 + tj + b] = acc[b];
+        for (int e = tid; e < 32 * 32; e += 256) sDi[(e >> 5) * 33 + (e & 31)] = Linv[(size_t)(i0 + (e >> 5)) * Mpad + i0 + (e & 31)];
+        __syncthreads();
+        double out[4] = {0.0, 0.0, 0.0, 0.0};
+        for (int k = 0; k <= ti; ++k) {
+            const double di = sDi[ti * 33 + k];
+#pragma unroll
+            for (int b = 0; b < 4; ++b) out[b] = fma(di, sT[k * 33 + tj + b], out[b]);
+        }
+#pragma unroll
+        for (int b = 0; b < 4; ++b) Linv[(size_t)(i0 + ti) * Mpad + c0 + tj + b] = -out[b];
+        __syncthreads();  // X_Ic visible to the whole CTA before the next block row reads it (global, same CTA)
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ q_sqrt, KL
+// LqT[r][i][j] = tril(q_sqrt[col0+r])[j][i]  (upper triangular), zero padded.
+__global__ void k_lq_prep(dgp_cond_desc d, int Mpad, double* __restrict__ LqT) {
+    __shared__ double tile[32][33];
+    const int r = blockIdx.z;
+    const int i0 = blockIdx.y * 32, j0 = blockIdx.x * 32;  // output tile rows i0.., cols j0..
+    const double* q = d.q_sqrt + (size_t)(d.col0 + r) * d.M * d.M;
+    // read q[j][i] for j in j0.., i in i0.. (coalesced along i)
+    for (int jj = threadIdx.y; jj < 32; jj += blockDim.y) {
+        const int j = j0 + jj, i = i0 + threadIdx.x;
+        tile[jj][threadIdx.x] = (j < d.M && i < d.M && i <= j) ? q[(size_t)j * d.M + i] : 0.0;
+    }
+    __syncthreads();
+    for (int ii = threadIdx.y; ii < 32; ii += blockDim.y)
+        LqT[((size_t)r * Mpad + i0 + ii) * Mpad + j0 + threadIdx.x] = tile[threadIdx.x][ii];
+}
+
+// KL = 0.5 (sum q_mu^2 - M R - sum log diag(Lq)^2 + sum Lq^2) for this conditional's columns (single CTA, deterministic)
+__global__ void __launch_bounds__(1024) k_kl(dgp_cond_desc d, double* __restrict__ kl_out) {
+    __shared__ double red[32];
+    const int M = d.M, R = d.R;
+    double s = 0.0;
+    const size_t nq = (size_t)R * M * M;
+    for (size_t e = threadIdx.x; e < nq; e += blockDim.x) {
+        const int r = (int)(e / ((size_t)M * M));
+        const int i = (int)((e / M) % M), j = (int)(e % M);
+        if (j <= i) {
+            const double v = d.q_sqrt[(size_t)(d.col0 + r) * M * M + (size_t)i * M + j];
+            s = fma(v, v, s);
+            if (i == j) s -= log(v * v);
+        }
+    }
+    for (int e = threadIdx.x; e < M * R; e += blockDim.x) {
+        const double v = d.q_mu[(size_t)(e / R) * d.ldr + d.col0 + (e % R)];
+        s = fma(v, v, s);
+    }
+    const double tot = block_sum(s, red);
+    if (threadIdx.x == 0) kl_out[0] = 0.5 * (tot - (double)M * R);
+}
+
+__global__ void k_transpose(const double* __restrict__ in, double* __restrict__ out, int n) {
+    __shared__ double tile[32][33];
+    const int i0 = blockIdx.y * 32, j0 = blockIdx.x * 32;
+    for (int ii = threadIdx.y; ii < 32; ii += blockDim.y) tile[ii][threadIdx.x] = in[(size_t)(i0 + ii) * n + j0 + threadIdx.x];
+    __syncthreads();
+    for (int jj = threadIdx.y; jj < 32; jj += blockDim.y) out[(size_t)(j0 + jj) * n + i0 + threadIdx.x] = tile[threadIdx.x][jj];
+}
+
+// SmI[r] -= I on the leading M x M block
+__global__ void k_sub_identity(double* __restrict__ S, int Mpad, int M) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < M) S[((size_t)blockIdx.y * Mpad + i) * Mpad + i] -= 1.0;
+}
+
+}  // namespace dgp
+
+using namespace dgp;
+
+extern "C" int32_t dgp_mpad(int32_t M) { return (M + 63) / 64 * 64; }
+
+extern "C" size_t dgp_cond_ws_bytes(const dgp_cond_desc* d, int64_t n_rows, int need_bwd) {
+    if (!d || d->M < 1 || d->R < 1 || n_rows < 0) return 0;
+    return ws_layout(*d, n_rows, need_bwd).total;
+}
+
+extern "C" int dgp_cond_prepare(const dgp_cond_desc* d, void* ws, size_t ws_bytes, int need_bwd, double* kl_out, void* stream_) {
+    int rc = check_desc(d);
+    if (rc != DGP_OK) return rc;
+    if (!ws) return DGP_ERR_ARG;
+    cudaStream_t st = (cudaStream_t)stream_;
+    // the caller sized the workspace for some n_rows; only the parameter part (independent of n_rows) is touched here
+    const WsLayout w = ws_layout(*d, 0, 0);
+    if (ws_bytes < w.total) return DGP_ERR_WORKSPACE;
+    const int Mpad = w.Mpad, Dp = w.Dp;
+    double* Zs = ws_ptr<double>(ws, w.Zs);
+    double* zn = ws_ptr<double>(ws, w.zn);
+    int32_t* ztask = ws_ptr<int32_t>(ws, w.ztask);
+    double* Lm = ws_ptr<double>(ws, w.Lm);
+    double* Linv = ws_ptr<double>(ws, w.Linv);
+    double* LqT = ws_ptr<double>(ws, w.LqT);
+    int32_t* status = ws_ptr<int32_t>(ws, w.status);
+
+    k_prep_z<<<(Mpad + 127) / 128, 128, 0, st>>>(*d, Mpad, Dp, Zs, zn, ztask); DGP_COUNT_LAUNCH();
+    k_kuu<<<dim3((Mpad + 127) / 128, Mpad), 128, 0, st>>>(*d, Mpad, Dp, Zs, zn, ztask, Lm); DGP_COUNT_LAUNCH();
+    const int NB = (Mpad <= 512) ? 32 : 16;
+    const size_t chol_smem = (32 * 33 + 32 + (size_t)(Mpad - NB) * (NB + 1)) * sizeof(double);
+    static bool attr_set = false;
+    if (!attr_set) {
+        if (cudaFuncSetAttribute(k_cholesky, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess) return DGP_ERR_LAUNCH;
+        attr_set = true;
+    }
+    k_cholesky<<<1, CHOL_THREADS, chol_smem, st>>>(Lm, Mpad, NB, status); DGP_COUNT_LAUNCH();
+    k_diag_inv<<<Mpad / 32, 32, 0, st>>>(Lm, Linv, Mpad); DGP_COUNT_LAUNCH();
+    k_tri_inv_cols<<<Mpad / 32, 256, 0, st>>>(Lm, Linv, Mpad); DGP_COUNT_LAUNCH();
+    k_lq_prep<<<dim3(Mpad / 32, Mpad / 32, d->R), dim3(32, 8), 0, st>>>(*d, Mpad, LqT); DGP_COUNT_LAUNCH();
+    if (kl_out) { k_kl<<<1, 1024, 0, st>>>(*d, kl_out); DGP_COUNT_LAUNCH(); }
+    if (need_bwd) {
+        const WsLayout wb = ws_layout(*d, 0, 1);  // LinvT and SmI offsets do not depend on n_rows
+        if (ws_bytes < wb.SmI + (size_t)Mpad * Mpad * d->R * sizeof(double)) return DGP_ERR_WORKSPACE;
+        double* LinvT = ws_ptr<double>(ws, wb.LinvT);
+        double* SmI = ws_ptr<double>(ws, wb.SmI);
+        k_transpose<<<dim3(Mpad / 32, Mpad / 32), dim3(32, 8), 0, st>>>(Linv, LinvT, Mpad); DGP_COUNT_LAUNCH();
+        // S_r = Lq_r Lq_r^T = LqT_r^T LqT_r :  A(i,k) = LqT[k][i], B(k,j) = LqT[k][j]
+        GemmArgs g{};
+        g.A = LqT; g.B = LqT; g.C = SmI;
+        g.I = Mpad; g.J = Mpad; g.K = Mpad;
+        g.sAi = 1; g.sAk = Mpad; g.sBk = Mpad; g.sBj = 1; g.sCi = Mpad; g.sCj = 1;
+        g.bA = g.bB = g.bC = (long long)Mpad * Mpad;
+        g.alpha = 1.0; g.beta = 0.0; g.batch = d->R;
+        rc = gemm_small(g, st);
+        if (rc != DGP_OK) return rc;
+        k_sub_identity<<<dim3((d->M + 127) / 128, d->R), 128, 0, st>>>(SmI, Mpad, d->M); DGP_COUNT_LAUNCH();
+    }
+    DGP_CHECK_LAUNCH();
+    return DGP_OK;
+}
+
+extern "C" int dgp_cond_status(const void* ws, void* stream_, int32_t* status_host) {
+    if (!ws || !status_host) return DGP_ERR_ARG;
+    cudaStream_t st = (cudaStream_t)stream_;
+    if (cudaMemcpyAsync(status_host, ws, sizeof(int32_t), cudaMemcpyDeviceToHost, st) != cudaSuccess) return DGP_ERR_LAUNCH;
+    if (cudaStreamSynchronize(st) != cudaSuccess) return DGP_ERR_LAUNCH;
+    return DGP_OK;
+}
+
+extern "C" const char* dgp_strerror(int code) {
+    switch (code) {
+        case DGP_OK: return "ok";
+        case DGP_ERR_ARG: return "invalid argument";
+        case DGP_ERR_LAUNCH: return "CUDA launch / runtime error";
+        case DGP_ERR_WORKSPACE: return "workspace too small";
+        case DGP_ERR_UNSUPPORTED: return "unsupported configuration";
+        default: return "unknown error";
+    }
+}
+extern "C" const char* dgp_version(void) { return "dgp_b200 0.1 (sm_100a)"; }
+extern "C" int64_t dgp_launch_count(void) { return (int64_t)g_launches; }

@@ -1,0 +1,149 @@
+/*
+ * dgp_b200.h -- C-ABI of the B200-native DSDGP hot path (libdgp_b200.so).
+ *
+ * The reference (aboustati/dgplib) has no FFI of its own: its hot path is a chain of GPflow/TensorFlow graph ops
+ * built by Python.  Each entry point below replaces the TF sub-graph emitted by the cited reference
+ * call site; the Python classes in dgplib_b200/ (same names as the reference's) bind them through ctypes.
+ *
+ * Conventions
+ *   - every pointer named in a "device" field/argument is a CUDA device pointer to fp64 (row-major) owned by the
+ *     caller; the library never allocates; scratch lives in caller-provided workspaces sized by the *_bytes calls
+ *   - `stream` is a cudaStream_t passed as void*; all work is enqueued on it and the call returns without syncing
+ *   - return value: 0 = enqueued, <0 = argument / launch error (dgp_strerror).  Numerical failure (Cholesky pivot
+ *     <= 0) is reported asynchronously in the int32 device word `status` of the layer workspace
+ *     (0 ok, k>0 = failed at pivot k-1), read with dgp_layer_status() after a stream sync
+ *   - stateless and re-entrant per stream
+ */
+#ifndef DGP_B200_H
+#define DGP_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DGP_KIND_RBF 0       /* gpflow.kernels.RBF      : s2 * exp(-r2/2)                                   */
+#define DGP_KIND_MATERN52 1  /* gpflow.kernels.Matern52 : s2 * (1+sqrt5 r+5/3 r^2) exp(-sqrt5 r), r=sqrt(r2+1e-12) */
+#define DGP_MAX_TASKS 16     /* kernels inside one SwitchedKernel                                             */
+#define DGP_MAX_D 64         /* kernel input dimension                                                       */
+#define DGP_MAX_R 64         /* outputs of one conditional                                                   */
+
+#define DGP_OK 0
+#define DGP_ERR_ARG (-1)
+#define DGP_ERR_LAUNCH (-2)
+#define DGP_ERR_WORKSPACE (-3)
+#define DGP_ERR_UNSUPPORTED (-4)
+
+/*
+ * One whitened sparse-GP conditional = one `gpflow.conditionals.conditional(Xnew, feature, kernel, q_mu,
+ * q_sqrt=q_sqrt, full_cov=False, white=True)` call: dgplib/layers.py:66-69 (Layer: one per layer) and
+ * dgplib/multikernel_layers.py:75-78 (MultikernelLayer: one per kernel, on a column slice of q_mu / q_sqrt).
+ */
+typedef struct dgp_cond_desc {
+    int32_t M;        /* inducing points (Layer.num_inducing, dgplib/layers.py:34)                              */
+    int32_t D;        /* kernel input_dim: the leading D columns of X / Z rows are the kernel's active dims      */
+    int32_t Dx;       /* row stride of X and Z in doubles: D, or D+1 when a task-id column is carried            */
+    int32_t R;        /* outputs of this conditional (output_dim, or offset = output_dim/num_kernels)             */
+    int32_t ldr;      /* row stride of q_mu / mean / var / eps / gradients in doubles (the layer's output_dim)     */
+    int32_t col0;     /* first output column of this conditional inside the layer: i*offset for kernel i of a      */
+                      /*     MultikernelLayer (dgplib/multikernel_layers.py:75-76), 0 for a Layer                  */
+    int32_t T;        /* 1 = stationary kernel (+White); >1 = SwitchedKernel over T kernels selected by the        */
+                      /*     integer task id in column Dx-1 (dgplib/specialized_kernels.py:23-72)                 */
+    int32_t kind[DGP_MAX_TASKS]; /* DGP_KIND_* of each of the T kernels                                          */
+    double jitter;    /* gpflow.settings.numerics.jitter_level = 1e-6 (dgplib/utils.py:12)                        */
+    /* device pointers */
+    const double* Z;      /* [M, Dx]   feature.Z (dgplib/layers.py:36-41)                                         */
+    const double* theta;  /* [T, 2+D]  per kernel: variance, White variance (0 if none), lengthscales[D]          */
+    const double* q_mu;   /* [M, ldr]    the layer's q_mu; this conditional uses columns col0 .. col0+R-1        */
+    const double* q_sqrt; /* [ldr, M, M] the layer's q_sqrt; rows col0 .. col0+R-1; only tril is read (band_part) */
+    const double* mean_A; /* [Dx, ldr]   Linear mean weights (gpflow Linear.A), or NULL for Zero                  */
+    const double* mean_b; /* [ldr]       Linear mean offset, or NULL                                              */
+} dgp_cond_desc;
+
+/* ---- parameter-only stage: Kuu(+jitter) -> Cholesky -> inverse factor, tril(q_sqrt)^T, KL ------------------- */
+/* bytes of the per-conditional workspace; need_bwd != 0 adds the buffers of the backward pass; n_rows bounds the
+ * number of rows (S*B) of any forward/backward call made with this workspace */
+size_t dgp_cond_ws_bytes(const dgp_cond_desc* d, int64_t n_rows, int need_bwd);
+/* Replaces: features.Kuu + tf.cholesky inside base_conditional, band_part(q_sqrt), and gauss_kl(q_mu, q_sqrt,
+ * K=None) of dgplib/layers.py:58-60.  kl_out (device, 1 double) receives this conditional's KL if not NULL. */
+int dgp_cond_prepare(const dgp_cond_desc* d, void* ws, size_t ws_bytes, int need_bwd, double* kl_out, void* stream);
+/* copies the Cholesky status word to the host (synchronises the stream) */
+int dgp_cond_status(const void* ws, void* stream, int32_t* status_host);
+
+/* All per-row arrays below (eps, mean, var, F, g_*) are the LAYER's arrays with row stride ldr (F: ldf); a
+ * conditional reads / writes only its own columns col0 .. col0+R-1. */
+/* ---- per-row stage, forward ----------------------------------------------------------------------------------
+ * Replaces: Kuf, matrix_triangular_solve, A^T q_mu, fvar = Knn - sum A^2 + sum (L^T A)^2, + mean_function(X)
+ * (dgplib/layers.py:65-71, flattened over samples as in :84-87) and normal_sample's diag branch
+ * (dgplib/utils.py:25-27).
+ *   X       [x_rows, Dx]; row n of the flattened [S*B] batch reads X row (n % x_rows): tile_over_samples
+ *           (dgplib/utils.py:15-18) without the copies
+ *   eps     [n_rows, ldr] N(0,1) draws, or NULL to draw Philox4x32-10 normals keyed by (seed, global row id, column)
+ *           with global row id = row_offset + (n / rows_per_sample) * sample_stride + n % rows_per_sample, so that a
+ *           shard holding rows_per_sample of sample_stride minibatch rows draws what the unsharded run draws
+ *           (rows_per_sample <= 0: n_rows; sample_stride <= 0: rows_per_sample)
+ *   mean,var[n_rows, ldr] outputs (this conditional's R columns)
+ *   F       [n_rows, ldf] sample mean + eps*sqrt(var) (NULL: skip).  When ldf > ldr the trailing column Dx-1 of X
+ *           is copied into column ldf-1 (task-label propagation, dgplib/multitask_dsdgp.py:20)
+ *   A_save  [n_rows, Mpad] Lm^-1 Kuf per row, kept for the backward pass (NULL: skip)
+ */
+int dgp_cond_forward(const dgp_cond_desc* d, const void* ws, const double* X, int64_t x_rows, int64_t n_rows,
+                     const double* eps, uint64_t seed, uint64_t row_offset, int64_t rows_per_sample,
+                     int64_t sample_stride, double* mean, double* var, double* F, int32_t ldf, double* A_save,
+                     void* stream);
+
+/* ---- likelihood ------------------------------------------------------------------------------------------------
+ * Gaussian / SwitchedLikelihood variational expectations, mean over S, sum over rows and outputs
+ * (dgplib/dsdgp.py:115-122), and their gradients.
+ *   Fmu, Fvar [n_rows, R];  Y [y_rows, ldy] (row n reads Y row n % y_rows; ldy = R, or R+1 with the task column)
+ *   lik_var   [T] device; T = 1 Gaussian, T > 1 SwitchedLikelihood
+ *   weight    = (num_data / B) / S   (dgplib/dsdgp.py:121, :128-129)
+ *   ve_sum    device double, += weight * sum VE      g_mu, g_var [n_rows, R] (NULL: forward only)
+ *   g_lik_var [T] device, += d/d lik_var
+ */
+int dgp_lik_gaussian(const double* Fmu, const double* Fvar, const double* Y, int64_t y_rows, int32_t ldy,
+                     int64_t n_rows, int32_t R, const double* lik_var, int32_t T, double weight, double* ve_sum,
+                     double* g_mu, double* g_var, double* g_lik_var, void* ws, size_t ws_bytes, void* stream);
+size_t dgp_lik_ws_bytes(int64_t n_rows, int32_t R);
+
+/* ---- per-row stage, backward ---------------------------------------------------------------------------------
+ * Reverse mode of dgp_cond_forward (what tf.gradients emits for dgplib/layers.py:65-71 and dgplib/utils.py:27).
+ *   g_mean_in, g_var_in [n_rows, ldr]  direct gradients of mean / var (last layer: from the likelihood), or NULL
+ *   g_F       [n_rows, ldgf] gradient of the sample F (from the next layer's gX), or NULL;  then
+ *             g_mean = g_mean_in + g_F,  g_var = g_var_in + g_F * (F - mean) / (2 var)
+ *   gX        [n_rows, Dx] gradient w.r.t. the input rows (NULL for the data layer); accumulate != 0 adds to it
+ * Row-summed parameter gradients are accumulated inside the workspace; dgp_cond_backward_params finishes them.
+ */
+int dgp_cond_backward(const dgp_cond_desc* d, void* ws, const double* X, int64_t x_rows, int64_t n_rows,
+                      const double* A_save, const double* mean, const double* var, const double* F, int32_t ldf,
+                      const double* g_mean_in, const double* g_var_in, const double* g_F, int32_t ldgf,
+                      double* gX, int32_t accumulate_gX, void* stream);
+/* Parameter-only tail: Cholesky / Kuu / KL reverse mode.  Outputs (device, this conditional's part OVERWRITTEN):
+ *   gZ [M, Dx], gtheta [T, 2+D], gq_mu [M, ldr] (columns col0..), gq_sqrt [ldr, M, M] (rows col0..)
+ *   kl_weight: this rank's share of the KL term (1/world_size) so that an all-reduce(sum) over ranks is exact */
+int dgp_cond_backward_params(const dgp_cond_desc* d, void* ws, double kl_weight, double* gZ, double* gtheta,
+                             double* gq_mu, double* gq_sqrt, void* stream);
+
+/* ---- stand-alone kernel-matrix entry points (dgplib_b200.specialized_kernels; gpflow Kernel.K / Kdiag) -------
+ *   K [n1, n2] = k(X1, X2) (White contributes nothing, as in gpflow when X2 is given);  symmetric != 0 computes
+ *   k(X1, X1) + White on the diagonal.  Kdiag [n1]. */
+int dgp_kernel_K(const dgp_cond_desc* d, const double* X1, int64_t n1, const double* X2, int64_t n2,
+                 int32_t symmetric, double* K, void* stream);
+int dgp_kernel_Kdiag(const dgp_cond_desc* d, const double* X1, int64_t n1, double* Kdiag, void* stream);
+
+/* ---- utilities ------------------------------------------------------------------------------------------------ */
+int32_t dgp_mpad(int32_t M);                 /* padded inducing count used for A_save rows and the workspaces      */
+int dgp_philox_normal(double* out, int64_t n_rows, int32_t R, int32_t ld, uint64_t seed, uint64_t row_offset,
+                      int64_t rows_per_sample, int64_t sample_stride,
+                      void* stream);         /* the same draws dgp_cond_forward makes when eps == NULL             */
+const char* dgp_strerror(int code);
+const char* dgp_version(void);
+/* number of kernels this library has launched since load (bench.py's gpu_launches) */
+int64_t dgp_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DGP_B200_H */

@@ -1,0 +1,132 @@
+// FP64 peak microbenchmark for B200 (sm_100a): register-resident DMMA m8n8k4 and DFMA issue rates.
+// Used once to establish the "FP64 tensor peak" roofline denominator; not on the product path.
+#include <cstdio>
+#include <cstdlib>
+#include <cuda_runtime.h>
+
+#define CK(x) do { cudaError_t e = (x); if (e != cudaSuccess) { printf("CUDA error %s at %d\n", cudaGetErrorString(e), __LINE__); exit(1);} } while (0)
+
+__device__ __forceinline__ void dmma884(double& d0, double& d1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                 : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
+}
+
+template <int NACC>
+__global__ void k_dmma(double* out, int iters, double a0, double b0) {
+    double acc[NACC][2];
+#pragma unroll
+    for (int i = 0; i < NACC; ++i) { acc[i][0] = 0.0; acc[i][1] = 0.0; }
+    double a = a0 + threadIdx.x * 1e-9, b = b0;
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int i = 0; i < NACC; ++i) dmma884(acc[i][0], acc[i][1], a, b);
+    }
+    double s = 0;
+#pragma unroll
+    for (int i = 0; i < NACC; ++i) s += acc[i][0] + acc[i][1];
+    out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
+template <int NACC>
+__global__ void k_dfma(double* out, int iters, double a0, double b0) {
+    double acc[NACC];
+#pragma unroll
+    for (int i = 0; i < NACC; ++i) acc[i] = i;
+    double a = a0 + threadIdx.x * 1e-9, b = b0;
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int i = 0; i < NACC; ++i) acc[i] = fma(acc[i], a, b);
+    }
+    double s = 0;
+#pragma unroll
+    for (int i = 0; i < NACC; ++i) s += acc[i];
+    out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
+// DMMA with shared-memory operand loads each k-step (32x32 warp tile: 4 A + 4 B LDS.64 per 16 DMMA)
+__global__ void k_dmma_lds(double* out, int iters) {
+    __shared__ double sA[64 * 20];
+    __shared__ double sB[64 * 20];
+    for (int i = threadIdx.x; i < 64 * 20; i += blockDim.x) { sA[i] = 1e-3 * i; sB[i] = 1e-4 * i; }
+    __syncthreads();
+    const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+    double acc[4][4][2];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { acc[i][j][0] = 0; acc[i][j][1] = 0; }
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk) {
+            double a[4], b[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) a[i] = sA[(i * 8 + g) * 20 + kk * 4 + t];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) b[j] = sB[(j * 8 + g) * 20 + kk * 4 + t];
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+        }
+    }
+    double s = 0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) s += acc[i][j][0] + acc[i][j][1];
+    out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
+template <typename F>
+float time_ms(F f) {
+    cudaEvent_t e0, e1;
+    CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+    f();  // warm
+    CK(cudaDeviceSynchronize());
+    float best = 1e30f;
+    for (int r = 0; r < 5; ++r) {
+        CK(cudaEventRecord(e0));
+        f();
+        CK(cudaEventRecord(e1));
+        CK(cudaEventSynchronize(e1));
+        float ms; CK(cudaEventElapsedTime(&ms, e0, e1));
+        if (ms < best) best = ms;
+    }
+    return best;
+}
+
+int main() {
+    cudaDeviceProp p; CK(cudaGetDeviceProperties(&p, 0));
+    int sms = p.multiProcessorCount;
+    printf("device %s sms %d clock %d kHz\n", p.name, sms, p.clockRate);
+    double* out; CK(cudaMalloc(&out, sizeof(double) * sms * 8 * 1024));
+    const int iters = 20000;
+    for (int warps = 4; warps <= 32; warps *= 2) {
+        for (int ctas = 1; ctas <= 2; ++ctas) {
+            int threads = warps * 32 / ctas;
+            if (threads > 1024 || threads < 32) continue;
+            {
+                float ms = time_ms([&] { k_dmma<8><<<sms * ctas, threads>>>(out, iters, 1.0, 1.0); });
+                double fl = 2.0 * 256 * 8 * (double)iters * warps * sms;
+                printf("DMMA884 acc=8  warps/SM=%2d ctas/SM=%d : %.3f ms  %.2f TFLOP/s\n", warps, ctas, ms, fl / ms * 1e-9);
+            }
+            {
+                float ms = time_ms([&] { k_dmma<16><<<sms * ctas, threads>>>(out, iters, 1.0, 1.0); });
+                double fl = 2.0 * 256 * 16 * (double)iters * warps * sms;
+                printf("DMMA884 acc=16 warps/SM=%2d ctas/SM=%d : %.3f ms  %.2f TFLOP/s\n", warps, ctas, ms, fl / ms * 1e-9);
+            }
+            {
+                float ms = time_ms([&] { k_dfma<16><<<sms * ctas, threads>>>(out, iters, 1.0000001, 1e-9); });
+                double fl = 2.0 * 32 * 16 * (double)iters * warps * sms;
+                printf("DFMA    acc=16 warps/SM=%2d ctas/SM=%d : %.3f ms  %.2f TFLOP/s\n", warps, ctas, ms, fl / ms * 1e-9);
+            }
+        }
+    }
+    for (int warps = 4; warps <= 16; warps *= 2) {
+        float ms = time_ms([&] { k_dmma_lds<<<sms, warps * 32>>>(out, 2000); });
+        double fl = 2.0 * 256 * 64 * 2000.0 * warps * sms;
+        printf("DMMA884+LDS 32x32 warp tile warps/SM=%2d : %.3f ms  %.2f TFLOP/s\n", warps, ms, fl / ms * 1e-9);
+    }
+    CK(cudaFree(out));
+    return 0;
+}
