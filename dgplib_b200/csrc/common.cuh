@@ -39,7 +39,7 @@ struct WsLayout {
     size_t gmv;        // [n_rows][2R] combined g_mean | g_var of this conditional
     size_t gram;       // [nsplit][R+1][Mpad][Mpad]  split-K partials of G_r (r<R) and P (r==R)
     size_t part;       // [ncta][npart] per-CTA partials: T2z[Mpad][Dp], cs[Mpad], dq_mu[Mpad][R], th[T][2+Dp]
-    size_t tail;       // [R+4][Mpad][Mpad] scratch of the parameter tail
+    size_t tail;       // [2R+4][Mpad][Mpad] scratch of the parameter tail (Gfull, Tq, Lbar, T1, T2, T3)
     size_t total;
 };
 
@@ -74,7 +74,7 @@ static inline WsLayout ws_layout(const dgp_cond_desc& d, int64_t n_rows, int nee
         w.SmI = o;   o += align256(mm * d.R);
         w.gram = o;  o += align256(mm * (d.R + 1) * w.nsplit);
         w.part = o;  o += align256(size_t(w.ncta) * w.npart * sizeof(double));
-        w.tail = o;  o += align256(mm * (d.R + 4));
+        w.tail = o;  o += align256(mm * (2 * d.R + 4));
         w.gmv = o;   o += align256(size_t(n_rows) * 2 * d.R * sizeof(double));
         w.dKuf = o;  o += align256(size_t(n_rows) * w.Mpad * sizeof(double));
     }

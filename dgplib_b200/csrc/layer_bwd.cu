@@ -1,0 +1,495 @@
+// Reverse mode of the per-row stage of one whitened conditional (what tf.gradients emits for the graph of
+// gpflow's base_conditional(white=True) called at dgplib/layers.py:65-71, and for normal_sample, dgplib/utils.py:27).
+// Formulas: SURVEY.md Appendix B, rearranged so that only A = Lm^-1 Kuf has to be kept from the forward pass:
+//
+//   g_mean = g_mean_in + g_F ;  g_var = g_var_in + g_F (F - mean) / (2 var)
+//   dA   = q_mu g_mean^T + 2 sum_r (S_r - I) (A . g_var_r),   S_r = Lq_r Lq_r^T      [dense streamed GEMM, K = R M]
+//   dKuf = Lm^-T dA                                                                   [upper-triangular streamed GEMM]
+//   dX, dZ, d lengthscale, d variance from dKuf . k'(r2)                              [per tile, small]
+//   G_r  = sum_n g_var[n,r] a_n a_n^T  (-> d q_sqrt_r = 2 tril(G_r Lq_r)),  P = sum_n dKuf_n a_n^T (-> d Lm = -tril P)
+//                                                                                     [split-K Gram kernel over the rows]
+// k_cond_bwd : one CTA per SM walks row tiles; A tile arrives by bulk async copy (TMA engine), dA / dKuf live in
+//              shared memory, dKuf leaves by bulk async store; row-summed pieces go to per-CTA partial buffers
+//              (no atomics: bitwise reproducible).
+// k_gram     : 64x64 output tiles x split-K over the rows, fp64 DMMA, partials per split (no atomics).
+#include "stream_gemm.cuh"
+
+namespace dgp {
+
+struct BwdArgs {
+    dgp_cond_desc d;
+    int Mpad, Dp;
+    const double* Zs; const double* zn; const int32_t* ztask;
+    const double* LinvT; const double* SmI;
+    const double* X; long long x_rows, n_rows;
+    const double* A_save; const double* mean; const double* var; const double* F; int ldf;
+    const double* g_mean_in; const double* g_var_in; const double* g_F; int ldgf;
+    double* gX; int accumulate_gX;
+    double* dKuf; double* gmv; double* part; int npart;
+    int ntiles;
+};
+
+template <class C>
+struct BwdSmem {
+    int ldb, xld;
+    int Bt, Dt, Wst, xs, xn, gm, gv, rs, dv, rowq, xtask, bar, total_doubles;
+    __host__ __device__ BwdSmem(int Mpad, int Dp, int R) {
+        ldb = Mpad + 4;
+        xld = Dp + 4;
+        int o = 0;
+        Bt = o; o += C::NT * ldb;
+        Dt = o; o += C::NT * ldb;
+        Wst = o; o += C::STAGES * C::STAGE_DOUBLES;
+        xs = o; o += C::NT * xld;
+        xn = o; o += C::NT;
+        gm = o; o += C::NT * R;
+        gv = o; o += C::NT * R;
+        rs = o; o += C::NT;
+        dv = o; o += C::NT;
+        rowq = o; o += C::NT * (2 + Dp);
+        xtask = o; o += C::NT / 2 + 1;
+        bar = o; o += 2;
+        total_doubles = o;
+    }
+};
+
+template <class C>
+__global__ void __launch_bounds__(C::NTHREADS, 1) k_cond_bwd(BwdArgs a) {
+    extern __shared__ __align__(128) double smem[];
+    const dgp_cond_desc& d = a.d;
+    const BwdSmem<C> L(a.Mpad, a.Dp, d.R);
+    double* Bt = smem + L.Bt;
+    double* Dt = smem + L.Dt;
+    double* Wst = smem + L.Wst;
+    double* xs = smem + L.xs;
+    double* xn = smem + L.xn;
+    double* gm = smem + L.gm;
+    double* gv = smem + L.gv;
+    double* rs = smem + L.rs;
+    double* dv = smem + L.dv;
+    double* rowq = smem + L.rowq;
+    int32_t* xtask = reinterpret_cast<int32_t*>(smem + L.xtask);
+    uint64_t* bar = reinterpret_cast<uint64_t*>(smem + L.bar);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int Mpad = a.Mpad, Dp = a.Dp, ldb = L.ldb, xld = L.xld, R = d.R;
+    const int nb = (Mpad + C::MB - 1) / C::MB;
+    const int thd = 2 + d.D;
+    const int nq = 2 + Dp;
+
+    // this CTA's partial buffers (accumulated across tiles and across calls; zeroed by dgp_cond_prepare)
+    double* pT2z = a.part + (size_t)blockIdx.x * a.npart;   // [Mpad][Dp]
+    double* pcs = pT2z + (size_t)Mpad * Dp;                  // [Mpad]
+    double* pqmu = pcs + Mpad;                               // [Mpad][R]
+    double* pth = pqmu + (size_t)Mpad * R;                   // [T][2+Dp]
+
+    if (tid == 0) {
+        mbar_init(bar, 1);
+        mbar_fence_init();
+    }
+    __syncthreads();
+    uint32_t parity = 0;
+
+    for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
+        const long long n0 = (long long)tile * C::NT;
+        const int nvalid = (int)((a.n_rows - n0 < C::NT) ? (a.n_rows - n0) : C::NT);
+        bulk_wait_read0();   // previous tile's dKuf store has finished reading Dt
+        __syncthreads();     // every warp is done with the previous tile
+
+        // ---- A tile: HBM -> Bt by bulk async copies, completion on the mbarrier
+        if (tid == 0) {
+            mbar_expect_tx(bar, (uint32_t)(nvalid * Mpad * sizeof(double)));
+            for (int n = 0; n < nvalid; ++n)
+                bulk_g2s(Bt + n * ldb, a.A_save + (size_t)(n0 + n) * Mpad, (uint32_t)(Mpad * sizeof(double)), bar);
+        }
+        for (int e = tid; e < (C::NT - nvalid) * Mpad; e += C::NTHREADS)   // ragged tile: zero rows
+            Bt[(nvalid + e / Mpad) * ldb + e % Mpad] = 0.0;
+
+        // ---- per-row setup: scaled inputs, combined upstream gradients
+        for (int n = tid; n < C::NT; n += C::NTHREADS) {
+            long long gn = n0 + n;
+            if (gn >= a.n_rows) gn = a.n_rows - 1;
+            const double* xr = a.X + (size_t)(gn % a.x_rows) * d.Dx;
+            int tk = 0;
+            if (d.T > 1) {
+                tk = (int)xr[d.Dx - 1];
+                if (tk < 0 || tk >= d.T) tk = -1;
+            }
+            xtask[n] = tk;
+            const double* th = d.theta + (size_t)(tk < 0 ? 0 : tk) * thd;
+            double s = 0.0;
+            for (int k = 0; k < Dp; ++k) {
+                double v = 0.0;
+                if (k < d.D) v = xr[k] / th[2 + k];
+                xs[n * xld + k] = v;
+                s = fma(v, v, s);
+            }
+            xn[n] = s;
+        }
+        for (int idx = tid; idx < C::NT * R; idx += C::NTHREADS) {
+            const int n = idx / R, r = idx % R;
+            const long long gn = n0 + n;
+            double gmean = 0.0, gvar = 0.0;
+            if (gn < a.n_rows) {
+                const size_t o = (size_t)gn * d.ldr + d.col0 + r;
+                if (a.g_mean_in) gmean = a.g_mean_in[o];
+                if (a.g_var_in) gvar = a.g_var_in[o];
+                if (a.g_F) {
+                    const double gf = a.g_F[(size_t)gn * a.ldgf + d.col0 + r];
+                    gmean += gf;
+                    gvar += gf * (a.F[(size_t)gn * a.ldf + d.col0 + r] - a.mean[o]) / (2.0 * a.var[o]);
+                }
+                a.gmv[(size_t)gn * 2 * R + r] = gmean;
+                a.gmv[(size_t)gn * 2 * R + R + r] = gvar;
+            }
+            gm[idx] = gmean;
+            gv[idx] = gvar;
+        }
+        mbar_wait(bar, parity);
+        parity ^= 1;
+        // (run_phase starts with a __syncthreads)
+
+        // ---- phase dA: Dt = q_mu g_mean^T + 2 sum_r (S_r - I) (A . g_var_r)
+        {
+            auto segfn = [&](int s) {
+                Seg sg;
+                sg.i = s / R;
+                sg.r = s % R;
+                sg.W = a.SmI + (size_t)sg.r * Mpad * Mpad;
+                sg.kc0 = 0;
+                sg.kc1 = Mpad / C::KC;
+                sg.flush = (sg.r == R - 1);
+                return sg;
+            };
+            auto epi = [&](Acc<C>& acc, const Seg& sg) {
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const int row = acc_row<C>(sg.i, q);
+                    if (row < Mpad) {
+#pragma unroll
+                        for (int j = 0; j < C::NJ; ++j)
+#pragma unroll
+                            for (int e = 0; e < 2; ++e) {
+                                const int n = acc_col<C>(j, e);
+                                double v = 2.0 * acc.v[q][j][e];
+                                if (row < d.M) {
+                                    const double* qm = d.q_mu + (size_t)row * d.ldr + d.col0;
+                                    for (int r = 0; r < R; ++r) v = fma(qm[r], gm[n * R + r], v);
+                                }
+                                Dt[n * ldb + row] = v;
+                            }
+                    }
+                }
+            };
+            run_phase<C, MASK_DENSE, true>(nb * R, segfn, epi, Wst, Bt, ldb, Mpad, gv, R);
+        }
+
+        // ---- phase dK: Dt <- Lm^-T Dt, block rows top-down, in place
+        {
+            auto segfn = [&](int s) {
+                Seg sg;
+                sg.W = a.LinvT;
+                sg.i = s;
+                sg.kc0 = s * C::MB / C::KC;
+                sg.kc1 = Mpad / C::KC;
+                sg.r = 0;
+                sg.flush = true;
+                return sg;
+            };
+            auto epi = [&](Acc<C>& acc, const Seg& sg) {
+                __syncthreads();
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const int row = acc_row<C>(sg.i, q);
+                    if (row < Mpad) {
+#pragma unroll
+                        for (int j = 0; j < C::NJ; ++j) {
+                            Dt[acc_col<C>(j, 0) * ldb + row] = acc.v[q][j][0];
+                            Dt[acc_col<C>(j, 1) * ldb + row] = acc.v[q][j][1];
+                        }
+                    }
+                }
+            };
+            run_phase<C, MASK_UPPER, false>(nb, segfn, epi, Wst, Dt, ldb, Mpad, nullptr, 0);
+        }
+        __syncthreads();
+
+        // ---- dKuf tile -> HBM (for the Gram kernel)
+        fence_async_smem();
+        if (tid < nvalid) {
+            bulk_s2g(a.dKuf + (size_t)(n0 + tid) * Mpad, Dt + tid * ldb, (uint32_t)(Mpad * sizeof(double)));
+            bulk_commit();
+        }
+        // ---- d q_mu partial: sum_n A[n][m] g_mean[n][r]   (reads Bt while the store drains)
+        for (int idx = tid; idx < d.M * R; idx += C::NTHREADS) {
+            const int m = idx / R, r = idx % R;
+            double s = 0.0;
+            for (int n = 0; n < nvalid; ++n) s = fma(Bt[n * ldb + m], gm[n * R + r], s);
+            pqmu[idx] += s;
+        }
+        bulk_wait_read0();
+        __syncthreads();
+
+        // ---- Dt <- Gr2 = dKuf . variance . k'(r2);  per-row sums: rs = sum_m Gr2, dv = sum_m dKuf k(r2)/variance
+        for (int n = warp; n < C::NT; n += C::NWARPS) {
+            const int tx = xtask[n];
+            double srs = 0.0, sdv = 0.0;
+            const double varn = (tx >= 0) ? d.theta[(size_t)tx * thd] : 0.0;
+            const int kind = d.kind[tx < 0 ? 0 : tx];
+            for (int m = lane; m < Mpad; m += 32) {
+                double out = 0.0;
+                if (n < nvalid && m < d.M && tx >= 0 && a.ztask[m] == tx) {
+                    const double* zr = a.Zs + (size_t)m * Dp;
+                    double c = 0.0;
+                    for (int k = 0; k < Dp; ++k) c = fma(zr[k], xs[n * xld + k], c);
+                    const double r2 = a.zn[m] + xn[n] - 2.0 * c;
+                    double kv, dk;
+                    kern_val_grad(kind, r2, kv, dk);
+                    const double gk = Dt[n * ldb + m];
+                    sdv = fma(gk, kv, sdv);
+                    out = gk * varn * dk;
+                    srs += out;
+                }
+                Dt[n * ldb + m] = out;
+            }
+            srs = warp_sum(srs);
+            sdv = warp_sum(sdv);
+            if (lane == 0) { rs[n] = srs; dv[n] = sdv; }
+        }
+        __syncthreads();
+
+        // ---- T1[n][k] = sum_m Gr2[n][m] zs[m][k]  ->  gX, lengthscale row terms
+        for (int idx = tid; idx < C::NT * Dp; idx += C::NTHREADS) {
+            const int n = idx / Dp, k = idx % Dp;
+            double t1 = 0.0;
+            for (int m = 0; m < d.M; ++m) t1 = fma(Dt[n * ldb + m], a.Zs[(size_t)m * Dp + k], t1);
+            const double xv = xs[n * xld + k];
+            rowq[n * nq + 2 + k] = xv * xv * rs[n] - 2.0 * xv * t1;
+            const long long gn = n0 + n;
+            if (a.gX && gn < a.n_rows && k < d.D) {
+                const int tx = xtask[n];
+                double gx = 0.0;
+                if (tx >= 0) gx = 2.0 * (xv * rs[n] - t1) / d.theta[(size_t)tx * thd + 2 + k];
+                if (d.mean_A)
+                    for (int r = 0; r < R; ++r) gx = fma(gm[n * R + r], d.mean_A[(size_t)k * d.ldr + d.col0 + r], gx);
+                double* o = a.gX + (size_t)gn * d.Dx + k;
+                *o = a.accumulate_gX ? (*o + gx) : gx;
+            }
+        }
+        // columns of X the kernel does not see (task id): only the Linear mean reaches them
+        if (a.gX && d.Dx > d.D) {
+            for (int idx = tid; idx < C::NT * (d.Dx - d.D); idx += C::NTHREADS) {
+                const int n = idx / (d.Dx - d.D), k = d.D + idx % (d.Dx - d.D);
+                const long long gn = n0 + n;
+                if (gn < a.n_rows) {
+                    double gx = 0.0;
+                    if (d.mean_A)
+                        for (int r = 0; r < R; ++r) gx = fma(gm[n * R + r], d.mean_A[(size_t)k * d.ldr + d.col0 + r], gx);
+                    double* o = a.gX + (size_t)gn * d.Dx + k;
+                    *o = a.accumulate_gX ? (*o + gx) : gx;
+                }
+            }
+        }
+        // Kdiag terms: d variance += sum_r g_var, d white += sum_r g_var
+        for (int n = tid; n < C::NT; n += C::NTHREADS) {
+            double s = 0.0;
+            if (n < nvalid) for (int r = 0; r < R; ++r) s += gv[n * R + r];
+            rowq[n * nq + 0] = dv[n] + s;
+            rowq[n * nq + 1] = s;
+        }
+        // T2z[m][k] = sum_n Gr2[n][m] xs[n][k],  cs[m] = sum_n Gr2[n][m]
+        for (int idx = tid; idx < d.M * Dp; idx += C::NTHREADS) {
+            const int m = idx / Dp, k = idx % Dp;
+            double s = 0.0;
+            for (int n = 0; n < nvalid; ++n) s = fma(Dt[n * ldb + m], xs[n * xld + k], s);
+            pT2z[idx] += s;
+        }
+        for (int m = tid; m < d.M; m += C::NTHREADS) {
+            double s = 0.0;
+            for (int n = 0; n < nvalid; ++n) s += Dt[n * ldb + m];
+            pcs[m] += s;
+        }
+        __syncthreads();
+        // per-task hyper-parameter row terms, summed in row order by one thread per column (deterministic)
+        if (tid < nq) {
+            for (int n = 0; n < nvalid; ++n) {
+                const int tx = xtask[n];
+                if (tx >= 0) pth[tx * nq + tid] += rowq[n * nq + tid];
+            }
+        }
+    }
+    bulk_wait_read0();
+}
+
+template <class C>
+static int launch_bwd(const BwdArgs& a, cudaStream_t st) {
+    const BwdSmem<C> L(a.Mpad, a.Dp, a.d.R);
+    const size_t bytes = (size_t)L.total_doubles * sizeof(double);
+    if (bytes > 227 * 1024) return DGP_ERR_UNSUPPORTED;
+    static size_t configured = 0;
+    if (bytes > configured) {
+        if (cudaFuncSetAttribute(k_cond_bwd<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes) != cudaSuccess) return DGP_ERR_LAUNCH;
+        configured = bytes;
+    }
+    k_cond_bwd<C><<<device_sm_count(), C::NTHREADS, bytes, st>>>(a);
+    DGP_COUNT_LAUNCH();
+    return cudaGetLastError() == cudaSuccess ? DGP_OK : DGP_ERR_LAUNCH;
+}
+
+// ------------------------------------------------------------------------------------------------ Gram kernel
+// out[s][mat][m1][m2] += sum_{n in split s} w_mat[n] P_mat[n][m1] A[n][m2]   for 64x64 tiles with tile(m1) >= tile(m2)
+//   mat <  R : P = A,    w = g_var[:, mat]      (G_r, symmetric)
+//   mat == R : P = dKuf, w = 1                  (P = dKuf^T A)
+struct GramArgs {
+    int Mpad, R, nsplit;
+    long long n_rows, rows_per_split;
+    const double* A; const double* dKuf; const double* gmv;
+    double* gram;
+};
+constexpr int GR_THREADS = 128, GR_STAGES = 3, GR_KC = 16, GR_LD = 68;
+
+__global__ void __launch_bounds__(GR_THREADS, 4) k_gram(GramArgs a) {
+    extern __shared__ __align__(128) double gsm[];
+    double (*Ps)[GR_KC * GR_LD] = reinterpret_cast<double (*)[GR_KC * GR_LD]>(gsm);
+    double (*Qs)[GR_KC * GR_LD] = reinterpret_cast<double (*)[GR_KC * GR_LD]>(gsm + GR_STAGES * GR_KC * GR_LD);
+    double (*wsm)[GR_KC] = reinterpret_cast<double (*)[GR_KC]>(gsm + 2 * GR_STAGES * GR_KC * GR_LD);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
+    const int wm = warp >> 1, wn = warp & 1;
+    // tile pair from the linear index over the lower-triangular tile set
+    int p = blockIdx.x, bi = 0;
+    while ((bi + 1) * (bi + 2) / 2 <= p) ++bi;
+    const int bj = p - bi * (bi + 1) / 2;
+    const int mat = blockIdx.y, split = blockIdx.z;
+    const int Mpad = a.Mpad, R = a.R;
+    const double* Psrc = (mat < R ? a.A : a.dKuf) + bi * 64;
+    const double* Qsrc = a.A + bj * 64;
+    const long long nbeg = (long long)split * a.rows_per_split;
+    long long nend = nbeg + a.rows_per_split;
+    if (nend > a.n_rows) nend = a.n_rows;
+    const int nchunks = nend > nbeg ? (int)((nend - nbeg + GR_KC - 1) / GR_KC) : 0;
+
+    double acc[4][4][2];
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { acc[q][j][0] = 0.0; acc[q][j][1] = 0.0; }
+
+    auto issue = [&](int c, int stage) {
+        if (c < nchunks) {
+            const long long r0 = nbeg + (long long)c * GR_KC;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const int e = tid + q * GR_THREADS;  // 0..511 : row = e/32, 16-byte column = e%32
+                const int row = e >> 5, cc = e & 31;
+                long long n = r0 + row;
+                if (n >= nend) n = nend - 1;  // clamped rows get weight 0
+                cp_async16(&Ps[stage][row * GR_LD + cc * 2], Psrc + (size_t)n * Mpad + cc * 2);
+                cp_async16(&Qs[stage][row * GR_LD + cc * 2], Qsrc + (size_t)n * Mpad + cc * 2);
+            }
+            if (tid < GR_KC) {
+                const long long n = r0 + tid;
+                double w = 0.0;
+                if (n < nend) w = (mat < R) ? a.gmv[(size_t)n * 2 * R + R + mat] : 1.0;
+                wsm[stage][tid] = w;
+            }
+        }
+        cp_async_commit();
+    };
+    issue(0, 0);
+    issue(1, 1);
+    int stage = 0, lstage = 2;
+    for (int c = 0; c < nchunks; ++c) {
+        cp_async_wait<GR_STAGES - 2>();
+        __syncthreads();
+        issue(c + 2, lstage);
+        lstage = (lstage + 1 == GR_STAGES) ? 0 : lstage + 1;
+        const double* P = Ps[stage];
+        const double* Q = Qs[stage];
+        const double* W = wsm[stage];
+        stage = (stage + 1 == GR_STAGES) ? 0 : stage + 1;
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk) {
+            const double w = W[kk * 4 + t];
+            double af[4], bf[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) af[q] = P[(kk * 4 + t) * GR_LD + wm * 32 + q * 8 + g] * w;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) bf[j] = Q[(kk * 4 + t) * GR_LD + wn * 32 + j * 8 + g];
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) dmma884(acc[q][j], af[q], bf[j]);
+        }
+    }
+    cp_async_wait<0>();
+    if (nchunks == 0) return;
+    double* out = a.gram + ((size_t)split * (R + 1) + mat) * Mpad * Mpad;
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const int m1 = bi * 64 + wm * 32 + q * 8 + g;
+                const int m2 = bj * 64 + wn * 32 + j * 8 + 2 * t + e;
+                out[(size_t)m1 * Mpad + m2] += acc[q][j][e];
+            }
+}
+
+}  // namespace dgp
+
+using namespace dgp;
+
+extern "C" int dgp_cond_backward(const dgp_cond_desc* d, void* ws, const double* X, int64_t x_rows, int64_t n_rows,
+                                 const double* A_save, const double* mean, const double* var, const double* F, int32_t ldf,
+                                 const double* g_mean_in, const double* g_var_in, const double* g_F, int32_t ldgf,
+                                 double* gX, int32_t accumulate_gX, void* stream) {
+    int rc = check_desc(d);
+    if (rc != DGP_OK) return rc;
+    if (!ws || !X || !A_save || x_rows < 1 || n_rows < 0) return DGP_ERR_ARG;
+    if (g_F && (!F || !mean || !var || ldgf < d->ldr || ldf < d->ldr)) return DGP_ERR_ARG;
+    if (!g_F && !g_mean_in && !g_var_in) return DGP_ERR_ARG;
+    if (n_rows == 0) return DGP_OK;
+    const WsLayout w = ws_layout(*d, n_rows, 1);
+    if (w.Mpad > 512) return DGP_ERR_UNSUPPORTED;  // backward tiles for M > 512 are not instantiated
+    cudaStream_t st = (cudaStream_t)stream;
+    BwdArgs a{};
+    a.d = *d;
+    a.Mpad = w.Mpad; a.Dp = w.Dp;
+    a.Zs = ws_ptr<double>(ws, w.Zs); a.zn = ws_ptr<double>(ws, w.zn); a.ztask = ws_ptr<int32_t>(ws, w.ztask);
+    a.LinvT = ws_ptr<double>(ws, w.LinvT); a.SmI = ws_ptr<double>(ws, w.SmI);
+    a.X = X; a.x_rows = x_rows; a.n_rows = n_rows;
+    a.A_save = A_save; a.mean = mean; a.var = var; a.F = F; a.ldf = ldf;
+    a.g_mean_in = g_mean_in; a.g_var_in = g_var_in; a.g_F = g_F; a.ldgf = ldgf;
+    a.gX = gX; a.accumulate_gX = accumulate_gX;
+    a.dKuf = ws_ptr<double>(ws, w.dKuf); a.gmv = ws_ptr<double>(ws, w.gmv);
+    a.part = ws_ptr<double>(ws, w.part); a.npart = w.npart;
+    if (w.Mpad <= 256) {
+        using C = TileCfg<4, 2, 32, 3>;
+        a.ntiles = (int)((n_rows + C::NT - 1) / C::NT);
+        rc = launch_bwd<C>(a, st);
+    } else {
+        using C = TileCfg<4, 2, 16, 3>;
+        a.ntiles = (int)((n_rows + C::NT - 1) / C::NT);
+        rc = launch_bwd<C>(a, st);
+    }
+    if (rc != DGP_OK) return rc;
+
+    GramArgs ga{};
+    ga.Mpad = w.Mpad; ga.R = d->R; ga.nsplit = w.nsplit; ga.n_rows = n_rows;
+    long long rps = (n_rows + w.nsplit - 1) / w.nsplit;
+    ga.rows_per_split = (rps + GR_KC - 1) / GR_KC * GR_KC;
+    ga.A = A_save; ga.dKuf = a.dKuf; ga.gmv = a.gmv;
+    ga.gram = ws_ptr<double>(ws, w.gram);
+    const int nbt = w.Mpad / 64;
+    const size_t gsm_bytes = (size_t)(2 * GR_STAGES * GR_KC * GR_LD + GR_STAGES * GR_KC) * sizeof(double);
+    static bool gram_attr = false;
+    if (!gram_attr) {
+        if (cudaFuncSetAttribute(k_gram, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gsm_bytes) != cudaSuccess) return DGP_ERR_LAUNCH;
+        gram_attr = true;
+    }
+    k_gram<<<dim3(nbt * (nbt + 1) / 2, d->R + 1, w.nsplit), GR_THREADS, gsm_bytes, st>>>(ga);
+    DGP_COUNT_LAUNCH();
+    DGP_CHECK_LAUNCH();
+    return DGP_OK;
+}

@@ -379,6 +379,10 @@ extern "C" int dgp_cond_prepare(const dgp_cond_desc* d, void* ws, size_t ws_byte
         rc = gemm_small(g, st);
         if (rc != DGP_OK) return rc;
         k_sub_identity<<<dim3((d->M + 127) / 128, d->R), 128, 0, st>>>(SmI, Mpad, d->M); DGP_COUNT_LAUNCH();
+        // row-summed accumulators of the backward pass start from zero; dgp_cond_backward adds to them (row chunks)
+        if (ws_bytes < wb.tail) return DGP_ERR_WORKSPACE;
+        if (cudaMemsetAsync(ws_ptr<char>(ws, wb.gram), 0, wb.part - wb.gram, st) != cudaSuccess) return DGP_ERR_LAUNCH;
+        if (cudaMemsetAsync(ws_ptr<char>(ws, wb.part), 0, wb.tail - wb.part, st) != cudaSuccess) return DGP_ERR_LAUNCH;
     }
     DGP_CHECK_LAUNCH();
     return DGP_OK;
