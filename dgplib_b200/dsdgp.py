@@ -1,0 +1,189 @@
+"""DSDGP -- doubly stochastic deep GP model with the surface of dgplib/dsdgp.py (Salimbeni & Deisenroth 2017).
+
+The graph the reference builds with TensorFlow (`_propagate`, `_build_predict`, `_build_likelihood`,
+dgplib/dsdgp.py:84-130) is executed here by the fused sm_100a kernels behind `Engine`; gradients of the ELBO w.r.t.
+every trainable parameter come from hand-written backward kernels and are exposed to torch.autograd / torch.optim as
+one autograd node.  Noise draws: the reference uses unseeded tf.random_normal (dgplib/utils.py:26); here they are
+Philox4x32-10 draws keyed by (seed, layer, global row, output) unless explicit `eps` tensors are injected.
+"""
+import numpy as np
+import torch
+
+from . import settings
+from .engine import Engine, elbo_autograd, _dev_tensor
+from .mean_functions import Zero
+from .params import Parameterized
+
+
+class _Minibatch:
+    """gpflow.params.Minibatch(v, batch_size, seed): repeat -> shuffle(buffer=N, seed) -> batch, one batch per
+    evaluation.  X and Y use the same seed so the shuffles stay aligned (dgplib/dsdgp.py:78-79)."""
+
+    def __init__(self, n, batch_size, seed):
+        self.n, self.batch_size = n, int(batch_size)
+        self.rng = np.random.RandomState(seed)
+        self.perm = self.rng.permutation(n)
+        self.pos = 0
+
+    def next_indices(self):
+        idx = []
+        need = self.batch_size
+        while need > 0:
+            if self.pos == self.n:
+                self.perm = self.rng.permutation(self.n)
+                self.pos = 0
+            take = min(need, self.n - self.pos)
+            idx.append(self.perm[self.pos:self.pos + take])
+            self.pos += take
+            need -= take
+        return np.concatenate(idx)
+
+
+class DSDGP(Parameterized):
+    """Doubly Stochastic Deep Gaussian Process Model."""
+
+    multitask = False
+
+    def __init__(self, X, Y, Z, layers, likelihood, num_latent=None, minibatch_size=None, num_samples=1,
+                 mean_function=Zero(), name=None, seed=1234, device=None):
+        """
+        - X is a data matrix, size N x D; Y is a data matrix, size N x R; Z inducing inputs, size M x D.
+        - layers is an instance of Sequential; likelihood a Gaussian / SwitchedLikelihood.
+        - minibatch_size, if not None, turns on minibatching; num_samples is the number of Monte Carlo samples.
+        - seed keys the in-kernel Philox noise; device is the CUDA device used at compile() time.
+        """
+        super().__init__(name=name)
+        X, Y, Z = (np.asarray(a, dtype=np.float64) for a in (X, Y, Z))
+        assert X.shape[0] == Y.shape[0]
+        assert Z.shape[1] == X.shape[1]
+        self.num_data, D_X = X.shape
+        self.num_samples = num_samples
+        self.D_Y = num_latent or Y.shape[1]
+        self.mean_function = mean_function      # kept for API parity; unused by the reference too
+        layers.initialize_params(X, Z)
+        if layers._initialized:
+            self.layers = layers
+        else:
+            raise ValueError("Layers were not initialized")
+        self.dims = self.layers.get_dims()
+        self.likelihood = likelihood
+        self.minibatch_size = minibatch_size
+        self._mb = None if minibatch_size is None else _Minibatch(self.num_data, minibatch_size, seed=0)
+        # data stays on the host (pinned when CUDA is present); every evaluation copies its minibatch to the device
+        self.X = torch.from_numpy(X.copy())
+        self.Y = torch.from_numpy(Y.copy())
+        if torch.cuda.is_available():
+            self.X, self.Y = self.X.pin_memory(), self.Y.pin_memory()
+        self.seed = int(seed)
+        self._step = 0
+        self._device = device
+        self._engine = None
+        self.chunk_rows = None      # optional bound on minibatch rows processed per kernel pass (memory)
+        self._dist = None
+
+    # ------------------------------------------------------------------------------------------------ plumbing
+    def compile(self, device=None):
+        """Move parameters to the GPU and build the kernel descriptors (gpflow Model.compile())."""
+        from . import _cabi
+        _cabi.require_cuda()
+        dev = torch.device(device or self._device or f"cuda:{torch.cuda.current_device()}")
+        self.to(dev)
+        self._engine = Engine(self.layers.layers, self.likelihood, multitask=self.multitask, device=dev)
+        return self
+
+    @property
+    def engine(self):
+        if self._engine is None:
+            self.compile()
+        return self._engine
+
+    def distribute(self, process_group=None):
+        """Shard every minibatch's rows over the ranks of a torch.distributed process group (one process per GPU);
+        the flat gradient buffer is summed with one NCCL all-reduce per evaluation."""
+        import torch.distributed as dist
+        self._dist = (dist, process_group)
+        return self
+
+    def _next_batch(self):
+        if self._mb is None:
+            return self.X, self.Y
+        idx = torch.from_numpy(self._mb.next_indices())
+        return self.X[idx], self.Y[idx]
+
+    def _eval_kwargs(self, X, Y, eps, seed):
+        kw = dict(X=X, Y=Y, S=self.num_samples, eps=eps, seed=self.seed + self._step if seed is None else seed,
+                  num_data=self.num_data, chunk_rows=self.chunk_rows)
+        if self._dist is not None:
+            dist, group = self._dist
+            W, r = dist.get_world_size(group), dist.get_rank(group)
+            B = X.shape[0]
+            lo, hi = (B * r) // W, (B * (r + 1)) // W
+            kw.update(X=X[lo:hi], Y=Y[lo:hi], row_offset=lo, global_batch=B, world_size=W,
+                      all_reduce=lambda t: dist.all_reduce(t, group=group))
+            if eps is not None:
+                kw["eps"] = [e[:, lo:hi] for e in eps]
+        return kw
+
+    # ------------------------------------------------------------------------------------------------ reference API
+    def _propagate(self, Xnew, full_cov=False, num_samples=1, eps=None, seed=None):
+        """Propagate points Xnew through the DGP cascade: (Fs, Fmeans, Fvars), lists of [S, N, .] CUDA tensors."""
+        if full_cov:
+            raise NotImplementedError("full_cov=True is outside the B200 hot path (SURVEY.md 8f, rank 3)")
+        return self.engine.propagate(Xnew, num_samples, eps=eps, seed=self.seed if seed is None else seed)
+
+    def _build_predict(self, Xnew, full_cov=False, num_samples=1, eps=None, seed=None):
+        Fs, Fmeans, Fvars = self._propagate(Xnew, full_cov, num_samples, eps=eps, seed=seed)
+        return Fmeans[-1], Fvars[-1]
+
+    def _build_likelihood(self, eps=None, seed=None, X=None, Y=None):
+        """Variational bound on the marginal likelihood (dgplib/dsdgp.py:107-130) of the next minibatch, as a CUDA
+        scalar attached to torch.autograd (call .backward() or hand it to a torch optimiser)."""
+        if X is None:
+            X, Y = self._next_batch()
+        self._step += 1
+        return elbo_autograd(self.engine, **self._eval_kwargs(X, Y, eps, seed))
+
+    def compute_log_likelihood(self, eps=None, seed=None):
+        """gpflow Model.compute_log_likelihood(): the ELBO of one minibatch as a Python float."""
+        with torch.no_grad():
+            return float(self._build_likelihood(eps=eps, seed=seed))
+
+    def elbo_and_grad(self, X=None, Y=None, eps=None, seed=None):
+        """One fused ELBO + gradient evaluation; returns (elbo tensor, grads of engine.params())."""
+        if X is None:
+            X, Y = self._next_batch()
+        self._step += 1
+        eng = self.engine
+        return eng.elbo(eng.params(), need_grad=True, **self._eval_kwargs(X, Y, eps, seed))
+
+    def predict_f(self, Xnew, num_samples, eps=None, seed=None):
+        """Mean and variance of the final layer at Xnew: two [S, N, D_Y] arrays (dgplib/dsdgp.py:133-139)."""
+        mean, var = self._build_predict(Xnew, False, num_samples, eps=eps, seed=seed)
+        return mean.cpu().numpy(), var.cpu().numpy()
+
+    def predict_all_layers(self, Xnew, num_samples, eps=None, seed=None):
+        """(Fs, Fmeans, Fvars) for every layer (dgplib/dsdgp.py:152-158)."""
+        out = self._propagate(Xnew, False, num_samples, eps=eps, seed=seed)
+        return tuple([t.cpu().numpy() for t in lst] for lst in out)
+
+    def predict_f_full_cov(self, Xnew, num_samples):
+        raise NotImplementedError("predict_f_full_cov is outside the B200 hot path (SURVEY.md 8f, rank 3)")
+
+    def predict_all_layers_full_cov(self, Xnew, num_samples):
+        raise NotImplementedError("predict_all_layers_full_cov is outside the B200 hot path (SURVEY.md 8f, rank 3)")
+
+    def predict_f_samples(self, Xnew, num_samples):
+        raise NotImplementedError("predict_f_samples needs the full-covariance path (SURVEY.md 8f, rank 3)")
+
+    def predict_y(self, Xnew, num_samples=1, eps=None, seed=None):
+        """Mean and variance of held-out data at Xnew (dgplib/dsdgp.py:188-194).  The reference propagates a single
+        sample (`_build_predict(Xnew)` defaults to num_samples=1); num_samples > 1 is a superset for sweeps."""
+        mean, var = self._build_predict(Xnew, False, num_samples, eps=eps, seed=seed)
+        lik = self.likelihood
+        if hasattr(lik, "likelihood_list"):
+            # gpflow SwitchedLikelihood.predict_mean_and_var concatenates every likelihood's prediction on axis 1
+            vs = [var + l.variance.constrained().detach() for l in lik.likelihood_list]
+            mean, var = torch.cat([mean] * len(vs), 1), torch.cat(vs, 1)
+        else:
+            var = var + lik.variance.constrained().detach()
+        return mean.cpu().numpy(), var.cpu().numpy()

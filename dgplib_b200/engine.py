@@ -1,0 +1,429 @@
+"""Host-side driver of the DSDGP hot path: packs the model's parameters into C-ABI descriptors, owns the device
+workspaces and row buffers, and sequences the sm_100a kernels of libdgp_b200.so for
+
+    propagate      DSDGP._propagate            dgplib/dsdgp.py:84-99   (+ multitask_dsdgp.py:9-26)
+    elbo / grad    DSDGP._build_likelihood     dgplib/dsdgp.py:107-130 (+ tf.gradients of it)
+
+PyTorch is used for device memory, streams and (multi-GPU) the NCCL all-reduce of the flat gradient buffer; every
+arithmetic step is a kernel of the extension.  There is no CPU / eager fallback.
+"""
+import ctypes
+
+import numpy as np
+import torch
+
+from . import _cabi, settings
+from .mean_functions import Linear
+
+_F64 = torch.float64
+
+
+def _dev_tensor(x, device):
+    if isinstance(x, np.ndarray):
+        x = torch.from_numpy(np.ascontiguousarray(x, dtype=np.float64))
+    return x.detach().to(device=device, dtype=_F64).contiguous()
+
+
+class _Cond:
+    """One whitened conditional (kernel + inducing points + a column slice of q_mu / q_sqrt): descriptor + workspace."""
+
+    def __init__(self, kernel, feature, col0, R, layer, Dx):
+        self.kernel, self.feature, self.layer = kernel, feature, layer
+        parts = kernel.task_kernels()          # raises NotImplementedError for unsupported kernels
+        self.T = len(parts)
+        self.kinds = [p[0] for p in parts]
+        d = _cabi.CondDesc()
+        d.M = layer.num_inducing
+        d.Dx = Dx
+        if kernel.switched:
+            # SwitchedKernel strips the id column, then slices (dgplib/specialized_kernels.py:34-38)
+            d.D = min(kernel.input_dim, Dx - 1)
+        else:
+            d.D = kernel.input_dim
+        d.R, d.ldr, d.col0, d.T = R, layer.output_dim, col0, self.T
+        for t, k in enumerate(self.kinds):
+            d.kind[t] = k
+        d.jitter = settings.jitter_level
+        self.desc = d
+        self.D = d.D
+        self.ws = None
+        self.ws_rows = -1
+        self.ws_bwd = False
+        self._keep = None
+
+    def theta(self):
+        """[T, 2 + D] constrained hyper-parameters (variance, White variance or 0, lengthscales), autograd-attached."""
+        rows = []
+        for (_, var, white, ls) in self.kernel.task_kernels():
+            w = torch.zeros((), dtype=_F64, device=var.device) if white is None else white
+            if ls.shape[0] != self.D:
+                ls = ls[:self.D]
+            rows.append(torch.cat([var.reshape(1), w.reshape(1), ls]))
+        return torch.stack(rows)
+
+    def bind(self, Z, theta, q_mu, q_sqrt, mean_A, mean_b):
+        d = self.desc
+        self._keep = (Z, theta, q_mu, q_sqrt, mean_A, mean_b)
+        d.Z, d.theta, d.q_mu, d.q_sqrt = Z.data_ptr(), theta.data_ptr(), q_mu.data_ptr(), q_sqrt.data_ptr()
+        d.mean_A = mean_A.data_ptr() if mean_A is not None else None
+        d.mean_b = mean_b.data_ptr() if mean_b is not None else None
+
+    def ensure_ws(self, n_rows, need_bwd, device):
+        if self.ws is not None and self.ws_rows >= n_rows and (self.ws_bwd or not need_bwd):
+            return
+        nbytes = _cabi.lib().dgp_cond_ws_bytes(ctypes.byref(self.desc), n_rows, 1 if need_bwd else 0)
+        if nbytes == 0:
+            raise _cabi.DgpError("dgp_cond_ws_bytes rejected the descriptor")
+        self.ws = torch.empty(nbytes, dtype=torch.uint8, device=device)
+        self.ws_rows, self.ws_bwd = n_rows, bool(need_bwd)
+
+    def ref(self):
+        return ctypes.byref(self.desc)
+
+
+class Engine:
+    """Compiled form of (Sequential, likelihood): the thing DSDGP calls every step."""
+
+    def __init__(self, layers, likelihood=None, multitask=False, device=None):
+        _cabi.require_cuda()
+        _cabi.lib()
+        self.device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
+        self.layers = list(layers)
+        self.likelihood = likelihood
+        self.multitask = bool(multitask)
+        self.conds = []            # per layer: list of _Cond
+        for layer in self.layers:
+            Dx = layer.feature[0].Z.shape[1] if not hasattr(layer.feature, "Z") else layer.feature.Z.shape[1]
+            self.conds.append([_Cond(k, f, c0, R, layer, Dx) for (k, f, c0, R) in layer.conditionals()])
+        self._rows = {}
+        self._lik_ws = None
+        self.last_status = None
+
+    # ------------------------------------------------------------------------------------------ parameters
+    def _lik_variances(self):
+        lik = self.likelihood
+        if hasattr(lik, "likelihood_list"):
+            return torch.stack([l.variance.constrained() for l in lik.likelihood_list])
+        return lik.variance.constrained().reshape(1)
+
+    def params(self):
+        """Constrained, autograd-attached parameter tensors in the flat order used by the gradient buffer:
+        per layer [Z_c, theta_c for each conditional c] + [q_mu, q_sqrt]; then the likelihood variances."""
+        out = []
+        for layer, conds in zip(self.layers, self.conds):
+            for c in conds:
+                out.append(c.feature.Z.constrained())
+                out.append(c.theta())
+            out.append(layer.q_mu.constrained())
+            out.append(layer.q_sqrt.constrained())
+        if self.likelihood is not None:
+            out.append(self._lik_variances())
+        return out
+
+    def _bind(self, params):
+        """params: detached contiguous CUDA tensors in params() order."""
+        it = iter(params)
+        for layer, conds in zip(self.layers, self.conds):
+            zt = [(next(it), next(it)) for _ in conds]
+            q_mu, q_sqrt = next(it), next(it)
+            mA = mb = None
+            if isinstance(layer.mean_function, Linear):
+                mA = _dev_tensor(layer.mean_function.A.constrained(), self.device)
+                mb = _dev_tensor(layer.mean_function.b.constrained(), self.device)
+                if mA.shape != (conds[0].desc.Dx, layer.output_dim):
+                    raise ValueError(f"Linear mean A has shape {tuple(mA.shape)}, expected "
+                                     f"{(conds[0].desc.Dx, layer.output_dim)}")
+            for c, (Z, th) in zip(conds, zt):
+                c.bind(Z, th, q_mu, q_sqrt, mA, mb)
+        self._lik_var = next(it) if self.likelihood is not None else None
+
+    def _detached(self, params=None):
+        params = self.params() if params is None else params
+        return [_dev_tensor(p, self.device) for p in params]
+
+    # ------------------------------------------------------------------------------------------ buffers
+    def _row_buffers(self, n_rows, save):
+        key = (n_rows, bool(save))
+        buf = self._rows.get(key)
+        if buf is None:
+            dev = self.device
+            buf = {"mean": [], "var": [], "F": [], "A": [], "gX": []}
+            for l, (layer, conds) in enumerate(zip(self.layers, self.conds)):
+                R = layer.output_dim
+                ldf = R + (1 if self.multitask else 0)
+                buf["mean"].append(torch.empty(n_rows, R, dtype=_F64, device=dev))
+                buf["var"].append(torch.empty(n_rows, R, dtype=_F64, device=dev))
+                buf["F"].append(torch.empty(n_rows, ldf, dtype=_F64, device=dev))
+                if save:
+                    buf["A"].append([torch.empty(n_rows, _cabi.mpad(layer.num_inducing), dtype=_F64, device=dev)
+                                     for _ in conds])
+                    buf["gX"].append(torch.empty(n_rows, conds[0].desc.Dx, dtype=_F64, device=dev) if l > 0 else None)
+            if save:
+                RL = self.layers[-1].output_dim
+                buf["g_mu"] = torch.empty(n_rows, RL, dtype=_F64, device=dev)
+                buf["g_var"] = torch.empty(n_rows, RL, dtype=_F64, device=dev)
+            if len(self._rows) > 8:
+                self._rows.clear()
+            self._rows[key] = buf
+        return buf
+
+    def _prepare(self, n_rows, need_bwd, kl):
+        lib, st = _cabi.lib(), _cabi.stream_ptr()
+        i = 0
+        for conds in self.conds:
+            for c in conds:
+                c.ensure_ws(n_rows, need_bwd, self.device)
+                _cabi.check(lib.dgp_cond_prepare(c.ref(), _cabi.ptr(c.ws), c.ws.numel(), 1 if need_bwd else 0,
+                                                 ctypes.c_void_p(kl[i:].data_ptr()) if kl is not None else None, st),
+                            "dgp_cond_prepare")
+                i += 1
+
+    def check_status(self):
+        """Raises if a Cholesky factorisation failed (the reference surfaces this as TF's InvalidArgumentError)."""
+        lib, st = _cabi.lib(), _cabi.stream_ptr()
+        for l, conds in enumerate(self.conds):
+            for c in conds:
+                s = ctypes.c_int32(0)
+                _cabi.check(lib.dgp_cond_status(_cabi.ptr(c.ws), st, ctypes.byref(s)), "dgp_cond_status")
+                if s.value != 0:
+                    raise _cabi.DgpError(f"Cholesky of Kuu failed in layer {l} at pivot {s.value - 1}: "
+                                         "Kuu + jitter is not positive definite")
+
+    # ------------------------------------------------------------------------------------------ forward
+    def _forward_rows(self, X, S, eps, seed, row_offset, sample_stride, buf, save, last_F):
+        """One pass of the cascade over the S * B rows of X [B, Dx0].  eps: list of [S*B, R_l] tensors or None."""
+        lib, st = _cabi.lib(), _cabi.stream_ptr()
+        B = X.shape[0]
+        n = S * B
+        inp, x_rows = X, B
+        L = len(self.layers)
+        for l, (layer, conds) in enumerate(zip(self.layers, self.conds)):
+            want_F = last_F or l < L - 1
+            Fbuf = buf["F"][l] if want_F else None
+            for ci, c in enumerate(conds):
+                _cabi.check(lib.dgp_cond_forward(
+                    c.ref(), _cabi.ptr(c.ws), _cabi.ptr(inp), x_rows, n,
+                    _cabi.ptr(eps[l]) if (eps is not None and want_F) else None,
+                    ctypes.c_uint64(seed + 0x9E3779B97F4A7C15 * (l + 1) & 0xFFFFFFFFFFFFFFFF), row_offset, B,
+                    sample_stride if sample_stride else B,
+                    _cabi.ptr(buf["mean"][l]), _cabi.ptr(buf["var"][l]), _cabi.ptr(Fbuf) if want_F else None,
+                    Fbuf.shape[1] if want_F else layer.output_dim,
+                    _cabi.ptr(buf["A"][l][ci]) if save else None, st), "dgp_cond_forward")
+            inp, x_rows = Fbuf, n
+
+    def propagate(self, X, S, eps=None, seed=0, params=None):
+        """Fs, Fmeans, Fvars as lists of [S, B, .] CUDA tensors (DSDGP._propagate, dgplib/dsdgp.py:84-99)."""
+        with torch.no_grad():
+            X = _dev_tensor(X, self.device)
+            self._bind(self._detached(params))
+            B = X.shape[0]
+            n = S * B
+            buf = self._row_buffers(n, False)
+            self._prepare(n, False, None)
+            eps_flat = None
+            if eps is not None:
+                eps_flat = [_dev_tensor(e, self.device).reshape(n, -1) for e in eps]
+            self._forward_rows(X, S, eps_flat, seed, 0, B, buf, False, True)
+            self.check_status()
+            Fs = [f.reshape(S, B, -1).clone() for f in buf["F"]]
+            means = [m.reshape(S, B, -1).clone() for m in buf["mean"]]
+            vars_ = [v.reshape(S, B, -1).clone() for v in buf["var"]]
+            return Fs, means, vars_
+
+    # ------------------------------------------------------------------------------------------ ELBO (+ grad)
+    def grad_layout(self, params):
+        """Offsets of [elbo, grads of params()...] inside the flat fp64 gradient buffer."""
+        offs, o = [], 1
+        for p in params:
+            offs.append(o)
+            o += p.numel()
+        return offs, o
+
+    def elbo(self, params, X, Y, S, eps=None, seed=0, num_data=None, need_grad=True, row_offset=0,
+             global_batch=None, world_size=1, all_reduce=None, chunk_rows=None, check=True):
+        """ELBO (dgplib/dsdgp.py:107-130) of the minibatch rows X [B, Dx], Y [B, ldy] held by THIS rank, and -- if
+        need_grad -- its gradient w.r.t. every tensor of params().  Returns (elbo 0-dim tensor, [grad tensors]).
+
+        Multi-GPU: each rank passes its own row shard; `global_batch` is the whole minibatch size, `row_offset` the
+        shard's first row in it, and `all_reduce(flat)` sums the flat buffer over ranks (NCCL).  The KL term enters
+        with weight 1/world_size on every rank so the sum is exact."""
+        lib, st = _cabi.lib(), _cabi.stream_ptr()
+        with torch.no_grad():
+            dev = self.device
+            X, Y = _dev_tensor(X, dev), _dev_tensor(Y, dev)
+            params = [_dev_tensor(p, dev) for p in params]
+            self._bind(params)
+            B = X.shape[0]
+            Bg = global_batch if global_batch is not None else B
+            num_data = Bg if num_data is None else num_data
+            weight = (float(num_data) / float(Bg)) / float(S)
+            ncond = sum(len(c) for c in self.conds)
+            offs, total = self.grad_layout(params)
+            flat = torch.zeros(total + ncond, dtype=_F64, device=dev)   # [elbo | grads | kl per conditional]
+            kl = flat[total:]
+            Bc = B if not chunk_rows else max(1, min(B, int(chunk_rows)))
+            self._prepare(S * Bc, need_grad, kl)
+            if self._lik_ws is None:
+                self._lik_ws = torch.empty(lib.dgp_lik_ws_bytes(0, 1), dtype=torch.uint8, device=dev)
+            L = len(self.layers)
+            RL = self.layers[-1].output_dim
+            T_lik = self._lik_var.numel()
+            ldy = Y.shape[1]
+            g_lik = flat[offs[-1]:offs[-1] + T_lik]
+            eps_full = None
+            if eps is not None:
+                eps_full = [_dev_tensor(e, dev).reshape(S, B, -1) for e in eps]
+            for b0 in range(0, B, Bc):
+                b1 = min(B, b0 + Bc)
+                nb = b1 - b0
+                n = S * nb
+                Xc, Yc = X[b0:b1], Y[b0:b1]
+                buf = self._row_buffers(n, need_grad)
+                eps_c = None
+                if eps_full is not None:
+                    eps_c = [e[:, b0:b1].reshape(n, -1).contiguous() for e in eps_full]
+                self._forward_rows(Xc, S, eps_c, seed, row_offset + b0, Bg, buf, need_grad, False)
+                _cabi.check(lib.dgp_lik_gaussian(
+                    _cabi.ptr(buf["mean"][-1]), _cabi.ptr(buf["var"][-1]), _cabi.ptr(Yc), nb, ldy, n, RL,
+                    _cabi.ptr(self._lik_var), T_lik, weight, ctypes.c_void_p(flat.data_ptr()),
+                    _cabi.ptr(buf["g_mu"]) if need_grad else None, _cabi.ptr(buf["g_var"]) if need_grad else None,
+                    ctypes.c_void_p(g_lik.data_ptr()) if need_grad else None,
+                    _cabi.ptr(self._lik_ws), self._lik_ws.numel(), st), "dgp_lik_gaussian")
+                if not need_grad:
+                    continue
+                for l in range(L - 1, -1, -1):
+                    layer, conds = self.layers[l], self.conds[l]
+                    inp = Xc if l == 0 else buf["F"][l - 1]
+                    x_rows = nb if l == 0 else n
+                    last = (l == L - 1)
+                    gF = None if last else buf["gX"][l + 1]
+                    for ci, c in enumerate(conds):
+                        _cabi.check(lib.dgp_cond_backward(
+                            c.ref(), _cabi.ptr(c.ws), _cabi.ptr(inp), x_rows, n, _cabi.ptr(buf["A"][l][ci]),
+                            _cabi.ptr(buf["mean"][l]), _cabi.ptr(buf["var"][l]),
+                            None if last else _cabi.ptr(buf["F"][l]), buf["F"][l].shape[1],
+                            _cabi.ptr(buf["g_mu"]) if last else None, _cabi.ptr(buf["g_var"]) if last else None,
+                            _cabi.ptr(gF) if gF is not None else None, gF.shape[1] if gF is not None else 0,
+                            _cabi.ptr(buf["gX"][l]) if l > 0 else None, 1 if ci > 0 else 0, st), "dgp_cond_backward")
+            klw = 1.0 / float(world_size)
+            if need_grad:
+                it = iter(zip(params, offs))
+                for layer, conds in zip(self.layers, self.conds):
+                    zt = [(next(it), next(it)) for _ in conds]
+                    (q_mu, o_mu), (q_sqrt, o_sqrt) = next(it), next(it)
+                    for c, ((Z, oZ), (th, oT)) in zip(conds, zt):
+                        base = flat.data_ptr()
+                        _cabi.check(lib.dgp_cond_backward_params(
+                            c.ref(), _cabi.ptr(c.ws), klw, ctypes.c_void_p(base + 8 * oZ), ctypes.c_void_p(base + 8 * oT),
+                            ctypes.c_void_p(base + 8 * o_mu), ctypes.c_void_p(base + 8 * o_sqrt), st),
+                            "dgp_cond_backward_params")
+            flat[0] -= klw * kl.sum()
+            if all_reduce is not None and world_size > 1:
+                all_reduce(flat[:total])
+            if check:
+                self.check_status()
+            grads = None
+            if need_grad:
+                grads = [flat[o:o + p.numel()].view(p.shape) for p, o in zip(params, offs)]
+            return flat[0], grads
+
+
+class _ElboFn(torch.autograd.Function):
+    """ELBO as one autograd node: forward runs the fused forward AND backward kernels; backward scales the stored
+    gradients.  The softplus chain of positive parameters is left to torch (it sits outside this node)."""
+
+    @staticmethod
+    def forward(ctx, engine, kwargs, *params):
+        need = any(ctx.needs_input_grad[2:])
+        val, grads = engine.elbo(list(params), need_grad=need, **kwargs)
+        ctx.grads = grads
+        return val.clone()
+
+    @staticmethod
+    def backward(ctx, g):
+        if ctx.grads is None:
+            return (None, None) + tuple(None for _ in ctx.needs_input_grad[2:])
+        return (None, None) + tuple(g * gr for gr in ctx.grads)
+
+
+def elbo_autograd(engine, **kwargs):
+    return _ElboFn.apply(engine, kwargs, *engine.params())
+
+
+# ---------------------------------------------------------------------------------------------- single-layer helpers
+def _layer_engine(layer):
+    eng = getattr(layer, "_dgp_engine", None)
+    if eng is None or eng.device.index != torch.cuda.current_device():
+        eng = Engine([layer], None, multitask=False)
+        object.__setattr__(layer, "_dgp_engine", eng)
+    return eng
+
+
+def layer_predict(layer, Xnew, stochastic=True):
+    """Layer._build_predict (dgplib/layers.py:62-94), diag branch.  Returns CUDA tensors."""
+    eng = _layer_engine(layer)
+    X = _dev_tensor(Xnew, eng.device)
+    if stochastic:
+        S, N, D = X.shape
+        flat = X.reshape(S * N, D)          # dgplib/layers.py:84-85
+    else:
+        S, (N, D) = 1, X.shape
+        flat = X
+    _, means, vars_ = eng.propagate(flat, 1, eps=[torch.zeros(S * N, layer.output_dim, dtype=_F64)])
+    mean, var = means[0][0], vars_[0][0]
+    if stochastic:
+        return mean.reshape(S, N, -1), var.reshape(S, N, -1)
+    return mean, var
+
+
+def layer_kl(layer):
+    eng = _layer_engine(layer)
+    with torch.no_grad():
+        eng._bind(eng._detached())
+        ncond = len(eng.conds[0])
+        kl = torch.zeros(ncond, dtype=_F64, device=eng.device)
+        eng._prepare(1, False, kl)
+        return kl.sum()
+
+
+def _kernel_desc(kernel, Dx, device):
+    parts = kernel.task_kernels()
+    d = _cabi.CondDesc()
+    d.T = len(parts)
+    d.Dx = Dx
+    d.D = min(kernel.input_dim, Dx - 1) if kernel.switched else kernel.input_dim
+    d.M = d.R = d.ldr = 1
+    for t, p in enumerate(parts):
+        d.kind[t] = p[0]
+    rows = []
+    for (_, var, white, ls) in parts:
+        w = torch.zeros((), dtype=_F64) if white is None else white
+        rows.append(torch.cat([var.reshape(1).cpu(), w.reshape(1).cpu(), ls[:d.D].cpu()]))
+    theta = _dev_tensor(torch.stack(rows), device)
+    d.theta = theta.data_ptr()
+    return d, theta
+
+
+def kernel_K(kernel, X, X2=None):
+    """gpflow Kernel.K(X, X2) on the GPU (dgp_kernel_K)."""
+    _cabi.require_cuda()
+    dev = torch.device(f"cuda:{torch.cuda.current_device()}")
+    X = _dev_tensor(X, dev)
+    d, theta = _kernel_desc(kernel, X.shape[1], dev)
+    X2d = None if X2 is None else _dev_tensor(X2, dev)
+    n2 = X.shape[0] if X2 is None else X2d.shape[0]
+    K = torch.empty(X.shape[0], n2, dtype=_F64, device=dev)
+    _cabi.check(_cabi.lib().dgp_kernel_K(ctypes.byref(d), _cabi.ptr(X), X.shape[0], _cabi.ptr(X2d), n2,
+                                         1 if X2 is None else 0, _cabi.ptr(K), _cabi.stream_ptr()), "dgp_kernel_K")
+    return K
+
+
+def kernel_Kdiag(kernel, X):
+    _cabi.require_cuda()
+    dev = torch.device(f"cuda:{torch.cuda.current_device()}")
+    X = _dev_tensor(X, dev)
+    d, theta = _kernel_desc(kernel, X.shape[1], dev)
+    out = torch.empty(X.shape[0], dtype=_F64, device=dev)
+    _cabi.check(_cabi.lib().dgp_kernel_Kdiag(ctypes.byref(d), _cabi.ptr(X), X.shape[0], _cabi.ptr(out),
+                                             _cabi.stream_ptr()), "dgp_kernel_Kdiag")
+    return out
