@@ -1,0 +1,315 @@
+#!/usr/bin/env python
+"""Benchmark of the DSDGP ELBO+gradient hot path (BASELINE.json metric): rows/s = B*S*evals/s.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload T|C2|C1|C3s] [--impl ours|reference]
+
+N > 1 is launched by the driver with torch.distributed.run (one rank per GPU, NCCL).  Prints ONE JSON line (rank 0).
+`value`  : device-timed throughput, inputs resident in HBM.
+`e2e`    : the same metric through the public API (DSDGP.elbo_and_grad) with the minibatch copied from pinned host
+           memory and the ELBO read back every step.
+`roofline`: dominant kernel's algorithmic flops / CUDA-event time vs the measured fp64 DMMA peak.
+`cpu_baseline` / --impl reference: the oracle (op-for-op restatement of the reference graph in PyTorch-CPU fp64; TF 1.8 /
+           GPflow 1.2 cannot be installed here) on the box's host cores, bounded sample.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: L, M, D, N (dataset rows), B (minibatch rows per GPU), S, kind
+    "T":   dict(L=3, M=256, D=8, N=100_000, B=10_000, S=10, kind="rbf",
+                desc="3-layer DSDGP RBF M=256 D=8 N=100k minibatch 10k S=10 (north_star target line = configs[1] with M=256)"),
+    "C2":  dict(L=3, M=128, D=8, N=100_000, B=10_000, S=10, kind="rbf",
+                desc="configs[1]: 3-layer DSDGP RBF M=128 D=8 N=100k minibatch 10k S=10"),
+    "C1":  dict(L=2, M=50, D=1, N=1000, B=1000, S=1, kind="rbf", desc="configs[0]: 2-layer RBF M=50 D=1 N=1000 S=1"),
+    "C3s": dict(L=5, M=500, D=16, N=1_000_000, B=10_000, S=16, kind="matern52",
+                desc="configs[2] per-GPU shard: 5-layer Matern52 M=500 D=16 minibatch 80k/8 S=16"),
+}
+FP64_PEAK_TFLOPS = 37.1   # profiles/fp64_peak_r01.txt: DMMA.8x8x4 issue-rate microbenchmark on this pool's B200
+                          # (cuBLAS DGEMM 8192^3: 35.5).  MEASURED_PEAKS.json holds no fp64 figure.
+
+
+def flops_per_row_layer(M, D_in, R):
+    """SURVEY.md 8(d) forward flop convention per row-layer; ELBO+grad = 3x."""
+    return 2 * M * D_in + M * M + 2 * M * R + 2 * M + R * (M * M + 2 * M)
+
+
+def build_model(w, n_gpus):
+    import dgplib_b200 as dg
+    from dgplib_b200.cascade import Sequential
+    from dgplib_b200.kernels import RBF, Matern52, White
+    from dgplib_b200.layers import InputLayer, HiddenLayer, OutputLayer
+    from dgplib_b200.likelihoods import Gaussian
+    from dgplib_b200.mean_functions import Linear
+    L, M, D, N, B, S = w["L"], w["M"], w["D"], w["N"], w["B"], w["S"]
+    rng = np.random.RandomState(0)
+    X = rng.randn(N, D)
+    Y = np.sin(X.sum(1, keepdims=True)) + 0.1 * rng.randn(N, 1)
+    if D == 1:
+        X = rng.uniform(0, 1, (N, 1))
+    Z = X[rng.permutation(N)[:M]].copy()
+    dims = [D] * L + [1]
+    cls_k = RBF if w["kind"] == "rbf" else Matern52
+    layers = []
+    for l in range(L):
+        cls = InputLayer if l == 0 else (OutputLayer if l == L - 1 else HiddenLayer)
+        kern = cls_k(dims[l], variance=1.0, lengthscales=float(np.sqrt(dims[l]))) + White(dims[l], variance=1e-5)
+        mf = Linear(A=np.zeros((dims[l], dims[l + 1]))) if l < L - 1 else None
+        layers.append(cls(dims[l], dims[l + 1], M, kern, mean_function=mf))
+    import contextlib, io
+    with contextlib.redirect_stdout(io.StringIO()):
+        model = dg.DSDGP(X, Y, Z, Sequential(layers), Gaussian(variance=0.1), minibatch_size=B * n_gpus, num_samples=S,
+                         seed=1234)
+    rs = np.random.RandomState(1)
+    for layer in model.layers.layers:
+        Mq, R = layer.q_mu.shape
+        layer.q_mu.assign(0.1 * rs.randn(Mq, R))
+        layer.q_sqrt.assign(np.eye(Mq)[None] + 0.1 * np.tril(rs.randn(R, Mq, Mq)))
+    return model
+
+
+def workload_flops_per_row(w):
+    dims = [w["D"]] * w["L"] + [1]
+    return sum(flops_per_row_layer(w["M"], dims[l], dims[l + 1]) for l in range(w["L"]))
+
+
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(gpu_index), f"--query-gpu={self.Q}",
+                                       "--format=csv,noheader,nounits", "-lms", "100"], stdout=self.f,
+                                      stderr=subprocess.DEVNULL)
+        except OSError:
+            self.p = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        if self.p is None:
+            return out
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.p.kill()
+        self.f.flush()
+        rows = [r.split(",") for r in open(self.f.name).read().strip().splitlines() if r.count(",") >= 8]
+        os.unlink(self.f.name)
+        if not rows:
+            return out
+        sm = sorted(float(r[1]) for r in rows)
+        out["sm_mhz"] = sm[len(sm) // 2]
+        out["sm_max_mhz"] = float(rows[0][2])
+        out["power_w_max"] = max(float(r[3]) for r in rows)
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for i, nm in enumerate(names):
+            if any("Active" == r[5 + i].strip() for r in rows):
+                out["reasons"].append(nm)
+        out["samples"] = len(rows)
+        return out
+
+
+def cpu_oracle_throughput(model, w, sample_rows, reps, threads=None):
+    """Oracle ELBO+grad on the host cores over `sample_rows` minibatch rows (x S samples); best of `reps`."""
+    from oracle import dsdgp_oracle as O
+    from oracle.bridge import oracle_layers, oracle_lik, t
+    threads = threads or os.cpu_count()
+    torch.set_num_threads(threads)
+    layers, lik = oracle_layers(model.layers.layers), oracle_lik(model.likelihood)
+    S = w["S"]
+    X = model.X[:sample_rows].clone()
+    Y = model.Y[:sample_rows].clone()
+    eps = [torch.randn(S, sample_rows, l["q_mu"].shape[1], dtype=torch.float64) for l in layers]
+    best = float("inf")
+    for i in range(reps + 1):          # first pass is the warm-up
+        t0 = time.perf_counter()
+        O.elbo_and_grad(layers, lik, X, Y, S, eps, num_data=w["N"])
+        dt = time.perf_counter() - t0
+        if i > 0:
+            best = min(best, dt)
+    return sample_rows * S / best, best, torch.get_num_threads()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--workload", default="T", choices=sorted(WORKLOADS))
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--cpu-rows", type=int, default=0, help="minibatch rows of the CPU baseline sample (0 = auto)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    w = WORKLOADS[args.workload]
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    S, B = w["S"], w["B"]
+    metric = "DSDGP ELBO+grad rows/s (B*S*evals/s)"
+    config = {"workload": f"{args.workload}: {w['desc']}", "layers": w["L"], "M": w["M"], "D": w["D"], "S": S,
+              "minibatch_rows_per_gpu": B, "global_minibatch_rows": B * max(world, 1), "kernel": w["kind"],
+              "sharding": f"dp{max(world, 1)} over minibatch rows",
+              "l2": "per-step working set (A tiles, dKuf) is >1 GB, far above the 126 MB L2; no flush needed"}
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        model = build_model(w, 1)
+        rows = args.cpu_rows or max(256, min(B, int(2.0e11 / (3 * workload_flops_per_row(w) * S))))
+        vals = []
+        for _ in range(max(1, args.steps)):
+            v, dt, thr = cpu_oracle_throughput(model, w, rows, 1)
+            vals.append(v)
+        v = float(np.mean(vals))
+        line = {"impl": "reference", "metric": metric, "value": v, "unit": "rows/s", "n_gpus": args.gpus,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * rows * S / v, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config,
+                "cpu_baseline": {"value": v, "unit": "rows/s", "cores": thr, "kind": "port",
+                                 "sample": f"{rows} of {B} minibatch rows x S={S}: oracle (PyTorch-CPU fp64 restatement "
+                                           "of the reference graph; TF 1.8/GPflow 1.2 not installable), fwd+autograd bwd"},
+                "e2e": {"value": v, "unit": "rows/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(line))
+        return
+
+    # ------------------------------------------------------------------------------------------------ our arm
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (B200); there is no CPU fallback for the product path")
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local_rank}"))
+    from dgplib_b200 import _cabi
+    model = build_model(w, world)
+    model.compile(f"cuda:{local_rank}")
+    if dist is not None:
+        model.distribute()
+    eng = model.engine
+    dev = eng.device
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    # ---- device-resident leg: this rank's shard of one global minibatch already in HBM
+    Bg = B * world
+    Xb, Yb = model.X[:Bg], model.Y[:Bg]
+    lo = B * rank
+    Xd, Yd = Xb[lo:lo + B].to(dev), Yb[lo:lo + B].to(dev)
+    params = [p.detach() for p in eng.params()]
+    ar = (lambda tns: dist.all_reduce(tns)) if dist is not None else None
+
+    def step_dev(i):
+        return eng.elbo(params, Xd, Yd, S, eps=None, seed=1234 + i, num_data=w["N"], need_grad=True, row_offset=lo,
+                        global_batch=Bg, world_size=world, all_reduce=ar, check=False)
+
+    for i in range(max(3, args.warmup)):
+        step_dev(i)
+    eng.check_status()
+    sync_all()
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    time.sleep(0.3)
+    eng.timers = {}
+    l0 = _cabi.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(args.steps):
+        val, _ = step_dev(100 + i)
+    e1.record()
+    sync_all()
+    launches = _cabi.launch_count() - l0
+    ms = e0.elapsed_time(e1)
+    timers = eng.timer_summary()
+    eng.timers = None
+    clocks = sampler.stop() if sampler is not None else None
+    if dist is not None:
+        tm = torch.tensor([ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+        ms = float(tm)
+    elbo_val = float(val)
+    rows_per_step = Bg * S
+    value = rows_per_step * args.steps / (ms * 1e-3)
+
+    # ---- end-to-end leg: public API, pinned host minibatch -> device every step, ELBO read back every step
+    for i in range(2):
+        v, _ = model.elbo_and_grad()
+        float(v)
+    sync_all()
+    t0 = torch.cuda.Event(enable_timing=True)
+    t1 = torch.cuda.Event(enable_timing=True)
+    t0.record()
+    for i in range(args.steps):
+        v, g = model.elbo_and_grad()
+        float(v)                                   # D2H read of the step's result
+    t1.record()
+    sync_all()
+    ms_e2e = t0.elapsed_time(t1)
+    if dist is not None:
+        tm = torch.tensor([ms_e2e], dtype=torch.float64, device=dev)
+        dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+        ms_e2e = float(tm)
+    e2e_value = rows_per_step * args.steps / (ms_e2e * 1e-3)
+    Dx, ldy = model.X.shape[1], model.Y.shape[1]
+    h2d = B * (Dx + ldy) * 8       # per rank, the rows it copies
+    d2h = 8
+
+    # ---- roofline of the dominant kernel (CUDA events on the launching stream, inside the timed region above)
+    dims = [w["D"]] * w["L"] + [1]
+    M = w["M"]
+    per_kernel = {}
+    for l in range(w["L"]):
+        Din, R = dims[l], dims[l + 1]
+        n_rows = B * S
+        per_kernel[f"fwd.l{l}"] = n_rows * flops_per_row_layer(M, Din, R)
+        per_kernel[f"bwd.l{l}"] = n_rows * (2 * R * M * M + M * M + 2 * M * R + 6 * M * Din)   # dA dense + Lm^-T + d q_mu + kernel bwd
+        per_kernel[f"gram.l{l}"] = n_rows * (R + 1) * M * M                                      # G_r (sym) + P (tril)
+    dom = max((k for k in timers if k in per_kernel), key=lambda k: timers[k][1])
+    n_l, ms_l = timers[dom]
+    achieved = per_kernel[dom] * n_l / (ms_l * 1e-3) / 1e12
+    step_alg_flops = 3 * workload_flops_per_row(w) * B * S
+    roofline = {"bound": "tensor", "kernel": dom, "achieved": achieved, "peak": FP64_PEAK_TFLOPS, "unit": "TFLOP/s",
+                "frac": achieved / FP64_PEAK_TFLOPS, "traffic": None,
+                "peak_source": "fp64 DMMA.8x8x4 issue-rate microbenchmark on this pool's B200 (profiles/fp64_peak_r01.txt); "
+                               "MEASURED_PEAKS.json has no fp64 entry (its bf16 tcgen05 peak does not apply: there is "
+                               "no fp64 tcgen05 kind)",
+                "kernel_ms": {k: round(v[1] / max(args.steps, 1), 4) for k, v in sorted(timers.items())},
+                "step_algorithmic_tflops": step_alg_flops * args.steps / (ms * 1e-3) / 1e12 * 1.0,
+                "step_frac_of_peak": step_alg_flops * args.steps / (ms * 1e-3) / 1e12 / FP64_PEAK_TFLOPS}
+
+    line = {"metric": metric, "value": value, "unit": "rows/s", "n_gpus": world, "steps": args.steps,
+            "warmup": max(3, args.warmup), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config, "elbo": elbo_val,
+            "e2e": {"value": e2e_value, "unit": "rows/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "ms_per_step": ms_e2e / args.steps},
+            "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline}
+
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        rows = args.cpu_rows or max(256, min(B, int(2.0e11 / (3 * workload_flops_per_row(w) * S))))
+        v, dt, thr = cpu_oracle_throughput(model.cpu() if False else model, w, rows, 2)
+        line["cpu_baseline"] = {"value": v, "unit": "rows/s", "cores": thr, "kind": "port",
+                                "sample": f"{rows} of {B} minibatch rows x S={S}, best of 2 after 1 warm-up ({dt:.2f} s/eval): "
+                                          "oracle = PyTorch-CPU fp64 restatement of the reference graph"}
+    if rank == 0:
+        print(json.dumps(line))
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -473,13 +473,21 @@ extern "C" int dgp_cond_backward(const dgp_cond_desc* d, void* ws, const double*
         a.ntiles = (int)((n_rows + C::NT - 1) / C::NT);
         rc = launch_bwd<C>(a, st);
     }
-    if (rc != DGP_OK) return rc;
+    return rc;
+}
 
+extern "C" int dgp_cond_backward_gram(const dgp_cond_desc* d, void* ws, const double* A_save, int64_t n_rows, void* stream) {
+    int rc = check_desc(d);
+    if (rc != DGP_OK) return rc;
+    if (!ws || !A_save || n_rows < 0) return DGP_ERR_ARG;
+    if (n_rows == 0) return DGP_OK;
+    const WsLayout w = ws_layout(*d, n_rows, 1);
+    cudaStream_t st = (cudaStream_t)stream;
     GramArgs ga{};
     ga.Mpad = w.Mpad; ga.R = d->R; ga.nsplit = w.nsplit; ga.n_rows = n_rows;
     long long rps = (n_rows + w.nsplit - 1) / w.nsplit;
     ga.rows_per_split = (rps + GR_KC - 1) / GR_KC * GR_KC;
-    ga.A = A_save; ga.dKuf = a.dKuf; ga.gmv = a.gmv;
+    ga.A = A_save; ga.dKuf = ws_ptr<double>(ws, w.dKuf); ga.gmv = ws_ptr<double>(ws, w.gmv);
     ga.gram = ws_ptr<double>(ws, w.gram);
     const int nbt = w.Mpad / 64;
     const size_t gsm_bytes = (size_t)(2 * GR_STAGES * GR_KC * GR_LD + GR_STAGES * GR_KC) * sizeof(double);

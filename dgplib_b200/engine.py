@@ -98,6 +98,26 @@ class Engine:
         self._rows = {}
         self._lik_ws = None
         self.last_status = None
+        self.timers = None         # set to {} to collect CUDA-event timings per kernel class (bench.py)
+
+    def _timed(self, key, fn):
+        """Run fn() (which enqueues kernels on the current stream); when timers are on, bracket it with CUDA events
+        recorded on that same stream."""
+        if self.timers is None:
+            return fn()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        out = fn()
+        e1.record()
+        self.timers.setdefault(key, []).append((e0, e1))
+        return out
+
+    def timer_summary(self):
+        """{key: (launches, total ms)} -- call after a stream sync."""
+        out = {}
+        for k, evs in (self.timers or {}).items():
+            out[k] = (len(evs), sum(a.elapsed_time(b) for a, b in evs))
+        return out
 
     # ------------------------------------------------------------------------------------------ parameters
     def _lik_variances(self):
@@ -201,14 +221,14 @@ class Engine:
             want_F = last_F or l < L - 1
             Fbuf = buf["F"][l] if want_F else None
             for ci, c in enumerate(conds):
-                _cabi.check(lib.dgp_cond_forward(
+                self._timed(f"fwd.l{l}", lambda: _cabi.check(lib.dgp_cond_forward(
                     c.ref(), _cabi.ptr(c.ws), _cabi.ptr(inp), x_rows, n,
                     _cabi.ptr(eps[l]) if (eps is not None and want_F) else None,
                     ctypes.c_uint64(seed + 0x9E3779B97F4A7C15 * (l + 1) & 0xFFFFFFFFFFFFFFFF), row_offset, B,
                     sample_stride if sample_stride else B,
                     _cabi.ptr(buf["mean"][l]), _cabi.ptr(buf["var"][l]), _cabi.ptr(Fbuf) if want_F else None,
                     Fbuf.shape[1] if want_F else layer.output_dim,
-                    _cabi.ptr(buf["A"][l][ci]) if save else None, st), "dgp_cond_forward")
+                    _cabi.ptr(buf["A"][l][ci]) if save else None, st), "dgp_cond_forward"))
             inp, x_rows = Fbuf, n
 
     def propagate(self, X, S, eps=None, seed=0, params=None):
@@ -262,7 +282,7 @@ class Engine:
             flat = torch.zeros(total + ncond, dtype=_F64, device=dev)   # [elbo | grads | kl per conditional]
             kl = flat[total:]
             Bc = B if not chunk_rows else max(1, min(B, int(chunk_rows)))
-            self._prepare(S * Bc, need_grad, kl)
+            self._timed("prepare", lambda: self._prepare(S * Bc, need_grad, kl))
             if self._lik_ws is None:
                 self._lik_ws = torch.empty(lib.dgp_lik_ws_bytes(0, 1), dtype=torch.uint8, device=dev)
             L = len(self.layers)
@@ -283,12 +303,12 @@ class Engine:
                 if eps_full is not None:
                     eps_c = [e[:, b0:b1].reshape(n, -1).contiguous() for e in eps_full]
                 self._forward_rows(Xc, S, eps_c, seed, row_offset + b0, Bg, buf, need_grad, False)
-                _cabi.check(lib.dgp_lik_gaussian(
+                self._timed("lik", lambda: _cabi.check(lib.dgp_lik_gaussian(
                     _cabi.ptr(buf["mean"][-1]), _cabi.ptr(buf["var"][-1]), _cabi.ptr(Yc), nb, ldy, n, RL,
                     _cabi.ptr(self._lik_var), T_lik, weight, ctypes.c_void_p(flat.data_ptr()),
                     _cabi.ptr(buf["g_mu"]) if need_grad else None, _cabi.ptr(buf["g_var"]) if need_grad else None,
                     ctypes.c_void_p(g_lik.data_ptr()) if need_grad else None,
-                    _cabi.ptr(self._lik_ws), self._lik_ws.numel(), st), "dgp_lik_gaussian")
+                    _cabi.ptr(self._lik_ws), self._lik_ws.numel(), st), "dgp_lik_gaussian"))
                 if not need_grad:
                     continue
                 for l in range(L - 1, -1, -1):
@@ -298,13 +318,15 @@ class Engine:
                     last = (l == L - 1)
                     gF = None if last else buf["gX"][l + 1]
                     for ci, c in enumerate(conds):
-                        _cabi.check(lib.dgp_cond_backward(
+                        self._timed(f"bwd.l{l}", lambda: _cabi.check(lib.dgp_cond_backward(
                             c.ref(), _cabi.ptr(c.ws), _cabi.ptr(inp), x_rows, n, _cabi.ptr(buf["A"][l][ci]),
                             _cabi.ptr(buf["mean"][l]), _cabi.ptr(buf["var"][l]),
                             None if last else _cabi.ptr(buf["F"][l]), buf["F"][l].shape[1],
                             _cabi.ptr(buf["g_mu"]) if last else None, _cabi.ptr(buf["g_var"]) if last else None,
                             _cabi.ptr(gF) if gF is not None else None, gF.shape[1] if gF is not None else 0,
-                            _cabi.ptr(buf["gX"][l]) if l > 0 else None, 1 if ci > 0 else 0, st), "dgp_cond_backward")
+                            _cabi.ptr(buf["gX"][l]) if l > 0 else None, 1 if ci > 0 else 0, st), "dgp_cond_backward"))
+                        self._timed(f"gram.l{l}", lambda: _cabi.check(lib.dgp_cond_backward_gram(
+                            c.ref(), _cabi.ptr(c.ws), _cabi.ptr(buf["A"][l][ci]), n, st), "dgp_cond_backward_gram"))
             klw = 1.0 / float(world_size)
             if need_grad:
                 it = iter(zip(params, offs))
@@ -313,10 +335,10 @@ class Engine:
                     (q_mu, o_mu), (q_sqrt, o_sqrt) = next(it), next(it)
                     for c, ((Z, oZ), (th, oT)) in zip(conds, zt):
                         base = flat.data_ptr()
-                        _cabi.check(lib.dgp_cond_backward_params(
+                        self._timed("params_bwd", lambda: _cabi.check(lib.dgp_cond_backward_params(
                             c.ref(), _cabi.ptr(c.ws), klw, ctypes.c_void_p(base + 8 * oZ), ctypes.c_void_p(base + 8 * oT),
                             ctypes.c_void_p(base + 8 * o_mu), ctypes.c_void_p(base + 8 * o_sqrt), st),
-                            "dgp_cond_backward_params")
+                            "dgp_cond_backward_params"))
             flat[0] -= klw * kl.sum()
             if all_reduce is not None and world_size > 1:
                 all_reduce(flat[:total])

@@ -114,12 +114,16 @@ size_t dgp_lik_ws_bytes(int64_t n_rows, int32_t R);
  *   g_F       [n_rows, ldgf] gradient of the sample F (from the next layer's gX), or NULL;  then
  *             g_mean = g_mean_in + g_F,  g_var = g_var_in + g_F * (F - mean) / (2 var)
  *   gX        [n_rows, Dx] gradient w.r.t. the input rows (NULL for the data layer); accumulate != 0 adds to it
- * Row-summed parameter gradients are accumulated inside the workspace; dgp_cond_backward_params finishes them.
+ * dgp_cond_backward leaves dKuf and the combined g_mean / g_var in the workspace; dgp_cond_backward_gram (call it next,
+ * same n_rows / A_save) reduces them over the rows into the Gram accumulators G_r = sum_n g_var[n,r] a_n a_n^T and
+ * P = sum_n dKuf_n a_n^T.  Row-summed parameter gradients are accumulated inside the workspace (several row chunks
+ * may be pushed between one dgp_cond_prepare and dgp_cond_backward_params, which finishes them).
  */
 int dgp_cond_backward(const dgp_cond_desc* d, void* ws, const double* X, int64_t x_rows, int64_t n_rows,
                       const double* A_save, const double* mean, const double* var, const double* F, int32_t ldf,
                       const double* g_mean_in, const double* g_var_in, const double* g_F, int32_t ldgf,
                       double* gX, int32_t accumulate_gX, void* stream);
+int dgp_cond_backward_gram(const dgp_cond_desc* d, void* ws, const double* A_save, int64_t n_rows, void* stream);
 /* Parameter-only tail: Cholesky / Kuu / KL reverse mode.  Outputs (device, this conditional's part OVERWRITTEN):
  *   gZ [M, Dx], gtheta [T, 2+D], gq_mu [M, ldr] (columns col0..), gq_sqrt [ldr, M, M] (rows col0..)
  *   kl_weight: this rank's share of the KL term (1/world_size) so that an all-reduce(sum) over ranks is exact */

@@ -19,37 +19,7 @@ def t(x):
     return torch.tensor(np.array(x, dtype=np.float64), dtype=T64)
 
 
-def oracle_kernel(k):
-    if isinstance(k, SwitchedKernel):
-        return {"kind": "switched", "kernels": [oracle_kernel(kk) for kk in k.kernels]}
-    stat, white = k, None
-    if isinstance(k, Sum):
-        stat = [kk for kk in k.kernels if isinstance(kk, Stationary)][0]
-        ws = [kk for kk in k.kernels if isinstance(kk, White)]
-        white = t(sum(float(w.variance.value) for w in ws)) if ws else None
-    return {"kind": "rbf" if isinstance(stat, RBF) else "matern52", "input_dim": stat.input_dim,
-            "variance": t(stat.variance.value), "lengthscales": t(stat.lengthscales.value), "white": white}
-
-
-def oracle_layers(model_layers):
-    out = []
-    for layer in model_layers:
-        groups, zcache = [], {}
-        for (k, f, c0, R) in layer.conditionals():
-            if id(f) not in zcache:
-                zcache[id(f)] = t(f.Z.value)
-            groups.append({"kernel": oracle_kernel(k), "Z": zcache[id(f)]})
-        mean = None
-        if isinstance(layer.mean_function, Linear):
-            mean = {"A": t(layer.mean_function.A.value), "b": t(layer.mean_function.b.value)}
-        out.append({"groups": groups, "q_mu": t(layer.q_mu.value), "q_sqrt": t(layer.q_sqrt.value), "mean": mean})
-    return out
-
-
-def oracle_lik(lik):
-    if isinstance(lik, SwitchedLikelihood):
-        return {"kind": "switched", "variances": [t(l.variance.value) for l in lik.likelihood_list]}
-    return {"kind": "gaussian", "variance": t(lik.variance.value)}
+from oracle.bridge import oracle_kernel, oracle_layers, oracle_lik  # noqa: E402,F401
 
 
 def randomize_q(model, seed=1, scale=0.1):
