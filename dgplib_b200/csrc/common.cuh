@@ -17,6 +17,17 @@ extern long long g_launches;  // bench.py's gpu_launches (host-side count of our
     } while (0)
 
 static inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
+
+// Tiled operand layout streamed by the row-tile kernels (stream_gemm.cuh): [block row][chunk][128 rows][20 doubles]
+constexpr int TILE_MB = 128;   // rows of a staged chunk
+constexpr int TILE_KC = 16;    // depth of a staged chunk
+constexpr int TILE_WLD = 20;   // padded row pitch of a staged chunk (doubles): conflict-free DMMA A-fragment loads
+constexpr int TILE_DOUBLES = TILE_MB * TILE_WLD;
+__host__ __device__ inline int tiled_mpad(int Mpad) { return (Mpad + TILE_MB - 1) / TILE_MB * TILE_MB; }
+__host__ __device__ inline size_t tiled_doubles(int Mpad) {
+    const int mt = tiled_mpad(Mpad);
+    return (size_t)(mt / TILE_MB) * (mt / TILE_KC) * TILE_DOUBLES;
+}
 static inline size_t align256(size_t x) { return (x + 255) & ~size_t(255); }
 
 // ------------------------------------------------------------------------------------------------ workspace layout
@@ -32,9 +43,14 @@ struct WsLayout {
     size_t Lm;         // [Mpad][Mpad] Kuu(+jitter) -> Cholesky factor in place (pad = identity)
     size_t Linv;       // [Mpad][Mpad] Lm^-1 (lower)
     size_t LqT;        // [R][Mpad][Mpad] tril(q_sqrt_r)^T (upper), pad zero
+    size_t LinvTl;     // tiled copy of Linv        (streamed by the forward kernel)
+    size_t LqTTl;      // [R] tiled copies of LqT_r (streamed by the forward kernel)
+    size_t tl;         // doubles of one tiled matrix
     // backward only
     size_t LinvT;      // [Mpad][Mpad]
     size_t SmI;        // [R][Mpad][Mpad] tril(q_sqrt_r) tril(q_sqrt_r)^T - I
+    size_t LinvTTl;    // tiled copy of LinvT       (streamed by the backward kernel)
+    size_t SmITl;      // [R] tiled copies of SmI_r (streamed by the backward kernel)
     size_t dKuf;       // [n_rows][Mpad]
     size_t gmv;        // [n_rows][2R] combined g_mean | g_var of this conditional
     size_t gram;       // [nsplit][R+1][Mpad][Mpad]  split-K partials of G_r (r<R) and P (r==R)
@@ -60,6 +76,9 @@ static inline WsLayout ws_layout(const dgp_cond_desc& d, int64_t n_rows, int nee
     w.Lm = o;     o += align256(mm);
     w.Linv = o;   o += align256(mm);
     w.LqT = o;    o += align256(mm * d.R);
+    w.tl = tiled_doubles(w.Mpad);
+    w.LinvTl = o; o += align256(w.tl * sizeof(double));
+    w.LqTTl = o;  o += align256(w.tl * sizeof(double) * d.R);
     if (need_bwd) {
         // split-K factor of the Gram kernel: enough CTAs to fill the machine ~3x (independent of n_rows so that every
         // offset except the two row-sized buffers at the end is a function of the descriptor only)
@@ -72,6 +91,8 @@ static inline WsLayout ws_layout(const dgp_cond_desc& d, int64_t n_rows, int nee
         w.npart = round_up(w.Mpad * w.Dp + w.Mpad + w.Mpad * d.R + d.T * (2 + w.Dp), 32);
         w.LinvT = o; o += align256(mm);
         w.SmI = o;   o += align256(mm * d.R);
+        w.LinvTTl = o; o += align256(w.tl * sizeof(double));
+        w.SmITl = o;   o += align256(w.tl * sizeof(double) * d.R);
         w.gram = o;  o += align256(mm * (d.R + 1) * w.nsplit);
         w.part = o;  o += align256(size_t(w.ncta) * w.npart * sizeof(double));
         w.tail = o;  o += align256(mm * (2 * d.R + 4));

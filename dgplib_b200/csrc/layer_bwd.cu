@@ -20,7 +20,7 @@ struct BwdArgs {
     dgp_cond_desc d;
     int Mpad, Dp;
     const double* Zs; const double* zn; const int32_t* ztask;
-    const double* LinvT; const double* SmI;
+    const double* LinvT; const double* SmI; size_t tl;   // tiled copies (stream_gemm.cuh)
     const double* X; long long x_rows, n_rows;
     const double* A_save; const double* mean; const double* var; const double* F; int ldf;
     const double* g_mean_in; const double* g_var_in; const double* g_F; int ldgf;
@@ -32,7 +32,7 @@ struct BwdArgs {
 template <class C>
 struct BwdSmem {
     int ldb, xld;
-    int Bt, Dt, Wst, xs, xn, gm, gv, rs, dv, rowq, xtask, bar, total_doubles;
+    int Bt, Dt, Wst, xs, xn, gm, gv, rs, dv, rowq, xtask, bar, bars, total_doubles;
     __host__ __device__ BwdSmem(int Mpad, int Dp, int R) {
         ldb = Mpad + 4;
         xld = Dp + 4;
@@ -49,12 +49,13 @@ struct BwdSmem {
         rowq = o; o += C::NT * (2 + Dp);
         xtask = o; o += C::NT / 2 + 1;
         bar = o; o += 2;
+        bars = o; o += 2 * C::STAGES;
         total_doubles = o;
     }
 };
 
 template <class C>
-__global__ void __launch_bounds__(C::NTHREADS, 1) k_cond_bwd(BwdArgs a) {
+__global__ void __launch_bounds__(C::NTHREADS, 1) k_cond_bwd(const __grid_constant__ BwdArgs a) {
     extern __shared__ __align__(128) double smem[];
     const dgp_cond_desc& d = a.d;
     const BwdSmem<C> L(a.Mpad, a.Dp, d.R);
@@ -70,6 +71,7 @@ __global__ void __launch_bounds__(C::NTHREADS, 1) k_cond_bwd(BwdArgs a) {
     double* rowq = smem + L.rowq;
     int32_t* xtask = reinterpret_cast<int32_t*>(smem + L.xtask);
     uint64_t* bar = reinterpret_cast<uint64_t*>(smem + L.bar);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L.bars);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int Mpad = a.Mpad, Dp = a.Dp, ldb = L.ldb, xld = L.xld, R = d.R;
@@ -83,18 +85,51 @@ __global__ void __launch_bounds__(C::NTHREADS, 1) k_cond_bwd(BwdArgs a) {
     double* pqmu = pcs + Mpad;                               // [Mpad][R]
     double* pth = pqmu + (size_t)Mpad * R;                   // [T][2+Dp]
 
+    // segment lists of the two streamed phases (shared by the producer warp and the consumers)
+    auto seg_dA = [&](int s) {      // dA block row i accumulates over all r: dense S_r - I
+        Seg sg;
+        sg.i = s / R;
+        sg.r = s % R;
+        sg.W = a.SmI + (size_t)sg.r * a.tl;
+        sg.kc0 = 0;
+        sg.kc1 = Mpad / C::KC;
+        sg.flush = (sg.r == R - 1);
+        return sg;
+    };
+    auto seg_dK = [&](int s) {      // dKuf = LinvT * dA, block rows top-down, in place
+        Seg sg;
+        sg.W = a.LinvT;
+        sg.i = s;
+        sg.kc0 = s * C::MB / C::KC;
+        sg.kc1 = Mpad / C::KC;
+        sg.r = 0;
+        sg.flush = true;
+        return sg;
+    };
+
+    Pipe pipe;
+    pipe_init<C>(pipe, bars, Wst);
     if (tid == 0) {
         mbar_init(bar, 1);
         mbar_fence_init();
     }
-    __syncthreads();
+    __syncthreads();   // the only CTA-wide barrier
+    if (warp == C::NWARPS) {
+        if (lane == 0) {
+            for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
+                produce_phase<C>(pipe, nb * R, seg_dA, Mpad);
+                produce_phase<C>(pipe, nb, seg_dK, Mpad);
+            }
+        }
+        return;
+    }
     uint32_t parity = 0;
 
     for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
         const long long n0 = (long long)tile * C::NT;
         const int nvalid = (int)((a.n_rows - n0 < C::NT) ? (a.n_rows - n0) : C::NT);
         bulk_wait_read0();   // previous tile's dKuf store has finished reading Dt
-        __syncthreads();     // every warp is done with the previous tile
+        consumer_sync<C>();  // every warp is done with the previous tile
 
         // ---- A tile: HBM -> Bt by bulk async copies, completion on the mbarrier
         if (tid == 0) {
@@ -102,11 +137,11 @@ __global__ void __launch_bounds__(C::NTHREADS, 1) k_cond_bwd(BwdArgs a) {
             for (int n = 0; n < nvalid; ++n)
                 bulk_g2s(Bt + n * ldb, a.A_save + (size_t)(n0 + n) * Mpad, (uint32_t)(Mpad * sizeof(double)), bar);
         }
-        for (int e = tid; e < (C::NT - nvalid) * Mpad; e += C::NTHREADS)   // ragged tile: zero rows
+        for (int e = tid; e < (C::NT - nvalid) * Mpad; e += C::NCONS)   // ragged tile: zero rows
             Bt[(nvalid + e / Mpad) * ldb + e % Mpad] = 0.0;
 
         // ---- per-row setup: scaled inputs, combined upstream gradients
-        for (int n = tid; n < C::NT; n += C::NTHREADS) {
+        for (int n = tid; n < C::NT; n += C::NCONS) {
             long long gn = n0 + n;
             if (gn >= a.n_rows) gn = a.n_rows - 1;
             const double* xr = a.X + (size_t)(gn % a.x_rows) * d.Dx;
@@ -126,7 +161,7 @@ __global__ void __launch_bounds__(C::NTHREADS, 1) k_cond_bwd(BwdArgs a) {
             }
             xn[n] = s;
         }
-        for (int idx = tid; idx < C::NT * R; idx += C::NTHREADS) {
+        for (int idx = tid; idx < C::NT * R; idx += C::NCONS) {
             const int n = idx / R, r = idx % R;
             const long long gn = n0 + n;
             double gmean = 0.0, gvar = 0.0;
@@ -147,20 +182,10 @@ __global__ void __launch_bounds__(C::NTHREADS, 1) k_cond_bwd(BwdArgs a) {
         }
         mbar_wait(bar, parity);
         parity ^= 1;
-        // (run_phase starts with a __syncthreads)
+        // (run_phase starts with a consumer barrier)
 
         // ---- phase dA: Dt = q_mu g_mean^T + 2 sum_r (S_r - I) (A . g_var_r)
         {
-            auto segfn = [&](int s) {
-                Seg sg;
-                sg.i = s / R;
-                sg.r = s % R;
-                sg.W = a.SmI + (size_t)sg.r * Mpad * Mpad;
-                sg.kc0 = 0;
-                sg.kc1 = Mpad / C::KC;
-                sg.flush = (sg.r == R - 1);
-                return sg;
-            };
             auto epi = [&](Acc<C>& acc, const Seg& sg) {
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
@@ -181,23 +206,13 @@ __global__ void __launch_bounds__(C::NTHREADS, 1) k_cond_bwd(BwdArgs a) {
                     }
                 }
             };
-            run_phase<C, MASK_DENSE, true>(nb * R, segfn, epi, Wst, Bt, ldb, Mpad, gv, R);
+            run_phase<C, MASK_DENSE, true>(pipe, nb * R, seg_dA, epi, Bt, ldb, Mpad, gv, R);
         }
 
         // ---- phase dK: Dt <- Lm^-T Dt, block rows top-down, in place
         {
-            auto segfn = [&](int s) {
-                Seg sg;
-                sg.W = a.LinvT;
-                sg.i = s;
-                sg.kc0 = s * C::MB / C::KC;
-                sg.kc1 = Mpad / C::KC;
-                sg.r = 0;
-                sg.flush = true;
-                return sg;
-            };
             auto epi = [&](Acc<C>& acc, const Seg& sg) {
-                __syncthreads();
+                consumer_sync<C>();
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
                     const int row = acc_row<C>(sg.i, q);
@@ -210,9 +225,9 @@ __global__ void __launch_bounds__(C::NTHREADS, 1) k_cond_bwd(BwdArgs a) {
                     }
                 }
             };
-            run_phase<C, MASK_UPPER, false>(nb, segfn, epi, Wst, Dt, ldb, Mpad, nullptr, 0);
+            run_phase<C, MASK_UPPER, false>(pipe, nb, seg_dK, epi, Dt, ldb, Mpad, nullptr, 0);
         }
-        __syncthreads();
+        consumer_sync<C>();
 
         // ---- dKuf tile -> HBM (for the Gram kernel)
         fence_async_smem();
@@ -221,14 +236,14 @@ __global__ void __launch_bounds__(C::NTHREADS, 1) k_cond_bwd(BwdArgs a) {
             bulk_commit();
         }
         // ---- d q_mu partial: sum_n A[n][m] g_mean[n][r]   (reads Bt while the store drains)
-        for (int idx = tid; idx < d.M * R; idx += C::NTHREADS) {
+        for (int idx = tid; idx < d.M * R; idx += C::NCONS) {
             const int m = idx / R, r = idx % R;
             double s = 0.0;
             for (int n = 0; n < nvalid; ++n) s = fma(Bt[n * ldb + m], gm[n * R + r], s);
             pqmu[idx] += s;
         }
         bulk_wait_read0();
-        __syncthreads();
+        consumer_sync<C>();
 
         // ---- Dt <- Gr2 = dKuf . variance . k'(r2);  per-row sums: rs = sum_m Gr2, dv = sum_m dKuf k(r2)/variance
         for (int n = warp; n < C::NT; n += C::NWARPS) {
@@ -256,10 +271,10 @@ __global__ void __launch_bounds__(C::NTHREADS, 1) k_cond_bwd(BwdArgs a) {
             sdv = warp_sum(sdv);
             if (lane == 0) { rs[n] = srs; dv[n] = sdv; }
         }
-        __syncthreads();
+        consumer_sync<C>();
 
         // ---- T1[n][k] = sum_m Gr2[n][m] zs[m][k]  ->  gX, lengthscale row terms
-        for (int idx = tid; idx < C::NT * Dp; idx += C::NTHREADS) {
+        for (int idx = tid; idx < C::NT * Dp; idx += C::NCONS) {
             const int n = idx / Dp, k = idx % Dp;
             double t1 = 0.0;
             for (int m = 0; m < d.M; ++m) t1 = fma(Dt[n * ldb + m], a.Zs[(size_t)m * Dp + k], t1);
@@ -278,7 +293,7 @@ __global__ void __launch_bounds__(C::NTHREADS, 1) k_cond_bwd(BwdArgs a) {
         }
         // columns of X the kernel does not see (task id): only the Linear mean reaches them
         if (a.gX && d.Dx > d.D) {
-            for (int idx = tid; idx < C::NT * (d.Dx - d.D); idx += C::NTHREADS) {
+            for (int idx = tid; idx < C::NT * (d.Dx - d.D); idx += C::NCONS) {
                 const int n = idx / (d.Dx - d.D), k = d.D + idx % (d.Dx - d.D);
                 const long long gn = n0 + n;
                 if (gn < a.n_rows) {
@@ -291,25 +306,25 @@ __global__ void __launch_bounds__(C::NTHREADS, 1) k_cond_bwd(BwdArgs a) {
             }
         }
         // Kdiag terms: d variance += sum_r g_var, d white += sum_r g_var
-        for (int n = tid; n < C::NT; n += C::NTHREADS) {
+        for (int n = tid; n < C::NT; n += C::NCONS) {
             double s = 0.0;
             if (n < nvalid) for (int r = 0; r < R; ++r) s += gv[n * R + r];
             rowq[n * nq + 0] = dv[n] + s;
             rowq[n * nq + 1] = s;
         }
         // T2z[m][k] = sum_n Gr2[n][m] xs[n][k],  cs[m] = sum_n Gr2[n][m]
-        for (int idx = tid; idx < d.M * Dp; idx += C::NTHREADS) {
+        for (int idx = tid; idx < d.M * Dp; idx += C::NCONS) {
             const int m = idx / Dp, k = idx % Dp;
             double s = 0.0;
             for (int n = 0; n < nvalid; ++n) s = fma(Dt[n * ldb + m], xs[n * xld + k], s);
             pT2z[idx] += s;
         }
-        for (int m = tid; m < d.M; m += C::NTHREADS) {
+        for (int m = tid; m < d.M; m += C::NCONS) {
             double s = 0.0;
             for (int n = 0; n < nvalid; ++n) s += Dt[n * ldb + m];
             pcs[m] += s;
         }
-        __syncthreads();
+        consumer_sync<C>();
         // per-task hyper-parameter row terms, summed in row order by one thread per column (deterministic)
         if (tid < nq) {
             for (int n = 0; n < nvalid; ++n) {
@@ -457,22 +472,27 @@ extern "C" int dgp_cond_backward(const dgp_cond_desc* d, void* ws, const double*
     a.d = *d;
     a.Mpad = w.Mpad; a.Dp = w.Dp;
     a.Zs = ws_ptr<double>(ws, w.Zs); a.zn = ws_ptr<double>(ws, w.zn); a.ztask = ws_ptr<int32_t>(ws, w.ztask);
-    a.LinvT = ws_ptr<double>(ws, w.LinvT); a.SmI = ws_ptr<double>(ws, w.SmI);
+    a.LinvT = ws_ptr<double>(ws, w.LinvTTl); a.SmI = ws_ptr<double>(ws, w.SmITl); a.tl = w.tl;
     a.X = X; a.x_rows = x_rows; a.n_rows = n_rows;
     a.A_save = A_save; a.mean = mean; a.var = var; a.F = F; a.ldf = ldf;
     a.g_mean_in = g_mean_in; a.g_var_in = g_var_in; a.g_F = g_F; a.ldgf = ldgf;
     a.gX = gX; a.accumulate_gX = accumulate_gX;
     a.dKuf = ws_ptr<double>(ws, w.dKuf); a.gmv = ws_ptr<double>(ws, w.gmv);
     a.part = ws_ptr<double>(ws, w.part); a.npart = w.npart;
-    if (w.Mpad <= 256) {
-        using C = TileCfg<4, 2, 32, 3>;
-        a.ntiles = (int)((n_rows + C::NT - 1) / C::NT);
-        rc = launch_bwd<C>(a, st);
-    } else {
-        using C = TileCfg<4, 2, 16, 3>;
-        a.ntiles = (int)((n_rows + C::NT - 1) / C::NT);
-        rc = launch_bwd<C>(a, st);
+#define DGP_TRY_BWD(NTV, STG)                                                         \
+    {                                                                                 \
+        using C = TileCfg<4, 2, NTV, STG>;                                            \
+        a.ntiles = (int)((n_rows + C::NT - 1) / C::NT);                               \
+        rc = launch_bwd<C>(a, st);                                                    \
+        if (rc != DGP_ERR_UNSUPPORTED) return rc;                                     \
     }
+    if (w.Mpad <= 256) {
+        DGP_TRY_BWD(32, 4) DGP_TRY_BWD(32, 3) DGP_TRY_BWD(32, 2)
+    } else {
+        DGP_TRY_BWD(16, 4) DGP_TRY_BWD(16, 3) DGP_TRY_BWD(16, 2)
+    }
+#undef DGP_TRY_BWD
+    rc = DGP_ERR_UNSUPPORTED;
     return rc;
 }
 

@@ -17,7 +17,7 @@ struct FwdArgs {
     dgp_cond_desc d;
     int Mpad, Dp;
     const double* Zs; const double* zn; const int32_t* ztask;
-    const double* Linv; const double* LqT;
+    const double* Linv; const double* LqT; size_t tl;   // tiled copies (stream_gemm.cuh)
     const double* X; long long x_rows, n_rows;
     const double* eps; unsigned long long seed, row_offset; long long rows_per_sample, sample_stride;
     double* mean; double* var; double* F; int ldf; double* A_save;
@@ -28,7 +28,7 @@ template <class C>
 struct FwdSmem {
     // offsets in doubles inside the dynamic shared memory block
     int ldb, xld;
-    int Bt, Wst, xs, xn, kd, sumsq, usqp, xtask, total_doubles;
+    int Bt, Wst, xs, xn, kd, sumsq, usqp, xtask, bars, total_doubles;
     __host__ __device__ FwdSmem(int Mpad, int Dp) {
         ldb = Mpad + 4;
         xld = Dp + 4;
@@ -41,12 +41,13 @@ struct FwdSmem {
         sumsq = o; o += C::NT;
         usqp = o; o += 2 * C::WM * C::NT;
         xtask = o; o += C::NT / 2 + 1;  // int32[NT]
+        bars = o; o += 2 * C::STAGES;     // uint64 full[STAGES], empty[STAGES]
         total_doubles = o;
     }
 };
 
 template <class C>
-__global__ void __launch_bounds__(C::NTHREADS, 1) k_cond_fwd(FwdArgs a) {
+__global__ void __launch_bounds__(C::NTHREADS, 1) k_cond_fwd(const __grid_constant__ FwdArgs a) {
     extern __shared__ __align__(128) double smem[];
     const FwdSmem<C> L(a.Mpad, a.Dp);
     double* Bt = smem + L.Bt;
@@ -57,6 +58,7 @@ __global__ void __launch_bounds__(C::NTHREADS, 1) k_cond_fwd(FwdArgs a) {
     double* sumsq = smem + L.sumsq;
     double* usqp = smem + L.usqp;
     int32_t* xtask = reinterpret_cast<int32_t*>(smem + L.xtask);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L.bars);
 
     const dgp_cond_desc& d = a.d;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
@@ -65,15 +67,54 @@ __global__ void __launch_bounds__(C::NTHREADS, 1) k_cond_fwd(FwdArgs a) {
     const int nb = (Mpad + C::MB - 1) / C::MB;
     const int thd = 2 + d.D;
 
+    // segment lists of the two streamed phases (shared by the producer warp and the consumers)
+    auto seg_T = [&](int s) {       // A = Linv * Kuf, block rows bottom-up so the tile is updated in place
+        Seg sg;
+        sg.W = a.Linv;
+        sg.i = nb - 1 - s;
+        sg.kc0 = 0;
+        int kend = (sg.i + 1) * C::MB;
+        if (kend > Mpad) kend = Mpad;
+        sg.kc1 = kend / C::KC;
+        sg.r = 0;
+        sg.flush = true;
+        return sg;
+    };
+    auto seg_U = [&](int s) {       // U_r = LqT_r * A for r < R, block rows top-down
+        Seg sg;
+        sg.r = s / nb;
+        sg.i = s % nb;
+        sg.W = a.LqT + (size_t)sg.r * a.tl;
+        sg.kc0 = sg.i * C::MB / C::KC;
+        sg.kc1 = Mpad / C::KC;
+        sg.flush = true;
+        return sg;
+    };
+
+    Pipe pipe;
+    pipe_init<C>(pipe, bars, Wst);
+    __syncthreads();   // the only CTA-wide barrier: mbarriers are initialised
+
+    if (warp == C::NWARPS) {
+        // ---- producer warp: stream every W chunk of every tile of this CTA, in consumption order
+        if (lane == 0) {
+            for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
+                produce_phase<C>(pipe, nb, seg_T, Mpad);
+                produce_phase<C>(pipe, nb * d.R, seg_U, Mpad);
+            }
+        }
+        return;
+    }
+
     for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
         const long long n0 = (long long)tile * C::NT;
         // the previous tile's bulk store of Bt must have finished reading shared memory, and every warp must be done
         // with the previous tile, before Bt / xs are overwritten
         bulk_wait_read0();
-        __syncthreads();
+        consumer_sync<C>();
 
         // ---- tile setup: scaled inputs, norms, task ids, Kdiag
-        for (int n = tid; n < C::NT; n += C::NTHREADS) {
+        for (int n = tid; n < C::NT; n += C::NCONS) {
             long long gn = n0 + n;
             if (gn >= a.n_rows) gn = a.n_rows - 1;  // ragged last tile: compute on a valid row, never store it
             const double* xr = a.X + (size_t)(gn % a.x_rows) * d.Dx;
@@ -94,7 +135,7 @@ __global__ void __launch_bounds__(C::NTHREADS, 1) k_cond_fwd(FwdArgs a) {
             xn[n] = s;
             kd[n] = (tk < 0) ? 0.0 : th[0] + th[1];  // Stationary.Kdiag + White.Kdiag
         }
-        __syncthreads();
+        consumer_sync<C>();
 
         // ---- phase K: Bt[n][m] = k(z_m, x_n); cross term z.x on the tensor cores
         for (int mt = warp; mt < Mpad / 8; mt += C::NWARPS) {
@@ -118,24 +159,12 @@ __global__ void __launch_bounds__(C::NTHREADS, 1) k_cond_fwd(FwdArgs a) {
                 }
             }
         }
-        // (run_phase starts with a __syncthreads)
+        // (run_phase starts with a consumer barrier)
 
-        // ---- phase T: A = Linv * Kuf, block rows bottom-up so the tile is updated in place
+        // ---- phase T: A = Linv * Kuf, in place
         {
-            auto segfn = [&](int s) {
-                Seg sg;
-                sg.W = a.Linv;
-                sg.i = nb - 1 - s;
-                sg.kc0 = 0;
-                int kend = (sg.i + 1) * C::MB;
-                if (kend > Mpad) kend = Mpad;
-                sg.kc1 = kend / C::KC;
-                sg.r = 0;
-                sg.flush = true;
-                return sg;
-            };
             auto epi = [&](Acc<C>& acc, const Seg& sg) {
-                __syncthreads();  // all warps finished reading this block row's k-range of Bt
+                consumer_sync<C>();  // all warps finished reading this block row's k-range of Bt
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
                     const int row = acc_row<C>(sg.i, q);
@@ -148,9 +177,9 @@ __global__ void __launch_bounds__(C::NTHREADS, 1) k_cond_fwd(FwdArgs a) {
                     }
                 }
             };
-            run_phase<C, MASK_LOWER, false>(nb, segfn, epi, Wst, Bt, ldb, Mpad, nullptr, 0);
+            run_phase<C, MASK_LOWER, false>(pipe, nb, seg_T, epi, Bt, ldb, Mpad, nullptr, 0);
         }
-        __syncthreads();
+        consumer_sync<C>();
 
         // ---- E1: A tile -> HBM; mean = A^T q_mu + mean_fn(x); sumsq = sum_m A^2
         if (a.A_save) {
@@ -160,7 +189,7 @@ __global__ void __launch_bounds__(C::NTHREADS, 1) k_cond_fwd(FwdArgs a) {
                 bulk_commit();
             }
         }
-        for (int idx = tid; idx < C::NT * d.R; idx += C::NTHREADS) {
+        for (int idx = tid; idx < C::NT * d.R; idx += C::NCONS) {
             const int n = idx / d.R, r = idx % d.R;
             const double* arow = Bt + n * ldb;
             const double* qm = d.q_mu + d.col0 + r;
@@ -181,23 +210,13 @@ __global__ void __launch_bounds__(C::NTHREADS, 1) k_cond_fwd(FwdArgs a) {
                 a.mean[(size_t)gn * d.ldr + d.col0 + r] = s;
             }
         }
-        // (run_phase starts with a __syncthreads: sumsq and the mean stores are ordered before E2)
+        // (run_phase starts with a consumer barrier: sumsq and the mean stores are ordered before E2)
 
         // ---- phase U + E2
         {
             double colsq[C::NJ][2];
 #pragma unroll
             for (int j = 0; j < C::NJ; ++j) { colsq[j][0] = 0.0; colsq[j][1] = 0.0; }
-            auto segfn = [&](int s) {
-                Seg sg;
-                sg.r = s / nb;
-                sg.i = s % nb;
-                sg.W = a.LqT + (size_t)sg.r * Mpad * Mpad;
-                sg.kc0 = sg.i * C::MB / C::KC;
-                sg.kc1 = Mpad / C::KC;
-                sg.flush = true;
-                return sg;
-            };
             auto epi = [&](Acc<C>& acc, const Seg& sg) {
 #pragma unroll
                 for (int q = 0; q < 4; ++q)
@@ -220,7 +239,7 @@ __global__ void __launch_bounds__(C::NTHREADS, 1) k_cond_fwd(FwdArgs a) {
                         if (g == 0) part[wm * C::NT + acc_col<C>(j, e)] = v;
                         colsq[j][e] = 0.0;
                     }
-                __syncthreads();
+                consumer_sync<C>();
                 if (tid < C::NT) {
                     const int n = tid;
                     const long long gn = n0 + n;
@@ -248,7 +267,7 @@ __global__ void __launch_bounds__(C::NTHREADS, 1) k_cond_fwd(FwdArgs a) {
                     }
                 }
             };
-            run_phase<C, MASK_UPPER, false>(nb * d.R, segfn, epi, Wst, Bt, ldb, Mpad, nullptr, 0);
+            run_phase<C, MASK_UPPER, false>(pipe, nb * d.R, seg_U, epi, Bt, ldb, Mpad, nullptr, 0);
         }
     }
     bulk_wait_read0();
@@ -288,24 +307,29 @@ extern "C" int dgp_cond_forward(const dgp_cond_desc* d, const void* ws, const do
     a.d = *d;
     a.Mpad = w.Mpad; a.Dp = w.Dp;
     a.Zs = ws_ptr<double>(ws, w.Zs); a.zn = ws_ptr<double>(ws, w.zn); a.ztask = ws_ptr<int32_t>(ws, w.ztask);
-    a.Linv = ws_ptr<double>(ws, w.Linv); a.LqT = ws_ptr<double>(ws, w.LqT);
+    a.Linv = ws_ptr<double>(ws, w.LinvTl); a.LqT = ws_ptr<double>(ws, w.LqTTl); a.tl = w.tl;
     a.X = X; a.x_rows = x_rows; a.n_rows = n_rows;
     a.eps = eps; a.seed = seed; a.row_offset = row_offset;
     a.rows_per_sample = rows_per_sample > 0 ? rows_per_sample : n_rows;
     a.sample_stride = sample_stride > 0 ? sample_stride : a.rows_per_sample;
     a.mean = mean; a.var = var; a.F = F; a.ldf = ldf; a.A_save = A_save;
     cudaStream_t st = (cudaStream_t)stream;
-    if (w.Mpad <= 256) {
-        using C = TileCfg<4, 2, 64, 3>;
-        a.ntiles = (int)((n_rows + C::NT - 1) / C::NT);
-        return launch_fwd<C>(a, st);
-    } else if (w.Mpad <= 512) {
-        using C = TileCfg<4, 2, 32, 3>;
-        a.ntiles = (int)((n_rows + C::NT - 1) / C::NT);
-        return launch_fwd<C>(a, st);
-    } else {
-        using C = TileCfg<4, 2, 16, 3>;
-        a.ntiles = (int)((n_rows + C::NT - 1) / C::NT);
-        return launch_fwd<C>(a, st);
+    // row-tile width by inducing count (the A tile must fit in shared memory); ring depth 4, or 3 / 2 when the
+    // per-row side buffers (large D) leave less room
+#define DGP_TRY_FWD(NTV, STG)                                                         \
+    {                                                                                 \
+        using C = TileCfg<4, 2, NTV, STG>;                                            \
+        a.ntiles = (int)((n_rows + C::NT - 1) / C::NT);                               \
+        rc = launch_fwd<C>(a, st);                                                    \
+        if (rc != DGP_ERR_UNSUPPORTED) return rc;                                     \
     }
+    if (w.Mpad <= 256) {
+        DGP_TRY_FWD(64, 4) DGP_TRY_FWD(64, 3) DGP_TRY_FWD(64, 2)
+    } else if (w.Mpad <= 512) {
+        DGP_TRY_FWD(32, 4) DGP_TRY_FWD(32, 3) DGP_TRY_FWD(32, 2)
+    } else {
+        DGP_TRY_FWD(16, 4) DGP_TRY_FWD(16, 3) DGP_TRY_FWD(16, 2)
+    }
+#undef DGP_TRY_FWD
+    return DGP_ERR_UNSUPPORTED;
 }

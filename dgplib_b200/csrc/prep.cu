@@ -10,6 +10,7 @@
 #include "common.cuh"
 #define DGP_GEMM_SMALL_IMPL
 #include "gemm_small.cuh"
+#include "stream_gemm.cuh"
 
 namespace dgp {
 
@@ -315,6 +316,27 @@ __global__ void k_transpose(const double* __restrict__ in, double* __restrict__ 
     for (int jj = threadIdx.y; jj < 32; jj += blockDim.y) out[(size_t)(j0 + jj) * n + i0 + threadIdx.x] = tile[threadIdx.x][jj];
 }
 
+// row-major [batch][Mpad][Mpad] -> tiled [batch][block row][chunk][128][20] (zero padded)
+__global__ void k_retile(const double* __restrict__ src, double* __restrict__ dst, int Mpad, size_t tl) {
+    const size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= tl) return;
+    const int c = (int)(e % TILE_WLD);
+    const int row = (int)((e / TILE_WLD) % TILE_MB);
+    const size_t tile = e / TILE_DOUBLES;
+    const int nch = tiled_mpad(Mpad) / TILE_KC;
+    const int kc = (int)(tile % nch), bi = (int)(tile / nch);
+    const int i = bi * TILE_MB + row, k = kc * TILE_KC + c;
+    double v = 0.0;
+    if (c < TILE_KC && i < Mpad && k < Mpad) v = src[(size_t)blockIdx.y * Mpad * Mpad + (size_t)i * Mpad + k];
+    dst[(size_t)blockIdx.y * tl + e] = v;
+}
+int retile(const double* src, double* dst, int Mpad, int batch, cudaStream_t st) {
+    const size_t tl = tiled_doubles(Mpad);
+    k_retile<<<dim3((unsigned)((tl + 255) / 256), batch), 256, 0, st>>>(src, dst, Mpad, tl);
+    DGP_COUNT_LAUNCH();
+    return cudaGetLastError() == cudaSuccess ? DGP_OK : DGP_ERR_LAUNCH;
+}
+
 // SmI[r] -= I on the leading M x M block
 __global__ void k_sub_identity(double* __restrict__ S, int Mpad, int M) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -363,9 +385,11 @@ extern "C" int dgp_cond_prepare(const dgp_cond_desc* d, void* ws, size_t ws_byte
     k_tri_inv_cols<<<Mpad / 32, 256, 0, st>>>(Lm, Linv, Mpad); DGP_COUNT_LAUNCH();
     k_lq_prep<<<dim3(Mpad / 32, Mpad / 32, d->R), dim3(32, 8), 0, st>>>(*d, Mpad, LqT); DGP_COUNT_LAUNCH();
     if (kl_out) { k_kl<<<1, 1024, 0, st>>>(*d, kl_out); DGP_COUNT_LAUNCH(); }
+    if ((rc = retile(Linv, ws_ptr<double>(ws, w.LinvTl), Mpad, 1, st)) != DGP_OK) return rc;
+    if ((rc = retile(LqT, ws_ptr<double>(ws, w.LqTTl), Mpad, d->R, st)) != DGP_OK) return rc;
     if (need_bwd) {
         const WsLayout wb = ws_layout(*d, 0, 1);  // LinvT and SmI offsets do not depend on n_rows
-        if (ws_bytes < wb.SmI + (size_t)Mpad * Mpad * d->R * sizeof(double)) return DGP_ERR_WORKSPACE;
+        if (ws_bytes < wb.tail) return DGP_ERR_WORKSPACE;
         double* LinvT = ws_ptr<double>(ws, wb.LinvT);
         double* SmI = ws_ptr<double>(ws, wb.SmI);
         k_transpose<<<dim3(Mpad / 32, Mpad / 32), dim3(32, 8), 0, st>>>(Linv, LinvT, Mpad); DGP_COUNT_LAUNCH();
@@ -379,6 +403,8 @@ extern "C" int dgp_cond_prepare(const dgp_cond_desc* d, void* ws, size_t ws_byte
         rc = gemm_small(g, st);
         if (rc != DGP_OK) return rc;
         k_sub_identity<<<dim3((d->M + 127) / 128, d->R), 128, 0, st>>>(SmI, Mpad, d->M); DGP_COUNT_LAUNCH();
+        if ((rc = retile(LinvT, ws_ptr<double>(ws, wb.LinvTTl), Mpad, 1, st)) != DGP_OK) return rc;
+        if ((rc = retile(SmI, ws_ptr<double>(ws, wb.SmITl), Mpad, d->R, st)) != DGP_OK) return rc;
         // row-summed accumulators of the backward pass start from zero; dgp_cond_backward adds to them (row chunks)
         if (ws_bytes < wb.tail) return DGP_ERR_WORKSPACE;
         if (cudaMemsetAsync(ws_ptr<char>(ws, wb.gram), 0, wb.part - wb.gram, st) != cudaSuccess) return DGP_ERR_LAUNCH;

@@ -2,15 +2,20 @@
 //
 //     C[block-row i][NT columns]  (+)=  W[block-row i][k-range]  x  Bt[NT columns][k-range]^T
 //
-// W  : an Mpad x Mpad parameter matrix in global memory (L2-resident: Lm^-1, tril(q_sqrt_r)^T, ...), streamed in
-//      MB x 16 chunks through a STAGES-deep cp.async ring in shared memory (row pitch 20 doubles = conflict-free
-//      A-fragment loads for DMMA.8x8x4);
+// W  : an Mpad x Mpad parameter matrix (Lm^-1, tril(q_sqrt_r)^T, S_r - I, Lm^-T), pre-tiled in global memory by the
+//      parameter stage as [block row][16-deep chunk][128 rows][20 doubles] (dgp::retile), so that one chunk is ONE
+//      contiguous 20 KB block.  A dedicated producer warp streams the chunks with bulk async copies (TMA engine,
+//      cp.async.bulk + mbarrier complete_tx) into a STAGES-deep shared-memory ring; the 20-double pitch makes the
+//      DMMA A-fragment loads conflict-free.
 // Bt : the resident row tile in shared memory, stored [n][k] with pitch Mpad+4 (conflict-free B-fragment loads);
-// C  : fp64 tensor-core accumulators in registers.  Warp grid WM x WN; a warp owns 4 interleaved 8-row tiles
-//      (rows (q*WM+wm)*8 ..) so that triangular skipping stays balanced across warps, and NJ = NT/(8 WN) column tiles.
+// C  : fp64 tensor-core accumulators (DMMA.8x8x4) in registers.  Consumer warp grid WM x WN; a warp owns 4
+//      interleaved 8-row tiles (rows (q*WM+wm)*8 ..) so that triangular skipping stays balanced across warps, and
+//      NJ = NT/(8 WN) column tiles.
 //
-// A phase is a list of segments (matrix, block row, chunk range); the cp.async pipeline runs across segment
-// boundaries, and an epilogue functor consumes the accumulators whenever a segment is flagged `flush`.
+// Synchronisation is mbarrier-only inside a phase: full[stage] (producer -> consumers, transaction bytes) and
+// empty[stage] (one arrival per consumer warp).  There is no CTA-wide barrier in the main loop, so warps drift freely
+// and the tensor pipe never drains at chunk boundaries.  A phase is a list of segments (matrix, block row, chunk
+// range); the ring position runs across segments, phases and tiles, and the producer runs ahead across all of them.
 #pragma once
 #include "common.cuh"
 
@@ -18,19 +23,25 @@ namespace dgp {
 
 enum { MASK_LOWER = 0, MASK_UPPER = 1, MASK_DENSE = 2 };
 
+// host: row-major [Mpad][Mpad] (batched) -> tiled layout (defined in prep.cu)
+int retile(const double* src, double* dst, int Mpad, int batch, cudaStream_t st);
+
 template <int WM_, int WN_, int NT_, int STAGES_>
 struct TileCfg {
     static constexpr int WM = WM_, WN = WN_, NT = NT_, STAGES = STAGES_;
-    static constexpr int NWARPS = WM * WN, NTHREADS = NWARPS * 32;
-    static constexpr int MB = 32 * WM;         // rows per block row
-    static constexpr int NJ = NT / (8 * WN);   // 8-column tiles per warp
-    static constexpr int KC = 16, WLD = 20;    // chunk depth and padded pitch of a staged W chunk
-    static constexpr int STAGE_DOUBLES = MB * WLD;
+    static constexpr int NWARPS = WM * WN;              // consumer warps
+    static constexpr int NCONS = NWARPS * 32;           // consumer threads
+    static constexpr int NTHREADS = NCONS + 32;         // + one producer warp
+    static constexpr int MB = 32 * WM;                  // rows per block row
+    static constexpr int NJ = NT / (8 * WN);            // 8-column tiles per warp
+    static constexpr int KC = TILE_KC, WLD = TILE_WLD;
+    static constexpr int STAGE_DOUBLES = TILE_DOUBLES;
+    static_assert(MB == TILE_MB, "the tiled operand layout assumes 128-row block rows (WM = 4)");
     static_assert(NT % (8 * WN) == 0, "NT must be a multiple of 8*WN");
 };
 
 struct Seg {
-    const double* W;  // matrix base (row-major, pitch Mpad)
+    const double* W;  // tiled matrix base
     int i;            // block row
     int kc0, kc1;     // chunk range [kc0, kc1)
     int r;            // output index (weights / epilogue bookkeeping)
@@ -48,90 +59,141 @@ struct Acc {
     }
 };
 
-// Runs one phase.  WEIGHTED: the B fragment of column n is multiplied by wts[n * wld + seg.r] (backward pass).
+// ring state; every thread (producer and consumers) advances its own copy identically
+struct Pipe {
+    uint64_t* full;    // [STAGES]
+    uint64_t* empty;   // [STAGES]
+    double* stages;    // [STAGES][TILE_DOUBLES]
+    uint32_t stage;    // slot of the next chunk
+    uint32_t round;    // how many times the ring has wrapped (parity source)
+};
+
+template <class C>
+__device__ __forceinline__ void pipe_init(Pipe& p, uint64_t* bars, double* stages) {
+    p.full = bars;
+    p.empty = bars + C::STAGES;
+    p.stages = stages;
+    p.stage = 0;
+    p.round = 0;
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < C::STAGES; ++s) {
+            mbar_init(&p.full[s], 1);
+            mbar_init(&p.empty[s], C::NWARPS);
+        }
+        mbar_fence_init();
+    }
+}
+template <class C>
+__device__ __forceinline__ void pipe_advance(Pipe& p) {
+    if (++p.stage == C::STAGES) { p.stage = 0; ++p.round; }
+}
+
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" :: "r"(smem_u32(bar)) : "memory");
+}
+// barrier among the consumer threads only (the producer warp never joins it)
+template <class C>
+__device__ __forceinline__ void consumer_sync() {
+    asm volatile("bar.sync 1, %0;\n" :: "n"(C::NCONS) : "memory");
+}
+
+// ---- producer side: one elected lane enqueues every chunk of the phase
+template <class C, class SegFn>
+__device__ __forceinline__ void produce_phase(Pipe& p, int nseg, SegFn segfn, int Mpad) {
+    const int nch = tiled_mpad(Mpad) / C::KC;   // chunks per block row in the tiled layout
+    for (int s = 0; s < nseg; ++s) {
+        const Seg sg = segfn(s);
+        for (int kc = sg.kc0; kc < sg.kc1; ++kc) {
+            if (p.round > 0) mbar_wait(&p.empty[p.stage], (p.round - 1) & 1);
+            mbar_expect_tx(&p.full[p.stage], (uint32_t)(C::STAGE_DOUBLES * sizeof(double)));
+            bulk_g2s(p.stages + (size_t)p.stage * C::STAGE_DOUBLES,
+                     sg.W + ((size_t)sg.i * nch + kc) * C::STAGE_DOUBLES,
+                     (uint32_t)(C::STAGE_DOUBLES * sizeof(double)), &p.full[p.stage]);
+            pipe_advance<C>(p);
+        }
+    }
+}
+
+// One staged W chunk (16 deep) against the resident tile for the warp's tiles q in [QLO, QHI).
+//   Aw = &Ws[(wm*8 + g) * WLD + t]          tile q adds q*WM*8 rows
+//   Bw = &Bt[(wn*NJ*8 + g) * ldb + k0 + t]  column tile j adds j*8 rows of Bt
+template <class C, int QLO, int QHI, bool WEIGHTED>
+__device__ __forceinline__ void chunk_mma(Acc<C>& acc, const double* __restrict__ Aw, const double* __restrict__ Bw,
+                                          int ldb, const double (&wv)[C::NJ]) {
+#pragma unroll
+    for (int kk = 0; kk < 4; ++kk) {
+        double b[C::NJ];
+#pragma unroll
+        for (int j = 0; j < C::NJ; ++j) {
+            b[j] = Bw[j * 8 * ldb + kk * 4];
+            if (WEIGHTED) b[j] *= wv[j];
+        }
+#pragma unroll
+        for (int q = QLO; q < QHI; ++q) {
+            const double a = Aw[q * C::WM * 8 * C::WLD + kk * 4];
+#pragma unroll
+            for (int j = 0; j < C::NJ; ++j) dmma884(acc.v[q][j], a, b[j]);
+        }
+    }
+}
+
+// ---- consumer side.  WEIGHTED: the B fragment of column n is multiplied by wts[n * wld + seg.r] (backward pass).
+// Starts with a consumer barrier (Bt is complete, previous phase's epilogue writes are visible).
 template <class C, int MASK, bool WEIGHTED, class SegFn, class EpiFn>
-__device__ __forceinline__ void run_phase(int nseg, SegFn segfn, EpiFn epi, double* __restrict__ Wst,
-                                          const double* __restrict__ Bt, int ldb, int Mpad,
-                                          const double* __restrict__ wts, int wld) {
+__device__ __forceinline__ void run_phase(Pipe& p, int nseg, SegFn segfn, EpiFn epi, const double* __restrict__ Bt,
+                                          int ldb, int Mpad, const double* __restrict__ wts, int wld) {
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int g = lane >> 2, t = lane & 3;
     const int wm = warp / C::WN, wn = warp % C::WN;
 
     Acc<C> acc;
     acc.clear();
-    __syncthreads();  // every warp is done with the staging ring (previous phase) and Bt is up to date
+    consumer_sync<C>();
 
-    // ---- loader state (runs STAGES-1 chunks ahead of the consumer, across segment boundaries)
-    int ls = 0;
-    Seg lseg = segfn(0);
-    int lkc = lseg.kc0;
-    auto issue_load = [&](int stage) {
-        if (ls < nseg) {
-            const int row0 = lseg.i * C::MB;
-            const double* src = lseg.W + (size_t)row0 * Mpad + (size_t)lkc * C::KC;
-            double* dst = Wst + stage * C::STAGE_DOUBLES;
-            for (int e = tid; e < C::MB * 8; e += C::NTHREADS) {
-                const int row = e >> 3, c = e & 7;
-                if (row0 + row < Mpad) cp_async16(dst + row * C::WLD + c * 2, src + (size_t)row * Mpad + c * 2);
-            }
-            if (++lkc == lseg.kc1) {
-                if (++ls < nseg) {
-                    lseg = segfn(ls);
-                    lkc = lseg.kc0;
-                }
-            }
-        }
-        cp_async_commit();  // committed even when empty so that group counting stays uniform
-    };
-#pragma unroll
-    for (int s = 0; s < C::STAGES - 1; ++s) issue_load(s);
-
-    int stage = 0, lstage = C::STAGES - 1;
     for (int cs = 0; cs < nseg; ++cs) {
         const Seg seg = segfn(cs);
         const int row0 = seg.i * C::MB;
-        double wv[C::NJ];
+        double wv[C::NJ] = {};
         if (WEIGHTED) {
 #pragma unroll
             for (int j = 0; j < C::NJ; ++j) wv[j] = wts[(wn * C::NJ * 8 + j * 8 + g) * wld + seg.r];
         }
         for (int kc = seg.kc0; kc < seg.kc1; ++kc) {
-            cp_async_wait<C::STAGES - 2>();
-            __syncthreads();
-            issue_load(lstage);
-            lstage = (lstage + 1 == C::STAGES) ? 0 : lstage + 1;
-            const double* Ws = Wst + stage * C::STAGE_DOUBLES;
-            stage = (stage + 1 == C::STAGES) ? 0 : stage + 1;
-#pragma unroll
-            for (int kk = 0; kk < 4; ++kk) {
-                const int kbase = kc * C::KC + kk * 4;
-                double b[C::NJ];
-#pragma unroll
-                for (int j = 0; j < C::NJ; ++j) {
-                    b[j] = Bt[(wn * C::NJ * 8 + j * 8 + g) * ldb + kbase + t];
-                    if (WEIGHTED) b[j] *= wv[j];
-                }
-#pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    const int mt = q * C::WM + wm;
-                    const int mrow0 = row0 + mt * 8;
-                    bool active = mrow0 < Mpad;
-                    if (MASK == MASK_LOWER) active = active && (mrow0 + 7 >= kbase);
-                    if (MASK == MASK_UPPER) active = active && (mrow0 <= kbase + 3);
-                    if (active) {
-                        const double a = Ws[(mt * 8 + g) * C::WLD + kk * 4 + t];
-#pragma unroll
-                        for (int j = 0; j < C::NJ; ++j) dmma884(acc.v[q][j], a, b[j]);
-                    }
-                }
+            // Active 8-row tiles of this warp for the chunk: a contiguous range [qlo, qhi) of its 4 interleaved tiles.
+            // Skipping uses real (warp-uniform) branches: a predicated-off DMMA still occupies the fp64 tensor pipe
+            // for its full 16 cycles (measured with ncu), so predication would save nothing.
+            const int k0 = kc * C::KC;
+            int qlo = 0, qhi = 4;
+            while (qhi > 0 && row0 + ((qhi - 1) * C::WM + wm) * 8 >= Mpad) --qhi;
+            if (MASK == MASK_LOWER)
+                while (qlo < qhi && row0 + (qlo * C::WM + wm) * 8 + 7 < k0) ++qlo;
+            if (MASK == MASK_UPPER)
+                while (qhi > qlo && row0 + ((qhi - 1) * C::WM + wm) * 8 > k0 + C::KC - 1) --qhi;
+            const double* Bw = Bt + (wn * C::NJ * 8 + g) * ldb + k0 + t;
+            const double* Aw = p.stages + (size_t)p.stage * C::STAGE_DOUBLES + (wm * 8 + g) * C::WLD + t;
+            mbar_wait(&p.full[p.stage], p.round & 1);
+            switch ((qlo << 3) | qhi) {
+                case (0 << 3) | 4: chunk_mma<C, 0, 4, WEIGHTED>(acc, Aw, Bw, ldb, wv); break;
+                case (1 << 3) | 4: chunk_mma<C, 1, 4, WEIGHTED>(acc, Aw, Bw, ldb, wv); break;
+                case (2 << 3) | 4: chunk_mma<C, 2, 4, WEIGHTED>(acc, Aw, Bw, ldb, wv); break;
+                case (3 << 3) | 4: chunk_mma<C, 3, 4, WEIGHTED>(acc, Aw, Bw, ldb, wv); break;
+                case (0 << 3) | 3: chunk_mma<C, 0, 3, WEIGHTED>(acc, Aw, Bw, ldb, wv); break;
+                case (0 << 3) | 2: chunk_mma<C, 0, 2, WEIGHTED>(acc, Aw, Bw, ldb, wv); break;
+                case (0 << 3) | 1: chunk_mma<C, 0, 1, WEIGHTED>(acc, Aw, Bw, ldb, wv); break;
+                case (1 << 3) | 3: chunk_mma<C, 1, 3, WEIGHTED>(acc, Aw, Bw, ldb, wv); break;
+                case (1 << 3) | 2: chunk_mma<C, 1, 2, WEIGHTED>(acc, Aw, Bw, ldb, wv); break;
+                case (2 << 3) | 3: chunk_mma<C, 2, 3, WEIGHTED>(acc, Aw, Bw, ldb, wv); break;
+                default: break;  // qlo == qhi: nothing to do for this warp in this chunk
             }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&p.empty[p.stage]);   // this warp is done reading the slot
+            pipe_advance<C>(p);
         }
         if (seg.flush) {
             epi(acc, seg);
             acc.clear();
         }
     }
-    cp_async_wait<0>();
 }
 
 // Accumulator element (q, j, e) of the calling thread maps to
