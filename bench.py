@@ -275,7 +275,7 @@ def main():
     per_kernel = {}
     for l in range(w["L"]):
         Din, R = dims[l], dims[l + 1]
-        n_rows = B * S
+        n_rows = B * S if l > 0 else B      # the first layer is evaluated once per data row (sample sharing)
         per_kernel[f"fwd.l{l}"] = n_rows * flops_per_row_layer(M, Din, R)
         per_kernel[f"bwd.l{l}"] = n_rows * (2 * R * M * M + M * M + 2 * M * R + 6 * M * Din)   # dA dense + Lm^-T + d q_mu + kernel bwd
         per_kernel[f"gram.l{l}"] = n_rows * (R + 1) * M * M                                      # G_r (sym) + P (tril)

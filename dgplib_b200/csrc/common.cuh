@@ -46,6 +46,7 @@ struct WsLayout {
     size_t LinvTl;     // tiled copy of Linv        (streamed by the forward kernel)
     size_t LqTTl;      // [R] tiled copies of LqT_r (streamed by the forward kernel)
     size_t tl;         // doubles of one tiled matrix
+    size_t klpart;     // [R][(Mpad/32)^2] per-tile partial sums of the KL term (written by k_lq_prep)
     // backward only
     size_t LinvT;      // [Mpad][Mpad]
     size_t SmI;        // [R][Mpad][Mpad] tril(q_sqrt_r) tril(q_sqrt_r)^T - I
@@ -55,6 +56,7 @@ struct WsLayout {
     size_t gmv;        // [n_rows][2R] combined g_mean | g_var of this conditional
     size_t gram;       // [nsplit][R+1][Mpad][Mpad]  split-K partials of G_r (r<R) and P (r==R)
     size_t part;       // [ncta][npart] per-CTA partials: T2z[Mpad][Dp], cs[Mpad], dq_mu[Mpad][R], th[T][2+Dp]
+    size_t psum;       // [npart] the per-CTA partials summed over CTAs (fixed order)
     size_t tail;       // [2R+4][Mpad][Mpad] scratch of the parameter tail (Gfull, Tq, Lbar, T1, T2, T3)
     size_t total;
 };
@@ -79,14 +81,23 @@ static inline WsLayout ws_layout(const dgp_cond_desc& d, int64_t n_rows, int nee
     w.tl = tiled_doubles(w.Mpad);
     w.LinvTl = o; o += align256(w.tl * sizeof(double));
     w.LqTTl = o;  o += align256(w.tl * sizeof(double) * d.R);
+    w.klpart = o; o += align256(size_t(d.R) * (w.Mpad / 32) * (w.Mpad / 32) * sizeof(double));
     if (need_bwd) {
         // split-K factor of the Gram kernel: enough CTAs to fill the machine ~3x (independent of n_rows so that every
         // offset except the two row-sized buffers at the end is a function of the descriptor only)
         const int nb = w.Mpad / 64;
         const int tiles = (d.R + 1) * nb * (nb + 1) / 2;
-        int ns = (3 * w.ncta + tiles - 1) / tiles;
-        if (ns < 1) ns = 1;
-        if (ns > 64) ns = 64;
+        // k_gram runs 4 CTAs per SM: pick the split count that fills 1..3 waves of 4*ncta slots best
+        const int slots = 4 * w.ncta;
+        int ns = 1;
+        double best = 0.0;
+        for (int wv = 1; wv <= 3; ++wv) {
+            int c = (wv * slots) / tiles;
+            if (c < 1) c = 1;
+            if (c > 64) c = 64;
+            const double util = (double)c * tiles / ((double)((c * tiles + slots - 1) / slots) * slots);
+            if (util > best + 0.02) { best = util; ns = c; }
+        }
         w.nsplit = ns;
         w.npart = round_up(w.Mpad * w.Dp + w.Mpad + w.Mpad * d.R + d.T * (2 + w.Dp), 32);
         w.LinvT = o; o += align256(mm);
@@ -95,6 +106,7 @@ static inline WsLayout ws_layout(const dgp_cond_desc& d, int64_t n_rows, int nee
         w.SmITl = o;   o += align256(w.tl * sizeof(double) * d.R);
         w.gram = o;  o += align256(mm * (d.R + 1) * w.nsplit);
         w.part = o;  o += align256(size_t(w.ncta) * w.npart * sizeof(double));
+        w.psum = o;  o += align256(size_t(w.npart) * sizeof(double));
         w.tail = o;  o += align256(mm * (2 * d.R + 4));
         w.gmv = o;   o += align256(size_t(n_rows) * 2 * d.R * sizeof(double));
         w.dKuf = o;  o += align256(size_t(n_rows) * w.Mpad * sizeof(double));

@@ -325,12 +325,14 @@ __global__ void __launch_bounds__(C::NTHREADS, 1) k_cond_bwd(const __grid_consta
             pcs[m] += s;
         }
         consumer_sync<C>();
-        // per-task hyper-parameter row terms, summed in row order by one thread per column (deterministic)
-        if (tid < nq) {
-            for (int n = 0; n < nvalid; ++n) {
-                const int tx = xtask[n];
-                if (tx >= 0) pth[tx * nq + tid] += rowq[n * nq + tid];
-            }
+        // per-task hyper-parameter row terms, summed in row order by one thread per (task, column) (deterministic);
+        // the sum stays in a register so that the global partial sees one read-modify-write per tile
+        for (int idx = tid; idx < d.T * nq; idx += C::NCONS) {
+            const int tk = idx / nq, c = idx % nq;
+            double s = 0.0;
+            for (int n = 0; n < nvalid; ++n)
+                if (xtask[n] == tk) s += rowq[n * nq + c];
+            pth[idx] += s;
         }
     }
     bulk_wait_read0();

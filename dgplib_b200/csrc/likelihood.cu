@@ -64,6 +64,43 @@ __global__ void k_philox_normal(double* __restrict__ out, long long n_rows, int 
     out[(size_t)n * ld + r] = philox_normal(seed, rid, (uint32_t)r);
 }
 
+// ---- layer-0 sample sharing.  tile_over_samples (dgplib/utils.py:15-18) makes the S copies of a data row identical, so
+// the first layer's conditional is evaluated once per data row and only the sampling step runs per (sample, row):
+//   expand : F[s*B + b, c] = mean[b, c] + eps[s*B + b, c] * sqrt(var[b, c])   (+ task-id column copy when ldf > ldr)
+//   reduce : g_mean[b, c] = sum_s g_F[s*B+b, c] ;  g_var[b, c] = sum_s g_F[s*B+b, c] (F[s*B+b, c] - mean[b, c]) / (2 var[b, c])
+__global__ void k_sample_expand(const double* __restrict__ mean, const double* __restrict__ var, const double* __restrict__ eps,
+                                unsigned long long seed, unsigned long long row_offset, long long sstride, int S,
+                                long long B, int R, int ldr, double* __restrict__ F, int ldf, const double* __restrict__ X,
+                                int Dx) {
+    const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= (long long)S * B * R) return;
+    const int c = (int)(e % R);
+    const long long n = e / R, b = n % B, s = n / B;
+    const double mu = mean[(size_t)b * ldr + c], v = var[(size_t)b * ldr + c];
+    const double z = eps ? eps[(size_t)n * ldr + c]
+                         : philox_normal(seed, row_offset + (unsigned long long)s * sstride + b, (uint32_t)c);
+    F[(size_t)n * ldf + c] = mu + z * sqrt(v);
+    if (c == 0 && ldf > ldr) F[(size_t)n * ldf + ldf - 1] = X[(size_t)b * Dx + Dx - 1];
+}
+__global__ void k_sample_reduce(const double* __restrict__ gF, int ldgf, const double* __restrict__ F, int ldf,
+                                const double* __restrict__ mean, const double* __restrict__ var, int S, long long B, int R,
+                                int ldr, double* __restrict__ g_mean, double* __restrict__ g_var) {
+    const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= B * R) return;
+    const int c = (int)(e % R);
+    const long long b = e / R;
+    const double mu = mean[(size_t)b * ldr + c], inv = 1.0 / (2.0 * var[(size_t)b * ldr + c]);
+    double gm = 0.0, gv = 0.0;
+    for (int s = 0; s < S; ++s) {
+        const size_t n = (size_t)s * B + b;
+        const double g = gF[n * ldgf + c];
+        gm += g;
+        gv = fma(g * (F[n * ldf + c] - mu), inv, gv);
+    }
+    g_mean[(size_t)b * ldr + c] = gm;
+    g_var[(size_t)b * ldr + c] = gv;
+}
+
 // gpflow Kernel.K / Kdiag for the descriptor's kernel (stand-alone entry points; not on the ELBO path)
 __global__ void k_kernel_K(dgp_cond_desc d, const double* __restrict__ X1, long long n1, const double* __restrict__ X2,
                            long long n2, int symmetric, double* __restrict__ K) {
@@ -132,6 +169,30 @@ extern "C" int dgp_philox_normal(double* out, int64_t n_rows, int32_t R, int32_t
     const long long ss = sample_stride > 0 ? sample_stride : rps;
     const long long total = (long long)n_rows * R;
     k_philox_normal<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(out, n_rows, R, ld, seed, row_offset, rps, ss);
+    DGP_COUNT_LAUNCH();
+    DGP_CHECK_LAUNCH();
+    return DGP_OK;
+}
+
+extern "C" int dgp_sample_expand(const double* mean, const double* var, const double* eps, uint64_t seed, uint64_t row_offset,
+                                 int64_t sample_stride, int32_t S, int64_t B, int32_t R, int32_t ldr, double* F, int32_t ldf,
+                                 const double* X, int32_t Dx, void* stream) {
+    if (!mean || !var || !F || S < 1 || B < 0 || R < 1 || ldr < R || ldf < ldr) return DGP_ERR_ARG;
+    if (ldf > ldr && (!X || Dx < 1)) return DGP_ERR_ARG;
+    if (B == 0) return DGP_OK;
+    const long long total = (long long)S * B * R;
+    k_sample_expand<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+        mean, var, eps, seed, row_offset, sample_stride > 0 ? sample_stride : B, S, B, R, ldr, F, ldf, X, Dx);
+    DGP_COUNT_LAUNCH();
+    DGP_CHECK_LAUNCH();
+    return DGP_OK;
+}
+extern "C" int dgp_sample_reduce(const double* g_F, int32_t ldgf, const double* F, int32_t ldf, const double* mean,
+                                 const double* var, int32_t S, int64_t B, int32_t R, int32_t ldr, double* g_mean,
+                                 double* g_var, void* stream) {
+    if (!g_F || !F || !mean || !var || !g_mean || !g_var || S < 1 || B < 0 || R < 1 || ldr < R || ldf < ldr || ldgf < R) return DGP_ERR_ARG;
+    if (B == 0) return DGP_OK;
+    k_sample_reduce<<<(unsigned)((B * R + 127) / 128), 128, 0, (cudaStream_t)stream>>>(g_F, ldgf, F, ldf, mean, var, S, B, R, ldr, g_mean, g_var);
     DGP_COUNT_LAUNCH();
     DGP_CHECK_LAUNCH();
     return DGP_OK;

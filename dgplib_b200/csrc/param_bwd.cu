@@ -42,16 +42,22 @@ __global__ void k_gq_sqrt(dgp_cond_desc d, int Mpad, const double* __restrict__ 
     gq_sqrt[o] = v;
 }
 
-// (c) d q_mu = sum over CTA partials - klw q_mu
-__global__ void k_gq_mu(dgp_cond_desc d, int Mpad, int Dp, const double* __restrict__ part, int ncta, int npart, double klw,
+// sum the per-CTA partial buffers of k_cond_bwd over the CTAs, in CTA order (deterministic)
+__global__ void k_part_reduce(const double* __restrict__ part, int ncta, int npart, double* __restrict__ psum) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= npart) return;
+    double s = 0.0;
+    for (int c = 0; c < ncta; ++c) s += part[(size_t)c * npart + e];
+    psum[e] = s;
+}
+
+// (c) d q_mu = row-summed partials - klw q_mu
+__global__ void k_gq_mu(dgp_cond_desc d, int Mpad, int Dp, const double* __restrict__ psum, double klw,
                         double* __restrict__ gq_mu) {
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= d.M * d.R) return;
-    const size_t off = (size_t)Mpad * Dp + Mpad + idx;
-    double s = 0.0;
-    for (int c = 0; c < ncta; ++c) s += part[(size_t)c * npart + off];
     const size_t o = (size_t)(idx / d.R) * d.ldr + d.col0 + idx % d.R;
-    gq_mu[o] = s - klw * d.q_mu[o];
+    gq_mu[o] = psum[(size_t)Mpad * Dp + Mpad + idx] - klw * d.q_mu[o];
 }
 
 // Phi: lower triangle with halved diagonal, in place
@@ -112,53 +118,45 @@ k_kuu_bwd(dgp_cond_desc d, int Mpad, int Dp, const double* __restrict__ Zs, cons
     if (tid == 0) rowp[(size_t)i * nq + 1] = T3[(size_t)i * Mpad + i];
 }
 
-// (f) final assembly of d Z and d theta (single CTA; fixed summation order)
-__global__ void __launch_bounds__(256)
-k_finish(dgp_cond_desc d, int Mpad, int Dp, const double* __restrict__ Zs, const int32_t* __restrict__ ztask,
-         const double* __restrict__ part, int ncta, int npart, const double* __restrict__ rowp,
-         const double* __restrict__ dzs, double* __restrict__ cs_sum, double* __restrict__ gZ, double* __restrict__ gtheta) {
-    const int tid = threadIdx.x;
+// (f) final assembly of d Z ...
+__global__ void k_finish_Z(dgp_cond_desc d, int Mpad, int Dp, const double* __restrict__ Zs, const int32_t* __restrict__ ztask,
+                           const double* __restrict__ psum, const double* __restrict__ dzs, double* __restrict__ gZ) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= d.M * d.Dx) return;
+    const int m = idx / d.Dx, k = idx % d.Dx;
+    double v = 0.0;
+    const int tm = ztask[m];
+    if (k < d.D && tm >= 0) {
+        const double t2 = psum[(size_t)m * Dp + k], cs = psum[(size_t)Mpad * Dp + m];
+        const double zs = Zs[(size_t)m * Dp + k];
+        v = (dzs[(size_t)m * Dp + k] + 2.0 * (zs * cs - t2)) / d.theta[(size_t)tm * (2 + d.D) + 2 + k];
+    }
+    gZ[idx] = v;
+}
+// ... and of d theta[t][c] (one warp per entry, lanes stride over the inducing rows, fixed-order shuffle sum)
+__global__ void k_finish_theta(dgp_cond_desc d, int Mpad, int Dp, const double* __restrict__ Zs,
+                               const int32_t* __restrict__ ztask, const double* __restrict__ psum,
+                               const double* __restrict__ rowp, double* __restrict__ gtheta) {
     const int nq = 2 + Dp, thd = 2 + d.D;
-    // d Z
-    for (int idx = tid; idx < d.M * d.Dx; idx += blockDim.x) {
-        const int m = idx / d.Dx, k = idx % d.Dx;
-        double v = 0.0;
-        const int tm = ztask[m];
-        if (k < d.D && tm >= 0) {
-            double t2 = 0.0, cs = 0.0;
-            for (int c = 0; c < ncta; ++c) {
-                const double* p = part + (size_t)c * npart;
-                t2 += p[(size_t)m * Dp + k];
-                cs += p[(size_t)Mpad * Dp + m];
-            }
-            if (k == 0) cs_sum[m] = cs;
-            const double zs = Zs[(size_t)m * Dp + k];
-            v = (dzs[(size_t)m * Dp + k] + 2.0 * (zs * cs - t2)) / d.theta[(size_t)tm * thd + 2 + k];
-        }
-        gZ[idx] = v;
-    }
-    __syncthreads();
-    // d theta[t][c]
-    for (int idx = tid; idx < d.T * thd; idx += blockDim.x) {
-        const int tk = idx / thd, c = idx % thd;
-        const int pc = c;  // column inside the partial layouts (pad dims never reach here since c - 2 < D)
-        double s = 0.0;
-        for (int b = 0; b < ncta; ++b) s += part[(size_t)b * npart + (size_t)Mpad * Dp + Mpad + (size_t)Mpad * d.R + tk * nq + pc];
+    const int idx = blockIdx.x, lane = threadIdx.x;
+    const int tk = idx / thd, c = idx % thd;
+    const double* cs = psum + (size_t)Mpad * Dp;
+    double s = 0.0;
+    for (int m = lane; m < d.M; m += 32) {
         if (c == 0) {
-            for (int m = 0; m < d.M; ++m) if (ztask[m] == tk) s += rowp[(size_t)m * nq + 0];
+            if (ztask[m] == tk) s += rowp[(size_t)m * nq + 0];
         } else if (c == 1) {
-            if (d.T == 1) for (int m = 0; m < d.M; ++m) s += rowp[(size_t)m * nq + 1];
-        } else {
+            if (d.T == 1) s += rowp[(size_t)m * nq + 1];
+        } else if (ztask[m] == tk) {
             const int k = c - 2;
-            for (int m = 0; m < d.M; ++m) {
-                if (ztask[m] != tk) continue;
-                const double zs = Zs[(size_t)m * Dp + k];
-                s += zs * zs * cs_sum[m] + rowp[(size_t)m * nq + 2 + k];
-            }
-            s *= -2.0 / d.theta[(size_t)tk * thd + c];
+            const double zs = Zs[(size_t)m * Dp + k];
+            s += zs * zs * cs[m] + rowp[(size_t)m * nq + 2 + k];
         }
-        gtheta[idx] = s;
     }
+    s = warp_sum(s);
+    s += psum[(size_t)Mpad * Dp + Mpad + (size_t)Mpad * d.R + tk * nq + c];
+    if (c >= 2) s *= -2.0 / d.theta[(size_t)tk * thd + c];
+    if (lane == 0) gtheta[idx] = s;
 }
 
 }  // namespace dgp
@@ -201,7 +199,9 @@ extern "C" int dgp_cond_backward_params(const dgp_cond_desc* d, void* ws, double
     g.bA = g.bB = g.bC = (long long)mm; g.alpha = 1.0; g.beta = 0.0; g.lower_tiles_only = 1;
     if ((rc = gemm_small(g, st)) != DGP_OK) return rc;
     k_gq_sqrt<<<dim3((d->M + 127) / 128, d->M, R), 128, 0, st>>>(*d, Mpad, Tq, kl_weight, gq_sqrt); DGP_COUNT_LAUNCH();
-    k_gq_mu<<<(d->M * R + 127) / 128, 128, 0, st>>>(*d, Mpad, Dp, part, w.ncta, w.npart, kl_weight, gq_mu); DGP_COUNT_LAUNCH();
+    double* psum = ws_ptr<double>(ws, w.psum);
+    k_part_reduce<<<(w.npart + 127) / 128, 128, 0, st>>>(part, w.ncta, w.npart, psum); DGP_COUNT_LAUNCH();
+    k_gq_mu<<<(d->M * R + 127) / 128, 128, 0, st>>>(*d, Mpad, Dp, psum, kl_weight, gq_mu); DGP_COUNT_LAUNCH();
     // T1 = Lm^T Lbar ; Phi ; T2 = Linv^T T1 ; T3 = T2 Linv
     g = GemmArgs{};
     g.A = Lm; g.B = Lbar; g.C = T1; g.I = g.J = g.K = Mpad; g.batch = 1;
@@ -215,9 +215,9 @@ extern "C" int dgp_cond_backward_params(const dgp_cond_desc* d, void* ws, double
     // Kuu reverse mode; rowp / dzs / cs_sum reuse the (now free) T1 buffer
     double* rowp = T1;
     double* dzs = rowp + (size_t)Mpad * (2 + Dp);
-    double* cs_sum = dzs + (size_t)Mpad * Dp;
     k_kuu_bwd<<<d->M, 128, 0, st>>>(*d, Mpad, Dp, Zs, zn, ztask, T3, rowp, dzs); DGP_COUNT_LAUNCH();
-    k_finish<<<1, 256, 0, st>>>(*d, Mpad, Dp, Zs, ztask, part, w.ncta, w.npart, rowp, dzs, cs_sum, gZ, gtheta); DGP_COUNT_LAUNCH();
+    k_finish_Z<<<(d->M * d->Dx + 127) / 128, 128, 0, st>>>(*d, Mpad, Dp, Zs, ztask, psum, dzs, gZ); DGP_COUNT_LAUNCH();
+    k_finish_theta<<<d->T * (2 + d->D), 32, 0, st>>>(*d, Mpad, Dp, Zs, ztask, psum, rowp, gtheta); DGP_COUNT_LAUNCH();
     DGP_CHECK_LAUNCH();
     return DGP_OK;
 }

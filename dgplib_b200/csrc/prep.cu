@@ -269,37 +269,48 @@ k_tri_inv_cols(const double* __restrict__ L, double* __restrict__ Linv, int Mpad
 }
 
 // ------------------------------------------------------------------------------------------------ q_sqrt, KL
-// LqT[r][i][j] = tril(q_sqrt[col0+r])[j][i]  (upper triangular), zero padded.
-__global__ void k_lq_prep(dgp_cond_desc d, int Mpad, double* __restrict__ LqT) {
+// LqT[r][i][j] = tril(q_sqrt[col0+r])[j][i]  (upper triangular), zero padded.  The same pass accumulates this tile's
+// share of the whitened KL term: sum over the lower triangle of q^2, minus log(q_ii^2) on the diagonal.
+__global__ void k_lq_prep(dgp_cond_desc d, int Mpad, double* __restrict__ LqT, double* __restrict__ klpart) {
     __shared__ double tile[32][33];
+    __shared__ double red[32];
     const int r = blockIdx.z;
     const int i0 = blockIdx.y * 32, j0 = blockIdx.x * 32;  // output tile rows i0.., cols j0..
     const double* q = d.q_sqrt + (size_t)(d.col0 + r) * d.M * d.M;
+    double s = 0.0;
     // read q[j][i] for j in j0.., i in i0.. (coalesced along i)
     for (int jj = threadIdx.y; jj < 32; jj += blockDim.y) {
         const int j = j0 + jj, i = i0 + threadIdx.x;
-        tile[jj][threadIdx.x] = (j < d.M && i < d.M && i <= j) ? q[(size_t)j * d.M + i] : 0.0;
+        double v = 0.0;
+        if (j < d.M && i < d.M && i <= j) {
+            v = q[(size_t)j * d.M + i];
+            s = fma(v, v, s);
+            if (i == j) s -= log(v * v);
+        }
+        tile[jj][threadIdx.x] = v;
     }
     __syncthreads();
     for (int ii = threadIdx.y; ii < 32; ii += blockDim.y)
         LqT[((size_t)r * Mpad + i0 + ii) * Mpad + j0 + threadIdx.x] = tile[threadIdx.x][ii];
+    // deterministic block sum (thread id = y * 32 + x)
+    s = warp_sum(s);
+    if (threadIdx.x == 0) red[threadIdx.y] = s;
+    __syncthreads();
+    if (threadIdx.x == 0 && threadIdx.y == 0) {
+        double tot = 0.0;
+        for (int w = 0; w < (int)blockDim.y; ++w) tot += red[w];
+        klpart[((size_t)r * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x] = tot;
+    }
 }
 
-// KL = 0.5 (sum q_mu^2 - M R - sum log diag(Lq)^2 + sum Lq^2) for this conditional's columns (single CTA, deterministic)
-__global__ void __launch_bounds__(1024) k_kl(dgp_cond_desc d, double* __restrict__ kl_out) {
+// KL = 0.5 (sum q_mu^2 - M R - sum log diag(Lq)^2 + sum Lq^2) for this conditional's columns: sums the per-tile partials
+// of k_lq_prep and the q_mu term (one CTA, fixed order)
+__global__ void __launch_bounds__(256) k_kl(dgp_cond_desc d, const double* __restrict__ klpart, int npartial,
+                                            double* __restrict__ kl_out) {
     __shared__ double red[32];
     const int M = d.M, R = d.R;
     double s = 0.0;
-    const size_t nq = (size_t)R * M * M;
-    for (size_t e = threadIdx.x; e < nq; e += blockDim.x) {
-        const int r = (int)(e / ((size_t)M * M));
-        const int i = (int)((e / M) % M), j = (int)(e % M);
-        if (j <= i) {
-            const double v = d.q_sqrt[(size_t)(d.col0 + r) * M * M + (size_t)i * M + j];
-            s = fma(v, v, s);
-            if (i == j) s -= log(v * v);
-        }
-    }
+    for (int e = threadIdx.x; e < npartial; e += blockDim.x) s += klpart[e];
     for (int e = threadIdx.x; e < M * R; e += blockDim.x) {
         const double v = d.q_mu[(size_t)(e / R) * d.ldr + d.col0 + (e % R)];
         s = fma(v, v, s);
@@ -383,8 +394,9 @@ extern "C" int dgp_cond_prepare(const dgp_cond_desc* d, void* ws, size_t ws_byte
     k_cholesky<<<1, CHOL_THREADS, chol_smem, st>>>(Lm, Mpad, NB, status); DGP_COUNT_LAUNCH();
     k_diag_inv<<<Mpad / 32, 32, 0, st>>>(Lm, Linv, Mpad); DGP_COUNT_LAUNCH();
     k_tri_inv_cols<<<Mpad / 32, 256, 0, st>>>(Lm, Linv, Mpad); DGP_COUNT_LAUNCH();
-    k_lq_prep<<<dim3(Mpad / 32, Mpad / 32, d->R), dim3(32, 8), 0, st>>>(*d, Mpad, LqT); DGP_COUNT_LAUNCH();
-    if (kl_out) { k_kl<<<1, 1024, 0, st>>>(*d, kl_out); DGP_COUNT_LAUNCH(); }
+    double* klpart = ws_ptr<double>(ws, w.klpart);
+    k_lq_prep<<<dim3(Mpad / 32, Mpad / 32, d->R), dim3(32, 8), 0, st>>>(*d, Mpad, LqT, klpart); DGP_COUNT_LAUNCH();
+    if (kl_out) { k_kl<<<1, 256, 0, st>>>(*d, klpart, d->R * (Mpad / 32) * (Mpad / 32), kl_out); DGP_COUNT_LAUNCH(); }
     if ((rc = retile(Linv, ws_ptr<double>(ws, w.LinvTl), Mpad, 1, st)) != DGP_OK) return rc;
     if ((rc = retile(LqT, ws_ptr<double>(ws, w.LqTTl), Mpad, d->R, st)) != DGP_OK) return rc;
     if (need_bwd) {

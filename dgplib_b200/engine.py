@@ -162,41 +162,66 @@ class Engine:
         return [_dev_tensor(p, self.device) for p in params]
 
     # ------------------------------------------------------------------------------------------ buffers
-    def _row_buffers(self, n_rows, save):
-        key = (n_rows, bool(save))
+    def _rows_of(self, l, S, nb):
+        """Rows the conditionals of layer l see for nb data rows: the first layer is evaluated once per data row
+        (tile_over_samples makes its S copies identical), every later layer on all S * nb samples."""
+        return nb if l == 0 else S * nb
+
+    def _row_buffers(self, S, nb, save):
+        key = (S, nb, bool(save))
         buf = self._rows.get(key)
         if buf is None:
             dev = self.device
+            n = S * nb
             buf = {"mean": [], "var": [], "F": [], "A": [], "gX": []}
             for l, (layer, conds) in enumerate(zip(self.layers, self.conds)):
                 R = layer.output_dim
                 ldf = R + (1 if self.multitask else 0)
-                buf["mean"].append(torch.empty(n_rows, R, dtype=_F64, device=dev))
-                buf["var"].append(torch.empty(n_rows, R, dtype=_F64, device=dev))
-                buf["F"].append(torch.empty(n_rows, ldf, dtype=_F64, device=dev))
+                rows = self._rows_of(l, S, nb)
+                buf["mean"].append(torch.empty(rows, R, dtype=_F64, device=dev))
+                buf["var"].append(torch.empty(rows, R, dtype=_F64, device=dev))
+                buf["F"].append(torch.empty(n, ldf, dtype=_F64, device=dev))
                 if save:
-                    buf["A"].append([torch.empty(n_rows, _cabi.mpad(layer.num_inducing), dtype=_F64, device=dev)
+                    buf["A"].append([torch.empty(rows, _cabi.mpad(layer.num_inducing), dtype=_F64, device=dev)
                                      for _ in conds])
-                    buf["gX"].append(torch.empty(n_rows, conds[0].desc.Dx, dtype=_F64, device=dev) if l > 0 else None)
+                    buf["gX"].append(torch.empty(n, conds[0].desc.Dx, dtype=_F64, device=dev) if l > 0 else None)
             if save:
-                RL = self.layers[-1].output_dim
-                buf["g_mu"] = torch.empty(n_rows, RL, dtype=_F64, device=dev)
-                buf["g_var"] = torch.empty(n_rows, RL, dtype=_F64, device=dev)
+                RL, R0 = self.layers[-1].output_dim, self.layers[0].output_dim
+                rows_last = self._rows_of(len(self.layers) - 1, S, nb)
+                buf["g_mu"] = torch.empty(rows_last, RL, dtype=_F64, device=dev)
+                buf["g_var"] = torch.empty(rows_last, RL, dtype=_F64, device=dev)
+                buf["g_mean0"] = torch.empty(nb, R0, dtype=_F64, device=dev)
+                buf["g_var0"] = torch.empty(nb, R0, dtype=_F64, device=dev)
             if len(self._rows) > 8:
                 self._rows.clear()
             self._rows[key] = buf
         return buf
 
-    def _prepare(self, n_rows, need_bwd, kl):
-        lib, st = _cabi.lib(), _cabi.stream_ptr()
-        i = 0
-        for conds in self.conds:
-            for c in conds:
-                c.ensure_ws(n_rows, need_bwd, self.device)
-                _cabi.check(lib.dgp_cond_prepare(c.ref(), _cabi.ptr(c.ws), c.ws.numel(), 1 if need_bwd else 0,
-                                                 ctypes.c_void_p(kl[i:].data_ptr()) if kl is not None else None, st),
-                            "dgp_cond_prepare")
-                i += 1
+    def _side_streams(self):
+        if getattr(self, "_streams", None) is None:
+            self._streams = [torch.cuda.Stream(device=self.device) for _ in self.layers]
+        return self._streams
+
+    def _prepare(self, S, nb, need_bwd, kl):
+        """Parameter-only stage of every conditional (Kuu, Cholesky, inverse factor, tiled operands, KL).  The layers are
+        independent of each other and of the data, so each layer's chain runs on its own stream; returns one event per
+        layer for the main stream to wait on just before that layer's first row kernel."""
+        lib = _cabi.lib()
+        main = torch.cuda.current_stream()
+        start = main.record_event()
+        events, i = [], 0
+        for l, (conds, side) in enumerate(zip(self.conds, self._side_streams())):
+            side.wait_event(start)
+            with torch.cuda.stream(side):
+                for c in conds:
+                    c.ensure_ws(self._rows_of(l, S, nb), need_bwd, self.device)
+                    self._timed("prepare", lambda: _cabi.check(lib.dgp_cond_prepare(
+                        c.ref(), _cabi.ptr(c.ws), c.ws.numel(), 1 if need_bwd else 0,
+                        ctypes.c_void_p(kl[i:].data_ptr()) if kl is not None else None, _cabi.stream_ptr()),
+                        "dgp_cond_prepare"))
+                    i += 1
+                events.append(side.record_event())
+        return events
 
     def check_status(self):
         """Raises if a Cholesky factorisation failed (the reference surfaces this as TF's InvalidArgumentError)."""
@@ -210,25 +235,38 @@ class Engine:
                                          "Kuu + jitter is not positive definite")
 
     # ------------------------------------------------------------------------------------------ forward
-    def _forward_rows(self, X, S, eps, seed, row_offset, sample_stride, buf, save, last_F):
-        """One pass of the cascade over the S * B rows of X [B, Dx0].  eps: list of [S*B, R_l] tensors or None."""
+    def _layer_seed(self, seed, l):
+        return ctypes.c_uint64((seed + 0x9E3779B97F4A7C15 * (l + 1)) & 0xFFFFFFFFFFFFFFFF)
+
+    def _forward_rows(self, X, S, eps, seed, row_offset, sample_stride, buf, save, last_F, prep_events):
+        """One pass of the cascade over the data rows X [nb, Dx0] and their S samples.
+        eps: list of [S*nb, R_l] tensors or None (Philox)."""
         lib, st = _cabi.lib(), _cabi.stream_ptr()
-        B = X.shape[0]
-        n = S * B
-        inp, x_rows = X, B
+        main = torch.cuda.current_stream()
+        nb = X.shape[0]
+        n = S * nb
+        inp, x_rows = X, nb
         L = len(self.layers)
+        stride = sample_stride if sample_stride else nb
         for l, (layer, conds) in enumerate(zip(self.layers, self.conds)):
+            main.wait_event(prep_events[l])
             want_F = last_F or l < L - 1
             Fbuf = buf["F"][l] if want_F else None
+            rows = self._rows_of(l, S, nb)
+            fused_F = want_F and l > 0        # layer 0 samples are drawn by dgp_sample_expand (S per data row)
             for ci, c in enumerate(conds):
                 self._timed(f"fwd.l{l}", lambda: _cabi.check(lib.dgp_cond_forward(
-                    c.ref(), _cabi.ptr(c.ws), _cabi.ptr(inp), x_rows, n,
-                    _cabi.ptr(eps[l]) if (eps is not None and want_F) else None,
-                    ctypes.c_uint64(seed + 0x9E3779B97F4A7C15 * (l + 1) & 0xFFFFFFFFFFFFFFFF), row_offset, B,
-                    sample_stride if sample_stride else B,
-                    _cabi.ptr(buf["mean"][l]), _cabi.ptr(buf["var"][l]), _cabi.ptr(Fbuf) if want_F else None,
-                    Fbuf.shape[1] if want_F else layer.output_dim,
+                    c.ref(), _cabi.ptr(c.ws), _cabi.ptr(inp), x_rows, rows,
+                    _cabi.ptr(eps[l]) if (eps is not None and fused_F) else None,
+                    self._layer_seed(seed, l), row_offset, nb, stride,
+                    _cabi.ptr(buf["mean"][l]), _cabi.ptr(buf["var"][l]), _cabi.ptr(Fbuf) if fused_F else None,
+                    Fbuf.shape[1] if fused_F else layer.output_dim,
                     _cabi.ptr(buf["A"][l][ci]) if save else None, st), "dgp_cond_forward"))
+            if l == 0 and want_F:
+                self._timed("sample.l0", lambda: _cabi.check(lib.dgp_sample_expand(
+                    _cabi.ptr(buf["mean"][0]), _cabi.ptr(buf["var"][0]), _cabi.ptr(eps[0]) if eps is not None else None,
+                    self._layer_seed(seed, 0), row_offset, stride, S, nb, layer.output_dim, layer.output_dim,
+                    _cabi.ptr(Fbuf), Fbuf.shape[1], _cabi.ptr(X), X.shape[1], st), "dgp_sample_expand"))
             inp, x_rows = Fbuf, n
 
     def propagate(self, X, S, eps=None, seed=0, params=None):
@@ -238,16 +276,20 @@ class Engine:
             self._bind(self._detached(params))
             B = X.shape[0]
             n = S * B
-            buf = self._row_buffers(n, False)
-            self._prepare(n, False, None)
+            buf = self._row_buffers(S, B, False)
+            events = self._prepare(S, B, False, None)
             eps_flat = None
             if eps is not None:
                 eps_flat = [_dev_tensor(e, self.device).reshape(n, -1) for e in eps]
-            self._forward_rows(X, S, eps_flat, seed, 0, B, buf, False, True)
+            self._forward_rows(X, S, eps_flat, seed, 0, B, buf, False, True, events)
             self.check_status()
+
+            def view(t):
+                return (t.unsqueeze(0).expand(S, *t.shape) if t.shape[0] == B and S * B != B
+                        else t.reshape(S, B, -1)).clone()
             Fs = [f.reshape(S, B, -1).clone() for f in buf["F"]]
-            means = [m.reshape(S, B, -1).clone() for m in buf["mean"]]
-            vars_ = [v.reshape(S, B, -1).clone() for v in buf["var"]]
+            means = [view(m) for m in buf["mean"]]
+            vars_ = [view(v) for v in buf["var"]]
             return Fs, means, vars_
 
     # ------------------------------------------------------------------------------------------ ELBO (+ grad)
@@ -270,41 +312,71 @@ class Engine:
         lib, st = _cabi.lib(), _cabi.stream_ptr()
         with torch.no_grad():
             dev = self.device
+            main = torch.cuda.current_stream()
             X, Y = _dev_tensor(X, dev), _dev_tensor(Y, dev)
             params = [_dev_tensor(p, dev) for p in params]
             self._bind(params)
             B = X.shape[0]
             Bg = global_batch if global_batch is not None else B
             num_data = Bg if num_data is None else num_data
-            weight = (float(num_data) / float(Bg)) / float(S)
+            L = len(self.layers)
+            # (num_data / B) / S (dgplib/dsdgp.py:121, :128-129); a 1-layer model's S samples are identical copies
+            S_lik = S if L > 1 else 1
+            weight = (float(num_data) / float(Bg)) / float(S_lik)
             ncond = sum(len(c) for c in self.conds)
             offs, total = self.grad_layout(params)
             flat = torch.zeros(total + ncond, dtype=_F64, device=dev)   # [elbo | grads | kl per conditional]
             kl = flat[total:]
             Bc = B if not chunk_rows else max(1, min(B, int(chunk_rows)))
-            self._timed("prepare", lambda: self._prepare(S * Bc, need_grad, kl))
+            events = self._prepare(S, Bc, need_grad, kl)
             if self._lik_ws is None:
                 self._lik_ws = torch.empty(lib.dgp_lik_ws_bytes(0, 1), dtype=torch.uint8, device=dev)
-            L = len(self.layers)
             RL = self.layers[-1].output_dim
             T_lik = self._lik_var.numel()
             ldy = Y.shape[1]
             g_lik = flat[offs[-1]:offs[-1] + T_lik]
+            klw = 1.0 / float(world_size)
             eps_full = None
             if eps is not None:
                 eps_full = [_dev_tensor(e, dev).reshape(S, B, -1) for e in eps]
-            for b0 in range(0, B, Bc):
+            tail_events = []
+
+            def run_tail(l):
+                """Parameter-only backward tail of layer l on its side stream (overlaps the earlier layers' rows)."""
+                side = self._side_streams()[l]
+                side.wait_event(main.record_event())
+                with torch.cuda.stream(side):
+                    for c, ((Z, oZ), (th, oT)) in zip(self.conds[l], self._zt_offsets[l]):
+                        base = flat.data_ptr()
+                        o_mu, o_sqrt = self._q_offsets[l]
+                        self._timed("params_bwd", lambda: _cabi.check(lib.dgp_cond_backward_params(
+                            c.ref(), _cabi.ptr(c.ws), klw, ctypes.c_void_p(base + 8 * oZ), ctypes.c_void_p(base + 8 * oT),
+                            ctypes.c_void_p(base + 8 * o_mu), ctypes.c_void_p(base + 8 * o_sqrt), _cabi.stream_ptr()),
+                            "dgp_cond_backward_params"))
+                    tail_events.append(side.record_event())
+
+            # offsets of each layer's gradient slots
+            it = iter(zip(params, offs))
+            self._zt_offsets, self._q_offsets = [], []
+            for conds in self.conds:
+                self._zt_offsets.append([(next(it), next(it)) for _ in conds])
+                (_, o_mu), (_, o_sqrt) = next(it), next(it)
+                self._q_offsets.append((o_mu, o_sqrt))
+
+            nchunks = (B + Bc - 1) // Bc
+            for ck, b0 in enumerate(range(0, B, Bc)):
                 b1 = min(B, b0 + Bc)
                 nb = b1 - b0
                 n = S * nb
                 Xc, Yc = X[b0:b1], Y[b0:b1]
-                buf = self._row_buffers(n, need_grad)
+                buf = self._row_buffers(S, nb, need_grad)
                 eps_c = None
                 if eps_full is not None:
                     eps_c = [e[:, b0:b1].reshape(n, -1).contiguous() for e in eps_full]
-                self._forward_rows(Xc, S, eps_c, seed, row_offset + b0, Bg, buf, need_grad, False)
+                self._forward_rows(Xc, S, eps_c, seed, row_offset + b0, Bg, buf, need_grad, False, events)
+                n_lik = self._rows_of(L - 1, S, nb)
                 self._timed("lik", lambda: _cabi.check(lib.dgp_lik_gaussian(
-                    _cabi.ptr(buf["mean"][-1]), _cabi.ptr(buf["var"][-1]), _cabi.ptr(Yc), nb, ldy, n, RL,
+                    _cabi.ptr(buf["mean"][-1]), _cabi.ptr(buf["var"][-1]), _cabi.ptr(Yc), nb, ldy, n_lik, RL,
                     _cabi.ptr(self._lik_var), T_lik, weight, ctypes.c_void_p(flat.data_ptr()),
                     _cabi.ptr(buf["g_mu"]) if need_grad else None, _cabi.ptr(buf["g_var"]) if need_grad else None,
                     ctypes.c_void_p(g_lik.data_ptr()) if need_grad else None,
@@ -314,31 +386,40 @@ class Engine:
                 for l in range(L - 1, -1, -1):
                     layer, conds = self.layers[l], self.conds[l]
                     inp = Xc if l == 0 else buf["F"][l - 1]
-                    x_rows = nb if l == 0 else n
+                    rows = self._rows_of(l, S, nb)
+                    x_rows = nb if l <= 1 else n
+                    if l == 0:
+                        x_rows = nb
+                    elif l == 1:
+                        x_rows = n
                     last = (l == L - 1)
                     gF = None if last else buf["gX"][l + 1]
+                    g_mean_in = buf["g_mu"] if last else None
+                    g_var_in = buf["g_var"] if last else None
+                    Fl = None if last else buf["F"][l]
+                    if l == 0 and not last:
+                        # fold the S sample gradients of every data row into (g_mean, g_var) of the shared conditional
+                        self._timed("sample.l0", lambda: _cabi.check(lib.dgp_sample_reduce(
+                            _cabi.ptr(gF), gF.shape[1], _cabi.ptr(buf["F"][0]), buf["F"][0].shape[1],
+                            _cabi.ptr(buf["mean"][0]), _cabi.ptr(buf["var"][0]), S, nb, layer.output_dim,
+                            layer.output_dim, _cabi.ptr(buf["g_mean0"]), _cabi.ptr(buf["g_var0"]), st),
+                            "dgp_sample_reduce"))
+                        g_mean_in, g_var_in, gF, Fl = buf["g_mean0"], buf["g_var0"], None, None
                     for ci, c in enumerate(conds):
                         self._timed(f"bwd.l{l}", lambda: _cabi.check(lib.dgp_cond_backward(
-                            c.ref(), _cabi.ptr(c.ws), _cabi.ptr(inp), x_rows, n, _cabi.ptr(buf["A"][l][ci]),
+                            c.ref(), _cabi.ptr(c.ws), _cabi.ptr(inp), x_rows, rows, _cabi.ptr(buf["A"][l][ci]),
                             _cabi.ptr(buf["mean"][l]), _cabi.ptr(buf["var"][l]),
-                            None if last else _cabi.ptr(buf["F"][l]), buf["F"][l].shape[1],
-                            _cabi.ptr(buf["g_mu"]) if last else None, _cabi.ptr(buf["g_var"]) if last else None,
+                            _cabi.ptr(Fl) if Fl is not None else None, buf["F"][l].shape[1],
+                            _cabi.ptr(g_mean_in) if g_mean_in is not None else None,
+                            _cabi.ptr(g_var_in) if g_var_in is not None else None,
                             _cabi.ptr(gF) if gF is not None else None, gF.shape[1] if gF is not None else 0,
                             _cabi.ptr(buf["gX"][l]) if l > 0 else None, 1 if ci > 0 else 0, st), "dgp_cond_backward"))
                         self._timed(f"gram.l{l}", lambda: _cabi.check(lib.dgp_cond_backward_gram(
-                            c.ref(), _cabi.ptr(c.ws), _cabi.ptr(buf["A"][l][ci]), n, st), "dgp_cond_backward_gram"))
-            klw = 1.0 / float(world_size)
-            if need_grad:
-                it = iter(zip(params, offs))
-                for layer, conds in zip(self.layers, self.conds):
-                    zt = [(next(it), next(it)) for _ in conds]
-                    (q_mu, o_mu), (q_sqrt, o_sqrt) = next(it), next(it)
-                    for c, ((Z, oZ), (th, oT)) in zip(conds, zt):
-                        base = flat.data_ptr()
-                        self._timed("params_bwd", lambda: _cabi.check(lib.dgp_cond_backward_params(
-                            c.ref(), _cabi.ptr(c.ws), klw, ctypes.c_void_p(base + 8 * oZ), ctypes.c_void_p(base + 8 * oT),
-                            ctypes.c_void_p(base + 8 * o_mu), ctypes.c_void_p(base + 8 * o_sqrt), st),
-                            "dgp_cond_backward_params"))
+                            c.ref(), _cabi.ptr(c.ws), _cabi.ptr(buf["A"][l][ci]), rows, st), "dgp_cond_backward_gram"))
+                    if ck == nchunks - 1:
+                        run_tail(l)
+            for ev in tail_events:
+                main.wait_event(ev)
             flat[0] -= klw * kl.sum()
             if all_reduce is not None and world_size > 1:
                 all_reduce(flat[:total])
@@ -404,7 +485,8 @@ def layer_kl(layer):
         eng._bind(eng._detached())
         ncond = len(eng.conds[0])
         kl = torch.zeros(ncond, dtype=_F64, device=eng.device)
-        eng._prepare(1, False, kl)
+        for ev in eng._prepare(1, 1, False, kl):
+            torch.cuda.current_stream().wait_event(ev)
         return kl.sum()
 
 

@@ -94,6 +94,20 @@ int dgp_cond_forward(const dgp_cond_desc* d, const void* ws, const double* X, in
                      int64_t sample_stride, double* mean, double* var, double* F, int32_t ldf, double* A_save,
                      void* stream);
 
+/* ---- first-layer sample sharing -------------------------------------------------------------------------------
+ * tile_over_samples (dgplib/utils.py:15-18, used at dgplib/dsdgp.py:89) hands the first layer S identical copies of
+ * every data row, so its conditional is the same for all of them: call dgp_cond_forward on the B data rows only
+ * (F = NULL), then draw the S samples per row with dgp_sample_expand; in the backward pass dgp_sample_reduce folds the
+ * S sample gradients of a row into (g_mean, g_var) [B, ldr], which go to dgp_cond_backward as g_mean_in / g_var_in.
+ *   F[s*B + b, c] = mean[b, c] + eps[s*B + b, c] * sqrt(var[b, c]),  eps == NULL: Philox keyed (seed, row_offset +
+ *   s * sample_stride + b, c) -- the draws dgp_cond_forward would make.  ldf > ldr: column ldf-1 = X[b, Dx-1]. */
+int dgp_sample_expand(const double* mean, const double* var, const double* eps, uint64_t seed, uint64_t row_offset,
+                      int64_t sample_stride, int32_t S, int64_t B, int32_t R, int32_t ldr, double* F, int32_t ldf,
+                      const double* X, int32_t Dx, void* stream);
+int dgp_sample_reduce(const double* g_F, int32_t ldgf, const double* F, int32_t ldf, const double* mean,
+                      const double* var, int32_t S, int64_t B, int32_t R, int32_t ldr, double* g_mean, double* g_var,
+                      void* stream);
+
 /* ---- likelihood ------------------------------------------------------------------------------------------------
  * Gaussian / SwitchedLikelihood variational expectations, mean over S, sum over rows and outputs
  * (dgplib/dsdgp.py:115-122), and their gradients.
