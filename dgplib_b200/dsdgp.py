@@ -12,6 +12,7 @@ import torch
 from . import settings
 from .engine import Engine, elbo_autograd, _dev_tensor
 from .mean_functions import Zero
+from .parallel import shard_range
 from .params import Parameterized
 
 
@@ -117,7 +118,7 @@ class DSDGP(Parameterized):
             dist, group = self._dist
             W, r = dist.get_world_size(group), dist.get_rank(group)
             B = X.shape[0]
-            lo, hi = (B * r) // W, (B * (r + 1)) // W
+            lo, hi = shard_range(B, r, W)
             kw.update(X=X[lo:hi], Y=Y[lo:hi], row_offset=lo, global_batch=B, world_size=W,
                       all_reduce=lambda t: dist.all_reduce(t, group=group))
             if eps is not None:

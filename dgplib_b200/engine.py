@@ -14,6 +14,7 @@ import torch
 
 from . import _cabi, settings
 from .mean_functions import Linear
+from .parallel import kl_weight
 
 _F64 = torch.float64
 
@@ -335,7 +336,7 @@ class Engine:
             T_lik = self._lik_var.numel()
             ldy = Y.shape[1]
             g_lik = flat[offs[-1]:offs[-1] + T_lik]
-            klw = 1.0 / float(world_size)
+            klw = kl_weight(world_size)
             eps_full = None
             if eps is not None:
                 eps_full = [_dev_tensor(e, dev).reshape(S, B, -1) for e in eps]

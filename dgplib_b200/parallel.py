@@ -1,0 +1,20 @@
+"""Row sharding of one minibatch over the ranks of a box: contiguous row ranges, all S samples of a
+row stay on the rank that owns the row; parameters (and the Kuu factors) are replicated; one all-reduce(sum) of the
+flat [elbo | gradients] buffer per evaluation, with the KL term weighted 1/world_size on every rank."""
+
+
+def shard_range(num_rows, rank, world_size):
+    """Rows [lo, hi) of a minibatch owned by `rank`."""
+    if not (0 <= rank < world_size):
+        raise ValueError("rank out of range")
+    return (num_rows * rank) // world_size, (num_rows * (rank + 1)) // world_size
+
+
+def kl_weight(world_size):
+    """Share of the (replicated) KL term a rank adds before the all-reduce; 1/2, 1/4, 1/8 are exact in binary."""
+    return 1.0 / float(world_size)
+
+
+def philox_row_id(row_offset, sample, local_row, sample_stride):
+    """Global row id that keys the Philox draw of (sample, local row): identical for any sharding of the rows."""
+    return row_offset + sample * sample_stride + local_row

@@ -7,7 +7,7 @@ baseline ("CPU restatement of the reference path"; TF 1.8 / GPflow 1.2 are not i
 
 Model description (plain dicts of torch float64 tensors; nothing is shared with ``dgplib_b200``):
 
-    kern  = {"kind": "rbf"|"matern52", "input_dim": D, "variance": t[], "lengthscales": t[] or t[D],
+    kern  = {"kind": "rbf"|"matern52"|"const" (test double), "input_dim": D, "variance": t[], "lengthscales": t[] or t[D],
              "white": t[] or None}
           | {"kind": "switched", "kernels": [kern, ...]}           # dgplib/specialized_kernels.py
     layer = {"groups": [{"kernel": kern, "Z": t[M, Dz]}, ...],    # 1 group = Layer; K groups = MultikernelLayer
@@ -36,6 +36,9 @@ def _scaled_sq_dist(X, X2, ls):
 
 
 def _stationary_K(kern, X, X2):
+    if kern["kind"] == "const":
+        # the reference's own test double: DummyKernel of tests/test_specialized_kernels.py:13-26, K = val * ones
+        return kern["variance"] * torch.ones(X.shape[0], X2.shape[0], dtype=X.dtype)
     r2 = _scaled_sq_dist(X, X2, kern["lengthscales"])
     if kern["kind"] == "rbf":
         return kern["variance"] * torch.exp(-r2 / 2.0)

@@ -1,0 +1,188 @@
+"""GPU parity of ONE whitened conditional through the raw C-ABI (dgp_cond_prepare / forward / backward / gram / params)
+against the oracle: forward values, the saved A = Lm^-1 Kuf, and every gradient (torch autograd of the oracle).
+Tolerance: BASELINE.json north_star, relative 1e-9 (per-tensor inf-norm)."""
+import ctypes
+
+import numpy as np
+import pytest
+import torch
+
+from dgplib_b200 import _cabi as C
+from oracle import dsdgp_oracle as O
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-9
+
+
+def rel(a, b):
+    b = b.detach()
+    return float((a.detach().cpu() - b).abs().max() / max(float(b.abs().max()), 1e-300))
+
+
+def run_conditional(cuda, M, D, R, N, kind, S=1, white=1e-5, linear=True, backward=True, seed=0):
+    rng = np.random.RandomState(seed)
+    X = torch.tensor(rng.randn(N, D))
+    Z = torch.tensor(rng.randn(M, D))
+    ls = torch.tensor(np.sqrt(D) * (0.8 + 0.4 * rng.rand(D)))
+    var = torch.tensor(1.3, dtype=torch.float64)
+    wh = torch.tensor(white, dtype=torch.float64)
+    q_mu = torch.tensor(0.1 * rng.randn(M, R))
+    q_sqrt = torch.tensor(np.eye(M)[None] + 0.1 * np.tril(rng.randn(R, M, M)) + 0.3 * np.triu(rng.randn(R, M, M), 1))
+    A = torch.tensor(rng.randn(D, R)) if linear else None
+    b = torch.tensor(rng.randn(R)) if linear else None
+    n = S * N
+    eps = torch.tensor(rng.randn(n, R))
+    gm_in, gv_in, gF = (torch.tensor(rng.randn(n, R)) for _ in range(3))
+    kern = {"kind": kind, "input_dim": D, "variance": var, "lengthscales": ls, "white": wh}
+    layer = {"groups": [{"kernel": kern, "Z": Z}], "q_mu": q_mu, "q_sqrt": q_sqrt,
+             "mean": {"A": A, "b": b} if linear else None}
+    leaves = [X, Z, var, ls, wh, q_mu, q_sqrt]
+    for p in leaves:
+        p.requires_grad_(True)
+    Xt = X[None].repeat(S, 1, 1)
+    m_ref, v_ref = O.layer_build_predict(layer, Xt)
+    m_ref, v_ref = m_ref.reshape(n, R), v_ref.reshape(n, R)
+    F_ref = m_ref + eps * v_ref ** 0.5
+    kl_ref = O.layer_kl(layer)
+    ref = None
+    if backward:
+        obj = (gm_in * m_ref).sum() + (gv_in * v_ref).sum() + (gF * F_ref).sum() - kl_ref
+        ref = dict(zip(["X", "Z", "var", "ls", "wh", "q_mu", "q_sqrt"], torch.autograd.grad(obj, leaves)))
+    for p in leaves:
+        p.requires_grad_(False)
+
+    lib = C.lib()
+    d = C.CondDesc()
+    d.M, d.D, d.Dx, d.R, d.ldr, d.col0, d.T = M, D, D, R, R, 0, 1
+    d.kind[0] = 0 if kind == "rbf" else 1
+    d.jitter = 1e-6
+    dev = cuda
+    theta = torch.cat([var.reshape(1), wh.reshape(1), ls]).to(dev)
+    Zd, qmd, qsd, Xd, epsd = (x.to(dev) for x in (Z, q_mu, q_sqrt, X, eps))
+    Ad = A.to(dev) if linear else None
+    bd = b.to(dev) if linear else None
+    d.Z, d.theta, d.q_mu, d.q_sqrt = Zd.data_ptr(), theta.data_ptr(), qmd.data_ptr(), qsd.data_ptr()
+    d.mean_A = Ad.data_ptr() if linear else None
+    d.mean_b = bd.data_ptr() if linear else None
+    nb = 1 if backward else 0
+    wsb = lib.dgp_cond_ws_bytes(ctypes.byref(d), n, nb)
+    ws = torch.zeros(wsb, dtype=torch.uint8, device=dev)
+    kl = torch.zeros(1, dtype=torch.float64, device=dev)
+    st = C.stream_ptr()
+    C.check(lib.dgp_cond_prepare(ctypes.byref(d), C.ptr(ws), wsb, nb, C.ptr(kl), st), "prepare")
+    status = ctypes.c_int32(-1)
+    C.check(lib.dgp_cond_status(C.ptr(ws), st, ctypes.byref(status)), "status")
+    assert status.value == 0
+    Mp = C.mpad(M)
+    mean = torch.zeros(n, R, dtype=torch.float64, device=dev)
+    varo, F = torch.zeros_like(mean), torch.zeros_like(mean)
+    Asave = torch.full((n, Mp), float("nan"), dtype=torch.float64, device=dev)
+    # the S copies of X are addressed by index arithmetic (x_rows = N), never materialised
+    C.check(lib.dgp_cond_forward(ctypes.byref(d), C.ptr(ws), C.ptr(Xd), N, n, C.ptr(epsd), 0, 0, 0, 0, C.ptr(mean),
+                                 C.ptr(varo), C.ptr(F), R, C.ptr(Asave), st), "forward")
+    torch.cuda.synchronize()
+    errs = {"kl": abs(kl.item() - kl_ref.item()) / max(abs(kl_ref.item()), 1e-12), "mean": rel(mean, m_ref),
+            "var": rel(varo, v_ref), "F": rel(F, F_ref)}
+    Kmm = O.kern_K(kern, Z) + 1e-6 * torch.eye(M, dtype=torch.float64)
+    A_ref = torch.linalg.solve_triangular(torch.linalg.cholesky(Kmm), O.kern_K(kern, Z, X), upper=False).t()
+    errs["A"] = rel(Asave[:N, :M], A_ref)
+    if Mp > M:
+        assert float(Asave[:, M:].abs().max()) == 0.0        # padded inducing rows stay exactly zero
+    if backward:
+        gX = torch.zeros(N * S, D, dtype=torch.float64, device=dev)
+        Xrep = Xd.repeat(S, 1).contiguous()                  # d/dX per flattened row: give every row its own X row
+        C.check(lib.dgp_cond_backward(ctypes.byref(d), C.ptr(ws), C.ptr(Xrep), n, n, C.ptr(Asave), C.ptr(mean),
+                                      C.ptr(varo), C.ptr(F), R, C.ptr(gm_in.to(dev)), C.ptr(gv_in.to(dev)),
+                                      C.ptr(gF.to(dev)), R, C.ptr(gX), 0, st), "backward")
+        C.check(lib.dgp_cond_backward_gram(ctypes.byref(d), C.ptr(ws), C.ptr(Asave), n, st), "gram")
+        gZ = torch.zeros(M, D, dtype=torch.float64, device=dev)
+        gth = torch.zeros(2 + D, dtype=torch.float64, device=dev)
+        gqm = torch.zeros(M, R, dtype=torch.float64, device=dev)
+        gqs = torch.full((R, M, M), float("nan"), dtype=torch.float64, device=dev)
+        C.check(lib.dgp_cond_backward_params(ctypes.byref(d), C.ptr(ws), 1.0, C.ptr(gZ), C.ptr(gth), C.ptr(gqm),
+                                             C.ptr(gqs), st), "params")
+        torch.cuda.synchronize()
+        errs.update({"gX": rel(gX.reshape(S, N, D).sum(0), ref["X"]), "gZ": rel(gZ, ref["Z"]),
+                     "gvar": rel(gth[0:1], ref["var"].reshape(1)), "gwhite": rel(gth[1:2], ref["wh"].reshape(1)),
+                     "gls": rel(gth[2:], ref["ls"]), "gq_mu": rel(gqm, ref["q_mu"]), "gq_sqrt": rel(gqs, ref["q_sqrt"])})
+        assert float(torch.triu(gqs, 1).abs().max()) == 0.0  # band_part: zero gradient above the diagonal
+    return errs
+
+
+CASES = [
+    # M, D, R, N, kind, S   (ragged tiles, padded M, every tile-width instantiation)
+    (50, 1, 1, 1000, "rbf", 1),
+    (64, 3, 2, 130, "rbf", 2),
+    (100, 8, 8, 777, "matern52", 1),
+    (128, 8, 8, 2050, "rbf", 2),
+    (256, 8, 8, 3000, "rbf", 1),
+    (300, 16, 4, 500, "matern52", 1),
+    (500, 16, 16, 700, "matern52", 1),
+    (7, 2, 1, 1, "rbf", 1),             # a single row
+    (33, 5, 3, 63, "matern52", 3),
+]
+
+
+@pytest.mark.parametrize("M,D,R,N,kind,S", CASES)
+def test_conditional_forward_backward_parity(cuda, M, D, R, N, kind, S):
+    errs = run_conditional(cuda, M, D, R, N, kind, S=S)
+    bad = {k: v for k, v in errs.items() if not v < TOL}
+    assert not bad, (bad, errs)
+
+
+def test_forward_only_large_M(cuda):
+    """M = 1000 (config 5's M=1024 class): forward tile width 16."""
+    errs = run_conditional(cuda, 1000, 8, 2, 300, "rbf", linear=False, backward=False)
+    assert max(errs.values()) < TOL, errs
+
+
+def test_zero_mean_function_and_no_white(cuda):
+    errs = run_conditional(cuda, 40, 4, 2, 200, "rbf", white=0.0, linear=False)
+    errs.pop("gwhite")          # no White kernel: that slot is unused
+    assert max(errs.values()) < TOL, errs
+
+
+def test_cholesky_failure_is_reported(cuda):
+    """Numerical failure convention: status word = failing pivot + 1 (the reference gets TF's InvalidArgumentError)."""
+    lib = C.lib()
+    M, D, R = 16, 2, 1
+    d = C.CondDesc()
+    d.M, d.D, d.Dx, d.R, d.ldr, d.col0, d.T = M, D, D, R, R, 0, 1
+    d.jitter = -2.0              # makes Kuu indefinite: k(z,z) + jitter = 1 - 2 < 0 at the first pivot
+    Z = torch.zeros(M, D, dtype=torch.float64, device=cuda)
+    theta = torch.tensor([1.0, 0.0, 1.0, 1.0], dtype=torch.float64, device=cuda)
+    q_mu = torch.zeros(M, R, dtype=torch.float64, device=cuda)
+    q_sqrt = torch.eye(M, dtype=torch.float64, device=cuda)[None].contiguous()
+    d.Z, d.theta, d.q_mu, d.q_sqrt = Z.data_ptr(), theta.data_ptr(), q_mu.data_ptr(), q_sqrt.data_ptr()
+    wsb = lib.dgp_cond_ws_bytes(ctypes.byref(d), 8, 0)
+    ws = torch.zeros(wsb, dtype=torch.uint8, device=cuda)
+    C.check(lib.dgp_cond_prepare(ctypes.byref(d), C.ptr(ws), wsb, 0, None, C.stream_ptr()), "prepare")
+    s = ctypes.c_int32(0)
+    C.check(lib.dgp_cond_status(C.ptr(ws), C.stream_ptr(), ctypes.byref(s)), "status")
+    assert s.value == 1
+
+
+def test_philox_draws(cuda):
+    """In-kernel noise: N(0,1) moments, reproducible, and independent of how rows are sharded."""
+    lib = C.lib()
+    n, R = 200_000, 4
+    a = torch.empty(n, R, dtype=torch.float64, device=cuda)
+    C.check(lib.dgp_philox_normal(C.ptr(a), n, R, R, 1234, 0, 0, 0, C.stream_ptr()), "philox")
+    b = torch.empty_like(a)
+    C.check(lib.dgp_philox_normal(C.ptr(b), n, R, R, 1234, 0, 0, 0, C.stream_ptr()), "philox")
+    assert torch.equal(a, b)
+    assert abs(float(a.mean())) < 5e-3 and abs(float(a.var()) - 1.0) < 1e-2
+    assert abs(float((a ** 4).mean()) - 3.0) < 0.1
+    c = torch.empty_like(a)
+    C.check(lib.dgp_philox_normal(C.ptr(c), n, R, R, 1235, 0, 0, 0, C.stream_ptr()), "philox")
+    assert abs(float((a * c).mean())) < 5e-3
+    # S = 4 samples of B = 1000 rows, drawn whole and as two row shards
+    S, B = 4, 1000
+    whole = torch.empty(S * B, R, dtype=torch.float64, device=cuda)
+    C.check(lib.dgp_philox_normal(C.ptr(whole), S * B, R, R, 7, 0, B, B, C.stream_ptr()), "philox")
+    lo = torch.empty(S * 400, R, dtype=torch.float64, device=cuda)
+    hi = torch.empty(S * 600, R, dtype=torch.float64, device=cuda)
+    C.check(lib.dgp_philox_normal(C.ptr(lo), S * 400, R, R, 7, 0, 400, B, C.stream_ptr()), "philox")
+    C.check(lib.dgp_philox_normal(C.ptr(hi), S * 600, R, R, 7, 400, 600, B, C.stream_ptr()), "philox")
+    w = whole.reshape(S, B, R)
+    assert torch.equal(w[:, :400], lo.reshape(S, 400, R)) and torch.equal(w[:, 400:], hi.reshape(S, 600, R))

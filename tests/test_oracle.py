@@ -1,0 +1,183 @@
+"""Pins the CPU oracle (no GPU): the reference's own exact goldens, the init-state identities, an independent
+closed-form SVGP bound, a 50-digit mpmath fixture and finite differences for the autograd gradients."""
+import json
+import os
+
+import numpy as np
+import torch
+
+from oracle import dsdgp_oracle as O
+
+T64 = torch.float64
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def t(x):
+    return torch.tensor(np.array(x, dtype=np.float64), dtype=T64)
+
+
+def const_kernel(val):
+    # DummyKernel of the reference's tests/test_specialized_kernels.py:13-26
+    return {"kind": "const", "input_dim": 3, "variance": t(val), "lengthscales": t(1.0), "white": None}
+
+
+# ------------------------------------------------------------------ the reference's exact goldens
+def test_switched_kernel_golden_K():
+    """tests/test_specialized_kernels.py:51-69 (10x5 golden gram of three constant kernels)."""
+    X1_ind = np.array([0, 1, 2, 2, 1, 0, 1, 0, 2, 1])[:, None]
+    X2_ind = np.array([0, 1, 2, 2, 1])[:, None]
+    rng = np.random.RandomState(42)
+    X1 = np.hstack([rng.randn(10, 3), X1_ind])
+    X2 = np.hstack([rng.randn(5, 3), X2_ind])
+    kern = {"kind": "switched", "kernels": [const_kernel(1.0), const_kernel(2.0), const_kernel(3.0)]}
+    reference = np.array([[1, 0, 0, 0, 0], [0, 2, 0, 0, 2], [0, 0, 3, 3, 0], [0, 0, 3, 3, 0], [0, 2, 0, 0, 2],
+                          [1, 0, 0, 0, 0], [0, 2, 0, 0, 2], [1, 0, 0, 0, 0], [0, 0, 3, 3, 0], [0, 2, 0, 0, 2]])
+    K = O.kern_K(kern, t(X1), t(X2)).numpy()
+    assert np.array_equal(K, reference)
+
+
+def test_switched_kernel_golden_Kdiag():
+    """tests/test_specialized_kernels.py:72-78: Kdiag == task id + 1."""
+    X1_ind = np.array([0, 1, 2, 2, 1, 0, 1, 0, 2, 1])[:, None]
+    X1 = np.hstack([np.random.RandomState(0).randn(10, 3), X1_ind])
+    kern = {"kind": "switched", "kernels": [const_kernel(1.0), const_kernel(2.0), const_kernel(3.0)]}
+    assert np.array_equal(O.kern_Kdiag(kern, t(X1)).numpy(), X1[:, -1] + 1)
+
+
+def test_find_weights_goldens():
+    """tests/test_layer.py:23-44."""
+    X = np.array([[2, 4], [1, 3], [0, 0], [0, 0]], dtype=float)
+    assert np.allclose(O.find_weights(2, 2, X), np.eye(2))
+    W = O.find_weights(2, 1, X)
+    assert W.shape == (2, 1) and np.allclose(W, np.array([-0.4, -0.91]).reshape(2, 1), atol=1e-2)
+    W = O.find_weights(1, 2, X)
+    assert W.shape == (1, 2) and np.allclose(W, np.array([[1, 0]]))
+    Wm = O.find_weights(2, 2, np.hstack([X, np.zeros((4, 1))]), multitask=True)
+    assert Wm.shape == (3, 2) and np.allclose(Wm[-1], 0)
+
+
+# ------------------------------------------------------------------ identities that follow from the reference's init
+def _layer(M, D, R, kind="rbf", seed=0, init=False, mean=True):
+    rng = np.random.RandomState(seed)
+    kern = {"kind": kind, "input_dim": D, "variance": t(1.3), "lengthscales": t(0.9 + 0.2 * rng.rand(D)), "white": t(1e-3)}
+    q_mu = np.zeros((M, R)) if init else 0.3 * rng.randn(M, R)
+    q_sqrt = np.tile(np.eye(M), (R, 1, 1)) if init else np.eye(M)[None] + 0.2 * np.tril(rng.randn(R, M, M))
+    return {"groups": [{"kernel": kern, "Z": t(rng.randn(M, D))}], "q_mu": t(q_mu), "q_sqrt": t(q_sqrt),
+            "mean": {"A": t(rng.randn(D, R)), "b": t(rng.randn(R))} if mean else None}
+
+
+def test_init_state_identities():
+    """dgplib/layers.py:52-56: q_mu = 0, q_sqrt = I  =>  mean = mean_fn(X), var = Kdiag, KL = 0."""
+    for kind in ("rbf", "matern52"):
+        layer = _layer(7, 3, 2, kind, init=True)
+        X = t(np.random.RandomState(1).randn(11, 3))
+        m, v = O.layer_build_predict(layer, X[None])
+        assert torch.allclose(m[0], X @ layer["mean"]["A"] + layer["mean"]["b"], atol=1e-14)
+        assert float((v - (1.3 + 1e-3)).abs().max()) < 1e-13
+        assert abs(float(O.layer_kl(layer))) < 1e-13
+
+
+def test_single_layer_matches_unwhitened_svgp_bound():
+    """Independent algebra: q(u) = N(Lm q_mu, Lm Lq Lq^T Lm^T); SVGP bound with the unwhitened KL."""
+    M, D, R, N = 6, 2, 1, 9
+    layer = _layer(M, D, R, mean=False, seed=3)
+    rng = np.random.RandomState(4)
+    X, Y = t(rng.randn(N, D)), t(rng.randn(N, R))
+    lik = {"kind": "gaussian", "variance": t(0.3)}
+    val = O.elbo([layer], lik, X, Y, 1, [torch.zeros(1, N, R, dtype=T64)])
+    kern, Z = layer["groups"][0]["kernel"], layer["groups"][0]["Z"]
+    Kuu = O.kern_K(kern, Z) + 1e-6 * torch.eye(M, dtype=T64)
+    Kuf = O.kern_K(kern, Z, X)
+    Lm = torch.linalg.cholesky(Kuu)
+    Lq = torch.tril(layer["q_sqrt"][0])
+    m_u = Lm @ layer["q_mu"][:, 0]
+    S_u = Lm @ Lq @ Lq.t() @ Lm.t()
+    Kinv = torch.linalg.inv(Kuu)
+    mu_f = Kuf.t() @ Kinv @ m_u
+    var_f = O.kern_Kdiag(kern, X) - (Kuf * (Kinv @ Kuf)).sum(0) + (Kuf * (Kinv @ S_u @ Kinv @ Kuf)).sum(0)
+    ve = O.gaussian_ve(mu_f, var_f, Y[:, 0], lik["variance"]).sum()
+    kl = 0.5 * (torch.trace(Kinv @ S_u) + m_u @ Kinv @ m_u - M + torch.logdet(Kuu) - torch.logdet(S_u))
+    assert abs(float(val) - float(ve - kl)) < 1e-8 * abs(float(val))
+
+
+def test_variance_two_form_identity():
+    layer = _layer(8, 2, 3, mean=False, seed=5)
+    X = t(np.random.RandomState(6).randn(12, 2))
+    kern, Z = layer["groups"][0]["kernel"], layer["groups"][0]["Z"]
+    _, v = O.conditional_white(X, Z, kern, layer["q_mu"], layer["q_sqrt"])
+    Lm = torch.linalg.cholesky(O.kern_K(kern, Z) + 1e-6 * torch.eye(8, dtype=T64))
+    A = torch.linalg.solve_triangular(Lm, O.kern_K(kern, Z, X), upper=False)
+    for r in range(3):
+        Lq = torch.tril(layer["q_sqrt"][r])
+        alt = O.kern_Kdiag(kern, X) - ((A * ((torch.eye(8, dtype=T64) - Lq @ Lq.t()) @ A)).sum(0))
+        assert torch.allclose(v[:, r], alt, rtol=1e-12, atol=1e-13)
+
+
+# ------------------------------------------------------------------ high-precision fixture
+def _from_fixture(m):
+    layers = []
+    for l in m["layers"]:
+        D = len(l["Z"][0])
+        kern = {"kind": "rbf", "input_dim": D, "variance": t(l["variance"]), "lengthscales": t(l["lengthscale"]),
+                "white": t(l["white"])}
+        mean = None
+        if l["mean_A"] is not None:
+            mean = {"A": t(l["mean_A"]), "b": torch.zeros(len(l["q_mu"][0]), dtype=T64)}
+        layers.append({"groups": [{"kernel": kern, "Z": t(l["Z"])}], "q_mu": t(l["q_mu"]), "q_sqrt": t(l["q_sqrt"]),
+                       "mean": mean})
+    return layers, {"kind": "gaussian", "variance": t(m["lik_variance"])}
+
+
+def test_oracle_matches_mpmath_fixture():
+    """tests/golden/tiny_elbo_mp.json: 50-digit ELBO of two tiny 2-layer models (python -m oracle.mp_arbiter)."""
+    fx = json.load(open(os.path.join(HERE, "golden", "tiny_elbo_mp.json")))
+    for m in fx["models"]:
+        layers, lik = _from_fixture(m)
+        val = O.elbo(layers, lik, t(m["X"]), t(m["Y"]), m["S"], [t(e) for e in m["eps"]], num_data=m["num_data"])
+        ref = float(m["elbo_mp"])
+        assert abs(float(val) - ref) < 1e-12 * abs(ref)
+
+
+def test_mp_arbiter_regenerates_fixture():
+    from oracle import mp_arbiter
+    fx = json.load(open(os.path.join(HERE, "golden", "tiny_elbo_mp.json")))
+    m = fx["models"][0]
+    again = mp_arbiter.elbo(mp_arbiter.tiny_model(0))
+    assert abs(float(again) - float(m["elbo_mp"])) < 1e-25
+
+
+# ------------------------------------------------------------------ gradients
+def test_autograd_matches_finite_differences():
+    rng = np.random.RandomState(7)
+    layers = [_layer(5, 2, 2, seed=8), _layer(5, 2, 1, "matern52", seed=9, mean=False)]
+    lik = {"kind": "gaussian", "variance": t(0.4)}
+    X, Y = t(rng.randn(7, 2)), t(rng.randn(7, 1))
+    eps = [t(rng.randn(2, 7, 2)), t(rng.randn(2, 7, 1))]
+    _, g = O.elbo_and_grad(layers, lik, X, Y, 2, eps, num_data=21)
+    lv = O.leaves(layers, lik)
+    for name in ("l0.g0.Z", "l0.q_sqrt", "l1.g0.kern.lengthscales", "l0.g0.kern.white", "l1.q_mu", "lik.variance"):
+        p = lv[name]
+        flat = p.view(-1)
+        for idx in (0, flat.numel() - 1):
+            if name.endswith("q_sqrt"):
+                idx = 0 if idx == 0 else flat.numel() - 1   # both on the lower triangle (first / last diagonal entry)
+            old = float(flat[idx])
+            h = 1e-6 * max(1.0, abs(old))
+            flat[idx] = old + h
+            fp = float(O.elbo(layers, lik, X, Y, 2, eps, num_data=21))
+            flat[idx] = old - h
+            fm = float(O.elbo(layers, lik, X, Y, 2, eps, num_data=21))
+            flat[idx] = old
+            fd = (fp - fm) / (2 * h)
+            an = float(g[name].reshape(-1)[idx])
+            assert abs(fd - an) < 1e-5 * max(1.0, abs(an)), (name, idx, fd, an)
+
+
+def test_multitask_predict_y_shape_quirk():
+    """tests/test_multitask_dsdgp.py:165-173: 10 test rows, two likelihoods -> (1, 20, 1)."""
+    layer = _layer(4, 1, 1, mean=False)
+    layer["groups"][0]["Z"] = t(np.hstack([np.random.RandomState(0).randn(4, 1), np.zeros((4, 1))]))
+    Xs = t(np.hstack([np.random.RandomState(1).randn(10, 1), np.random.RandomState(2).randint(0, 2, (10, 1))]))
+    lik = {"kind": "switched", "variances": [t(0.1), t(0.2)]}
+    mu, var = O.predict_y([layer], lik, Xs, [torch.zeros(1, 10, 1, dtype=T64)], multitask=True)
+    assert mu.shape == (1, 20, 1) and var.shape == (1, 20, 1)
