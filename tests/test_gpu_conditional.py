@@ -91,9 +91,10 @@ def run_conditional(cuda, M, D, R, N, kind, S=1, white=1e-5, linear=True, backwa
     if backward:
         gX = torch.zeros(N * S, D, dtype=torch.float64, device=dev)
         Xrep = Xd.repeat(S, 1).contiguous()                  # d/dX per flattened row: give every row its own X row
+        gmd, gvd, gFd = gm_in.to(dev), gv_in.to(dev), gF.to(dev)   # keep the device copies alive across the call
         C.check(lib.dgp_cond_backward(ctypes.byref(d), C.ptr(ws), C.ptr(Xrep), n, n, C.ptr(Asave), C.ptr(mean),
-                                      C.ptr(varo), C.ptr(F), R, C.ptr(gm_in.to(dev)), C.ptr(gv_in.to(dev)),
-                                      C.ptr(gF.to(dev)), R, C.ptr(gX), 0, st), "backward")
+                                      C.ptr(varo), C.ptr(F), R, C.ptr(gmd), C.ptr(gvd), C.ptr(gFd), R, C.ptr(gX), 0,
+                                      st), "backward")
         C.check(lib.dgp_cond_backward_gram(ctypes.byref(d), C.ptr(ws), C.ptr(Asave), n, st), "gram")
         gZ = torch.zeros(M, D, dtype=torch.float64, device=dev)
         gth = torch.zeros(2 + D, dtype=torch.float64, device=dev)
