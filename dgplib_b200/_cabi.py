@@ -9,7 +9,7 @@ import os
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libdgp_b200.so")
+LIB_PATH = os.environ.get("DGP_B200_LIB", os.path.join(_HERE, "libdgp_b200.so"))   # override: A/B builds only
 
 DGP_KIND_RBF = 0
 DGP_KIND_MATERN52 = 1

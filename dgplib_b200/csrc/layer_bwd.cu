@@ -14,6 +14,10 @@
 // k_gram     : 64x64 output tiles x split-K over the rows, fp64 DMMA, partials per split (no atomics).
 #include "stream_gemm.cuh"
 
+#ifndef DGP_BWD_WN
+#define DGP_BWD_WN 2   // consumer warp grid is 4 x WN
+#endif
+
 namespace dgp {
 
 struct BwdArgs {
@@ -481,17 +485,17 @@ extern "C" int dgp_cond_backward(const dgp_cond_desc* d, void* ws, const double*
     a.gX = gX; a.accumulate_gX = accumulate_gX;
     a.dKuf = ws_ptr<double>(ws, w.dKuf); a.gmv = ws_ptr<double>(ws, w.gmv);
     a.part = ws_ptr<double>(ws, w.part); a.npart = w.npart;
-#define DGP_TRY_BWD(NTV, STG)                                                         \
+#define DGP_TRY_BWD(WNV, NTV, STG)                                                        \
     {                                                                                 \
-        using C = TileCfg<4, 2, NTV, STG>;                                            \
+        using C = TileCfg<4, WNV, NTV, STG>;                                              \
         a.ntiles = (int)((n_rows + C::NT - 1) / C::NT);                               \
         rc = launch_bwd<C>(a, st);                                                    \
         if (rc != DGP_ERR_UNSUPPORTED) return rc;                                     \
     }
     if (w.Mpad <= 256) {
-        DGP_TRY_BWD(32, 4) DGP_TRY_BWD(32, 3) DGP_TRY_BWD(32, 2)
+        DGP_TRY_BWD(DGP_BWD_WN, 32, 4) DGP_TRY_BWD(DGP_BWD_WN, 32, 3) DGP_TRY_BWD(DGP_BWD_WN, 32, 2)
     } else {
-        DGP_TRY_BWD(16, 4) DGP_TRY_BWD(16, 3) DGP_TRY_BWD(16, 2)
+        DGP_TRY_BWD(2, 16, 4) DGP_TRY_BWD(2, 16, 3) DGP_TRY_BWD(2, 16, 2)
     }
 #undef DGP_TRY_BWD
     rc = DGP_ERR_UNSUPPORTED;

@@ -11,6 +11,10 @@
 // flattened samples (dgplib/layers.py:84-87), and normal_sample's diag branch (dgplib/utils.py:25-27).
 #include "stream_gemm.cuh"
 
+#ifndef DGP_FWD_WN
+#define DGP_FWD_WN 2   // consumer warp grid is 4 x WN
+#endif
+
 namespace dgp {
 
 struct FwdArgs {
@@ -143,9 +147,19 @@ __global__ void __launch_bounds__(C::NTHREADS, 1) k_cond_fwd(const __grid_consta
             const double znm = a.zn[m];
             const int ztm = a.ztask[m];
             const double* zrow = a.Zs + (size_t)m * Dp;
+            // the A fragments of this 8-row tile are reused by every column tile: keep them in registers (D <= 16)
+            double az[4];
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk) az[kk] = (kk * 4 < Dp) ? zrow[kk * 4 + t] : 0.0;
             for (int nt = 0; nt < C::NT / 8; ++nt) {
                 double c[2] = {0.0, 0.0};
-                for (int kk = 0; kk < Dp / 4; ++kk) dmma884(c, zrow[kk * 4 + t], xs[(nt * 8 + g) * xld + kk * 4 + t]);
+                if (Dp <= 16) {
+#pragma unroll
+                    for (int kk = 0; kk < 4; ++kk)
+                        if (kk * 4 < Dp) dmma884(c, az[kk], xs[(nt * 8 + g) * xld + kk * 4 + t]);
+                } else {
+                    for (int kk = 0; kk < Dp / 4; ++kk) dmma884(c, zrow[kk * 4 + t], xs[(nt * 8 + g) * xld + kk * 4 + t]);
+                }
 #pragma unroll
                 for (int e = 0; e < 2; ++e) {
                     const int n = nt * 8 + 2 * t + e;
@@ -316,19 +330,19 @@ extern "C" int dgp_cond_forward(const dgp_cond_desc* d, const void* ws, const do
     cudaStream_t st = (cudaStream_t)stream;
     // row-tile width by inducing count (the A tile must fit in shared memory); ring depth 4, or 3 / 2 when the
     // per-row side buffers (large D) leave less room
-#define DGP_TRY_FWD(NTV, STG)                                                         \
+#define DGP_TRY_FWD(WNV, NTV, STG)                                                        \
     {                                                                                 \
-        using C = TileCfg<4, 2, NTV, STG>;                                            \
+        using C = TileCfg<4, WNV, NTV, STG>;                                              \
         a.ntiles = (int)((n_rows + C::NT - 1) / C::NT);                               \
         rc = launch_fwd<C>(a, st);                                                    \
         if (rc != DGP_ERR_UNSUPPORTED) return rc;                                     \
     }
     if (w.Mpad <= 256) {
-        DGP_TRY_FWD(64, 4) DGP_TRY_FWD(64, 3) DGP_TRY_FWD(64, 2)
+        DGP_TRY_FWD(DGP_FWD_WN, 64, 4) DGP_TRY_FWD(DGP_FWD_WN, 64, 3) DGP_TRY_FWD(DGP_FWD_WN, 64, 2)
     } else if (w.Mpad <= 512) {
-        DGP_TRY_FWD(32, 4) DGP_TRY_FWD(32, 3) DGP_TRY_FWD(32, 2)
+        DGP_TRY_FWD(DGP_FWD_WN, 32, 4) DGP_TRY_FWD(DGP_FWD_WN, 32, 3) DGP_TRY_FWD(DGP_FWD_WN, 32, 2)
     } else {
-        DGP_TRY_FWD(16, 4) DGP_TRY_FWD(16, 3) DGP_TRY_FWD(16, 2)
+        DGP_TRY_FWD(2, 16, 4) DGP_TRY_FWD(2, 16, 3) DGP_TRY_FWD(2, 16, 2)
     }
 #undef DGP_TRY_FWD
     return DGP_ERR_UNSUPPORTED;

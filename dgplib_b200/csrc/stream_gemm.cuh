@@ -158,22 +158,31 @@ __device__ __forceinline__ void run_phase(Pipe& p, int nseg, SegFn segfn, EpiFn 
 #pragma unroll
             for (int j = 0; j < C::NJ; ++j) wv[j] = wts[(wn * C::NJ * 8 + j * 8 + g) * wld + seg.r];
         }
+        // Active 8-row tiles of this warp per chunk: a contiguous range [qlo, qhi) of its 4 interleaved tiles (tile q
+        // starts at row rbase + 32 q).  Skipping uses real (warp-uniform) branches: a predicated-off DMMA still occupies
+        // the fp64 tensor pipe for its full 16 cycles (measured with ncu), so predication would save nothing.
+        const int rbase = row0 + wm * 8;
+        int qmax = (Mpad - rbase + 31) >> 5;          // tiles with first row < Mpad
+        qmax = qmax < 0 ? 0 : (qmax > 4 ? 4 : qmax);
+        const double* Bw0 = Bt + (wn * C::NJ * 8 + g) * ldb + t;
+        const int aoff = (wm * 8 + g) * C::WLD + t;
         for (int kc = seg.kc0; kc < seg.kc1; ++kc) {
-            // Active 8-row tiles of this warp for the chunk: a contiguous range [qlo, qhi) of its 4 interleaved tiles.
-            // Skipping uses real (warp-uniform) branches: a predicated-off DMMA still occupies the fp64 tensor pipe
-            // for its full 16 cycles (measured with ncu), so predication would save nothing.
             const int k0 = kc * C::KC;
-            int qlo = 0, qhi = 4;
-            while (qhi > 0 && row0 + ((qhi - 1) * C::WM + wm) * 8 >= Mpad) --qhi;
-            if (MASK == MASK_LOWER)
-                while (qlo < qhi && row0 + (qlo * C::WM + wm) * 8 + 7 < k0) ++qlo;
-            if (MASK == MASK_UPPER)
-                while (qhi > qlo && row0 + ((qhi - 1) * C::WM + wm) * 8 > k0 + C::KC - 1) --qhi;
-            const double* Bw = Bt + (wn * C::NJ * 8 + g) * ldb + k0 + t;
-            const double* Aw = p.stages + (size_t)p.stage * C::STAGE_DOUBLES + (wm * 8 + g) * C::WLD + t;
+            int qlo = 0, qhi = qmax;
+            if (MASK == MASK_LOWER) {                 // tile active iff rbase + 32 q + 7 >= k0
+                qlo = (k0 - rbase + 24) >> 5;
+                qlo = qlo < 0 ? 0 : qlo;
+            }
+            if (MASK == MASK_UPPER) {                 // tile active iff rbase + 32 q <= k0 + 15
+                const int h = ((k0 + 15 - rbase) >> 5) + 1;
+                qhi = h < qmax ? (h < 0 ? 0 : h) : qmax;
+            }
+            const double* Bw = Bw0 + k0;
+            const double* Aw = p.stages + (size_t)p.stage * C::STAGE_DOUBLES + aoff;
             mbar_wait(&p.full[p.stage], p.round & 1);
-            switch ((qlo << 3) | qhi) {
-                case (0 << 3) | 4: chunk_mma<C, 0, 4, WEIGHTED>(acc, Aw, Bw, ldb, wv); break;
+            if (qlo == 0 && qhi == 4) {
+                chunk_mma<C, 0, 4, WEIGHTED>(acc, Aw, Bw, ldb, wv);
+            } else if (qlo < qhi) switch ((qlo << 3) | qhi) {
                 case (1 << 3) | 4: chunk_mma<C, 1, 4, WEIGHTED>(acc, Aw, Bw, ldb, wv); break;
                 case (2 << 3) | 4: chunk_mma<C, 2, 4, WEIGHTED>(acc, Aw, Bw, ldb, wv); break;
                 case (3 << 3) | 4: chunk_mma<C, 3, 4, WEIGHTED>(acc, Aw, Bw, ldb, wv); break;
@@ -183,7 +192,7 @@ __device__ __forceinline__ void run_phase(Pipe& p, int nseg, SegFn segfn, EpiFn 
                 case (1 << 3) | 3: chunk_mma<C, 1, 3, WEIGHTED>(acc, Aw, Bw, ldb, wv); break;
                 case (1 << 3) | 2: chunk_mma<C, 1, 2, WEIGHTED>(acc, Aw, Bw, ldb, wv); break;
                 case (2 << 3) | 3: chunk_mma<C, 2, 3, WEIGHTED>(acc, Aw, Bw, ldb, wv); break;
-                default: break;  // qlo == qhi: nothing to do for this warp in this chunk
+                default: break;
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(&p.empty[p.stage]);   // this warp is done reading the slot
