@@ -77,7 +77,7 @@ __global__ void __launch_bounds__(C::NTHREADS, 1) k_cond_bwd(const __grid_consta
     uint64_t* bar = reinterpret_cast<uint64_t*>(smem + L.bar);
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L.bars);
 
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
     const int Mpad = a.Mpad, Dp = a.Dp, ldb = L.ldb, xld = L.xld, R = d.R;
     const int nb = (Mpad + C::MB - 1) / C::MB;
     const int thd = 2 + d.D;
@@ -239,49 +239,170 @@ __global__ void __launch_bounds__(C::NTHREADS, 1) k_cond_bwd(const __grid_consta
             bulk_s2g(a.dKuf + (size_t)(n0 + tid) * Mpad, Dt + tid * ldb, (uint32_t)(Mpad * sizeof(double)));
             bulk_commit();
         }
-        // ---- d q_mu partial: sum_n A[n][m] g_mean[n][r]   (reads Bt while the store drains)
-        for (int idx = tid; idx < d.M * R; idx += C::NCONS) {
-            const int m = idx / R, r = idx % R;
-            double s = 0.0;
-            for (int n = 0; n < nvalid; ++n) s = fma(Bt[n * ldb + m], gm[n * R + r], s);
-            pqmu[idx] += s;
+        // ---- d q_mu partial: sum_n A[n][m] g_mean[n][r] on the tensor cores (reads Bt while the store drains).
+        //      Output tile rows = inducing index m, columns = output r, K = the NT rows of the tile.
+        for (int mt = warp; mt < Mpad / 8; mt += C::NWARPS) {
+            const int m0 = mt * 8;
+            for (int r0 = 0; r0 < R; r0 += 8) {
+                double c[2] = {0.0, 0.0};
+#pragma unroll
+                for (int ks = 0; ks < C::NT / 4; ++ks) {
+                    const int n = ks * 4 + t;
+                    const double bv = (r0 + g < R) ? gm[n * R + r0 + g] : 0.0;
+                    dmma884(c, Bt[n * ldb + m0 + g], bv);
+                }
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    const int m = m0 + g, r = r0 + 2 * t + e;
+                    if (m < d.M && r < R) pqmu[m * R + r] += c[e];
+                }
+            }
         }
         bulk_wait_read0();
         consumer_sync<C>();
 
         // ---- Dt <- Gr2 = dKuf . variance . k'(r2);  per-row sums: rs = sum_m Gr2, dv = sum_m dKuf k(r2)/variance
-        for (int n = warp; n < C::NT; n += C::NWARPS) {
-            const int tx = xtask[n];
-            double srs = 0.0, sdv = 0.0;
-            const double varn = (tx >= 0) ? d.theta[(size_t)tx * thd] : 0.0;
-            const int kind = d.kind[tx < 0 ? 0 : tx];
-            for (int m = lane; m < Mpad; m += 32) {
-                double out = 0.0;
-                if (n < nvalid && m < d.M && tx >= 0 && a.ztask[m] == tx) {
-                    const double* zr = a.Zs + (size_t)m * Dp;
-                    double c = 0.0;
-                    for (int k = 0; k < Dp; ++k) c = fma(zr[k], xs[n * xld + k], c);
-                    const double r2 = a.zn[m] + xn[n] - 2.0 * c;
-                    double kv, dk;
-                    kern_val_grad(kind, r2, kv, dk);
-                    const double gk = Dt[n * ldb + m];
-                    sdv = fma(gk, kv, sdv);
-                    out = gk * varn * dk;
-                    srs += out;
+        if (d.T == 1) {
+            // fast path (one kernel for every row): cross term z.x on the tensor cores as in the forward pass, the
+            // elementwise part in the accumulator layout (8 independent exp chains per thread); rs comes out of the T1
+            // contraction below (ones column), and only the tile total of dv is needed (all rows share the task).
+            const double varn = d.theta[0];
+            const int kind = d.kind[0];
+            double sdv = 0.0;
+            for (int mt = warp; mt < Mpad / 8; mt += C::NWARPS) {
+                const int m = mt * 8 + g;
+                const double znm = a.zn[m];
+                const double* zrow = a.Zs + (size_t)m * Dp;
+                double az[4];
+#pragma unroll
+                for (int kk = 0; kk < 4; ++kk) az[kk] = (kk * 4 < Dp) ? zrow[kk * 4 + t] : 0.0;
+#pragma unroll
+                for (int nt = 0; nt < C::NT / 8; ++nt) {
+                    double c[2] = {0.0, 0.0};
+                    if (Dp <= 16) {
+#pragma unroll
+                        for (int kk = 0; kk < 4; ++kk)
+                            if (kk * 4 < Dp) dmma884(c, az[kk], xs[(nt * 8 + g) * xld + kk * 4 + t]);
+                    } else {
+                        for (int kk = 0; kk < Dp / 4; ++kk) dmma884(c, zrow[kk * 4 + t], xs[(nt * 8 + g) * xld + kk * 4 + t]);
+                    }
+#pragma unroll
+                    for (int e = 0; e < 2; ++e) {
+                        const int n = nt * 8 + 2 * t + e;
+                        double out = 0.0;
+                        if (m < d.M && n < nvalid) {
+                            const double r2 = znm + xn[n] - 2.0 * c[e];
+                            double kv, dk;
+                            kern_val_grad(kind, r2, kv, dk);
+                            const double gk = Dt[n * ldb + m];
+                            sdv = fma(gk, kv, sdv);
+                            out = gk * varn * dk;
+                        }
+                        Dt[n * ldb + m] = out;
+                    }
                 }
-                Dt[n * ldb + m] = out;
             }
-            srs = warp_sum(srs);
             sdv = warp_sum(sdv);
-            if (lane == 0) { rs[n] = srs; dv[n] = sdv; }
+            if (lane == 0) rowq[warp] = sdv;          // rowq is free here; reduced in warp order below
+            consumer_sync<C>();
+            if (tid < C::NT) {
+                double tot = 0.0;
+                if (tid == 0)
+                    for (int w = 0; w < C::NWARPS; ++w) tot += rowq[w];
+                dv[tid] = tot;                          // the whole tile's sum is booked on row 0
+            }
+        } else {
+            for (int n = warp; n < C::NT; n += C::NWARPS) {
+                const int tx = xtask[n];
+                double srs = 0.0, sdv = 0.0;
+                const double varn = (tx >= 0) ? d.theta[(size_t)tx * thd] : 0.0;
+                const int kind = d.kind[tx < 0 ? 0 : tx];
+                for (int m = lane; m < Mpad; m += 32) {
+                    double out = 0.0;
+                    if (n < nvalid && m < d.M && tx >= 0 && a.ztask[m] == tx) {
+                        const double* zr = a.Zs + (size_t)m * Dp;
+                        double c = 0.0;
+                        for (int k = 0; k < Dp; ++k) c = fma(zr[k], xs[n * xld + k], c);
+                        const double r2 = a.zn[m] + xn[n] - 2.0 * c;
+                        double kv, dk;
+                        kern_val_grad(kind, r2, kv, dk);
+                        const double gk = Dt[n * ldb + m];
+                        sdv = fma(gk, kv, sdv);
+                        out = gk * varn * dk;
+                        srs += out;
+                    }
+                    Dt[n * ldb + m] = out;
+                }
+                srs = warp_sum(srs);
+                sdv = warp_sum(sdv);
+                if (lane == 0) { rs[n] = srs; dv[n] = sdv; }
+            }
         }
         consumer_sync<C>();
 
-        // ---- T1[n][k] = sum_m Gr2[n][m] zs[m][k]  ->  gX, lengthscale row terms
+        // ---- T1[n][k] = sum_m Gr2[n][m] zs[m][k] on the tensor cores; the K range (inducing index) is split over
+        //      KQ warp groups whose partial tiles are summed in fixed order through the (now free) A-tile buffer.
+        {
+            constexpr int NTT = C::NT / 8;                 // 8-row tiles of the row tile
+            constexpr int KQ = C::NWARPS / NTT;            // K splits
+            const int nt4 = warp % NTT, kq = warp / NTT;
+            const int kspan = Mpad / KQ;                   // Mpad is a multiple of 64, KQ of {2, 4}
+            double* t1p = Bt;                              // scratch [KQ][NT][Dp + 1]; column Dp = row sums of Gr2
+            for (int d0 = 0; d0 < Dp + 1; d0 += 8) {
+                double c[2] = {0.0, 0.0};
+                for (int ks = 0; ks < kspan / 4; ++ks) {
+                    const int m = kq * kspan + ks * 4 + t;
+                    const double bv = (d0 + g < Dp) ? a.Zs[(size_t)m * Dp + d0 + g] : (d0 + g == Dp ? 1.0 : 0.0);
+                    dmma884(c, Dt[(nt4 * 8 + g) * ldb + m], bv);
+                }
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    const int k = d0 + 2 * t + e;
+                    if (k <= Dp) t1p[(kq * C::NT + nt4 * 8 + g) * (Dp + 1) + k] = c[e];
+                }
+            }
+        }
+        // ---- T2z[m][k] = sum_n Gr2[n][m] xs[n][k] and cs[m] = sum_n Gr2[n][m] (a column of ones appended to xs)
+        for (int mt = warp; mt < Mpad / 8; mt += C::NWARPS) {
+            const int m0 = mt * 8;
+            for (int d0 = 0; d0 < Dp + 1; d0 += 8) {
+                double c[2] = {0.0, 0.0};
+                const int kcol = d0 + g;
+#pragma unroll
+                for (int ks = 0; ks < C::NT / 4; ++ks) {
+                    const int n = ks * 4 + t;
+                    const double bv = (kcol < Dp) ? xs[n * xld + kcol] : (kcol == Dp ? 1.0 : 0.0);
+                    dmma884(c, Dt[n * ldb + m0 + g], bv);
+                }
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    const int m = m0 + g, k = d0 + 2 * t + e;
+                    if (m < d.M) {
+                        if (k < Dp) pT2z[m * Dp + k] += c[e];
+                        else if (k == Dp) pcs[m] += c[e];
+                    }
+                }
+            }
+        }
+        consumer_sync<C>();
+        // ---- row sums of Gr2 from the ones column (fast path; the general path computed them above)
+        if (d.T == 1) {
+            constexpr int KQ = C::NWARPS / (C::NT / 8);
+            if (tid < C::NT) {
+                double r = 0.0;
+#pragma unroll
+                for (int q = 0; q < KQ; ++q) r += Bt[(q * C::NT + tid) * (Dp + 1) + Dp];
+                rs[tid] = r;
+            }
+            consumer_sync<C>();
+        }
+        // ---- finish T1 -> gX and the lengthscale row terms
         for (int idx = tid; idx < C::NT * Dp; idx += C::NCONS) {
             const int n = idx / Dp, k = idx % Dp;
+            constexpr int KQ = C::NWARPS / (C::NT / 8);
             double t1 = 0.0;
-            for (int m = 0; m < d.M; ++m) t1 = fma(Dt[n * ldb + m], a.Zs[(size_t)m * Dp + k], t1);
+#pragma unroll
+            for (int q = 0; q < KQ; ++q) t1 += Bt[(q * C::NT + n) * (Dp + 1) + k];
             const double xv = xs[n * xld + k];
             rowq[n * nq + 2 + k] = xv * xv * rs[n] - 2.0 * xv * t1;
             const long long gn = n0 + n;
@@ -315,18 +436,6 @@ __global__ void __launch_bounds__(C::NTHREADS, 1) k_cond_bwd(const __grid_consta
             if (n < nvalid) for (int r = 0; r < R; ++r) s += gv[n * R + r];
             rowq[n * nq + 0] = dv[n] + s;
             rowq[n * nq + 1] = s;
-        }
-        // T2z[m][k] = sum_n Gr2[n][m] xs[n][k],  cs[m] = sum_n Gr2[n][m]
-        for (int idx = tid; idx < d.M * Dp; idx += C::NCONS) {
-            const int m = idx / Dp, k = idx % Dp;
-            double s = 0.0;
-            for (int n = 0; n < nvalid; ++n) s = fma(Dt[n * ldb + m], xs[n * xld + k], s);
-            pT2z[idx] += s;
-        }
-        for (int m = tid; m < d.M; m += C::NCONS) {
-            double s = 0.0;
-            for (int n = 0; n < nvalid; ++n) s += Dt[n * ldb + m];
-            pcs[m] += s;
         }
         consumer_sync<C>();
         // per-task hyper-parameter row terms, summed in row order by one thread per (task, column) (deterministic);

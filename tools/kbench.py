@@ -41,3 +41,9 @@ for name, fn in (("fwd", fwd), ("bwd", bwd), ("gram", gram), ("prep", prep), ("t
         e0.record(); fn(); e1.record(); e1.synchronize(); ts.append(e0.elapsed_time(e1))
     out.append(f"{name} {min(ts):.3f}ms ({fl[name] / min(ts) * 1e-9:.1f}TF)")
 print(os.environ.get("DGP_B200_LIB", "default").split("/")[-1], f"M={M} D={D} R={R} N={N}:", " | ".join(out), flush=True)
+if os.environ.get("DGP_PHASES"):
+    bwd(); torch.cuda.synchronize()
+    ph = ws[256:256 + 96].view(torch.float64).cpu().numpy()
+    names = ["top-sync", "prologue", "A-wait", "dA", "dK", "store+dqmu", "store-wait", "Gr2", "T1/T2z", "finish"]
+    tot = ph[:10].sum()
+    print("bwd phases (cycles of CTA 0, all tiles):", {n: f"{v:.0f} ({100*v/tot:.1f}%)" for n, v in zip(names, ph[:10])})
