@@ -20,6 +20,12 @@
 
 namespace dgp {
 
+#ifdef DGP_PROFILE_PHASES
+#define PH(i) do { if (tid == 0) { long long now_ = clock64(); ph[i] += now_ - tlast; tlast = now_; } } while (0)
+#else
+#define PH(i) do {} while (0)
+#endif
+
 struct BwdArgs {
     dgp_cond_desc d;
     int Mpad, Dp;
@@ -29,7 +35,7 @@ struct BwdArgs {
     const double* A_save; const double* mean; const double* var; const double* F; int ldf;
     const double* g_mean_in; const double* g_var_in; const double* g_F; int ldgf;
     double* gX; int accumulate_gX;
-    double* dKuf; double* gmv; double* part; int npart;
+    double* dKuf; double* gmv; double* part; int npart; double* scal;
     int ntiles;
 };
 
@@ -128,12 +134,16 @@ __global__ void __launch_bounds__(C::NTHREADS, 1) k_cond_bwd(const __grid_consta
         return;
     }
     uint32_t parity = 0;
+#ifdef DGP_PROFILE_PHASES
+    long long ph[12] = {0}; long long tlast = clock64();
+#endif
 
     for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
         const long long n0 = (long long)tile * C::NT;
         const int nvalid = (int)((a.n_rows - n0 < C::NT) ? (a.n_rows - n0) : C::NT);
         bulk_wait_read0();   // previous tile's dKuf store has finished reading Dt
         consumer_sync<C>();  // every warp is done with the previous tile
+        PH(0);
 
         // ---- A tile: HBM -> Bt by bulk async copies, completion on the mbarrier
         if (tid == 0) {
@@ -184,8 +194,10 @@ __global__ void __launch_bounds__(C::NTHREADS, 1) k_cond_bwd(const __grid_consta
             gm[idx] = gmean;
             gv[idx] = gvar;
         }
+        PH(1);
         mbar_wait(bar, parity);
         parity ^= 1;
+        PH(2);
         // (run_phase starts with a consumer barrier)
 
         // ---- phase dA: Dt = q_mu g_mean^T + 2 sum_r (S_r - I) (A . g_var_r)
@@ -212,6 +224,7 @@ __global__ void __launch_bounds__(C::NTHREADS, 1) k_cond_bwd(const __grid_consta
             };
             run_phase<C, MASK_DENSE, true>(pipe, nb * R, seg_dA, epi, Bt, ldb, Mpad, gv, R);
         }
+        PH(3);
 
         // ---- phase dK: Dt <- Lm^-T Dt, block rows top-down, in place
         {
@@ -232,6 +245,7 @@ __global__ void __launch_bounds__(C::NTHREADS, 1) k_cond_bwd(const __grid_consta
             run_phase<C, MASK_UPPER, false>(pipe, nb, seg_dK, epi, Dt, ldb, Mpad, nullptr, 0);
         }
         consumer_sync<C>();
+        PH(4);
 
         // ---- dKuf tile -> HBM (for the Gram kernel)
         fence_async_smem();
@@ -258,8 +272,10 @@ __global__ void __launch_bounds__(C::NTHREADS, 1) k_cond_bwd(const __grid_consta
                 }
             }
         }
+        PH(5);
         bulk_wait_read0();
         consumer_sync<C>();
+        PH(6);
 
         // ---- Dt <- Gr2 = dKuf . variance . k'(r2);  per-row sums: rs = sum_m Gr2, dv = sum_m dKuf k(r2)/variance
         if (d.T == 1) {
@@ -340,6 +356,7 @@ __global__ void __launch_bounds__(C::NTHREADS, 1) k_cond_bwd(const __grid_consta
         }
         consumer_sync<C>();
 
+        PH(7);
         // ---- T1[n][k] = sum_m Gr2[n][m] zs[m][k] on the tensor cores; the K range (inducing index) is split over
         //      KQ warp groups whose partial tiles are summed in fixed order through the (now free) A-tile buffer.
         {
@@ -385,6 +402,7 @@ __global__ void __launch_bounds__(C::NTHREADS, 1) k_cond_bwd(const __grid_consta
             }
         }
         consumer_sync<C>();
+        PH(8);
         // ---- row sums of Gr2 from the ones column (fast path; the general path computed them above)
         if (d.T == 1) {
             constexpr int KQ = C::NWARPS / (C::NT / 8);
@@ -447,8 +465,12 @@ __global__ void __launch_bounds__(C::NTHREADS, 1) k_cond_bwd(const __grid_consta
                 if (xtask[n] == tk) s += rowq[n * nq + c];
             pth[idx] += s;
         }
+        PH(9);
     }
     bulk_wait_read0();
+#ifdef DGP_PROFILE_PHASES
+    if (blockIdx.x == 0 && tid == 0) for (int i = 0; i < 12; ++i) a.scal[i] = (double)ph[i];
+#endif
 }
 
 template <class C>
@@ -468,6 +490,7 @@ static int launch_bwd(const BwdArgs& a, cudaStream_t st) {
 
 // ------------------------------------------------------------------------------------------------ Gram kernel
 // out[s][mat][m1][m2] += sum_{n in split s} w_mat[n] P_mat[n][m1] A[n][m2]   for 64x64 tiles with tile(m1) >= tile(m2)
+//   (inside diagonal tiles the strictly-upper 32x32 quadrant is skipped: results are consumed at 32-block granularity)
 //   mat <  R : P = A,    w = g_var[:, mat]      (G_r, symmetric)
 //   mat == R : P = dKuf, w = 1                  (P = dKuf^T A)
 struct GramArgs {
@@ -497,6 +520,7 @@ __global__ void __launch_bounds__(GR_THREADS, 4) k_gram(GramArgs a) {
     long long nend = nbeg + a.rows_per_split;
     if (nend > a.n_rows) nend = a.n_rows;
     const int nchunks = nend > nbeg ? (int)((nend - nbeg + GR_KC - 1) / GR_KC) : 0;
+    const bool skip_mma = (bi == bj) && (wn > wm);
 
     double acc[4][4][2];
 #pragma unroll
@@ -537,6 +561,7 @@ __global__ void __launch_bounds__(GR_THREADS, 4) k_gram(GramArgs a) {
         const double* Q = Qs[stage];
         const double* W = wsm[stage];
         stage = (stage + 1 == GR_STAGES) ? 0 : stage + 1;
+        if (skip_mma) continue;     // strictly-upper 32x32 quadrant of a diagonal tile: never read downstream
 #pragma unroll
         for (int kk = 0; kk < 4; ++kk) {
             const double w = W[kk * 4 + t];
@@ -552,7 +577,7 @@ __global__ void __launch_bounds__(GR_THREADS, 4) k_gram(GramArgs a) {
         }
     }
     cp_async_wait<0>();
-    if (nchunks == 0) return;
+    if (nchunks == 0 || skip_mma) return;
     double* out = a.gram + ((size_t)split * (R + 1) + mat) * Mpad * Mpad;
 #pragma unroll
     for (int q = 0; q < 4; ++q)
@@ -593,7 +618,7 @@ extern "C" int dgp_cond_backward(const dgp_cond_desc* d, void* ws, const double*
     a.g_mean_in = g_mean_in; a.g_var_in = g_var_in; a.g_F = g_F; a.ldgf = ldgf;
     a.gX = gX; a.accumulate_gX = accumulate_gX;
     a.dKuf = ws_ptr<double>(ws, w.dKuf); a.gmv = ws_ptr<double>(ws, w.gmv);
-    a.part = ws_ptr<double>(ws, w.part); a.npart = w.npart;
+    a.part = ws_ptr<double>(ws, w.part); a.npart = w.npart; a.scal = ws_ptr<double>(ws, w.scal);
 #define DGP_TRY_BWD(WNV, NTV, STG)                                                        \
     {                                                                                 \
         using C = TileCfg<4, WNV, NTV, STG>;                                              \

@@ -17,6 +17,13 @@
 
 namespace dgp {
 
+// optional per-phase cycle counters of CTA 0 (debug builds: make EXTRA=-DDGP_PROFILE_PHASES; read by tools/kbench.py)
+#ifdef DGP_PROFILE_PHASES
+#define PH(i) do { if (tid == 0) { long long now_ = clock64(); ph[i] += now_ - tlast; tlast = now_; } } while (0)
+#else
+#define PH(i) do {} while (0)
+#endif
+
 struct FwdArgs {
     dgp_cond_desc d;
     int Mpad, Dp;
@@ -24,7 +31,7 @@ struct FwdArgs {
     const double* Linv; const double* LqT; size_t tl;   // tiled copies (stream_gemm.cuh)
     const double* X; long long x_rows, n_rows;
     const double* eps; unsigned long long seed, row_offset; long long rows_per_sample, sample_stride;
-    double* mean; double* var; double* F; int ldf; double* A_save;
+    double* mean; double* var; double* F; int ldf; double* A_save; double* scal;
     int ntiles;
 };
 
@@ -110,12 +117,16 @@ __global__ void __launch_bounds__(C::NTHREADS, 1) k_cond_fwd(const __grid_consta
         return;
     }
 
+#ifdef DGP_PROFILE_PHASES
+    long long ph[12] = {0}; long long tlast = clock64();
+#endif
     for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
         const long long n0 = (long long)tile * C::NT;
         // the previous tile's bulk store of Bt must have finished reading shared memory, and every warp must be done
         // with the previous tile, before Bt / xs are overwritten
         bulk_wait_read0();
         consumer_sync<C>();
+        PH(0);
 
         // ---- tile setup: scaled inputs, norms, task ids, Kdiag
         for (int n = tid; n < C::NT; n += C::NCONS) {
@@ -140,6 +151,7 @@ __global__ void __launch_bounds__(C::NTHREADS, 1) k_cond_fwd(const __grid_consta
             kd[n] = (tk < 0) ? 0.0 : th[0] + th[1];  // Stationary.Kdiag + White.Kdiag
         }
         consumer_sync<C>();
+        PH(1);
 
         // ---- phase K: Bt[n][m] = k(z_m, x_n); cross term z.x on the tensor cores
         for (int mt = warp; mt < Mpad / 8; mt += C::NWARPS) {
@@ -175,6 +187,7 @@ __global__ void __launch_bounds__(C::NTHREADS, 1) k_cond_fwd(const __grid_consta
         }
         // (run_phase starts with a consumer barrier)
 
+        PH(2);
         // ---- phase T: A = Linv * Kuf, in place
         {
             auto epi = [&](Acc<C>& acc, const Seg& sg) {
@@ -194,6 +207,7 @@ __global__ void __launch_bounds__(C::NTHREADS, 1) k_cond_fwd(const __grid_consta
             run_phase<C, MASK_LOWER, false>(pipe, nb, seg_T, epi, Bt, ldb, Mpad, nullptr, 0);
         }
         consumer_sync<C>();
+        PH(3);
 
         // ---- E1: A tile -> HBM; mean = A^T q_mu + mean_fn(x); sumsq = sum_m A^2
         if (a.A_save) {
@@ -226,6 +240,7 @@ __global__ void __launch_bounds__(C::NTHREADS, 1) k_cond_fwd(const __grid_consta
         }
         // (run_phase starts with a consumer barrier: sumsq and the mean stores are ordered before E2)
 
+        PH(4);
         // ---- phase U + E2
         {
             double colsq[C::NJ][2];
@@ -283,8 +298,12 @@ __global__ void __launch_bounds__(C::NTHREADS, 1) k_cond_fwd(const __grid_consta
             };
             run_phase<C, MASK_UPPER, false>(pipe, nb * d.R, seg_U, epi, Bt, ldb, Mpad, nullptr, 0);
         }
+        PH(5);
     }
     bulk_wait_read0();
+#ifdef DGP_PROFILE_PHASES
+    if (blockIdx.x == 0 && tid == 0) for (int i = 0; i < 12; ++i) a.scal[i] = (double)ph[i];
+#endif
 }
 
 template <class C>
@@ -327,6 +346,7 @@ extern "C" int dgp_cond_forward(const dgp_cond_desc* d, const void* ws, const do
     a.rows_per_sample = rows_per_sample > 0 ? rows_per_sample : n_rows;
     a.sample_stride = sample_stride > 0 ? sample_stride : a.rows_per_sample;
     a.mean = mean; a.var = var; a.F = F; a.ldf = ldf; a.A_save = A_save;
+    a.scal = const_cast<double*>(ws_ptr<double>(ws, w.scal));
     cudaStream_t st = (cudaStream_t)stream;
     // row-tile width by inducing count (the A tile must fit in shared memory); ring depth 4, or 3 / 2 when the
     // per-row side buffers (large D) leave less room

@@ -42,8 +42,11 @@ for name, fn in (("fwd", fwd), ("bwd", bwd), ("gram", gram), ("prep", prep), ("t
     out.append(f"{name} {min(ts):.3f}ms ({fl[name] / min(ts) * 1e-9:.1f}TF)")
 print(os.environ.get("DGP_B200_LIB", "default").split("/")[-1], f"M={M} D={D} R={R} N={N}:", " | ".join(out), flush=True)
 if os.environ.get("DGP_PHASES"):
+    def show(title, names):
+        ph = ws[256:256 + 96].view(torch.float64).cpu().numpy()
+        tot = ph[:len(names)].sum()
+        print(title, {n: f"{v:.0f} ({100 * v / tot:.1f}%)" for n, v in zip(names, ph)}, flush=True)
+    fwd(); torch.cuda.synchronize()
+    show("fwd phases (cycles of CTA 0, all its tiles):", ["top-sync", "setup", "K", "T", "E1", "U+E2"])
     bwd(); torch.cuda.synchronize()
-    ph = ws[256:256 + 96].view(torch.float64).cpu().numpy()
-    names = ["top-sync", "prologue", "A-wait", "dA", "dK", "store+dqmu", "store-wait", "Gr2", "T1/T2z", "finish"]
-    tot = ph[:10].sum()
-    print("bwd phases (cycles of CTA 0, all tiles):", {n: f"{v:.0f} ({100*v/tot:.1f}%)" for n, v in zip(names, ph[:10])})
+    show("bwd phases (cycles of CTA 0, all its tiles):", ["top-sync", "prologue", "A-wait", "dA", "dK", "store+dqmu", "store-wait", "Gr2", "T1/T2z", "finish"])
