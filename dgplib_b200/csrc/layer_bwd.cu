@@ -103,7 +103,7 @@ __global__ void __launch_bounds__(C::NTHREADS, 1) k_cond_bwd(const __grid_consta
         sg.W = a.SmI + (size_t)sg.r * a.tl;
         sg.kc0 = 0;
         sg.kc1 = Mpad / C::KC;
-        sg.flush = (sg.r == R - 1);
+        sg.flush = true;            // per-r flush: the column weights g_var[n, r] are applied to the accumulators
         return sg;
     };
     auto seg_dK = [&](int s) {      // dKuf = LinvT * dA, block rows top-down, in place
@@ -202,7 +202,22 @@ __global__ void __launch_bounds__(C::NTHREADS, 1) k_cond_bwd(const __grid_consta
 
         // ---- phase dA: Dt = q_mu g_mean^T + 2 sum_r (S_r - I) (A . g_var_r)
         {
+            // (S_r - I)(A . g_r) = ((S_r - I) A) . g_r: the weight belongs to the OUTPUT column, so the streamed GEMM runs
+            // unweighted and g_var[n, r] scales the accumulators once per (block row, r).  (Multiplying the B fragments
+            // inside the loop put a DMUL in front of every DMMA group; both share the fp64 pipe, and ncu showed 24 % of
+            // all warp stalls on those DMULs.)
+            Acc<C> tot;
+            tot.clear();
             auto epi = [&](Acc<C>& acc, const Seg& sg) {
+#pragma unroll
+                for (int j = 0; j < C::NJ; ++j)
+#pragma unroll
+                    for (int e = 0; e < 2; ++e) {
+                        const double w = gv[acc_col<C>(j, e) * R + sg.r];
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) tot.v[q][j][e] = fma(w, acc.v[q][j][e], tot.v[q][j][e]);
+                    }
+                if (sg.r != R - 1) return;
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
                     const int row = acc_row<C>(sg.i, q);
@@ -212,7 +227,7 @@ __global__ void __launch_bounds__(C::NTHREADS, 1) k_cond_bwd(const __grid_consta
 #pragma unroll
                             for (int e = 0; e < 2; ++e) {
                                 const int n = acc_col<C>(j, e);
-                                double v = 2.0 * acc.v[q][j][e];
+                                double v = 2.0 * tot.v[q][j][e];
                                 if (row < d.M) {
                                     const double* qm = d.q_mu + (size_t)row * d.ldr + d.col0;
                                     for (int r = 0; r < R; ++r) v = fma(qm[r], gm[n * R + r], v);
@@ -221,8 +236,9 @@ __global__ void __launch_bounds__(C::NTHREADS, 1) k_cond_bwd(const __grid_consta
                             }
                     }
                 }
+                tot.clear();
             };
-            run_phase<C, MASK_DENSE, true>(pipe, nb * R, seg_dA, epi, Bt, ldb, Mpad, gv, R);
+            run_phase<C, MASK_DENSE, false>(pipe, nb * R, seg_dA, epi, Bt, ldb, Mpad, nullptr, 0);
         }
         PH(3);
 
@@ -499,7 +515,13 @@ struct GramArgs {
     const double* A; const double* dKuf; const double* gmv;
     double* gram;
 };
-constexpr int GR_THREADS = 128, GR_STAGES = 3, GR_KC = 16, GR_LD = 68;
+#ifndef DGP_GR_KC
+#define DGP_GR_KC 16
+#endif
+#ifndef DGP_GR_STAGES
+#define DGP_GR_STAGES 3
+#endif
+constexpr int GR_THREADS = 128, GR_STAGES = DGP_GR_STAGES, GR_KC = DGP_GR_KC, GR_LD = 68;
 
 __global__ void __launch_bounds__(GR_THREADS, 4) k_gram(GramArgs a) {
     extern __shared__ __align__(128) double gsm[];
@@ -507,7 +529,9 @@ __global__ void __launch_bounds__(GR_THREADS, 4) k_gram(GramArgs a) {
     double (*Qs)[GR_KC * GR_LD] = reinterpret_cast<double (*)[GR_KC * GR_LD]>(gsm + GR_STAGES * GR_KC * GR_LD);
     double (*wsm)[GR_KC] = reinterpret_cast<double (*)[GR_KC]>(gsm + 2 * GR_STAGES * GR_KC * GR_LD);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
-    const int wm = warp >> 1, wn = warp & 1;
+    // warp w owns rows 16 w .. 16 w + 15 of the 64x64 tile and all 64 columns: two A fragments (scaled by the row
+    // weight: 2 DMUL per 16 DMMA) against eight B fragments per k-step
+    const int wm = warp;
     // tile pair from the linear index over the lower-triangular tile set
     int p = blockIdx.x, bi = 0;
     while ((bi + 1) * (bi + 2) / 2 <= p) ++bi;
@@ -520,20 +544,21 @@ __global__ void __launch_bounds__(GR_THREADS, 4) k_gram(GramArgs a) {
     long long nend = nbeg + a.rows_per_split;
     if (nend > a.n_rows) nend = a.n_rows;
     const int nchunks = nend > nbeg ? (int)((nend - nbeg + GR_KC - 1) / GR_KC) : 0;
-    const bool skip_mma = (bi == bj) && (wn > wm);
+    // diagonal tiles: the strictly-upper 32x32 quadrant (rows < 32, columns >= 32) is never read downstream
+    const int jmax = (bi == bj && wm < 2) ? 4 : 8;
 
-    double acc[4][4][2];
+    double acc[2][8][2];
 #pragma unroll
-    for (int q = 0; q < 4; ++q)
+    for (int q = 0; q < 2; ++q)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) { acc[q][j][0] = 0.0; acc[q][j][1] = 0.0; }
+        for (int j = 0; j < 8; ++j) { acc[q][j][0] = 0.0; acc[q][j][1] = 0.0; }
 
     auto issue = [&](int c, int stage) {
         if (c < nchunks) {
             const long long r0 = nbeg + (long long)c * GR_KC;
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                const int e = tid + q * GR_THREADS;  // 0..511 : row = e/32, 16-byte column = e%32
+            for (int q = 0; q < GR_KC / 4; ++q) {
+                const int e = tid + q * GR_THREADS;  // row = e/32, 16-byte column = e%32
                 const int row = e >> 5, cc = e & 31;
                 long long n = r0 + row;
                 if (n >= nend) n = nend - 1;  // clamped rows get weight 0
@@ -549,44 +574,53 @@ __global__ void __launch_bounds__(GR_THREADS, 4) k_gram(GramArgs a) {
         }
         cp_async_commit();
     };
-    issue(0, 0);
-    issue(1, 1);
-    int stage = 0, lstage = 2;
+#pragma unroll
+    for (int s0 = 0; s0 < GR_STAGES - 1; ++s0) issue(s0, s0);
+    int stage = 0, lstage = GR_STAGES - 1;
     for (int c = 0; c < nchunks; ++c) {
         cp_async_wait<GR_STAGES - 2>();
         __syncthreads();
-        issue(c + 2, lstage);
+        issue(c + GR_STAGES - 1, lstage);
         lstage = (lstage + 1 == GR_STAGES) ? 0 : lstage + 1;
         const double* P = Ps[stage];
         const double* Q = Qs[stage];
         const double* W = wsm[stage];
         stage = (stage + 1 == GR_STAGES) ? 0 : stage + 1;
-        if (skip_mma) continue;     // strictly-upper 32x32 quadrant of a diagonal tile: never read downstream
 #pragma unroll
-        for (int kk = 0; kk < 4; ++kk) {
+        for (int kk = 0; kk < GR_KC / 4; ++kk) {
             const double w = W[kk * 4 + t];
-            double af[4], bf[4];
+            double af[2], bf[8];
 #pragma unroll
-            for (int q = 0; q < 4; ++q) af[q] = P[(kk * 4 + t) * GR_LD + wm * 32 + q * 8 + g] * w;
+            for (int q = 0; q < 2; ++q) af[q] = P[(kk * 4 + t) * GR_LD + wm * 16 + q * 8 + g] * w;
+            if (jmax == 8) {
 #pragma unroll
-            for (int j = 0; j < 4; ++j) bf[j] = Q[(kk * 4 + t) * GR_LD + wn * 32 + j * 8 + g];
+                for (int j = 0; j < 8; ++j) bf[j] = Q[(kk * 4 + t) * GR_LD + j * 8 + g];
 #pragma unroll
-            for (int q = 0; q < 4; ++q)
+                for (int q = 0; q < 2; ++q)
 #pragma unroll
-                for (int j = 0; j < 4; ++j) dmma884(acc[q][j], af[q], bf[j]);
+                    for (int j = 0; j < 8; ++j) dmma884(acc[q][j], af[q], bf[j]);
+            } else {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) bf[j] = Q[(kk * 4 + t) * GR_LD + j * 8 + g];
+#pragma unroll
+                for (int q = 0; q < 2; ++q)
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) dmma884(acc[q][j], af[q], bf[j]);
+            }
         }
     }
     cp_async_wait<0>();
-    if (nchunks == 0 || skip_mma) return;
+    if (nchunks == 0) return;
     double* out = a.gram + ((size_t)split * (R + 1) + mat) * Mpad * Mpad;
 #pragma unroll
-    for (int q = 0; q < 4; ++q)
+    for (int q = 0; q < 2; ++q)
 #pragma unroll
-        for (int j = 0; j < 4; ++j)
+        for (int j = 0; j < 8; ++j)
 #pragma unroll
             for (int e = 0; e < 2; ++e) {
-                const int m1 = bi * 64 + wm * 32 + q * 8 + g;
-                const int m2 = bj * 64 + wn * 32 + j * 8 + 2 * t + e;
+                if (j >= jmax) continue;
+                const int m1 = bi * 64 + wm * 16 + q * 8 + g;
+                const int m2 = bj * 64 + j * 8 + 2 * t + e;
                 out[(size_t)m1 * Mpad + m2] += acc[q][j][e];
             }
 }

@@ -217,26 +217,41 @@ __global__ void __launch_bounds__(C::NTHREADS, 1) k_cond_fwd(const __grid_consta
                 bulk_commit();
             }
         }
-        for (int idx = tid; idx < C::NT * d.R; idx += C::NCONS) {
-            const int n = idx / d.R, r = idx % d.R;
-            const double* arow = Bt + n * ldb;
-            const double* qm = d.q_mu + d.col0 + r;
-            double s = 0.0, a2 = 0.0;
-            for (int m = 0; m < d.M; ++m) {
-                const double av = arow[m];
-                s = fma(av, qm[(size_t)m * d.ldr], s);
-                a2 = fma(av, av, a2);
-            }
-            const long long gn = n0 + n;
-            if (r == 0) sumsq[n] = a2;
-            if (gn < a.n_rows) {
-                if (d.mean_A) {
-                    const double* xr = a.X + (size_t)(gn % a.x_rows) * d.Dx;
-                    for (int k = 0; k < d.Dx; ++k) s = fma(xr[k], d.mean_A[(size_t)k * d.ldr + d.col0 + r], s);
-                    if (d.mean_b) s += d.mean_b[d.col0 + r];
+        // mean[n][r] = sum_m A[n][m] q_mu[m][r] on the tensor cores: one 8-row tile of the row tile per warp pass,
+        // K = inducing index (q_mu fragments straight from global / L1), then + mean_fn(x)
+        for (int nt = warp; nt < C::NT / 8; nt += C::NWARPS) {
+            for (int r0 = 0; r0 < d.R; r0 += 8) {
+                double c[2] = {0.0, 0.0};
+                const bool rok = (r0 + g < d.R);
+                const double* qcol = d.q_mu + d.col0 + r0 + g;
+                for (int m = 0; m < Mpad; m += 4) {
+                    const int mk = m + t;
+                    const double bv = (rok && mk < d.M) ? qcol[(size_t)mk * d.ldr] : 0.0;
+                    dmma884(c, Bt[(nt * 8 + g) * ldb + mk], bv);
                 }
-                a.mean[(size_t)gn * d.ldr + d.col0 + r] = s;
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    const int r = r0 + 2 * t + e;
+                    const long long gn = n0 + nt * 8 + g;
+                    if (r < d.R && gn < a.n_rows) {
+                        double sv = c[e];
+                        if (d.mean_A) {
+                            const double* xr = a.X + (size_t)(gn % a.x_rows) * d.Dx;
+                            for (int k = 0; k < d.Dx; ++k) sv = fma(xr[k], d.mean_A[(size_t)k * d.ldr + d.col0 + r], sv);
+                            if (d.mean_b) sv += d.mean_b[d.col0 + r];
+                        }
+                        a.mean[(size_t)gn * d.ldr + d.col0 + r] = sv;
+                    }
+                }
             }
+        }
+        // sumsq[n] = sum_m A[n][m]^2: one warp per row, lanes stride the inducing index
+        for (int n = warp; n < C::NT; n += C::NWARPS) {
+            const double* arow = Bt + n * ldb;
+            double a2 = 0.0;
+            for (int m = lane; m < d.M; m += 32) a2 = fma(arow[m], arow[m], a2);
+            a2 = warp_sum(a2);
+            if (lane == 0) sumsq[n] = a2;
         }
         // (run_phase starts with a consumer barrier: sumsq and the mean stores are ordered before E2)
 

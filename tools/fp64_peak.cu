@@ -77,6 +77,48 @@ __global__ void k_dmma_lds(double* out, int iters) {
     out[blockIdx.x * blockDim.x + threadIdx.x] = s;
 }
 
+// The streamed-GEMM inner loop of the product kernels without any synchronisation: A fragments from a 128x(16+4)
+// staged chunk (4 ring slots), B fragments from a resident NT x (256+4) tile; warp grid 4 x WN, 4 interleaved 8-row
+// tiles per warp.  Shows the ceiling of the smem-fed DMMA loop itself.
+template <int WN, int NT>
+__global__ void k_dmma_stream(double* out, int nchunks) {
+    extern __shared__ double sm[];
+    constexpr int NJ = NT / (8 * WN), LDB = 260;
+    double* Bt = sm;
+    double* Ws = sm + NT * LDB;
+    for (int i = threadIdx.x; i < NT * LDB + 4 * 128 * 20; i += blockDim.x) sm[i] = 1e-3 * (i % 97);
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+    const int wm = warp / WN, wn = warp % WN;
+    double acc[4][NJ][2];
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+#pragma unroll
+        for (int j = 0; j < NJ; ++j) { acc[q][j][0] = 0; acc[q][j][1] = 0; }
+    for (int c = 0; c < nchunks; ++c) {
+        const double* Aw = Ws + (c & 3) * 128 * 20 + (wm * 8 + g) * 20 + t;
+        const double* Bw = Bt + (wn * NJ * 8 + g) * LDB + (c & 15) * 16 + t;
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk) {
+            double b[NJ];
+#pragma unroll
+            for (int j = 0; j < NJ; ++j) b[j] = Bw[j * 8 * LDB + kk * 4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const double a = Aw[q * 32 * 20 + kk * 4];
+#pragma unroll
+                for (int j = 0; j < NJ; ++j) dmma884(acc[q][j][0], acc[q][j][1], a, b[j]);
+            }
+        }
+    }
+    double s = 0;
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+#pragma unroll
+        for (int j = 0; j < NJ; ++j) s += acc[q][j][0] + acc[q][j][1];
+    out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
 template <typename F>
 float time_ms(F f) {
     cudaEvent_t e0, e1;
@@ -126,6 +168,20 @@ int main() {
         float ms = time_ms([&] { k_dmma_lds<<<sms, warps * 32>>>(out, 2000); });
         double fl = 2.0 * 256 * 64 * 2000.0 * warps * sms;
         printf("DMMA884+LDS 32x32 warp tile warps/SM=%2d : %.3f ms  %.2f TFLOP/s\n", warps, ms, fl / ms * 1e-9);
+    }
+    {
+        const int nch = 20000;
+        auto run = [&](auto kern, int wn, int nt, const char* name) {
+            size_t bytes = (size_t)(nt * 260 + 4 * 128 * 20) * sizeof(double);
+            CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+            float ms = time_ms([&] { kern<<<sms, 4 * wn * 32, bytes>>>(out, nch); });
+            double fl = 2.0 * 256 * 16.0 * (nt / 8) * 4 * (double)nch * sms;   // 16 m-tiles x nt/8 n-tiles x 4 k-steps per chunk
+            printf("DMMA stream loop %s: %.3f ms  %.2f TFLOP/s\n", name, ms, fl / ms * 1e-9);
+        };
+        run(k_dmma_stream<2, 64>, 2, 64, "4x2 warps, NT=64 (NJ=4)");
+        run(k_dmma_stream<4, 64>, 4, 64, "4x4 warps, NT=64 (NJ=2)");
+        run(k_dmma_stream<2, 32>, 2, 32, "4x2 warps, NT=32 (NJ=2)");
+        run(k_dmma_stream<4, 32>, 4, 32, "4x4 warps, NT=32 (NJ=1)");
     }
     CK(cudaFree(out));
     return 0;
