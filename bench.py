@@ -34,6 +34,12 @@ WORKLOADS = {
     "C1":  dict(L=2, M=50, D=1, N=1000, B=1000, S=1, kind="rbf", desc="configs[0]: 2-layer RBF M=50 D=1 N=1000 S=1"),
     "C3s": dict(L=5, M=500, D=16, N=1_000_000, B=10_000, S=16, kind="matern52",
                 desc="configs[2] per-GPU shard: 5-layer Matern52 M=500 D=16 minibatch 80k/8 S=16"),
+    "C4":  dict(L=2, M=256, D=8, N=200_000, B=10_000, S=10, kind="rbf", tasks=8,
+                desc="configs[3]: multitask DSDGP, MultikernelInputLayer (8 RBF kernels) + SwitchedKernel output layer, "
+                     "SwitchedLikelihood, M=256, 8 tasks, N=200k, minibatch 10k S=10"),
+    "C5":  dict(L=3, M=1024, D=8, N=100_000, B=10_000, S=100, kind="rbf", predict=True,
+                desc="configs[4] per-GPU slice: predict_y sweep, 3-layer M=1024, S=100, 10k test points per step "
+                     "(forward only)"),
 }
 FP64_PEAK_TFLOPS = 37.1   # profiles/fp64_peak_r01.txt: DMMA.8x8x4 issue-rate microbenchmark on this pool's B200
                           # (cuBLAS DGEMM 8192^3: 35.5).  MEASURED_PEAKS.json holds no fp64 figure.
@@ -52,6 +58,8 @@ def build_model(w, n_gpus):
     from dgplib_b200.likelihoods import Gaussian
     from dgplib_b200.mean_functions import Linear
     L, M, D, N, B, S = w["L"], w["M"], w["D"], w["N"], w["B"], w["S"]
+    if w.get("tasks"):
+        return build_multitask_model(w, n_gpus)
     rng = np.random.RandomState(0)
     X = rng.randn(N, D)
     Y = np.sin(X.sum(1, keepdims=True)) + 0.1 * rng.randn(N, 1)
@@ -78,7 +86,47 @@ def build_model(w, n_gpus):
     return model
 
 
+def build_multitask_model(w, n_gpus):
+    """BASELINE configs[3]: task id column appended to X, Z, Y; MultikernelInputLayer with T RBF kernels
+    (lengthscale sqrt(D) (0.8 + 0.1 k)), SwitchedKernel output layer, SwitchedLikelihood of T Gaussians."""
+    import contextlib, io
+    import dgplib_b200 as dg
+    from dgplib_b200.cascade import MultitaskSequential
+    from dgplib_b200.kernels import RBF, White
+    from dgplib_b200.layers import OutputLayer
+    from dgplib_b200.likelihoods import Gaussian, SwitchedLikelihood
+    from dgplib_b200.mean_functions import Linear
+    from dgplib_b200.multikernel_layers import MultikernelInputLayer
+    from dgplib_b200.specialized_kernels import SwitchedKernel
+    M, D, N, B, S, T = w["M"], w["D"], w["N"], w["B"], w["S"], w["tasks"]
+    rng = np.random.RandomState(0)
+    Xv = rng.randn(N, D)
+    tid = rng.randint(0, T, (N, 1)).astype(np.float64)
+    X = np.hstack([Xv, tid])
+    Y = np.hstack([np.sin(Xv.sum(1, keepdims=True)) + 0.1 * rng.randn(N, 1), tid])
+    Z = X[rng.permutation(N)[:M]].copy()
+    il = MultikernelInputLayer(D, T, M, [RBF(D, lengthscales=float(np.sqrt(D) * (0.8 + 0.1 * k))) + White(D, 1e-5)
+                                         for k in range(T)], share_Z=False,
+                               mean_function=Linear(A=np.zeros((D + 1, T))), multitask=True)
+    ol = OutputLayer(T, 1, M, SwitchedKernel([RBF(T, lengthscales=float(np.sqrt(T))) + White(T, 1e-5) for _ in range(T)], T),
+                     multitask=True)
+    with contextlib.redirect_stdout(io.StringIO()):
+        model = dg.MultitaskDSDGP(X, Y, Z, MultitaskSequential([il, ol]),
+                                  SwitchedLikelihood([Gaussian(0.1) for _ in range(T)]), num_latent=1,
+                                  minibatch_size=B * n_gpus, num_samples=S, seed=1234)
+    rs = np.random.RandomState(1)
+    for layer in model.layers.layers:
+        Mq, R = layer.q_mu.shape
+        layer.q_mu.assign(0.1 * rs.randn(Mq, R))
+        layer.q_sqrt.assign(np.eye(Mq)[None] + 0.1 * np.tril(rs.randn(R, Mq, Mq)))
+    return model
+
+
 def workload_flops_per_row(w):
+    if w.get("tasks"):      # MultikernelLayer: F = K (2 M D + M^2) + 2 M R + 2 M K + R (M^2 + 2 M); SURVEY.md 8(d)
+        M, D, T = w["M"], w["D"], w["tasks"]
+        first = T * (2 * M * D + M * M) + 2 * M * T + 2 * M * T + T * (M * M + 2 * M)
+        return first + flops_per_row_layer(M, T, 1)
     dims = [w["D"]] * w["L"] + [1]
     return sum(flops_per_row_layer(w["M"], dims[l], dims[l + 1]) for l in range(w["L"]))
 
@@ -144,6 +192,80 @@ def cpu_oracle_throughput(model, w, sample_rows, reps, threads=None):
     return sample_rows * S / best, best, torch.get_num_threads()
 
 
+def run_predict(args, w, model, eng, rank, world, local_rank, dist, sync_all, metric, config):
+    """Forward-only sweep (BASELINE configs[4]): rows/s = N* S / t; every rank predicts its own slice of test points."""
+    import gc
+    from dgplib_b200 import _cabi
+    S, B = w["S"], w["B"]
+    dev = eng.device
+    metric = "DSDGP predict_y rows/s (N* x S / s, forward only)"
+    rng = np.random.RandomState(4 + rank)
+    Xs_host = torch.from_numpy(rng.randn(B, w["D"])).pin_memory()
+    Xs = Xs_host.to(dev)
+    params = [p.detach() for p in eng.params()]
+    chunk = 2048
+
+    def step_dev(i):
+        return eng.propagate(Xs, S, seed=100 + i, params=params, chunk_rows=chunk, last_only=True)
+
+    for i in range(max(3, args.warmup)):
+        step_dev(i)
+    sync_all()
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    time.sleep(1.5)
+    gc.collect(); gc.disable()
+    eng.timers = {}
+    l0 = _cabi.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(args.steps):
+        step_dev(1000 + i)
+    e1.record()
+    sync_all()
+    gc.enable()
+    launches = _cabi.launch_count() - l0
+    ms = e0.elapsed_time(e1)
+    timers = eng.timer_summary()
+    eng.timers = None
+    clocks = sampler.stop() if sampler is not None else None
+    # end to end: pinned host test points -> device, predict_y, mean/var back to the host every step
+    model.predict_chunk_rows = chunk
+    model.predict_y(Xs_host, num_samples=S)
+    sync_all()
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0.record()
+    for i in range(args.steps):
+        mu, var = model.predict_y(Xs_host, num_samples=S, seed=2000 + i)
+    t1.record()
+    sync_all()
+    ms_e2e = t0.elapsed_time(t1)
+    if dist is not None:
+        tm = torch.tensor([ms, ms_e2e], dtype=torch.float64, device=dev)
+        dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+        ms, ms_e2e = float(tm[0]), float(tm[1])
+    rows = B * S * world
+    per_kernel = {}
+    for l, conds in enumerate(eng.conds):
+        n_rows = B * S if l > 0 else B
+        per_kernel[f"fwd.l{l}"] = sum(n_rows * flops_per_row_layer(c.desc.M, c.desc.D, c.desc.R) for c in conds)
+    dom = max((k for k in timers if k in per_kernel), key=lambda k: timers[k][1])
+    n_l, ms_l = timers[dom]
+    achieved = per_kernel[dom] * args.steps / (ms_l * 1e-3) / 1e12
+    line = {"metric": metric, "value": rows * args.steps / (ms * 1e-3), "unit": "rows/s", "n_gpus": world,
+            "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": ms / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config,
+            "e2e": {"value": rows * args.steps / (ms_e2e * 1e-3), "unit": "rows/s", "h2d_bytes_per_step": B * w["D"] * 8,
+                    "d2h_bytes_per_step": 2 * S * B * 8, "ms_per_step": ms_e2e / args.steps},
+            "gpu_launches": int(launches), "clocks": clocks,
+            "roofline": {"bound": "tensor", "kernel": dom, "achieved": achieved, "peak": FP64_PEAK_TFLOPS,
+                         "unit": "TFLOP/s", "frac": achieved / FP64_PEAK_TFLOPS, "traffic": None,
+                         "kernel_ms": {k: round(v[1] / max(args.steps, 1), 4) for k, v in sorted(timers.items())}}}
+    if rank == 0:
+        print(json.dumps(line))
+    if dist is not None:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -207,6 +329,9 @@ def main():
             dist.barrier()
             torch.cuda.synchronize()
 
+    if w.get("predict"):
+        return run_predict(args, w, model, eng, rank, world, local_rank, dist, sync_all, metric, config)
+
     # ---- device-resident leg: this rank's shard of one global minibatch already in HBM
     Bg = B * world
     Xb, Yb = model.X[:Bg], model.Y[:Bg]
@@ -233,12 +358,14 @@ def main():
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     step_evs = []
+    host_t0 = time.perf_counter()
     for i in range(args.steps):
         val, _ = step_dev(100 + i)
         ev = torch.cuda.Event(enable_timing=True)
         ev.record()
         step_evs.append(ev)
     e1.record()
+    host_ms = (time.perf_counter() - host_t0) * 1e3 / args.steps     # host time to enqueue one step (no sync inside)
     sync_all()
     launches = _cabi.launch_count() - l0
     gc.enable()
@@ -291,18 +418,19 @@ def main():
     d2h = 8
 
     # ---- roofline of the dominant kernel (CUDA events on the launching stream, inside the timed region above)
-    dims = [w["D"]] * w["L"] + [1]
-    M = w["M"]
     per_kernel = {}
-    for l in range(w["L"]):
-        Din, R = dims[l], dims[l + 1]
+    for l, conds in enumerate(eng.conds):
         n_rows = B * S if l > 0 else B      # the first layer is evaluated once per data row (sample sharing)
-        per_kernel[f"fwd.l{l}"] = n_rows * flops_per_row_layer(M, Din, R)
-        per_kernel[f"bwd.l{l}"] = n_rows * (2 * R * M * M + M * M + 2 * M * R + 6 * M * Din)   # dA dense + Lm^-T + d q_mu + kernel bwd
-        per_kernel[f"gram.l{l}"] = n_rows * (R + 1) * M * M                                      # G_r (sym) + P (tril)
+        f = b = g = 0
+        for c in conds:
+            M, Din, R = c.desc.M, c.desc.D, c.desc.R
+            f += n_rows * flops_per_row_layer(M, Din, R)
+            b += n_rows * (2 * R * M * M + M * M + 2 * M * R + 6 * M * Din)   # dA dense + Lm^-T + d q_mu + kernel bwd
+            g += n_rows * (R + 1) * M * M                                      # G_r (sym) + P (tril)
+        per_kernel[f"fwd.l{l}"], per_kernel[f"bwd.l{l}"], per_kernel[f"gram.l{l}"] = f, b, g
     dom = max((k for k in timers if k in per_kernel), key=lambda k: timers[k][1])
     n_l, ms_l = timers[dom]
-    achieved = per_kernel[dom] * n_l / (ms_l * 1e-3) / 1e12
+    achieved = per_kernel[dom] * args.steps / (ms_l * 1e-3) / 1e12     # per_kernel sums a layer's conditionals
     step_alg_flops = 3 * workload_flops_per_row(w) * B * S
     roofline = {"bound": "tensor", "kernel": dom, "achieved": achieved, "peak": FP64_PEAK_TFLOPS, "unit": "TFLOP/s",
                 "frac": achieved / FP64_PEAK_TFLOPS,
@@ -321,7 +449,8 @@ def main():
             "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config, "elbo": elbo_val,
             "e2e": {"value": e2e_value, "unit": "rows/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": ms_e2e / args.steps},
-            "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "ms_steps": ms_steps}
+            "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "ms_steps": ms_steps,
+            "host_enqueue_ms_per_step": round(host_ms, 3)}
 
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         rows = args.cpu_rows or max(256, min(B, int(2.0e11 / (3 * workload_flops_per_row(w) * S))))

@@ -80,6 +80,7 @@ class DSDGP(Parameterized):
         self._device = device
         self._engine = None
         self.chunk_rows = None      # optional bound on minibatch rows processed per kernel pass (memory)
+        self.predict_chunk_rows = 1 << 15   # test rows pushed through the cascade per pass in predict_* (x S samples)
         self._dist = None
         self._staging = None
         self._prefetched = None
@@ -170,10 +171,14 @@ class DSDGP(Parameterized):
         """Propagate points Xnew through the DGP cascade: (Fs, Fmeans, Fvars), lists of [S, N, .] CUDA tensors."""
         if full_cov:
             raise NotImplementedError("full_cov=True is outside the B200 hot path (SURVEY.md 8f, rank 3)")
-        return self.engine.propagate(Xnew, num_samples, eps=eps, seed=self.seed if seed is None else seed)
+        return self.engine.propagate(Xnew, num_samples, eps=eps, seed=self.seed if seed is None else seed,
+                                     chunk_rows=self.predict_chunk_rows)
 
     def _build_predict(self, Xnew, full_cov=False, num_samples=1, eps=None, seed=None):
-        Fs, Fmeans, Fvars = self._propagate(Xnew, full_cov, num_samples, eps=eps, seed=seed)
+        if full_cov:
+            raise NotImplementedError("full_cov=True is outside the B200 hot path (SURVEY.md 8f, rank 3)")
+        _, Fmeans, Fvars = self.engine.propagate(Xnew, num_samples, eps=eps, seed=self.seed if seed is None else seed,
+                                                 chunk_rows=self.predict_chunk_rows, last_only=True)
         return Fmeans[-1], Fvars[-1]
 
     def _build_likelihood(self, eps=None, seed=None, X=None, Y=None):

@@ -199,29 +199,32 @@ class Engine:
         return buf
 
     def _side_streams(self):
+        """One side stream per conditional (parameter stages of different conditionals are independent)."""
         if getattr(self, "_streams", None) is None:
-            self._streams = [torch.cuda.Stream(device=self.device) for _ in self.layers]
+            self._streams = [[torch.cuda.Stream(device=self.device) for _ in conds] for conds in self.conds]
         return self._streams
 
     def _prepare(self, S, nb, need_bwd, kl):
-        """Parameter-only stage of every conditional (Kuu, Cholesky, inverse factor, tiled operands, KL).  The layers are
-        independent of each other and of the data, so each layer's chain runs on its own stream; returns one event per
-        layer for the main stream to wait on just before that layer's first row kernel."""
+        """Parameter-only stage of every conditional (Kuu, Cholesky, inverse factor, tiled operands, KL).  The
+        conditionals are independent of each other and of the data, so each chain runs on its own stream; returns, per
+        layer, the events the main stream waits on just before that layer's first row kernel."""
         lib = _cabi.lib()
         main = torch.cuda.current_stream()
         start = main.record_event()
         events, i = [], 0
-        for l, (conds, side) in enumerate(zip(self.conds, self._side_streams())):
-            side.wait_event(start)
-            with torch.cuda.stream(side):
-                for c in conds:
+        for l, (conds, sides) in enumerate(zip(self.conds, self._side_streams())):
+            evs = []
+            for c, side in zip(conds, sides):
+                side.wait_event(start)
+                with torch.cuda.stream(side):
                     c.ensure_ws(self._rows_of(l, S, nb), need_bwd, self.device)
                     self._timed("prepare", lambda: _cabi.check(lib.dgp_cond_prepare(
                         c.ref(), _cabi.ptr(c.ws), c.ws.numel(), 1 if need_bwd else 0,
                         ctypes.c_void_p(kl[i:].data_ptr()) if kl is not None else None, _cabi.stream_ptr()),
                         "dgp_cond_prepare"))
-                    i += 1
-                events.append(side.record_event())
+                    evs.append(side.record_event())
+                i += 1
+            events.append(evs)
         return events
 
     def check_status(self):
@@ -250,7 +253,8 @@ class Engine:
         L = len(self.layers)
         stride = sample_stride if sample_stride else nb
         for l, (layer, conds) in enumerate(zip(self.layers, self.conds)):
-            main.wait_event(prep_events[l])
+            for ev in prep_events[l]:
+                main.wait_event(ev)
             want_F = last_F or l < L - 1
             Fbuf = buf["F"][l] if want_F else None
             rows = self._rows_of(l, S, nb)
@@ -270,28 +274,49 @@ class Engine:
                     _cabi.ptr(Fbuf), Fbuf.shape[1], _cabi.ptr(X), X.shape[1], st), "dgp_sample_expand"))
             inp, x_rows = Fbuf, n
 
-    def propagate(self, X, S, eps=None, seed=0, params=None):
-        """Fs, Fmeans, Fvars as lists of [S, B, .] CUDA tensors (DSDGP._propagate, dgplib/dsdgp.py:84-99)."""
+    def propagate(self, X, S, eps=None, seed=0, params=None, chunk_rows=None, last_only=False):
+        """Fs, Fmeans, Fvars as lists of [S, B, .] CUDA tensors (DSDGP._propagate, dgplib/dsdgp.py:84-99).
+        chunk_rows bounds the data rows pushed through the cascade per pass (memory: S * chunk_rows rows are live per
+        layer), last_only returns only the final layer's (mean, var) -- what predict_f / predict_y need."""
         with torch.no_grad():
             X = _dev_tensor(X, self.device)
             self._bind(self._detached(params))
             B = X.shape[0]
-            n = S * B
-            buf = self._row_buffers(S, B, False)
-            events = self._prepare(S, B, False, None)
-            eps_flat = None
+            Bc = B if not chunk_rows else max(1, min(B, int(chunk_rows)))
+            events = self._prepare(S, Bc, False, None)
+            eps_full = None
             if eps is not None:
-                eps_flat = [_dev_tensor(e, self.device).reshape(n, -1) for e in eps]
-            self._forward_rows(X, S, eps_flat, seed, 0, B, buf, False, True, events)
+                eps_full = [_dev_tensor(e, self.device).reshape(S, B, -1) for e in eps]
+            L = len(self.layers)
+            dev = self.device
+            keep = [L - 1] if last_only else list(range(L))
+            out = {k: {l: None for l in keep} for k in ("F", "mean", "var")}
+            for l in keep:
+                R = self.layers[l].output_dim
+                ldf = R + (1 if self.multitask else 0)
+                out["mean"][l] = torch.empty(S, B, R, dtype=_F64, device=dev)
+                out["var"][l] = torch.empty(S, B, R, dtype=_F64, device=dev)
+                if not last_only:
+                    out["F"][l] = torch.empty(S, B, ldf, dtype=_F64, device=dev)
+            for b0 in range(0, B, Bc):
+                b1 = min(B, b0 + Bc)
+                nb = b1 - b0
+                buf = self._row_buffers(S, nb, False)
+                eps_c = None
+                if eps_full is not None:
+                    eps_c = [e[:, b0:b1].reshape(S * nb, -1).contiguous() for e in eps_full]
+                self._forward_rows(X[b0:b1], S, eps_c, seed, b0, B, buf, False, not last_only, events)
+                for l in keep:
+                    for key in ("mean", "var"):
+                        t = buf[key][l]
+                        src = t.unsqueeze(0).expand(S, *t.shape) if (l == 0 and S > 1) else t.reshape(S, nb, -1)
+                        out[key][l][:, b0:b1].copy_(src)
+                    if not last_only:
+                        out["F"][l][:, b0:b1].copy_(buf["F"][l].reshape(S, nb, -1))
             self.check_status()
-
-            def view(t):
-                return (t.unsqueeze(0).expand(S, *t.shape) if t.shape[0] == B and S * B != B
-                        else t.reshape(S, B, -1)).clone()
-            Fs = [f.reshape(S, B, -1).clone() for f in buf["F"]]
-            means = [view(m) for m in buf["mean"]]
-            vars_ = [view(v) for v in buf["var"]]
-            return Fs, means, vars_
+            if last_only:
+                return None, [out["mean"][L - 1]], [out["var"][L - 1]]
+            return ([out["F"][l] for l in keep], [out["mean"][l] for l in keep], [out["var"][l] for l in keep])
 
     # ------------------------------------------------------------------------------------------ ELBO (+ grad)
     def grad_layout(self, params):
@@ -343,18 +368,18 @@ class Engine:
             tail_events = []
 
             def run_tail(l):
-                """Parameter-only backward tail of layer l on its side stream (overlaps the earlier layers' rows)."""
-                side = self._side_streams()[l]
-                side.wait_event(main.record_event())
-                with torch.cuda.stream(side):
-                    for c, ((Z, oZ), (th, oT)) in zip(self.conds[l], self._zt_offsets[l]):
+                """Parameter-only backward tails of layer l on their side streams (overlap the earlier layers' rows)."""
+                done = main.record_event()
+                for c, side, ((Z, oZ), (th, oT)) in zip(self.conds[l], self._side_streams()[l], self._zt_offsets[l]):
+                    side.wait_event(done)
+                    with torch.cuda.stream(side):
                         base = flat.data_ptr()
                         o_mu, o_sqrt = self._q_offsets[l]
                         self._timed("params_bwd", lambda: _cabi.check(lib.dgp_cond_backward_params(
                             c.ref(), _cabi.ptr(c.ws), klw, ctypes.c_void_p(base + 8 * oZ), ctypes.c_void_p(base + 8 * oT),
                             ctypes.c_void_p(base + 8 * o_mu), ctypes.c_void_p(base + 8 * o_sqrt), _cabi.stream_ptr()),
                             "dgp_cond_backward_params"))
-                    tail_events.append(side.record_event())
+                        tail_events.append(side.record_event())
 
             # offsets of each layer's gradient slots
             it = iter(zip(params, offs))
@@ -486,8 +511,9 @@ def layer_kl(layer):
         eng._bind(eng._detached())
         ncond = len(eng.conds[0])
         kl = torch.zeros(ncond, dtype=_F64, device=eng.device)
-        for ev in eng._prepare(1, 1, False, kl):
-            torch.cuda.current_stream().wait_event(ev)
+        for evs in eng._prepare(1, 1, False, kl):
+            for ev in evs:
+                torch.cuda.current_stream().wait_event(ev)
         return kl.sum()
 
 
