@@ -171,10 +171,11 @@ class ClockSampler:
         return out
 
 
-def cpu_oracle_throughput(model, w, sample_rows, reps, threads=None):
-    """Oracle ELBO+grad on the host cores over `sample_rows` minibatch rows (x S samples); best of `reps`."""
+def cpu_oracle_throughput(model, w, sample_rows, reps, warmup=1, threads=None, best=True):
+    """Oracle on the host cores over `sample_rows` rows (x S samples): ELBO+grad (or, for the predict workload, the
+    forward sweep).  Returns (rows/s, seconds per evaluation, threads); best-of-`reps` or their mean."""
     from oracle import dsdgp_oracle as O
-    from oracle.bridge import oracle_layers, oracle_lik, t
+    from oracle.bridge import oracle_layers, oracle_lik
     threads = threads or os.cpu_count()
     torch.set_num_threads(threads)
     layers, lik = oracle_layers(model.layers.layers), oracle_lik(model.likelihood)
@@ -182,14 +183,29 @@ def cpu_oracle_throughput(model, w, sample_rows, reps, threads=None):
     X = model.X[:sample_rows].clone()
     Y = model.Y[:sample_rows].clone()
     eps = [torch.randn(S, sample_rows, l["q_mu"].shape[1], dtype=torch.float64) for l in layers]
-    best = float("inf")
-    for i in range(reps + 1):          # first pass is the warm-up
+    mt = bool(w.get("tasks"))
+    times = []
+    for i in range(warmup + reps):
         t0 = time.perf_counter()
-        O.elbo_and_grad(layers, lik, X, Y, S, eps, num_data=w["N"])
+        if w.get("predict"):
+            with torch.no_grad():
+                O.predict_y(layers, lik, X, eps, S=S, multitask=mt)
+        else:
+            O.elbo_and_grad(layers, lik, X, Y, S, eps, num_data=w["N"], multitask=mt)
         dt = time.perf_counter() - t0
-        if i > 0:
-            best = min(best, dt)
-    return sample_rows * S / best, best, torch.get_num_threads()
+        if i >= warmup:
+            times.append(dt)
+    dt = min(times) if best else float(np.mean(times))
+    return sample_rows * S / dt, dt, torch.get_num_threads()
+
+
+def cpu_sample_rows(w, args):
+    """Bounded sample of the workload for the CPU arm: about 2e11 algorithmic flops per evaluation (1-2 s on 16 cores),
+    never more than the minibatch, and small enough that the oracle's materialised [R, M, S*rows] tensors fit in RAM."""
+    if args.cpu_rows:
+        return args.cpu_rows
+    per_row = (1 if w.get("predict") else 3) * workload_flops_per_row(w) * w["S"]
+    return int(max(64, min(w["B"], 2.0e11 / per_row)))
 
 
 def run_predict(args, w, model, eng, rank, world, local_rank, dist, sync_all, metric, config):
@@ -291,18 +307,17 @@ def main():
         if rank != 0:
             return
         model = build_model(w, 1)
-        rows = args.cpu_rows or max(256, min(B, int(2.0e11 / (3 * workload_flops_per_row(w) * S))))
-        vals = []
-        for _ in range(max(1, args.steps)):
-            v, dt, thr = cpu_oracle_throughput(model, w, rows, 1)
-            vals.append(v)
-        v = float(np.mean(vals))
+        rows = cpu_sample_rows(w, args)
+        v, dt, thr = cpu_oracle_throughput(model, w, rows, max(1, args.steps), warmup=max(0, args.warmup), best=False)
+        if w.get("predict"):
+            metric = "DSDGP predict_y rows/s (N* x S / s, forward only)"
         line = {"impl": "reference", "metric": metric, "value": v, "unit": "rows/s", "n_gpus": args.gpus,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * rows * S / v, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config,
                 "cpu_baseline": {"value": v, "unit": "rows/s", "cores": thr, "kind": "port",
-                                 "sample": f"{rows} of {B} minibatch rows x S={S}: oracle (PyTorch-CPU fp64 restatement "
-                                           "of the reference graph; TF 1.8/GPflow 1.2 not installable), fwd+autograd bwd"},
+                                 "sample": f"{rows} of {B} rows x S={S} per step, mean of {max(1, args.steps)} steps after "
+                                           f"{max(0, args.warmup)} warm-up: oracle (PyTorch-CPU fp64 restatement of the "
+                                           "reference graph; TF 1.8/GPflow 1.2 not installable)"},
                 "e2e": {"value": v, "unit": "rows/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
         print(json.dumps(line))
         return
@@ -453,8 +468,8 @@ def main():
             "host_enqueue_ms_per_step": round(host_ms, 3)}
 
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        rows = args.cpu_rows or max(256, min(B, int(2.0e11 / (3 * workload_flops_per_row(w) * S))))
-        v, dt, thr = cpu_oracle_throughput(model.cpu() if False else model, w, rows, 2)
+        rows = cpu_sample_rows(w, args)
+        v, dt, thr = cpu_oracle_throughput(model, w, rows, 2, warmup=1)
         line["cpu_baseline"] = {"value": v, "unit": "rows/s", "cores": thr, "kind": "port",
                                 "sample": f"{rows} of {B} minibatch rows x S={S}, best of 2 after 1 warm-up ({dt:.2f} s/eval): "
                                           "oracle = PyTorch-CPU fp64 restatement of the reference graph"}

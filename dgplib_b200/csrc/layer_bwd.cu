@@ -661,6 +661,9 @@ extern "C" int dgp_cond_backward(const dgp_cond_desc* d, void* ws, const double*
         if (rc != DGP_ERR_UNSUPPORTED) return rc;                                     \
     }
     if (w.Mpad <= 256) {
+#ifdef DGP_BWD_STAGES
+        DGP_TRY_BWD(DGP_BWD_WN, 32, DGP_BWD_STAGES)
+#endif
         DGP_TRY_BWD(DGP_BWD_WN, 32, 4) DGP_TRY_BWD(DGP_BWD_WN, 32, 3) DGP_TRY_BWD(DGP_BWD_WN, 32, 2)
     } else {
         DGP_TRY_BWD(2, 16, 4) DGP_TRY_BWD(2, 16, 3) DGP_TRY_BWD(2, 16, 2)

@@ -120,20 +120,28 @@ __device__ __forceinline__ void produce_phase(Pipe& p, int nseg, SegFn segfn, in
 template <class C, int QLO, int QHI, bool WEIGHTED>
 __device__ __forceinline__ void chunk_mma(Acc<C>& acc, const double* __restrict__ Aw, const double* __restrict__ Bw,
                                           int ldb, const double (&wv)[C::NJ]) {
-#pragma unroll
-    for (int kk = 0; kk < 4; ++kk) {
-        double b[C::NJ];
+    // Software-pipelined over the four k-steps of the chunk: the fragments of step kk+1 are loaded (into their own
+    // registers) before the DMMAs of step kk are issued.  Left to itself ptxas reused one register pair for every A
+    // fragment and put each LDS directly in front of its DMMA (30 % short-scoreboard stalls on the DMMAs in ncu).
+    double af[2][4], bf[2][C::NJ];
+    auto load = [&](int kk, int buf) {
 #pragma unroll
         for (int j = 0; j < C::NJ; ++j) {
-            b[j] = Bw[j * 8 * ldb + kk * 4];
-            if (WEIGHTED) b[j] *= wv[j];
+            bf[buf][j] = Bw[j * 8 * ldb + kk * 4];
+            if (WEIGHTED) bf[buf][j] *= wv[j];
         }
 #pragma unroll
-        for (int q = QLO; q < QHI; ++q) {
-            const double a = Aw[q * C::WM * 8 * C::WLD + kk * 4];
+        for (int q = QLO; q < QHI; ++q) af[buf][q] = Aw[q * C::WM * 8 * C::WLD + kk * 4];
+    };
+    load(0, 0);
 #pragma unroll
-            for (int j = 0; j < C::NJ; ++j) dmma884(acc.v[q][j], a, b[j]);
-        }
+    for (int kk = 0; kk < 4; ++kk) {
+        if (kk + 1 < 4) load(kk + 1, (kk + 1) & 1);
+        asm volatile("" ::: "memory");   // keep the prefetch above the DMMA group
+#pragma unroll
+        for (int q = QLO; q < QHI; ++q)
+#pragma unroll
+            for (int j = 0; j < C::NJ; ++j) dmma884(acc.v[q][j], af[kk & 1][q], bf[kk & 1][j]);
     }
 }
 
@@ -168,31 +176,37 @@ __device__ __forceinline__ void run_phase(Pipe& p, int nseg, SegFn segfn, EpiFn 
         const int aoff = (wm * 8 + g) * C::WLD + t;
         for (int kc = seg.kc0; kc < seg.kc1; ++kc) {
             const int k0 = kc * C::KC;
-            int qlo = 0, qhi = qmax;
-            if (MASK == MASK_LOWER) {                 // tile active iff rbase + 32 q + 7 >= k0
-                qlo = (k0 - rbase + 24) >> 5;
-                qlo = qlo < 0 ? 0 : qlo;
-            }
-            if (MASK == MASK_UPPER) {                 // tile active iff rbase + 32 q <= k0 + 15
-                const int h = ((k0 + 15 - rbase) >> 5) + 1;
-                qhi = h < qmax ? (h < 0 ? 0 : h) : qmax;
-            }
             const double* Bw = Bw0 + k0;
             const double* Aw = p.stages + (size_t)p.stage * C::STAGE_DOUBLES + aoff;
-            mbar_wait(&p.full[p.stage], p.round & 1);
-            if (qlo == 0 && qhi == 4) {
+            if (MASK == MASK_DENSE && qmax == 4) {
+                // dense phase, full block row: no range bookkeeping at all
+                mbar_wait(&p.full[p.stage], p.round & 1);
                 chunk_mma<C, 0, 4, WEIGHTED>(acc, Aw, Bw, ldb, wv);
-            } else if (qlo < qhi) switch ((qlo << 3) | qhi) {
-                case (1 << 3) | 4: chunk_mma<C, 1, 4, WEIGHTED>(acc, Aw, Bw, ldb, wv); break;
-                case (2 << 3) | 4: chunk_mma<C, 2, 4, WEIGHTED>(acc, Aw, Bw, ldb, wv); break;
-                case (3 << 3) | 4: chunk_mma<C, 3, 4, WEIGHTED>(acc, Aw, Bw, ldb, wv); break;
-                case (0 << 3) | 3: chunk_mma<C, 0, 3, WEIGHTED>(acc, Aw, Bw, ldb, wv); break;
-                case (0 << 3) | 2: chunk_mma<C, 0, 2, WEIGHTED>(acc, Aw, Bw, ldb, wv); break;
-                case (0 << 3) | 1: chunk_mma<C, 0, 1, WEIGHTED>(acc, Aw, Bw, ldb, wv); break;
-                case (1 << 3) | 3: chunk_mma<C, 1, 3, WEIGHTED>(acc, Aw, Bw, ldb, wv); break;
-                case (1 << 3) | 2: chunk_mma<C, 1, 2, WEIGHTED>(acc, Aw, Bw, ldb, wv); break;
-                case (2 << 3) | 3: chunk_mma<C, 2, 3, WEIGHTED>(acc, Aw, Bw, ldb, wv); break;
-                default: break;
+            } else {
+                int qlo = 0, qhi = qmax;
+                if (MASK == MASK_LOWER) {                 // tile active iff rbase + 32 q + 7 >= k0
+                    qlo = (k0 - rbase + 24) >> 5;
+                    qlo = qlo < 0 ? 0 : qlo;
+                }
+                if (MASK == MASK_UPPER) {                 // tile active iff rbase + 32 q <= k0 + 15
+                    const int h = ((k0 + 15 - rbase) >> 5) + 1;
+                    qhi = h < qmax ? (h < 0 ? 0 : h) : qmax;
+                }
+                mbar_wait(&p.full[p.stage], p.round & 1);
+                if (qlo == 0 && qhi == 4) {
+                    chunk_mma<C, 0, 4, WEIGHTED>(acc, Aw, Bw, ldb, wv);
+                } else if (qlo < qhi) switch ((qlo << 3) | qhi) {
+                    case (1 << 3) | 4: chunk_mma<C, 1, 4, WEIGHTED>(acc, Aw, Bw, ldb, wv); break;
+                    case (2 << 3) | 4: chunk_mma<C, 2, 4, WEIGHTED>(acc, Aw, Bw, ldb, wv); break;
+                    case (3 << 3) | 4: chunk_mma<C, 3, 4, WEIGHTED>(acc, Aw, Bw, ldb, wv); break;
+                    case (0 << 3) | 3: chunk_mma<C, 0, 3, WEIGHTED>(acc, Aw, Bw, ldb, wv); break;
+                    case (0 << 3) | 2: chunk_mma<C, 0, 2, WEIGHTED>(acc, Aw, Bw, ldb, wv); break;
+                    case (0 << 3) | 1: chunk_mma<C, 0, 1, WEIGHTED>(acc, Aw, Bw, ldb, wv); break;
+                    case (1 << 3) | 3: chunk_mma<C, 1, 3, WEIGHTED>(acc, Aw, Bw, ldb, wv); break;
+                    case (1 << 3) | 2: chunk_mma<C, 1, 2, WEIGHTED>(acc, Aw, Bw, ldb, wv); break;
+                    case (2 << 3) | 3: chunk_mma<C, 2, 3, WEIGHTED>(acc, Aw, Bw, ldb, wv); break;
+                    default: break;
+                }
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(&p.empty[p.stage]);   // this warp is done reading the slot

@@ -119,6 +119,86 @@ __global__ void k_dmma_stream(double* out, int nchunks) {
     out[blockIdx.x * blockDim.x + threadIdx.x] = s;
 }
 
+// The same loop WITH the product's pipeline: a producer warp streams 20 KB chunks from global memory with cp.async.bulk
+// into a 4-slot ring, full/empty mbarriers, consumers wait/arrive per chunk (stream_gemm.cuh, dense phase).
+__device__ __forceinline__ unsigned s32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+template <int WN, int NT, int EPI>
+__global__ void k_dmma_stream_pipe(double* out, const double* W, int ntiles_src, int nchunks) {
+    extern __shared__ __align__(128) double sm[];
+    constexpr int NJ = NT / (8 * WN), LDB = 260, STAGES = 4, NW = 4 * WN;
+    double* Bt = sm;
+    double* Ws = sm + NT * LDB;
+    unsigned long long* bars = reinterpret_cast<unsigned long long*>(Ws + STAGES * 128 * 20);
+    for (int i = threadIdx.x; i < NT * LDB; i += blockDim.x) Bt[i] = 1e-3 * (i % 97);
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < STAGES; ++s) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(s32(&bars[s])), "r"(1));
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(s32(&bars[STAGES + s])), "r"(NW));
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+    auto wait = [&](unsigned long long* b, unsigned par) {
+        asm volatile("{\n.reg .pred p;\nW_%=:\nmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n@p bra D_%=;\nbra W_%=;\nD_%=:\n}\n"
+                     :: "r"(s32(b)), "r"(par) : "memory");
+    };
+    if (warp == NW) {
+        if (lane == 0) {
+            for (int c = 0; c < nchunks; ++c) {
+                const int st = c % STAGES, rd = c / STAGES;
+                if (rd > 0) wait(&bars[STAGES + st], (rd - 1) & 1);
+                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(s32(&bars[st])), "r"(128 * 20 * 8) : "memory");
+                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                             :: "r"(s32(Ws + st * 128 * 20)), "l"(W + (size_t)(c % ntiles_src) * 128 * 20), "r"(128 * 20 * 8), "r"(s32(&bars[st])) : "memory");
+            }
+        }
+        return;
+    }
+    const int wm = warp / WN, wn = warp % WN;
+    double acc[4][NJ][2], tot[4][NJ][2];
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+#pragma unroll
+        for (int j = 0; j < NJ; ++j) { acc[q][j][0] = 0; acc[q][j][1] = 0; tot[q][j][0] = 0; tot[q][j][1] = 0; }
+    for (int c = 0; c < nchunks; ++c) {
+        const int st = c % STAGES, rd = c / STAGES;
+        if (EPI && (c & 15) == 0 && c > 0) {
+#pragma unroll
+            for (int j = 0; j < NJ; ++j)
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    const double w = Bt[(wn * NJ * 8 + j * 8 + 2 * t + e) * LDB + (c >> 4 & 7)];
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) { tot[q][j][e] = fma(w, acc[q][j][e], tot[q][j][e]); acc[q][j][e] = 0; }
+                }
+        }
+        const double* Aw = Ws + st * 128 * 20 + (wm * 8 + g) * 20 + t;
+        const double* Bw = Bt + (wn * NJ * 8 + g) * LDB + (c & 15) * 16 + t;
+        wait(&bars[st], rd & 1);
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk) {
+            double b[NJ];
+#pragma unroll
+            for (int j = 0; j < NJ; ++j) b[j] = Bw[j * 8 * LDB + kk * 4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const double a = Aw[q * 32 * 20 + kk * 4];
+#pragma unroll
+                for (int j = 0; j < NJ; ++j) dmma884(acc[q][j][0], acc[q][j][1], a, b[j]);
+            }
+        }
+        __syncwarp();
+        if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(s32(&bars[STAGES + st])) : "memory");
+    }
+    double s = 0;
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+#pragma unroll
+        for (int j = 0; j < NJ; ++j) s += acc[q][j][0] + acc[q][j][1] + tot[q][j][0] + tot[q][j][1];
+    out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
 template <typename F>
 float time_ms(F f) {
     cudaEvent_t e0, e1;
@@ -182,6 +262,24 @@ int main() {
         run(k_dmma_stream<4, 64>, 4, 64, "4x4 warps, NT=64 (NJ=2)");
         run(k_dmma_stream<2, 32>, 2, 32, "4x2 warps, NT=32 (NJ=2)");
         run(k_dmma_stream<4, 32>, 4, 32, "4x4 warps, NT=32 (NJ=1)");
+    }
+    {
+        const int nch = 20000, nsrc = 512;
+        double* W; CK(cudaMalloc(&W, sizeof(double) * 128 * 20 * nsrc)); CK(cudaMemset(W, 0, sizeof(double) * 128 * 20 * nsrc));
+        auto run = [&](auto kern, int wn, int nt, const char* name) {
+            size_t bytes = (size_t)(nt * 260 + 4 * 128 * 20 + 16) * sizeof(double);
+            CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+            float ms = time_ms([&] { kern<<<sms, 4 * wn * 32 + 32, bytes>>>(out, W, nsrc, nch); });
+            double fl = 2.0 * 256 * 16.0 * (nt / 8) * 4 * (double)nch * sms;
+            printf("DMMA stream loop + TMA/mbarrier pipeline %s: %.3f ms  %.2f TFLOP/s\n", name, ms, fl / ms * 1e-9);
+        };
+        run(k_dmma_stream_pipe<2, 64, 0>, 2, 64, "4x2 warps, NT=64");
+        run(k_dmma_stream_pipe<4, 64, 0>, 4, 64, "4x4 warps, NT=64");
+        run(k_dmma_stream_pipe<2, 32, 0>, 2, 32, "4x2 warps, NT=32");
+        run(k_dmma_stream_pipe<4, 32, 0>, 4, 32, "4x4 warps, NT=32");
+        run(k_dmma_stream_pipe<4, 32, 1>, 4, 32, "4x4 warps, NT=32, scale-accumulate epilogue every 16 chunks");
+        run(k_dmma_stream_pipe<4, 64, 1>, 4, 64, "4x4 warps, NT=64, scale-accumulate epilogue every 16 chunks");
+        CK(cudaFree(W));
     }
     CK(cudaFree(out));
     return 0;
