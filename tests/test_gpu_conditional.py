@@ -187,3 +187,62 @@ def test_philox_draws(cuda):
     C.check(lib.dgp_philox_normal(C.ptr(hi), S * 600, R, R, 7, 400, 600, B, C.stream_ptr()), "philox")
     w = whole.reshape(S, B, R)
     assert torch.equal(w[:, :400], lo.reshape(S, 400, R)) and torch.equal(w[:, 400:], hi.reshape(S, 600, R))
+
+
+def test_ragged_tiles_do_not_write_out_of_bounds(cuda):
+    """Row counts that are not a multiple of any tile width: every output buffer is over-allocated and pre-filled with a
+    sentinel; nothing beyond the valid rows may change (compute-sanitizer is closed on this pool, so this is the guard)."""
+    lib = C.lib()
+    rng = np.random.RandomState(3)
+    M, D, R, N, PAD = 70, 3, 2, 77, 40
+    SENT = -12345.678
+    d = C.CondDesc()
+    d.M, d.D, d.Dx, d.R, d.ldr, d.col0, d.T = M, D, D, R, R, 0, 1
+    d.jitter = 1e-6
+    t = lambda x: torch.tensor(x, dtype=torch.float64, device=cuda)
+    X, Z = t(rng.randn(N, D)), t(rng.randn(M, D))
+    theta = t(np.concatenate([[1.0, 1e-4], np.ones(D)]))
+    q_mu, q_sqrt = t(0.1 * rng.randn(M, R)), t(np.eye(M)[None] + 0.1 * np.tril(rng.randn(R, M, M)))
+    d.Z, d.theta, d.q_mu, d.q_sqrt = Z.data_ptr(), theta.data_ptr(), q_mu.data_ptr(), q_sqrt.data_ptr()
+    wsb = lib.dgp_cond_ws_bytes(ctypes.byref(d), N, 1)
+    ws = torch.zeros(wsb, dtype=torch.uint8, device=cuda)
+    st = C.stream_ptr()
+    C.check(lib.dgp_cond_prepare(ctypes.byref(d), C.ptr(ws), wsb, 1, None, st), "prepare")
+    Mp = C.mpad(M)
+    full = lambda cols: torch.full((N + PAD, cols), SENT, dtype=torch.float64, device=cuda)
+    mean, var, F, A, gX = full(R), full(R), full(R), full(Mp), full(D)
+    C.check(lib.dgp_cond_forward(ctypes.byref(d), C.ptr(ws), C.ptr(X), N, N, None, 5, 0, 0, 0, C.ptr(mean), C.ptr(var),
+                                 C.ptr(F), R, C.ptr(A), st), "forward")
+    gm, gv = t(rng.randn(N, R)), t(rng.randn(N, R))
+    C.check(lib.dgp_cond_backward(ctypes.byref(d), C.ptr(ws), C.ptr(X), N, N, C.ptr(A), C.ptr(mean), C.ptr(var), None, R,
+                                  C.ptr(gm), C.ptr(gv), None, 0, C.ptr(gX), 0, st), "backward")
+    C.check(lib.dgp_cond_backward_gram(ctypes.byref(d), C.ptr(ws), C.ptr(A), N, st), "gram")
+    torch.cuda.synchronize()
+    for name, buf in (("mean", mean), ("var", var), ("F", F), ("A", A), ("gX", gX)):
+        assert bool((buf[N:] == SENT).all()), name
+        assert bool(torch.isfinite(buf[:N]).all()) and not bool((buf[:N] == SENT).any()), name
+
+
+def test_empty_and_unsupported_inputs(cuda):
+    lib = C.lib()
+    d = C.CondDesc()
+    d.M, d.D, d.Dx, d.R, d.ldr, d.col0, d.T = 16, 2, 2, 1, 1, 0, 1
+    d.jitter = 1e-6
+    Z = torch.zeros(16, 2, dtype=torch.float64, device=cuda)
+    theta = torch.ones(4, dtype=torch.float64, device=cuda)
+    q_mu = torch.zeros(16, 1, dtype=torch.float64, device=cuda)
+    q_sqrt = torch.eye(16, dtype=torch.float64, device=cuda)[None].contiguous()
+    d.Z, d.theta, d.q_mu, d.q_sqrt = Z.data_ptr(), theta.data_ptr(), q_mu.data_ptr(), q_sqrt.data_ptr()
+    ws = torch.zeros(lib.dgp_cond_ws_bytes(ctypes.byref(d), 8, 1), dtype=torch.uint8, device=cuda)
+    one = torch.zeros(8, 2, dtype=torch.float64, device=cuda)
+    # zero rows: a no-op that succeeds
+    assert lib.dgp_cond_forward(ctypes.byref(d), C.ptr(ws), C.ptr(one), 1, 0, None, 0, 0, 0, 0, C.ptr(one), C.ptr(one),
+                                None, 1, None, C.stream_ptr()) == 0
+    assert lib.dgp_philox_normal(C.ptr(one), 0, 1, 1, 0, 0, 0, 0, C.stream_ptr()) == 0
+    # too small a workspace is refused, not overrun
+    assert lib.dgp_cond_prepare(ctypes.byref(d), C.ptr(ws), 1024, 0, None, C.stream_ptr()) == -3
+    # backward tiles are instantiated for M <= 512 only (DESIGN.md 7)
+    d.M = 600
+    assert lib.dgp_cond_backward(ctypes.byref(d), C.ptr(ws), C.ptr(one), 1, 1, C.ptr(one), C.ptr(one), C.ptr(one), None, 1,
+                                 C.ptr(one), C.ptr(one), None, 0, None, 0, C.stream_ptr()) == -4
+    torch.cuda.synchronize()
