@@ -276,6 +276,12 @@ def run_predict(args, w, model, eng, rank, world, local_rank, dist, sync_all, me
             "roofline": {"bound": "tensor", "kernel": dom, "achieved": achieved, "peak": FP64_PEAK_TFLOPS,
                          "unit": "TFLOP/s", "frac": achieved / FP64_PEAK_TFLOPS, "traffic": None,
                          "kernel_ms": {k: round(v[1] / max(args.steps, 1), 4) for k, v in sorted(timers.items())}}}
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        rows_cpu = cpu_sample_rows(w, args)
+        v, dt, thr = cpu_oracle_throughput(model, w, rows_cpu, 2, warmup=1)
+        line["cpu_baseline"] = {"value": v, "unit": "rows/s", "cores": thr, "kind": "port",
+                                "sample": f"{rows_cpu} of {B} test rows x S={S}, best of 2 after 1 warm-up ({dt:.2f} s/sweep): "
+                                          "oracle = PyTorch-CPU fp64 restatement of the reference graph"}
     if rank == 0:
         print(json.dumps(line))
     if dist is not None:

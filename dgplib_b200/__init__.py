@@ -13,9 +13,10 @@ from . import cascade
 from . import multikernel_layers
 from . import utils
 from . import specialized_kernels
+from . import training
 
 from .dsdgp import DSDGP
 from .multitask_dsdgp import MultitaskDSDGP
 
 __all__ = ["DSDGP", "MultitaskDSDGP", "layers", "cascade", "multikernel_layers", "utils", "specialized_kernels",
-           "kernels", "likelihoods", "mean_functions", "settings"]
+           "kernels", "likelihoods", "mean_functions", "settings", "training"]

@@ -238,6 +238,19 @@ class DSDGP(Parameterized):
     def predict_f_samples(self, Xnew, num_samples):
         raise NotImplementedError("predict_f_samples needs the full-covariance path (SURVEY.md 8f, rank 3)")
 
+    def predict_y_moments(self, Xnew, num_samples=10, eps=None, seed=None):
+        """Moment-matched predictive mean and variance of held-out data over `num_samples` propagated samples
+        (what the notebooks plot): the equal-weight Gaussian mixture of predict_y's per-sample
+        predictions, mean = E_s[mu_s], var = E_s[var_s + mu_s^2] - mean^2.  Returns two [N, D_Y] arrays."""
+        mean, var = self._build_predict(Xnew, False, num_samples, eps=eps, seed=seed)
+        lik = self.likelihood
+        if hasattr(lik, "likelihood_list"):
+            raise NotImplementedError("predict_y_moments is defined for a Gaussian likelihood")
+        var = var + lik.variance.constrained().detach()
+        m = mean.mean(0)
+        v = (var + mean * mean).mean(0) - m * m
+        return m.cpu().numpy(), v.cpu().numpy()
+
     def predict_y(self, Xnew, num_samples=1, eps=None, seed=None):
         """Mean and variance of held-out data at Xnew (dgplib/dsdgp.py:188-194).  The reference propagates a single
         sample (`_build_predict(Xnew)` defaults to num_samples=1); num_samples > 1 is a superset for sweeps."""

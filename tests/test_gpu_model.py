@@ -358,3 +358,25 @@ def test_chunked_prediction_is_identical(cuda):
         for x, y in zip(la, lb):
             assert np.array_equal(x, y)
     assert np.allclose(fa[1][-1], a[0]) and a[0].shape == (5, 301, 1)
+
+
+def test_adam_optimizer_api_and_moment_matched_prediction(cuda):
+    """gpflow-style `AdamOptimizer(lr).minimize(model, maxiter)` (reference tests/test_dsdgp.py:56-60) on minibatches, then
+    the moment-matched predictive (mixture over samples) against the oracle's per-sample predictions."""
+    from dgplib_b200.training import AdamOptimizer
+    model, X, Y = build_dsdgp(L=2, M=20, D=2, N=200, S=4, minibatch=50)
+    model.compile()
+    Xd, Yd = torch.from_numpy(X), torch.from_numpy(Y)
+    fixed = lambda: float(model.engine.elbo(model.engine.params(), Xd, Yd, 4, seed=1, num_data=200, need_grad=False)[0])
+    before = fixed()
+    hist = AdamOptimizer(0.01).minimize(model, maxiter=60)
+    after = fixed()
+    assert len(hist) == 60 and np.isfinite(after) and after > before
+    Xs = np.random.RandomState(3).randn(25, 2)
+    eps = make_eps(model, 6, 25, seed=21)
+    m, v = model.predict_y_moments(Xs, 6, eps=eps)
+    ol, olik = oracle_layers(model.layers.layers), oracle_lik(model.likelihood)
+    mu, var = O.predict_y(ol, olik, t(Xs), [t(e) for e in eps], S=6)
+    m_ref = mu.mean(0)
+    v_ref = (var + mu * mu).mean(0) - m_ref * m_ref
+    assert m.shape == (25, 1) and rel_err(m, m_ref) < TOL and rel_err(v, v_ref) < 1e-8
