@@ -297,6 +297,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--cpu-rows", type=int, default=0, help="minibatch rows of the CPU baseline sample (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="launch every kernel eagerly instead of replaying a CUDA graph")
     args = ap.parse_args()
     w = WORKLOADS[args.workload]
     rank = int(os.environ.get("RANK", "0"))
@@ -361,10 +362,26 @@ def main():
     params = [p.detach() for p in eng.params()]
     ar = (lambda tns: dist.all_reduce(tns)) if dist is not None else None
 
-    def step_dev(i):
+    graphed = None
+    if not args.no_graph:
+        from dgplib_b200.engine import GraphedElbo
+        graphed = GraphedElbo(eng, params, Xd, Yd, S, num_data=w["N"], row_offset=lo, global_batch=Bg, world_size=world,
+                              base_seed=1234)
+        model.use_cuda_graph = True
+    config["launch"] = "eager" if graphed is None else "one CUDA graph per evaluation"
+
+    def step_eager(i):
         return eng.elbo(params, Xd, Yd, S, eps=None, seed=1234 + i, num_data=w["N"], need_grad=True, row_offset=lo,
                         global_batch=Bg, world_size=world, all_reduce=ar, check=False)
 
+    def step_dev(i):
+        if graphed is not None:
+            return graphed.run(params, Xd, Yd, i, all_reduce=ar)
+        return step_eager(i)
+
+    l0 = _cabi.launch_count()
+    step_eager(0)
+    launches_per_step = _cabi.launch_count() - l0
     for i in range(max(3, args.warmup)):
         step_dev(i)
     eng.check_status()
@@ -374,8 +391,6 @@ def main():
     import gc
     gc.collect()
     gc.disable()
-    eng.timers = {}
-    l0 = _cabi.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     step_evs = []
@@ -388,19 +403,23 @@ def main():
     e1.record()
     host_ms = (time.perf_counter() - host_t0) * 1e3 / args.steps     # host time to enqueue one step (no sync inside)
     sync_all()
-    launches = _cabi.launch_count() - l0
-    gc.enable()
     ms = e0.elapsed_time(e1)
-    step_evs = [e for e in step_evs if e is not None]
     ms_steps = [round(a.elapsed_time(b), 3) for a, b in zip([e0] + step_evs[:-1], step_evs)]
+    elbo_val = float(val)
+    # per-kernel CUDA-event times: the same K steps once more, launched eagerly with events around every C-ABI call
+    eng.timers = {}
+    for i in range(args.steps):
+        step_eager(100 + i)
+    sync_all()
+    gc.enable()
     timers = eng.timer_summary()
     eng.timers = None
     clocks = sampler.stop() if sampler is not None else None
+    launches = launches_per_step * args.steps * (2 if graphed is not None else 2)   # timed pass + per-kernel pass
     if dist is not None:
         tm = torch.tensor([ms], dtype=torch.float64, device=dev)
         dist.all_reduce(tm, op=dist.ReduceOp.MAX)
         ms = float(tm)
-    elbo_val = float(val)
     rows_per_step = Bg * S
     value = rows_per_step * args.steps / (ms * 1e-3)
 
@@ -462,6 +481,8 @@ def main():
                                "MEASURED_PEAKS.json has no fp64 entry (its bf16 tcgen05 peak does not apply: there is "
                                "no fp64 tcgen05 kind)",
                 "kernel_ms": {k: round(v[1] / max(args.steps, 1), 4) for k, v in sorted(timers.items())},
+                "kernel_timing": "CUDA events around every C-ABI call on its launching stream, K eagerly launched steps "
+                                 "run right after the timed K steps (which replay one CUDA graph per step)",
                 "step_algorithmic_tflops": step_alg_flops * args.steps / (ms * 1e-3) / 1e12 * 1.0,
                 "step_frac_of_peak": step_alg_flops * args.steps / (ms * 1e-3) / 1e12 / FP64_PEAK_TFLOPS}
 
@@ -470,7 +491,8 @@ def main():
             "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config, "elbo": elbo_val,
             "e2e": {"value": e2e_value, "unit": "rows/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": ms_e2e / args.steps},
-            "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "ms_steps": ms_steps,
+            "gpu_launches": int(launches), "gpu_launches_per_step": int(launches_per_step), "clocks": clocks,
+            "roofline": roofline, "ms_steps": ms_steps,
             "host_enqueue_ms_per_step": round(host_ms, 3)}
 
     if rank == 0 and world == 1 and not args.no_cpu_baseline:

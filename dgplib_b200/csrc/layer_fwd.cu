@@ -30,7 +30,8 @@ struct FwdArgs {
     const double* Zs; const double* zn; const int32_t* ztask;
     const double* Linv; const double* LqT; size_t tl;   // tiled copies (stream_gemm.cuh)
     const double* X; long long x_rows, n_rows;
-    const double* eps; unsigned long long seed, row_offset; long long rows_per_sample, sample_stride;
+    const double* eps; unsigned long long seed, row_offset; const unsigned long long* seed_dev;
+    long long rows_per_sample, sample_stride;
     double* mean; double* var; double* F; int ldf; double* A_save; double* scal;
     int ntiles;
 };
@@ -302,7 +303,7 @@ __global__ void __launch_bounds__(C::NTHREADS, 1) k_cond_fwd(const __grid_consta
                             } else {
                                 const unsigned long long rid = a.row_offset +
                                     (unsigned long long)(gn / a.rows_per_sample) * a.sample_stride + (gn % a.rows_per_sample);
-                                z = philox_normal(a.seed, rid, (uint32_t)col);
+                                z = philox_normal(a.seed + (a.seed_dev ? *a.seed_dev : 0ull), rid, (uint32_t)col);
                             }
                             a.F[(size_t)gn * a.ldf + col] = mu + z * sqrt(v);  // var ** 0.5, no clamp (dgplib/utils.py:27)
                             if (sg.r == 0 && d.col0 == 0 && a.ldf > d.ldr)
@@ -342,9 +343,9 @@ static int launch_fwd(const FwdArgs& a, cudaStream_t st) {
 using namespace dgp;
 
 extern "C" int dgp_cond_forward(const dgp_cond_desc* d, const void* ws, const double* X, int64_t x_rows, int64_t n_rows,
-                                const double* eps, uint64_t seed, uint64_t row_offset, int64_t rows_per_sample,
-                                int64_t sample_stride, double* mean, double* var, double* F, int32_t ldf,
-                                double* A_save, void* stream) {
+                                const double* eps, uint64_t seed, const uint64_t* seed_dev, uint64_t row_offset,
+                                int64_t rows_per_sample, int64_t sample_stride, double* mean, double* var, double* F,
+                                int32_t ldf, double* A_save, void* stream) {
     int rc = check_desc(d);
     if (rc != DGP_OK) return rc;
     if (!ws || !X || !mean || !var || x_rows < 1 || n_rows < 0) return DGP_ERR_ARG;
@@ -358,6 +359,7 @@ extern "C" int dgp_cond_forward(const dgp_cond_desc* d, const void* ws, const do
     a.Linv = ws_ptr<double>(ws, w.LinvTl); a.LqT = ws_ptr<double>(ws, w.LqTTl); a.tl = w.tl;
     a.X = X; a.x_rows = x_rows; a.n_rows = n_rows;
     a.eps = eps; a.seed = seed; a.row_offset = row_offset;
+    a.seed_dev = reinterpret_cast<const unsigned long long*>(seed_dev);
     a.rows_per_sample = rows_per_sample > 0 ? rows_per_sample : n_rows;
     a.sample_stride = sample_stride > 0 ? sample_stride : a.rows_per_sample;
     a.mean = mean; a.var = var; a.F = F; a.ldf = ldf; a.A_save = A_save;

@@ -69,7 +69,8 @@ __global__ void k_philox_normal(double* __restrict__ out, long long n_rows, int 
 //   expand : F[s*B + b, c] = mean[b, c] + eps[s*B + b, c] * sqrt(var[b, c])   (+ task-id column copy when ldf > ldr)
 //   reduce : g_mean[b, c] = sum_s g_F[s*B+b, c] ;  g_var[b, c] = sum_s g_F[s*B+b, c] (F[s*B+b, c] - mean[b, c]) / (2 var[b, c])
 __global__ void k_sample_expand(const double* __restrict__ mean, const double* __restrict__ var, const double* __restrict__ eps,
-                                unsigned long long seed, unsigned long long row_offset, long long sstride, int S,
+                                unsigned long long seed, const unsigned long long* seed_dev,
+                                unsigned long long row_offset, long long sstride, int S,
                                 long long B, int R, int ldr, double* __restrict__ F, int ldf, const double* __restrict__ X,
                                 int Dx) {
     const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -78,7 +79,8 @@ __global__ void k_sample_expand(const double* __restrict__ mean, const double* _
     const long long n = e / R, b = n % B, s = n / B;
     const double mu = mean[(size_t)b * ldr + c], v = var[(size_t)b * ldr + c];
     const double z = eps ? eps[(size_t)n * ldr + c]
-                         : philox_normal(seed, row_offset + (unsigned long long)s * sstride + b, (uint32_t)c);
+                         : philox_normal(seed + (seed_dev ? *seed_dev : 0ull),
+                                         row_offset + (unsigned long long)s * sstride + b, (uint32_t)c);
     F[(size_t)n * ldf + c] = mu + z * sqrt(v);
     if (c == 0 && ldf > ldr) F[(size_t)n * ldf + ldf - 1] = X[(size_t)b * Dx + Dx - 1];
 }
@@ -174,15 +176,16 @@ extern "C" int dgp_philox_normal(double* out, int64_t n_rows, int32_t R, int32_t
     return DGP_OK;
 }
 
-extern "C" int dgp_sample_expand(const double* mean, const double* var, const double* eps, uint64_t seed, uint64_t row_offset,
-                                 int64_t sample_stride, int32_t S, int64_t B, int32_t R, int32_t ldr, double* F, int32_t ldf,
+extern "C" int dgp_sample_expand(const double* mean, const double* var, const double* eps, uint64_t seed,
+                                 const uint64_t* seed_dev, uint64_t row_offset, int64_t sample_stride, int32_t S, int64_t B, int32_t R, int32_t ldr, double* F, int32_t ldf,
                                  const double* X, int32_t Dx, void* stream) {
     if (!mean || !var || !F || S < 1 || B < 0 || R < 1 || ldr < R || ldf < ldr) return DGP_ERR_ARG;
     if (ldf > ldr && (!X || Dx < 1)) return DGP_ERR_ARG;
     if (B == 0) return DGP_OK;
     const long long total = (long long)S * B * R;
     k_sample_expand<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
-        mean, var, eps, seed, row_offset, sample_stride > 0 ? sample_stride : B, S, B, R, ldr, F, ldf, X, Dx);
+        mean, var, eps, seed, reinterpret_cast<const unsigned long long*>(seed_dev), row_offset,
+        sample_stride > 0 ? sample_stride : B, S, B, R, ldr, F, ldf, X, Dx);
     DGP_COUNT_LAUNCH();
     DGP_CHECK_LAUNCH();
     return DGP_OK;

@@ -87,6 +87,9 @@ class DSDGP(Parameterized):
         # Cholesky status is read back (a 4-byte D2H + sync) every this many evaluations; 0 = only on demand
         # through engine.check_status()
         self.check_status_every = 1
+        # replay each evaluation of elbo_and_grad() as one CUDA graph (fixed minibatch shape; Philox noise only)
+        self.use_cuda_graph = False
+        self._graphs = {}
 
     # ------------------------------------------------------------------------------------------------ plumbing
     def compile(self, device=None):
@@ -213,10 +216,29 @@ class DSDGP(Parameterized):
         if self._dist is not None:
             dist, group = self._dist
             kw.update(world_size=dist.get_world_size(group), all_reduce=lambda t: dist.all_reduce(t, group=group))
-        out = eng.elbo(eng.params(), need_grad=True, **kw)
+        if self.use_cuda_graph and eps is None and seed is None:
+            out = self._graph_step(xd, yd, kw)
+        else:
+            out = eng.elbo(eng.params(), need_grad=True, **kw)
         self._staging["free"][slot] = main.record_event()
         if self._mb is not None:
             self._prefetched = self._stage_next()      # next step's rows travel while this step computes
+        return out
+
+    def _graph_step(self, xd, yd, kw):
+        from .engine import GraphedElbo
+        eng = self.engine
+        params = eng.params()
+        key = (tuple(xd.shape), tuple(yd.shape), kw["row_offset"], kw["global_batch"], kw.get("world_size", 1))
+        g = self._graphs.get(key)
+        if g is None:
+            g = GraphedElbo(eng, params, xd, yd, self.num_samples, num_data=self.num_data, row_offset=kw["row_offset"],
+                            global_batch=kw["global_batch"], world_size=kw.get("world_size", 1),
+                            chunk_rows=self.chunk_rows, base_seed=self.seed)
+            self._graphs[key] = g
+        out = g.run(params, xd, yd, self._step, all_reduce=kw.get("all_reduce"))
+        if kw.get("check"):
+            eng.check_status()
         return out
 
     def predict_f(self, Xnew, num_samples, eps=None, seed=None):

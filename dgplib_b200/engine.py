@@ -239,6 +239,10 @@ class Engine:
                                          "Kuu + jitter is not positive definite")
 
     # ------------------------------------------------------------------------------------------ forward
+    def _seed_dev_ptr(self):
+        sd = getattr(self, "_seed_dev", None)
+        return ctypes.c_void_p(sd.data_ptr()) if sd is not None else None
+
     def _layer_seed(self, seed, l):
         return ctypes.c_uint64((seed + 0x9E3779B97F4A7C15 * (l + 1)) & 0xFFFFFFFFFFFFFFFF)
 
@@ -263,14 +267,14 @@ class Engine:
                 self._timed(f"fwd.l{l}", lambda: _cabi.check(lib.dgp_cond_forward(
                     c.ref(), _cabi.ptr(c.ws), _cabi.ptr(inp), x_rows, rows,
                     _cabi.ptr(eps[l]) if (eps is not None and fused_F) else None,
-                    self._layer_seed(seed, l), row_offset, nb, stride,
+                    self._layer_seed(seed, l), self._seed_dev_ptr(), row_offset, nb, stride,
                     _cabi.ptr(buf["mean"][l]), _cabi.ptr(buf["var"][l]), _cabi.ptr(Fbuf) if fused_F else None,
                     Fbuf.shape[1] if fused_F else layer.output_dim,
                     _cabi.ptr(buf["A"][l][ci]) if save else None, st), "dgp_cond_forward"))
             if l == 0 and want_F:
                 self._timed("sample.l0", lambda: _cabi.check(lib.dgp_sample_expand(
                     _cabi.ptr(buf["mean"][0]), _cabi.ptr(buf["var"][0]), _cabi.ptr(eps[0]) if eps is not None else None,
-                    self._layer_seed(seed, 0), row_offset, stride, S, nb, layer.output_dim, layer.output_dim,
+                    self._layer_seed(seed, 0), self._seed_dev_ptr(), row_offset, stride, S, nb, layer.output_dim, layer.output_dim,
                     _cabi.ptr(Fbuf), Fbuf.shape[1], _cabi.ptr(X), X.shape[1], st), "dgp_sample_expand"))
             inp, x_rows = Fbuf, n
 
@@ -454,7 +458,56 @@ class Engine:
             grads = None
             if need_grad:
                 grads = [flat[o:o + p.numel()].view(p.shape) for p, o in zip(params, offs)]
+            self._last_flat = flat[:total]
             return flat[0], grads
+
+
+class GraphedElbo:
+    """One ELBO + gradient evaluation captured as a CUDA graph (fixed shapes): the ~100 launches of a step -- three
+    streams' worth of parameter-stage kernels, the row-tile kernels, the tails -- are replayed with a single launch, which
+    is what matters for small, launch-bound problems (BASELINE configs[0]) and trims the gaps of large ones.  Inputs are
+    copied into static buffers before each replay; the Philox seed is added on the device (dgp_cond_forward's seed_dev)."""
+
+    def __init__(self, engine, params, X, Y, S, num_data=None, row_offset=0, global_batch=None, world_size=1,
+                 chunk_rows=None, need_grad=True, base_seed=0):
+        self.eng = engine
+        dev = engine.device
+        self.key = (tuple(X.shape), tuple(Y.shape), S, num_data, row_offset, global_batch, world_size, chunk_rows)
+        self.Xs = _dev_tensor(X, dev).clone()
+        self.Ys = _dev_tensor(Y, dev).clone()
+        self.ps = [_dev_tensor(p, dev).clone() for p in params]
+        self.seed_host = torch.zeros(1, dtype=torch.int64).pin_memory()
+        self.seed_dev = torch.zeros(1, dtype=torch.int64, device=dev)
+        kw = dict(S=S, eps=None, seed=base_seed, num_data=num_data, need_grad=need_grad, row_offset=row_offset,
+                  global_batch=global_batch, world_size=world_size, all_reduce=None, chunk_rows=chunk_rows, check=False)
+        cur = torch.cuda.current_stream()
+        warm = torch.cuda.Stream(device=dev)
+        warm.wait_stream(cur)
+        with torch.cuda.stream(warm):                      # allocate every cached buffer before capture
+            for _ in range(2):
+                engine.elbo(self.ps, self.Xs, self.Ys, **kw)
+        cur.wait_stream(warm)
+        torch.cuda.synchronize(dev)
+        self.graph = torch.cuda.CUDAGraph()
+        engine._seed_dev = self.seed_dev
+        try:
+            with torch.cuda.graph(self.graph):
+                self.seed_dev.copy_(self.seed_host, non_blocking=True)
+                self.val, self.grads = engine.elbo(self.ps, self.Xs, self.Ys, **kw)
+                self.flat = engine._last_flat
+        finally:
+            engine._seed_dev = None
+
+    def run(self, params, X, Y, seed, all_reduce=None):
+        with torch.no_grad():
+            torch._foreach_copy_(self.ps, [p.detach() for p in params])
+            self.Xs.copy_(X, non_blocking=True)
+            self.Ys.copy_(Y, non_blocking=True)
+            self.seed_host[0] = int(seed) & 0x7FFFFFFFFFFFFFFF
+            self.graph.replay()
+            if all_reduce is not None:
+                all_reduce(self.flat)
+        return self.val, self.grads
 
 
 class _ElboFn(torch.autograd.Function):

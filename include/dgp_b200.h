@@ -83,16 +83,17 @@ int dgp_cond_status(const void* ws, void* stream, int32_t* status_host);
  *   eps     [n_rows, ldr] N(0,1) draws, or NULL to draw Philox4x32-10 normals keyed by (seed, global row id, column)
  *           with global row id = row_offset + (n / rows_per_sample) * sample_stride + n % rows_per_sample, so that a
  *           shard holding rows_per_sample of sample_stride minibatch rows draws what the unsharded run draws
- *           (rows_per_sample <= 0: n_rows; sample_stride <= 0: rows_per_sample)
+ *           (rows_per_sample <= 0: n_rows; sample_stride <= 0: rows_per_sample).  seed_dev (device, nullable) is added to
+ *           seed on the device, so that a captured CUDA graph can be replayed with fresh noise
  *   mean,var[n_rows, ldr] outputs (this conditional's R columns)
  *   F       [n_rows, ldf] sample mean + eps*sqrt(var) (NULL: skip).  When ldf > ldr the trailing column Dx-1 of X
  *           is copied into column ldf-1 (task-label propagation, dgplib/multitask_dsdgp.py:20)
  *   A_save  [n_rows, Mpad] Lm^-1 Kuf per row, kept for the backward pass (NULL: skip)
  */
 int dgp_cond_forward(const dgp_cond_desc* d, const void* ws, const double* X, int64_t x_rows, int64_t n_rows,
-                     const double* eps, uint64_t seed, uint64_t row_offset, int64_t rows_per_sample,
-                     int64_t sample_stride, double* mean, double* var, double* F, int32_t ldf, double* A_save,
-                     void* stream);
+                     const double* eps, uint64_t seed, const uint64_t* seed_dev, uint64_t row_offset,
+                     int64_t rows_per_sample, int64_t sample_stride, double* mean, double* var, double* F, int32_t ldf,
+                     double* A_save, void* stream);
 
 /* ---- first-layer sample sharing -------------------------------------------------------------------------------
  * tile_over_samples (dgplib/utils.py:15-18, used at dgplib/dsdgp.py:89) hands the first layer S identical copies of
@@ -101,8 +102,8 @@ int dgp_cond_forward(const dgp_cond_desc* d, const void* ws, const double* X, in
  * S sample gradients of a row into (g_mean, g_var) [B, ldr], which go to dgp_cond_backward as g_mean_in / g_var_in.
  *   F[s*B + b, c] = mean[b, c] + eps[s*B + b, c] * sqrt(var[b, c]),  eps == NULL: Philox keyed (seed, row_offset +
  *   s * sample_stride + b, c) -- the draws dgp_cond_forward would make.  ldf > ldr: column ldf-1 = X[b, Dx-1]. */
-int dgp_sample_expand(const double* mean, const double* var, const double* eps, uint64_t seed, uint64_t row_offset,
-                      int64_t sample_stride, int32_t S, int64_t B, int32_t R, int32_t ldr, double* F, int32_t ldf,
+int dgp_sample_expand(const double* mean, const double* var, const double* eps, uint64_t seed, const uint64_t* seed_dev,
+                      uint64_t row_offset, int64_t sample_stride, int32_t S, int64_t B, int32_t R, int32_t ldr, double* F, int32_t ldf,
                       const double* X, int32_t Dx, void* stream);
 int dgp_sample_reduce(const double* g_F, int32_t ldgf, const double* F, int32_t ldf, const double* mean,
                       const double* var, int32_t S, int64_t B, int32_t R, int32_t ldr, double* g_mean, double* g_var,

@@ -78,7 +78,7 @@ def run_conditional(cuda, M, D, R, N, kind, S=1, white=1e-5, linear=True, backwa
     varo, F = torch.zeros_like(mean), torch.zeros_like(mean)
     Asave = torch.full((n, Mp), float("nan"), dtype=torch.float64, device=dev)
     # the S copies of X are addressed by index arithmetic (x_rows = N), never materialised
-    C.check(lib.dgp_cond_forward(ctypes.byref(d), C.ptr(ws), C.ptr(Xd), N, n, C.ptr(epsd), 0, 0, 0, 0, C.ptr(mean),
+    C.check(lib.dgp_cond_forward(ctypes.byref(d), C.ptr(ws), C.ptr(Xd), N, n, C.ptr(epsd), 0, None, 0, 0, 0, C.ptr(mean),
                                  C.ptr(varo), C.ptr(F), R, C.ptr(Asave), st), "forward")
     torch.cuda.synchronize()
     errs = {"kl": abs(kl.item() - kl_ref.item()) / max(abs(kl_ref.item()), 1e-12), "mean": rel(mean, m_ref),
@@ -211,7 +211,7 @@ def test_ragged_tiles_do_not_write_out_of_bounds(cuda):
     Mp = C.mpad(M)
     full = lambda cols: torch.full((N + PAD, cols), SENT, dtype=torch.float64, device=cuda)
     mean, var, F, A, gX = full(R), full(R), full(R), full(Mp), full(D)
-    C.check(lib.dgp_cond_forward(ctypes.byref(d), C.ptr(ws), C.ptr(X), N, N, None, 5, 0, 0, 0, C.ptr(mean), C.ptr(var),
+    C.check(lib.dgp_cond_forward(ctypes.byref(d), C.ptr(ws), C.ptr(X), N, N, None, 5, None, 0, 0, 0, C.ptr(mean), C.ptr(var),
                                  C.ptr(F), R, C.ptr(A), st), "forward")
     gm, gv = t(rng.randn(N, R)), t(rng.randn(N, R))
     C.check(lib.dgp_cond_backward(ctypes.byref(d), C.ptr(ws), C.ptr(X), N, N, C.ptr(A), C.ptr(mean), C.ptr(var), None, R,
@@ -236,7 +236,7 @@ def test_empty_and_unsupported_inputs(cuda):
     ws = torch.zeros(lib.dgp_cond_ws_bytes(ctypes.byref(d), 8, 1), dtype=torch.uint8, device=cuda)
     one = torch.zeros(8, 2, dtype=torch.float64, device=cuda)
     # zero rows: a no-op that succeeds
-    assert lib.dgp_cond_forward(ctypes.byref(d), C.ptr(ws), C.ptr(one), 1, 0, None, 0, 0, 0, 0, C.ptr(one), C.ptr(one),
+    assert lib.dgp_cond_forward(ctypes.byref(d), C.ptr(ws), C.ptr(one), 1, 0, None, 0, None, 0, 0, 0, C.ptr(one), C.ptr(one),
                                 None, 1, None, C.stream_ptr()) == 0
     assert lib.dgp_philox_normal(C.ptr(one), 0, 1, 1, 0, 0, 0, 0, C.stream_ptr()) == 0
     # too small a workspace is refused, not overrun

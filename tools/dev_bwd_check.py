@@ -40,7 +40,7 @@ def run(M, D, R, N, kind="rbf", white=1e-5, seed=0, linear=True, use_gF=True):
     Mp = C.mpad(M)
     mean = torch.zeros(N, R, dtype=torch.float64, device=dev); varo = torch.zeros_like(mean); F = torch.zeros_like(mean)
     Asave = torch.zeros(N, Mp, dtype=torch.float64, device=dev)
-    C.check(lib.dgp_cond_forward(ctypes.byref(d), C.ptr(ws), C.ptr(Xd), N, N, C.ptr(epsd), 0, 0, 0, 0, C.ptr(mean), C.ptr(varo), C.ptr(F), R, C.ptr(Asave), C.stream_ptr()), "forward")
+    C.check(lib.dgp_cond_forward(ctypes.byref(d), C.ptr(ws), C.ptr(Xd), N, N, C.ptr(epsd), 0, None, 0, 0, 0, C.ptr(mean), C.ptr(varo), C.ptr(F), R, C.ptr(Asave), C.stream_ptr()), "forward")
     gX = torch.zeros(N, D, dtype=torch.float64, device=dev)
     gmd, gvd, gFd = gm_in.to(dev), gv_in.to(dev), gF.to(dev)
     C.check(lib.dgp_cond_backward(ctypes.byref(d), C.ptr(ws), C.ptr(Xd), N, N, C.ptr(Asave), C.ptr(mean), C.ptr(varo), C.ptr(F), R,

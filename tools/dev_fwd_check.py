@@ -38,7 +38,7 @@ def run(M, D, R, N, kind="rbf", S=1, white=1e-5, seed=0, linear=True):
     Mp = C.mpad(M)
     mean = torch.zeros(nrows, R, dtype=torch.float64, device=dev); varo = torch.zeros_like(mean); F = torch.zeros_like(mean)
     Asave = torch.zeros(nrows, Mp, dtype=torch.float64, device=dev)
-    C.check(lib.dgp_cond_forward(ctypes.byref(d), C.ptr(ws), C.ptr(Xd), N, nrows, C.ptr(epsd), 0, 0, 0, 0, C.ptr(mean), C.ptr(varo), C.ptr(F), R, C.ptr(Asave), C.stream_ptr()), "forward")
+    C.check(lib.dgp_cond_forward(ctypes.byref(d), C.ptr(ws), C.ptr(Xd), N, nrows, C.ptr(epsd), 0, None, 0, 0, 0, C.ptr(mean), C.ptr(varo), C.ptr(F), R, C.ptr(Asave), C.stream_ptr()), "forward")
     torch.cuda.synchronize()
     rel = lambda a, b: float((a.cpu() - b).abs().max() / b.abs().max())
     # A reference

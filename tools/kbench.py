@@ -25,7 +25,7 @@ Mp = C.mpad(M)
 mean = torch.zeros(N, R, dtype=torch.float64, device=dev); var = torch.zeros_like(mean); F = torch.zeros_like(mean)
 A = torch.zeros(N, Mp, dtype=torch.float64, device=dev)
 gm = t(rng.randn(N, R)); gv = t(rng.randn(N, R)); gF = t(rng.randn(N, R)); gX = torch.zeros(N, D, dtype=torch.float64, device=dev)
-def fwd(): C.check(lib.dgp_cond_forward(ctypes.byref(d), C.ptr(ws), C.ptr(X), N, N, None, 1, 0, 0, 0, C.ptr(mean), C.ptr(var), C.ptr(F), R, C.ptr(A), st), "fwd")
+def fwd(): C.check(lib.dgp_cond_forward(ctypes.byref(d), C.ptr(ws), C.ptr(X), N, N, None, 1, None, 0, 0, 0, C.ptr(mean), C.ptr(var), C.ptr(F), R, C.ptr(A), st), "fwd")
 def bwd(): C.check(lib.dgp_cond_backward(ctypes.byref(d), C.ptr(ws), C.ptr(X), N, N, C.ptr(A), C.ptr(mean), C.ptr(var), C.ptr(F), R, C.ptr(gm), C.ptr(gv), C.ptr(gF), R, C.ptr(gX), 0, st), "bwd")
 def gram(): C.check(lib.dgp_cond_backward_gram(ctypes.byref(d), C.ptr(ws), C.ptr(A), N, st), "gram")
 def prep(): C.check(lib.dgp_cond_prepare(ctypes.byref(d), C.ptr(ws), wsb, 1, None, st), "prepare")
