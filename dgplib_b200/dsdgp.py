@@ -186,11 +186,15 @@ class DSDGP(Parameterized):
 
     def _build_likelihood(self, eps=None, seed=None, X=None, Y=None):
         """Variational bound on the marginal likelihood (dgplib/dsdgp.py:107-130) of the next minibatch, as a CUDA
-        scalar attached to torch.autograd (call .backward() or hand it to a torch optimiser)."""
-        if X is None:
-            X, Y = self._next_batch()
-        self._step += 1
-        return elbo_autograd(self.engine, **self._eval_kwargs(X, Y, eps, seed))
+        scalar attached to torch.autograd (call .backward() or hand it to a torch optimiser).  The node's forward runs
+        the fused forward AND backward kernels (as one CUDA graph when use_cuda_graph is set)."""
+        if X is not None:
+            self._step += 1
+            return elbo_autograd(self.engine, **self._eval_kwargs(X, Y, eps, seed))
+        kw, finish = self._staged_step(eps, seed)
+        out = elbo_autograd(self.engine, **kw)
+        finish()
+        return out
 
     def compute_log_likelihood(self, eps=None, seed=None):
         """gpflow Model.compute_log_likelihood(): the ELBO of one minibatch as a Python float."""
@@ -204,6 +208,21 @@ class DSDGP(Parameterized):
         if X is not None:
             self._step += 1
             return eng.elbo(eng.params(), need_grad=True, **self._eval_kwargs(X, Y, eps, seed))
+        kw, finish = self._staged_step(eps, seed)
+        graph = kw.pop("_graph", None)
+        if graph is not None:
+            out = graph.run(eng.params(), kw["X"], kw["Y"], kw["seed"], all_reduce=kw.get("all_reduce"))
+            if kw.get("check"):
+                eng.check_status()
+        else:
+            out = eng.elbo(eng.params(), need_grad=True, **kw)
+        finish()
+        return out
+
+    def _staged_step(self, eps, seed):
+        """Arguments of Engine.elbo for the next minibatch taken from the model's own host data through the pinned,
+        double-buffered staging path, plus a callback to run once the step's kernels are enqueued."""
+        eng = self.engine
         staged = self._prefetched or self._stage_next()
         self._prefetched = None
         xd, yd, ready, lo, B, slot = staged
@@ -217,29 +236,25 @@ class DSDGP(Parameterized):
             dist, group = self._dist
             kw.update(world_size=dist.get_world_size(group), all_reduce=lambda t: dist.all_reduce(t, group=group))
         if self.use_cuda_graph and eps is None and seed is None:
-            out = self._graph_step(xd, yd, kw)
-        else:
-            out = eng.elbo(eng.params(), need_grad=True, **kw)
-        self._staging["free"][slot] = main.record_event()
-        if self._mb is not None:
-            self._prefetched = self._stage_next()      # next step's rows travel while this step computes
-        return out
+            kw["_graph"] = self._graph_for(xd, yd, kw)
 
-    def _graph_step(self, xd, yd, kw):
+        def finish():
+            self._staging["free"][slot] = main.record_event()
+            if self._mb is not None:
+                self._prefetched = self._stage_next()      # next step's rows travel while this step computes
+        return kw, finish
+
+    def _graph_for(self, xd, yd, kw):
         from .engine import GraphedElbo
         eng = self.engine
-        params = eng.params()
         key = (tuple(xd.shape), tuple(yd.shape), kw["row_offset"], kw["global_batch"], kw.get("world_size", 1))
         g = self._graphs.get(key)
         if g is None:
-            g = GraphedElbo(eng, params, xd, yd, self.num_samples, num_data=self.num_data, row_offset=kw["row_offset"],
-                            global_batch=kw["global_batch"], world_size=kw.get("world_size", 1),
-                            chunk_rows=self.chunk_rows, base_seed=self.seed)
+            g = GraphedElbo(eng, eng.params(), xd, yd, self.num_samples, num_data=self.num_data,
+                            row_offset=kw["row_offset"], global_batch=kw["global_batch"],
+                            world_size=kw.get("world_size", 1), chunk_rows=self.chunk_rows, base_seed=self.seed)
             self._graphs[key] = g
-        out = g.run(params, xd, yd, self._step, all_reduce=kw.get("all_reduce"))
-        if kw.get("check"):
-            eng.check_status()
-        return out
+        return g
 
     def predict_f(self, Xnew, num_samples, eps=None, seed=None):
         """Mean and variance of the final layer at Xnew: two [S, N, D_Y] arrays (dgplib/dsdgp.py:133-139)."""

@@ -478,6 +478,7 @@ class GraphedElbo:
         self.ps = [_dev_tensor(p, dev).clone() for p in params]
         self.seed_host = torch.zeros(1, dtype=torch.int64).pin_memory()
         self.seed_dev = torch.zeros(1, dtype=torch.int64, device=dev)
+        self.base_seed = int(base_seed)
         kw = dict(S=S, eps=None, seed=base_seed, num_data=num_data, need_grad=need_grad, row_offset=row_offset,
                   global_batch=global_batch, world_size=world_size, all_reduce=None, chunk_rows=chunk_rows, check=False)
         cur = torch.cuda.current_stream()
@@ -499,11 +500,12 @@ class GraphedElbo:
             engine._seed_dev = None
 
     def run(self, params, X, Y, seed, all_reduce=None):
+        """Replay with the given parameters, minibatch and (full) Philox seed; returns views of static buffers."""
         with torch.no_grad():
             torch._foreach_copy_(self.ps, [p.detach() for p in params])
             self.Xs.copy_(X, non_blocking=True)
             self.Ys.copy_(Y, non_blocking=True)
-            self.seed_host[0] = int(seed) & 0x7FFFFFFFFFFFFFFF
+            self.seed_host[0] = (int(seed) - self.base_seed) & 0x7FFFFFFFFFFFFFFF   # added to base_seed on the device
             self.graph.replay()
             if all_reduce is not None:
                 all_reduce(self.flat)
@@ -517,7 +519,16 @@ class _ElboFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, engine, kwargs, *params):
         need = any(ctx.needs_input_grad[2:])
-        val, grads = engine.elbo(list(params), need_grad=need, **kwargs)
+        kwargs = dict(kwargs)
+        graph = kwargs.pop("_graph", None)
+        if graph is not None and need:
+            val, grads = graph.run(list(params), kwargs["X"], kwargs["Y"], kwargs["seed"],
+                                   all_reduce=kwargs.get("all_reduce"))
+            if kwargs.get("check"):
+                engine.check_status()
+            grads = [g.clone() for g in grads]      # the graph's output buffers are overwritten by the next replay
+        else:
+            val, grads = engine.elbo(list(params), need_grad=need, **kwargs)
         ctx.grads = grads
         return val.clone()
 

@@ -2,6 +2,7 @@
 // Used once to establish the "FP64 tensor peak" roofline denominator; not on the product path.
 #include <cstdio>
 #include <cstdlib>
+#include <vector>
 #include <cuda_runtime.h>
 
 #define CK(x) do { cudaError_t e = (x); if (e != cudaSuccess) { printf("CUDA error %s at %d\n", cudaGetErrorString(e), __LINE__); exit(1);} } while (0)
@@ -129,7 +130,7 @@ __global__ void k_dmma_stream_pipe(double* out, const double* W, int ntiles_src,
     double* Bt = sm;
     double* Ws = sm + NT * LDB;
     unsigned long long* bars = reinterpret_cast<unsigned long long*>(Ws + STAGES * 128 * 20);
-    for (int i = threadIdx.x; i < NT * LDB; i += blockDim.x) Bt[i] = 1e-3 * (i % 97);
+    for (int i = threadIdx.x; i < NT * LDB; i += blockDim.x) Bt[i] = 1e-3 * (i % 97) + 1.2345678901234e-7 * ((i * 2654435761u) % 1000003u);
     if (threadIdx.x == 0) {
         for (int s = 0; s < STAGES; ++s) {
             asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(s32(&bars[s])), "r"(1));
@@ -266,6 +267,11 @@ int main() {
     {
         const int nch = 20000, nsrc = 512;
         double* W; CK(cudaMalloc(&W, sizeof(double) * 128 * 20 * nsrc)); CK(cudaMemset(W, 0, sizeof(double) * 128 * 20 * nsrc));
+        if (getenv("DGP_RANDOM_W")) {
+            std::vector<double> h((size_t)128 * 20 * nsrc);
+            for (size_t i = 0; i < h.size(); ++i) h[i] = (double)rand() / RAND_MAX - 0.5;
+            CK(cudaMemcpy(W, h.data(), h.size() * sizeof(double), cudaMemcpyHostToDevice));
+        }
         auto run = [&](auto kern, int wn, int nt, const char* name) {
             size_t bytes = (size_t)(nt * 260 + 4 * 128 * 20 + 16) * sizeof(double);
             CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
