@@ -51,6 +51,11 @@ SIGNATURES = {
                                          _i32, _vp]),
     "dgp_cond_backward_gram": (ctypes.c_int, [_P, _vp, _vp, _i64, _vp]),
     "dgp_cond_backward_params": (ctypes.c_int, [_P, _vp, _dbl, _vp, _vp, _vp, _vp, _vp]),
+    "dgp_cond_fullcov_ws_bytes": (_sz, [_P, _i64]),
+    "dgp_cond_fullcov": (ctypes.c_int, [_P, _vp, _vp, _i64, _vp, _vp, _vp, _sz, _vp]),
+    "dgp_chol_sample_ws_bytes": (_sz, [_i64, _i32]),
+    "dgp_chol_sample": (ctypes.c_int, [_vp, _i64, _i64, _i64, _i64, _i32, _dbl, _vp, _i32, _vp, _i64, _i64, _vp, _vp, _sz,
+                                       _vp, _vp]),
     "dgp_kernel_K": (ctypes.c_int, [_P, _vp, _i64, _vp, _i64, _i32, _vp, _vp]),
     "dgp_kernel_Kdiag": (ctypes.c_int, [_P, _vp, _i64, _vp, _vp]),
     "dgp_mpad": (_i32, [_i32]),

@@ -121,6 +121,8 @@ template <typename T>
 static inline const T* ws_ptr(const void* ws, size_t off) { return reinterpret_cast<const T*>(static_cast<const char*>(ws) + off); }
 
 int check_desc(const dgp_cond_desc* d);
+// batched in-place lower Cholesky of `batch` Mpad x Mpad matrices (Mpad multiple of 64, <= 1024); status[b] = failing pivot + 1
+int cholesky_batched(double* K, int Mpad, int batch, int32_t* status, cudaStream_t st);
 
 #ifdef __CUDACC__
 // ------------------------------------------------------------------------------------------------ PTX wrappers

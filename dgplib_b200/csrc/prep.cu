@@ -103,6 +103,8 @@ constexpr int CHOL_THREADS = 512;
 
 __global__ void __launch_bounds__(CHOL_THREADS, 1)
 k_cholesky(double* __restrict__ K, int Mpad, int NB, int32_t* __restrict__ status) {
+    K += (size_t)blockIdx.x * Mpad * Mpad;      // batched: one CTA per matrix
+    status += blockIdx.x;
     extern __shared__ double sm[];
     double* sD = sm;                 // [NB][33]
     double* sDinv = sD + 32 * 33;    // [32]
@@ -208,6 +210,19 @@ k_cholesky(double* __restrict__ K, int Mpad, int NB, int32_t* __restrict__ statu
         __syncthreads();
     }
     if (tid == 0) status[0] = s_fail;
+}
+
+int cholesky_batched(double* K, int Mpad, int batch, int32_t* status, cudaStream_t st) {
+    const int NB = (Mpad <= 512) ? 32 : 16;
+    const size_t chol_smem = (32 * 33 + 32 + (size_t)(Mpad - NB) * (NB + 1)) * sizeof(double);
+    static bool attr_set = false;
+    if (!attr_set) {
+        if (cudaFuncSetAttribute(k_cholesky, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess) return DGP_ERR_LAUNCH;
+        attr_set = true;
+    }
+    k_cholesky<<<batch, CHOL_THREADS, chol_smem, st>>>(K, Mpad, NB, status);
+    DGP_COUNT_LAUNCH();
+    return cudaGetLastError() == cudaSuccess ? DGP_OK : DGP_ERR_LAUNCH;
 }
 
 // ------------------------------------------------------------------------------------------------ triangular inverse
@@ -384,14 +399,7 @@ extern "C" int dgp_cond_prepare(const dgp_cond_desc* d, void* ws, size_t ws_byte
 
     k_prep_z<<<(Mpad + 127) / 128, 128, 0, st>>>(*d, Mpad, Dp, Zs, zn, ztask); DGP_COUNT_LAUNCH();
     k_kuu<<<dim3((Mpad + 127) / 128, Mpad), 128, 0, st>>>(*d, Mpad, Dp, Zs, zn, ztask, Lm); DGP_COUNT_LAUNCH();
-    const int NB = (Mpad <= 512) ? 32 : 16;
-    const size_t chol_smem = (32 * 33 + 32 + (size_t)(Mpad - NB) * (NB + 1)) * sizeof(double);
-    static bool attr_set = false;
-    if (!attr_set) {
-        if (cudaFuncSetAttribute(k_cholesky, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess) return DGP_ERR_LAUNCH;
-        attr_set = true;
-    }
-    k_cholesky<<<1, CHOL_THREADS, chol_smem, st>>>(Lm, Mpad, NB, status); DGP_COUNT_LAUNCH();
+    if ((rc = cholesky_batched(Lm, Mpad, 1, status, st)) != DGP_OK) return rc;
     k_diag_inv<<<Mpad / 32, 32, 0, st>>>(Lm, Linv, Mpad); DGP_COUNT_LAUNCH();
     k_tri_inv_cols<<<Mpad / 32, 256, 0, st>>>(Lm, Linv, Mpad); DGP_COUNT_LAUNCH();
     double* klpart = ws_ptr<double>(ws, w.klpart);

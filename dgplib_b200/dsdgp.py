@@ -173,13 +173,14 @@ class DSDGP(Parameterized):
     def _propagate(self, Xnew, full_cov=False, num_samples=1, eps=None, seed=None):
         """Propagate points Xnew through the DGP cascade: (Fs, Fmeans, Fvars), lists of [S, N, .] CUDA tensors."""
         if full_cov:
-            raise NotImplementedError("full_cov=True is outside the B200 hot path (SURVEY.md 8f, rank 3)")
+            return self.engine.propagate_full_cov(Xnew, num_samples, z=eps, seed=self.seed if seed is None else seed)
         return self.engine.propagate(Xnew, num_samples, eps=eps, seed=self.seed if seed is None else seed,
                                      chunk_rows=self.predict_chunk_rows)
 
     def _build_predict(self, Xnew, full_cov=False, num_samples=1, eps=None, seed=None):
         if full_cov:
-            raise NotImplementedError("full_cov=True is outside the B200 hot path (SURVEY.md 8f, rank 3)")
+            _, Fmeans, Fvars = self._propagate(Xnew, True, num_samples, eps=eps, seed=seed)
+            return Fmeans[-1], Fvars[-1]
         _, Fmeans, Fvars = self.engine.propagate(Xnew, num_samples, eps=eps, seed=self.seed if seed is None else seed,
                                                  chunk_rows=self.predict_chunk_rows, last_only=True)
         return Fmeans[-1], Fvars[-1]
@@ -266,14 +267,31 @@ class DSDGP(Parameterized):
         out = self._propagate(Xnew, False, num_samples, eps=eps, seed=seed)
         return tuple([t.cpu().numpy() for t in lst] for lst in out)
 
-    def predict_f_full_cov(self, Xnew, num_samples):
-        raise NotImplementedError("predict_f_full_cov is outside the B200 hot path (SURVEY.md 8f, rank 3)")
+    def predict_f_full_cov(self, Xnew, num_samples, eps=None, seed=None):
+        """Mean [S,N,D_Y] and covariance [S,N,N,D_Y] of the final layer at Xnew (dgplib/dsdgp.py:142-148); samples are
+        propagated with the full covariance across the N points (N <= 1024).  eps: per layer [S, R_l, N] draws."""
+        mean, var = self._build_predict(Xnew, True, num_samples, eps=eps, seed=seed)
+        return mean.cpu().numpy(), var.cpu().numpy()
 
-    def predict_all_layers_full_cov(self, Xnew, num_samples):
-        raise NotImplementedError("predict_all_layers_full_cov is outside the B200 hot path (SURVEY.md 8f, rank 3)")
+    def predict_all_layers_full_cov(self, Xnew, num_samples, eps=None, seed=None):
+        """(Fs, Fmeans, Fvars) for every layer with full covariances (dgplib/dsdgp.py:161-167)."""
+        out = self._propagate(Xnew, True, num_samples, eps=eps, seed=seed)
+        return tuple([t.cpu().numpy() for t in lst] for lst in out)
 
-    def predict_f_samples(self, Xnew, num_samples):
-        raise NotImplementedError("predict_f_samples needs the full-covariance path (SURVEY.md 8f, rank 3)")
+    def predict_f_samples(self, Xnew, num_samples, eps=None, V=None, seed=None):
+        """Samples of the final layer's posterior at Xnew, [num_samples, N, D_Y] (dgplib/dsdgp.py:170-185): one
+        full-covariance propagation, then mu + chol(var + jitter I) V per output.  V [D_Y, N, num_samples] injects the
+        final draws."""
+        mu, var = self._build_predict(Xnew, True, 1, eps=eps, seed=seed)
+        mu, var = mu[0], var[0]                                      # [N, D_Y], [N, N, D_Y]
+        N, DY = mu.shape
+        eng = self.engine
+        if V is None:
+            g = torch.Generator(device=eng.device)
+            g.manual_seed((self.seed if seed is None else seed) + 7919)
+            V = torch.randn(DY, N, num_samples, dtype=torch.float64, device=eng.device, generator=g)
+        out = eng.chol_sample(var.permute(2, 0, 1).contiguous(), V, mu.t().contiguous())    # [D_Y, N, num_samples]
+        return out.permute(2, 1, 0).contiguous().cpu().numpy()
 
     def predict_y_moments(self, Xnew, num_samples=10, eps=None, seed=None):
         """Moment-matched predictive mean and variance of held-out data over `num_samples` propagated samples

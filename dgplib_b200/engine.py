@@ -322,6 +322,89 @@ class Engine:
                 return None, [out["mean"][L - 1]], [out["var"][L - 1]]
             return ([out["F"][l] for l in keep], [out["mean"][l] for l in keep], [out["var"][l] for l in keep])
 
+    # ------------------------------------------------------------------------------------------ full covariance
+    def _layer_full_cov(self, l, X, lib, st):
+        """mean [N, R] and covariance [R, N, N] of layer l at the rows X [N, Dx] (one sample): the row kernel gives the
+        mean and A = Lm^-1 Kuf, dgp_cond_fullcov turns A into Knn - A^T A + (Lq^T A)^T (Lq^T A)."""
+        layer, conds = self.layers[l], self.conds[l]
+        N, R = X.shape[0], layer.output_dim
+        dev = self.device
+        mean = torch.empty(N, R, dtype=_F64, device=dev)
+        var_diag = torch.empty(N, R, dtype=_F64, device=dev)
+        fvar = torch.empty(R, N, N, dtype=_F64, device=dev)
+        for c in conds:
+            A = torch.empty(N, _cabi.mpad(layer.num_inducing), dtype=_F64, device=dev)
+            _cabi.check(lib.dgp_cond_forward(c.ref(), _cabi.ptr(c.ws), _cabi.ptr(X), N, N, None, 0, None, 0, 0, 0,
+                                             _cabi.ptr(mean), _cabi.ptr(var_diag), None, R, _cabi.ptr(A), st),
+                        "dgp_cond_forward")
+            nbytes = lib.dgp_cond_fullcov_ws_bytes(c.ref(), N)
+            if nbytes == 0:
+                raise _cabi.DgpError("full-covariance prediction supports at most 1024 points per call")
+            scratch = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+            out = fvar[c.desc.col0:c.desc.col0 + c.desc.R]
+            _cabi.check(lib.dgp_cond_fullcov(c.ref(), _cabi.ptr(c.ws), _cabi.ptr(X), N, _cabi.ptr(A),
+                                             ctypes.c_void_p(out.data_ptr()), _cabi.ptr(scratch), nbytes, st),
+                        "dgp_cond_fullcov")
+        return mean, fvar
+
+    def chol_sample(self, var, z, mean=None, jitter=None):
+        """mean + chol(var + jitter I) z for a batch: var [Bt, N, N], z [Bt, N, nz], mean [Bt, N] or None -> [Bt, N, nz]
+        (normal_sample's full-covariance branch, dgplib/utils.py:28-36)."""
+        lib, st = _cabi.lib(), _cabi.stream_ptr()
+        var, z = _dev_tensor(var, self.device), _dev_tensor(z, self.device)
+        Bt, N, nz = z.shape
+        mean = None if mean is None else _dev_tensor(mean, self.device)
+        out = torch.empty(Bt, N, nz, dtype=_F64, device=self.device)
+        nbytes = lib.dgp_chol_sample_ws_bytes(N, Bt)
+        if nbytes == 0:
+            raise _cabi.DgpError("full-covariance sampling supports at most 1024 points per call")
+        scratch = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
+        status = torch.zeros(Bt, dtype=torch.int32, device=self.device)
+        _cabi.check(lib.dgp_chol_sample(_cabi.ptr(var), N * N, N, 1, N, Bt,
+                                        settings.jitter_level if jitter is None else jitter, _cabi.ptr(z), nz,
+                                        _cabi.ptr(mean) if mean is not None else None, N, 1, _cabi.ptr(out),
+                                        _cabi.ptr(scratch), nbytes, ctypes.c_void_p(status.data_ptr()), st),
+                    "dgp_chol_sample")
+        bad = int(status.max())
+        if bad:
+            raise _cabi.DgpError(f"Cholesky of a predictive covariance failed at pivot {bad - 1}")
+        return out
+
+    def propagate_full_cov(self, X, S, z=None, seed=0, params=None):
+        """DSDGP._propagate(full_cov=True) (dgplib/dsdgp.py:84-99): Fs [S,N,R(+1)], Fmeans [S,N,R], Fvars [S,N,N,R] per
+        layer.  z[l] [S, R_l, N] are the N(0,1) draws of normal_sample's full-covariance branch (Philox when None)."""
+        lib, st = _cabi.lib(), _cabi.stream_ptr()
+        with torch.no_grad():
+            dev = self.device
+            X = _dev_tensor(X, dev)
+            self._bind(self._detached(params))
+            N = X.shape[0]
+            for evs in self._prepare(1, N, False, None):
+                for ev in evs:
+                    torch.cuda.current_stream().wait_event(ev)
+            Fs, Ms, Vs = [[] for _ in self.layers], [[] for _ in self.layers], [[] for _ in self.layers]
+            for s in range(S):
+                inp = X
+                for l, layer in enumerate(self.layers):
+                    R = layer.output_dim
+                    mean, fvar = self._layer_full_cov(l, inp, lib, st)
+                    if z is not None:
+                        zz = _dev_tensor(z[l], dev)[s].reshape(R, N, 1)
+                    else:
+                        zz = torch.empty(N, R, dtype=_F64, device=dev)
+                        _cabi.check(lib.dgp_philox_normal(_cabi.ptr(zz), N, R, R, self._layer_seed(seed, l), s * N, 0, 0,
+                                                          st), "dgp_philox_normal")
+                        zz = zz.t().contiguous().reshape(R, N, 1)
+                    F = self.chol_sample(fvar, zz, mean.t().contiguous())[:, :, 0].t().contiguous()   # [N, R]
+                    if self.multitask:
+                        F = torch.cat([F, inp[:, -1:]], 1)
+                    Fs[l].append(F)
+                    Ms[l].append(mean)
+                    Vs[l].append(fvar.permute(2, 1, 0).contiguous())        # [R,N,N] -> [N,N,R] (dgplib/layers.py:77)
+                    inp = F
+            self.check_status()
+            return ([torch.stack(f) for f in Fs], [torch.stack(m) for m in Ms], [torch.stack(v) for v in Vs])
+
     # ------------------------------------------------------------------------------------------ ELBO (+ grad)
     def grad_layout(self, params):
         """Offsets of [elbo, grads of params()...] inside the flat fp64 gradient buffer."""
@@ -550,6 +633,28 @@ def _layer_engine(layer):
         eng = Engine([layer], None, multitask=False)
         object.__setattr__(layer, "_dgp_engine", eng)
     return eng
+
+
+def layer_predict_full_cov(layer, Xnew, stochastic=True):
+    """Layer._build_predict(full_cov=True) (dgplib/layers.py:74-81): stochastic: [S,N,D] -> mean [S,N,R], var [S,N,N,R];
+    otherwise [N,D] -> mean [N,R], var [R,N,N] (gpflow's own layout, as the reference returns it there)."""
+    eng = _layer_engine(layer)
+    lib, st = _cabi.lib(), _cabi.stream_ptr()
+    with torch.no_grad():
+        X = _dev_tensor(Xnew, eng.device)
+        eng._bind(eng._detached())
+        rows = X.shape[1] if stochastic else X.shape[0]
+        for evs in eng._prepare(1, rows, False, None):
+            for ev in evs:
+                torch.cuda.current_stream().wait_event(ev)
+        if not stochastic:
+            return eng._layer_full_cov(0, X, lib, st)
+        means, vars_ = [], []
+        for s in range(X.shape[0]):
+            m, v = eng._layer_full_cov(0, X[s].contiguous(), lib, st)
+            means.append(m)
+            vars_.append(v.permute(2, 1, 0).contiguous())
+        return torch.stack(means), torch.stack(vars_)
 
 
 def layer_predict(layer, Xnew, stochastic=True):

@@ -42,9 +42,11 @@ class Layer(Parameterized):
 
     def _build_predict(self, Xnew, full_cov=False, stochastic=True):
         """(mean, var) of the layer at Xnew.  stochastic=True: Xnew [S,N,D] -> [S,N,R] each (samples flattened into
-        one conditional, dgplib/layers.py:82-87); stochastic=False: [N,D] -> [N,R]."""
+        one conditional, dgplib/layers.py:82-87); stochastic=False: [N,D] -> [N,R].  full_cov=True (N <= 1024):
+        var is [S,N,N,R] (dgplib/layers.py:74-81), or gpflow's [R,N,N] when stochastic=False."""
         if full_cov:
-            raise NotImplementedError("full_cov=True is outside the B200 hot path (SURVEY.md 8f, rank 3)")
+            from .engine import layer_predict_full_cov
+            return layer_predict_full_cov(self, Xnew, stochastic)
         from .engine import layer_predict
         return layer_predict(self, Xnew, stochastic)
 

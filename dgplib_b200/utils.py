@@ -20,6 +20,27 @@ def shape_as_list(X):
 def normal_sample(mean, var, full_cov=False, eps=None):
     """mean + z * var ** 0.5 (dgplib/utils.py:25-27); `eps` injects the draw for reproducibility."""
     if full_cov:
-        raise NotImplementedError("full-covariance sampling is outside the B200 hot path (SURVEY.md 8f, rank 3)")
+        # mean [S,N,D], var [S,N,N,D], z [S,D,N]: chol(var + jitter I) z per (sample, output), dgplib/utils.py:28-36
+        from .engine import Engine  # noqa: F401  (CUDA path)
+        from . import _cabi
+        _cabi.require_cuda()
+        S, N, D = mean.shape
+        z = torch.randn(S, D, N, dtype=mean.dtype, device=mean.device) if eps is None else eps
+        eng = _sampler()
+        out = eng.chol_sample(var.permute(0, 3, 1, 2).reshape(S * D, N, N).contiguous(), z.reshape(S * D, N, 1),
+                              mean.permute(0, 2, 1).reshape(S * D, N).contiguous())
+        return out.reshape(S, D, N).permute(0, 2, 1).contiguous()
     z = torch.randn_like(mean) if eps is None else eps
     return mean + z * var ** 0.5
+
+
+_SAMPLER = None
+
+
+def _sampler():
+    """A layer-less Engine: only its chol_sample (dgp_chol_sample) is used."""
+    global _SAMPLER
+    if _SAMPLER is None:
+        from .engine import Engine
+        _SAMPLER = Engine([], None)
+    return _SAMPLER

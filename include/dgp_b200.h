@@ -145,6 +145,24 @@ int dgp_cond_backward_gram(const dgp_cond_desc* d, void* ws, const double* A_sav
 int dgp_cond_backward_params(const dgp_cond_desc* d, void* ws, double kl_weight, double* gZ, double* gtheta,
                              double* gq_mu, double* gq_sqrt, void* stream);
 
+/* ---- full-covariance branch (small N: plots, posterior draws) ---------------------------------------------------
+ * dgp_cond_fullcov replaces base_conditional(full_cov=True) as called from dgplib/layers.py:74-81:
+ *   fvar[r] = k(X, X) - A^T A + (Lq_r^T A)^T (Lq_r^T A)   for the conditional's R outputs, fvar [R, n, n] (n <= 1024);
+ *   A_save [n, Mpad] comes from dgp_cond_forward on the same rows.
+ * dgp_chol_sample replaces normal_sample's full-covariance branch (dgplib/utils.py:28-36) and the sampling step of
+ * predict_f_samples (dgplib/dsdgp.py:170-185): for b < batch
+ *   out[b, :, :] = mean[b] + chol(var[b] + jitter I) z[b],  var[b](i, j) = var[b*stride_b + i*stride_i + j*stride_j],
+ *   z [batch, n, nz], out [batch, n, nz], mean[b](i) = mean[b*mean_stride_b + i*mean_stride_i] (NULL: zero).
+ *   status_dev (nullable) [batch]: failing pivot + 1 of each factorisation. */
+size_t dgp_cond_fullcov_ws_bytes(const dgp_cond_desc* d, int64_t n);
+int dgp_cond_fullcov(const dgp_cond_desc* d, const void* ws, const double* X, int64_t n, const double* A_save,
+                     double* fvar, void* scratch, size_t scratch_bytes, void* stream);
+size_t dgp_chol_sample_ws_bytes(int64_t n, int32_t batch);
+int dgp_chol_sample(const double* var, int64_t stride_b, int64_t stride_i, int64_t stride_j, int64_t n, int32_t batch,
+                    double jitter, const double* z, int32_t nz, const double* mean, int64_t mean_stride_b,
+                    int64_t mean_stride_i, double* out, void* scratch, size_t scratch_bytes, int32_t* status_dev,
+                    void* stream);
+
 /* ---- stand-alone kernel-matrix entry points (dgplib_b200.specialized_kernels; gpflow Kernel.K / Kdiag) -------
  *   K [n1, n2] = k(X1, X2) (White contributes nothing, as in gpflow when X2 is given);  symmetric != 0 computes
  *   k(X1, X1) + White on the diagonal.  Kdiag [n1]. */

@@ -125,6 +125,24 @@ def conditional_white(X, Z, kern, q_mu, q_sqrt):
     return fmean, fvar.t()
 
 
+def conditional_white_full_cov(X, Z, kern, q_mu, q_sqrt):
+    """base_conditional(full_cov=True): fvar [R, N, N] = Knn - A^T A + LTA^T LTA with Knn = kern.K(X) (symmetric call,
+    so White sits on its diagonal).  Called from dgplib/layers.py:66-69 with full_cov=True."""
+    M = Z.shape[0]
+    Kmm = kern_K(kern, Z) + JITTER * torch.eye(M, dtype=Z.dtype)
+    Kmn = kern_K(kern, Z, X)
+    Knn = kern_K(kern, X)
+    Lm = torch.linalg.cholesky(Kmm)
+    A = torch.linalg.solve_triangular(Lm, Kmn, upper=False)
+    fvar = Knn - A.t() @ A
+    fmean = A.t() @ q_mu
+    L = torch.tril(q_sqrt)
+    R = q_sqrt.shape[0]
+    LTA = L.transpose(1, 2) @ A.unsqueeze(0).expand(R, -1, -1)
+    fvar = fvar[None] + LTA.transpose(1, 2) @ LTA
+    return fmean, fvar                                             # [N,R], [R,N,N]
+
+
 def gauss_kl_white(q_mu, q_sqrt):
     """gpflow.kullback_leiblers.gauss_kl(q_mu, q_sqrt, K=None), called at dgplib/layers.py:60."""
     M, R = q_mu.shape
@@ -163,6 +181,62 @@ def layer_build_predict(layer, Xnew):
     S, N, D = Xnew.shape
     mean, var = layer_conditional(layer, Xnew.reshape(S * N, D))
     return mean.reshape(S, N, -1), var.reshape(S, N, -1)
+
+
+def layer_build_predict_full_cov(layer, Xnew):
+    """multisample_conditional, full_cov branch (dgplib/layers.py:74-81; multikernel_layers.py:79-83, :93-97): map over
+    the S samples, each conditional's [R,N,N] covariance transposed to [N,N,R].  Returns mean [S,N,R], var [S,N,N,R]."""
+    groups = layer["groups"]
+    R = layer["q_mu"].shape[1]
+    off = R // len(groups)
+    means, vars_ = [], []
+    for s in range(Xnew.shape[0]):
+        ms, vs = [], []
+        for i, g in enumerate(groups):
+            m, v = conditional_white_full_cov(Xnew[s], g["Z"], g["kernel"], layer["q_mu"][:, i * off:(i + 1) * off],
+                                              layer["q_sqrt"][i * off:(i + 1) * off])
+            ms.append(m)
+            vs.append(v.permute(2, 1, 0))                          # tf.transpose(v): [R,N,N] -> [N,N,R]
+        means.append(torch.cat(ms, -1) + mean_function(layer.get("mean"), Xnew[s], R))
+        vars_.append(torch.cat(vs, -1))
+    return torch.stack(means), torch.stack(vars_)
+
+
+def normal_sample_full_cov(mean, var, z):
+    """dgplib/utils.py:28-36: mean [S,N,D], var [S,N,N,D], z [S,D,N] -> mean + chol(var + jitter I) z per (s, d)."""
+    S, N, D = mean.shape
+    v = var.permute(0, 3, 1, 2) + JITTER * torch.eye(N, dtype=mean.dtype)[None, None]
+    chol = torch.linalg.cholesky(v)                                 # [S,D,N,N]
+    f = mean.permute(0, 2, 1) + (chol @ z.unsqueeze(-1))[..., 0]    # [S,D,N]
+    return f.permute(0, 2, 1)
+
+
+def propagate_full_cov(layers, Xnew, S, z, multitask=False):
+    """DSDGP._propagate with full_cov=True (dgplib/dsdgp.py:84-99); z[l] is the N(0,1) draw [S, R_l, N]."""
+    Fs = [tile_over_samples(Xnew, S)]
+    Fmeans, Fvars = [], []
+    for l, layer in enumerate(layers):
+        mean, var = layer_build_predict_full_cov(layer, Fs[-1])
+        F = normal_sample_full_cov(mean, var, z[l])
+        if multitask:
+            F = torch.cat([F, Fs[-1][:, :, -1:]], -1)
+        Fs.append(F)
+        Fmeans.append(mean)
+        Fvars.append(var)
+    return Fs[1:], Fmeans, Fvars
+
+
+def predict_f_samples(layers, Xnew, num_samples, z_layers, V, multitask=False):
+    """DSDGP.predict_f_samples (dgplib/dsdgp.py:170-185): one full-covariance propagation, then per output i
+    mu[:, i] + chol(var[:, :, i] + jitter I) V_i with V [D_Y, N, num_samples]; returns [num_samples, N, D_Y]."""
+    _, Fmeans, Fvars = propagate_full_cov(layers, Xnew, 1, z_layers, multitask)
+    mu, var = Fmeans[-1][0], Fvars[-1][0]
+    N = mu.shape[0]
+    out = []
+    for i in range(mu.shape[1]):
+        L = torch.linalg.cholesky(var[:, :, i] + JITTER * torch.eye(N, dtype=mu.dtype))
+        out.append(mu[:, i:i + 1] + L @ V[i])
+    return torch.stack(out).permute(2, 1, 0)
 
 
 def layer_kl(layer):

@@ -63,8 +63,11 @@ def test_layer_parameters_at_construction():
     assert layer.q_sqrt.shape == (2, 7, 7) and np.allclose(layer.q_sqrt.value, np.tile(np.eye(7), (2, 1, 1)))
     assert isinstance(layer.mean_function, Zero)
     assert Layer(3, 2, 7, RBF(3), multitask=True).feature.Z.shape == (7, 4)
-    with pytest.raises(NotImplementedError):
-        layer._build_predict(np.zeros((1, 2, 3)), full_cov=True)
+    import torch
+    if not torch.cuda.is_available():
+        from dgplib_b200._cabi import DgpError
+        with pytest.raises(DgpError):        # every compute path needs the GPU: no CPU fallback
+            layer._build_predict(np.zeros((1, 2, 3)), full_cov=True)
 
 
 # ---- reference tests/test_cascade.py
@@ -193,11 +196,16 @@ def test_positive_transform_and_kernel_parts():
         SwitchedLikelihood([Gaussian(), object()])
 
 
-def test_full_cov_paths_are_declared_out_of_scope():
+def test_compute_paths_fail_loudly_without_cuda():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("CUDA present")
+    from dgplib_b200._cabi import DgpError
     X, Y, Z = _toy()
     seq = Sequential([InputLayer(1, 1, 25, RBF(1)), OutputLayer(1, 1, 25, RBF(1))])
     model = dg.DSDGP(X=X, Y=Y, Z=Z, layers=seq, likelihood=Gaussian())
-    for call in (lambda: model.predict_f_full_cov(X, 1), lambda: model.predict_all_layers_full_cov(X, 1),
-                 lambda: model.predict_f_samples(X, 3), lambda: model._propagate(X, full_cov=True)):
-        with pytest.raises(NotImplementedError):
+    for call in (lambda: model.compute_log_likelihood(), lambda: model.predict_f(X, 1), lambda: model.predict_y(X),
+                 lambda: model.predict_f_full_cov(X, 1), lambda: model.predict_f_samples(X, 3),
+                 lambda: model.elbo_and_grad()):
+        with pytest.raises(DgpError):
             call()
