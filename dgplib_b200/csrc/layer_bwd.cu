@@ -98,13 +98,6 @@ __global__ void __launch_bounds__(C::NTHREADS, 1) k_cond_bwd(const __grid_consta
     // segment lists of the two streamed phases (shared by the producer warp and the consumers)
     auto seg_dA = [&](int s) {      // dA block row i accumulates over all r: dense S_r - I
         Seg sg;
-#ifdef DGP_EXP_ONESEG
-        {   // timing experiment only (wrong results): one long segment per block row, epilogue once, one hot matrix
-            sg.i = s / R; sg.r = s % R; sg.W = a.SmI; sg.kc0 = 0;
-            sg.kc1 = (sg.r == 0) ? R * (Mpad / C::KC) : 0; sg.flush = (sg.r == R - 1);
-            return sg;
-        }
-#endif
         sg.i = s / R;
         sg.r = s % R;
         sg.W = a.SmI + (size_t)sg.r * a.tl;
@@ -668,9 +661,6 @@ extern "C" int dgp_cond_backward(const dgp_cond_desc* d, void* ws, const double*
         if (rc != DGP_ERR_UNSUPPORTED) return rc;                                     \
     }
     if (w.Mpad <= 256) {
-#ifdef DGP_BWD_STAGES
-        DGP_TRY_BWD(DGP_BWD_WN, 32, DGP_BWD_STAGES)
-#endif
         DGP_TRY_BWD(DGP_BWD_WN, 32, 4) DGP_TRY_BWD(DGP_BWD_WN, 32, 3) DGP_TRY_BWD(DGP_BWD_WN, 32, 2)
     } else {
         DGP_TRY_BWD(2, 16, 4) DGP_TRY_BWD(2, 16, 3) DGP_TRY_BWD(2, 16, 2)

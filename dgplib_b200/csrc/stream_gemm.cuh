@@ -107,11 +107,7 @@ __device__ __forceinline__ void produce_phase(Pipe& p, int nseg, SegFn segfn, in
             if (p.round > 0) mbar_wait(&p.empty[p.stage], (p.round - 1) & 1);
             mbar_expect_tx(&p.full[p.stage], (uint32_t)(C::STAGE_DOUBLES * sizeof(double)));
             bulk_g2s(p.stages + (size_t)p.stage * C::STAGE_DOUBLES,
-#ifdef DGP_EXP_ONESEG
-                     sg.W + ((size_t)sg.i * nch + (kc % nch)) * C::STAGE_DOUBLES,
-#else
                      sg.W + ((size_t)sg.i * nch + kc) * C::STAGE_DOUBLES,
-#endif
                      (uint32_t)(C::STAGE_DOUBLES * sizeof(double)), &p.full[p.stage]);
             pipe_advance<C>(p);
         }
