@@ -423,6 +423,15 @@ class Engine:
         shard's first row in it, and `all_reduce(flat)` sums the flat buffer over ranks (NCCL).  The KL term enters
         with weight 1/world_size on every rank so the sum is exact."""
         lib, st = _cabi.lib(), _cabi.stream_ptr()
+        if need_grad:
+            for layer in self.layers:
+                mf = layer.mean_function
+                if isinstance(mf, Linear) and (mf.A.trainable or mf.b.trainable):
+                    # the reference freezes the Linear mean in initialize_forward (dgplib/layers.py:184-186); only an
+                    # OutputLayer built with its own Linear mean keeps it trainable -- there is no gradient kernel for it
+                    raise NotImplementedError("a trainable Linear mean function is not supported on the B200 path: call "
+                                              "mean_function.set_trainable(False), as the reference does for "
+                                              "Input/Hidden layers")
         with torch.no_grad():
             dev = self.device
             main = torch.cuda.current_stream()

@@ -402,3 +402,17 @@ def test_cuda_graph_replay_matches_eager(cuda):
         assert torch.equal(va, vb)
         for x, y in zip(ga, gb):
             assert torch.equal(x, y)
+
+
+def test_trainable_linear_mean_is_refused(cuda):
+    rng = np.random.RandomState(0)
+    X, Y, Z = rng.randn(40, 2), rng.randn(40, 1), rng.randn(8, 2)
+    il = InputLayer(2, 2, 8, RBF(2), mean_function=Linear(A=np.zeros((2, 2))))
+    ol = OutputLayer(2, 1, 8, RBF(2), mean_function=Linear(A=np.ones((2, 1))))     # stays trainable (layers.py:211-218)
+    model = dg.DSDGP(X, Y, Z, Sequential([il, ol]), Gaussian())
+    model.compile()
+    with pytest.raises(NotImplementedError):
+        model.elbo_and_grad()
+    ol.mean_function.set_trainable(False)
+    v, _ = model.elbo_and_grad()
+    assert torch.isfinite(v)
