@@ -415,7 +415,7 @@ def main():
     timers = eng.timer_summary()
     eng.timers = None
     clocks = sampler.stop() if sampler is not None else None
-    launches = launches_per_step * args.steps * (2 if graphed is not None else 2)   # timed pass + per-kernel pass
+    launches = launches_per_step * args.steps     # kernels of the timed K steps (replayed from the captured graph)
     if dist is not None:
         tm = torch.tensor([ms], dtype=torch.float64, device=dev)
         dist.all_reduce(tm, op=dist.ReduceOp.MAX)

@@ -506,7 +506,7 @@ static int launch_bwd(const BwdArgs& a, cudaStream_t st) {
 
 // ------------------------------------------------------------------------------------------------ Gram kernel
 // out[s][mat][m1][m2] += sum_{n in split s} w_mat[n] P_mat[n][m1] A[n][m2]   for 64x64 tiles with tile(m1) >= tile(m2)
-//   (inside diagonal tiles the strictly-upper 32x32 quadrant is skipped: results are consumed at 32-block granularity)
+//   (inside diagonal tiles only the 8x8 tiles on and below the tile diagonal are computed and consumed)
 //   mat <  R : P = A,    w = g_var[:, mat]      (G_r, symmetric)
 //   mat == R : P = dKuf, w = 1                  (P = dKuf^T A)
 struct GramArgs {
@@ -522,6 +522,38 @@ struct GramArgs {
 #define DGP_GR_STAGES 3
 #endif
 constexpr int GR_THREADS = 128, GR_STAGES = DGP_GR_STAGES, GR_KC = DGP_GR_KC, GR_LD = 68;
+
+// Diagonal 64x64 tile: only the 36 lower 8x8 tiles are needed.  Warp W takes tile rows W and 7-W (W+1 and 8-W tiles:
+// nine per warp, balanced), with compile-time bounds so that nothing is predicated off (a predicated-off DMMA still
+// occupies the fp64 pipe).  9/16 of the work of a full tile.
+template <int W>
+__device__ __forceinline__ void gram_diag_chunk(double (&accA)[8][2], double (&accB)[8][2], const double* __restrict__ P,
+                                                const double* __restrict__ Q, const double* __restrict__ Wt, int g, int t) {
+#pragma unroll
+    for (int kk = 0; kk < GR_KC / 4; ++kk) {
+        const double w = Wt[kk * 4 + t];
+        const double a0 = P[(kk * 4 + t) * GR_LD + W * 8 + g] * w;
+        const double a1 = P[(kk * 4 + t) * GR_LD + (7 - W) * 8 + g] * w;
+#pragma unroll
+        for (int j = 0; j <= 7 - W; ++j) {
+            const double b = Q[(kk * 4 + t) * GR_LD + j * 8 + g];
+            if (j <= W) dmma884(accA[j], a0, b);
+            dmma884(accB[j], a1, b);
+        }
+    }
+}
+template <int W>
+__device__ __forceinline__ void gram_diag_store(const double (&accA)[8][2], const double (&accB)[8][2], double* out, int Mpad,
+                                                int base, int g, int t) {
+#pragma unroll
+    for (int j = 0; j <= 7 - W; ++j)
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+            const int m2 = base + j * 8 + 2 * t + e;
+            if (j <= W) out[(size_t)(base + W * 8 + g) * Mpad + m2] += accA[j][e];
+            out[(size_t)(base + (7 - W) * 8 + g) * Mpad + m2] += accB[j][e];
+        }
+}
 
 __global__ void __launch_bounds__(GR_THREADS, 4) k_gram(GramArgs a) {
     extern __shared__ __align__(128) double gsm[];
@@ -544,8 +576,8 @@ __global__ void __launch_bounds__(GR_THREADS, 4) k_gram(GramArgs a) {
     long long nend = nbeg + a.rows_per_split;
     if (nend > a.n_rows) nend = a.n_rows;
     const int nchunks = nend > nbeg ? (int)((nend - nbeg + GR_KC - 1) / GR_KC) : 0;
-    // diagonal tiles: the strictly-upper 32x32 quadrant (rows < 32, columns >= 32) is never read downstream
-    const int jmax = (bi == bj && wm < 2) ? 4 : 8;
+    const bool diag = (bi == bj);     // diagonal tiles compute the lower 8x8 tiles only (gram_diag_chunk)
+    constexpr int jmax = 8;
 
     double acc[2][8][2];
 #pragma unroll
@@ -586,6 +618,15 @@ __global__ void __launch_bounds__(GR_THREADS, 4) k_gram(GramArgs a) {
         const double* Q = Qs[stage];
         const double* W = wsm[stage];
         stage = (stage + 1 == GR_STAGES) ? 0 : stage + 1;
+        if (diag) {
+            switch (wm) {      // acc[0] = tile row W, acc[1] = tile row 7-W
+                case 0: gram_diag_chunk<0>(acc[0], acc[1], P, Q, W, g, t); break;
+                case 1: gram_diag_chunk<1>(acc[0], acc[1], P, Q, W, g, t); break;
+                case 2: gram_diag_chunk<2>(acc[0], acc[1], P, Q, W, g, t); break;
+                default: gram_diag_chunk<3>(acc[0], acc[1], P, Q, W, g, t); break;
+            }
+            continue;
+        }
 #pragma unroll
         for (int kk = 0; kk < GR_KC / 4; ++kk) {
             const double w = W[kk * 4 + t];
@@ -612,6 +653,15 @@ __global__ void __launch_bounds__(GR_THREADS, 4) k_gram(GramArgs a) {
     cp_async_wait<0>();
     if (nchunks == 0) return;
     double* out = a.gram + ((size_t)split * (R + 1) + mat) * Mpad * Mpad;
+    if (diag) {
+        switch (wm) {
+            case 0: gram_diag_store<0>(acc[0], acc[1], out, Mpad, bi * 64, g, t); break;
+            case 1: gram_diag_store<1>(acc[0], acc[1], out, Mpad, bi * 64, g, t); break;
+            case 2: gram_diag_store<2>(acc[0], acc[1], out, Mpad, bi * 64, g, t); break;
+            default: gram_diag_store<3>(acc[0], acc[1], out, Mpad, bi * 64, g, t); break;
+        }
+        return;
+    }
 #pragma unroll
     for (int q = 0; q < 2; ++q)
 #pragma unroll

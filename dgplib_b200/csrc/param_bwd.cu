@@ -16,7 +16,7 @@ __global__ void k_gram_reduce(const double* __restrict__ gram, int nsplit, int R
     if (j >= Mpad) return;
     const size_t mm = (size_t)Mpad * Mpad;
     if (mat < R) {
-        const bool lower = (i / 32) >= (j / 32);   // k_gram fills 32x32 blocks on and below the block diagonal
+        const bool lower = (i / 8) >= (j / 8);     // k_gram fills the 8x8 tiles on and below the tile diagonal
         const size_t off = lower ? (size_t)i * Mpad + j : (size_t)j * Mpad + i;
         double s = 0.0;
         for (int sp = 0; sp < nsplit; ++sp) s += gram[((size_t)sp * (R + 1) + mat) * mm + off];
