@@ -49,7 +49,7 @@ SIGNATURES = {
     "dgp_lik_ws_bytes": (_sz, [_i64, _i32]),
     "dgp_cond_backward": (ctypes.c_int, [_P, _vp, _vp, _i64, _i64, _vp, _vp, _vp, _vp, _i32, _vp, _vp, _vp, _i32, _vp,
                                          _i32, _vp]),
-    "dgp_cond_backward_gram": (ctypes.c_int, [_P, _vp, _vp, _i64, _vp]),
+    "dgp_cond_backward_gram": (ctypes.c_int, [_P, _vp, _vp, _i64, _i32, _vp]),
     "dgp_cond_backward_params": (ctypes.c_int, [_P, _vp, _dbl, _vp, _vp, _vp, _vp, _vp]),
     "dgp_cond_fullcov_ws_bytes": (_sz, [_P, _i64]),
     "dgp_cond_fullcov": (ctypes.c_int, [_P, _vp, _vp, _i64, _vp, _vp, _vp, _sz, _vp]),

@@ -514,6 +514,7 @@ struct GramArgs {
     long long n_rows, rows_per_split;
     const double* A; const double* dKuf; const double* gmv;
     double* gram;
+    int accumulate;   // 0: this call owns the partial buffers (store), != 0: add to them (further row chunks)
 };
 #ifndef DGP_GR_KC
 #define DGP_GR_KC 16
@@ -544,14 +545,18 @@ __device__ __forceinline__ void gram_diag_chunk(double (&accA)[8][2], double (&a
 }
 template <int W>
 __device__ __forceinline__ void gram_diag_store(const double (&accA)[8][2], const double (&accB)[8][2], double* out, int Mpad,
-                                                int base, int g, int t) {
+                                                int base, int g, int t, bool add) {
 #pragma unroll
     for (int j = 0; j <= 7 - W; ++j)
 #pragma unroll
         for (int e = 0; e < 2; ++e) {
             const int m2 = base + j * 8 + 2 * t + e;
-            if (j <= W) out[(size_t)(base + W * 8 + g) * Mpad + m2] += accA[j][e];
-            out[(size_t)(base + (7 - W) * 8 + g) * Mpad + m2] += accB[j][e];
+            if (j <= W) {
+                double* o = out + (size_t)(base + W * 8 + g) * Mpad + m2;
+                *o = add ? (*o + accA[j][e]) : accA[j][e];
+            }
+            double* o = out + (size_t)(base + (7 - W) * 8 + g) * Mpad + m2;
+            *o = add ? (*o + accB[j][e]) : accB[j][e];
         }
 }
 
@@ -651,14 +656,15 @@ __global__ void __launch_bounds__(GR_THREADS, 4) k_gram(GramArgs a) {
         }
     }
     cp_async_wait<0>();
-    if (nchunks == 0) return;
+    const bool add = a.accumulate != 0;
+    if (nchunks == 0 && add) return;      // an empty split still has to store zeros when it owns the buffer
     double* out = a.gram + ((size_t)split * (R + 1) + mat) * Mpad * Mpad;
     if (diag) {
         switch (wm) {
-            case 0: gram_diag_store<0>(acc[0], acc[1], out, Mpad, bi * 64, g, t); break;
-            case 1: gram_diag_store<1>(acc[0], acc[1], out, Mpad, bi * 64, g, t); break;
-            case 2: gram_diag_store<2>(acc[0], acc[1], out, Mpad, bi * 64, g, t); break;
-            default: gram_diag_store<3>(acc[0], acc[1], out, Mpad, bi * 64, g, t); break;
+            case 0: gram_diag_store<0>(acc[0], acc[1], out, Mpad, bi * 64, g, t, add); break;
+            case 1: gram_diag_store<1>(acc[0], acc[1], out, Mpad, bi * 64, g, t, add); break;
+            case 2: gram_diag_store<2>(acc[0], acc[1], out, Mpad, bi * 64, g, t, add); break;
+            default: gram_diag_store<3>(acc[0], acc[1], out, Mpad, bi * 64, g, t, add); break;
         }
         return;
     }
@@ -671,7 +677,8 @@ __global__ void __launch_bounds__(GR_THREADS, 4) k_gram(GramArgs a) {
                 if (j >= jmax) continue;
                 const int m1 = bi * 64 + wm * 16 + q * 8 + g;
                 const int m2 = bj * 64 + j * 8 + 2 * t + e;
-                out[(size_t)m1 * Mpad + m2] += acc[q][j][e];
+                double* o = out + (size_t)m1 * Mpad + m2;
+                *o = add ? (*o + acc[q][j][e]) : acc[q][j][e];
             }
 }
 
@@ -720,11 +727,12 @@ extern "C" int dgp_cond_backward(const dgp_cond_desc* d, void* ws, const double*
     return rc;
 }
 
-extern "C" int dgp_cond_backward_gram(const dgp_cond_desc* d, void* ws, const double* A_save, int64_t n_rows, void* stream) {
+extern "C" int dgp_cond_backward_gram(const dgp_cond_desc* d, void* ws, const double* A_save, int64_t n_rows,
+                                      int32_t accumulate, void* stream) {
     int rc = check_desc(d);
     if (rc != DGP_OK) return rc;
     if (!ws || !A_save || n_rows < 0) return DGP_ERR_ARG;
-    if (n_rows == 0) return DGP_OK;
+    if (n_rows == 0 && accumulate) return DGP_OK;
     const WsLayout w = ws_layout(*d, n_rows, 1);
     cudaStream_t st = (cudaStream_t)stream;
     GramArgs ga{};
@@ -733,6 +741,7 @@ extern "C" int dgp_cond_backward_gram(const dgp_cond_desc* d, void* ws, const do
     ga.rows_per_split = (rps + GR_KC - 1) / GR_KC * GR_KC;
     ga.A = A_save; ga.dKuf = ws_ptr<double>(ws, w.dKuf); ga.gmv = ws_ptr<double>(ws, w.gmv);
     ga.gram = ws_ptr<double>(ws, w.gram);
+    ga.accumulate = accumulate;
     const int nbt = w.Mpad / 64;
     const size_t gsm_bytes = (size_t)(2 * GR_STAGES * GR_KC * GR_LD + GR_STAGES * GR_KC) * sizeof(double);
     static bool gram_attr = false;

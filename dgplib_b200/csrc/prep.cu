@@ -425,9 +425,9 @@ extern "C" int dgp_cond_prepare(const dgp_cond_desc* d, void* ws, size_t ws_byte
         k_sub_identity<<<dim3((d->M + 127) / 128, d->R), 128, 0, st>>>(SmI, Mpad, d->M); DGP_COUNT_LAUNCH();
         if ((rc = retile(LinvT, ws_ptr<double>(ws, wb.LinvTTl), Mpad, 1, st)) != DGP_OK) return rc;
         if ((rc = retile(SmI, ws_ptr<double>(ws, wb.SmITl), Mpad, d->R, st)) != DGP_OK) return rc;
-        // row-summed accumulators of the backward pass start from zero; dgp_cond_backward adds to them (row chunks)
+        // the per-CTA row-sum partials of the backward pass start from zero; dgp_cond_backward adds to them (row chunks).
+        // (The Gram partials are not cleared: the first dgp_cond_backward_gram call of an evaluation stores into them.)
         if (ws_bytes < wb.tail) return DGP_ERR_WORKSPACE;
-        if (cudaMemsetAsync(ws_ptr<char>(ws, wb.gram), 0, wb.part - wb.gram, st) != cudaSuccess) return DGP_ERR_LAUNCH;
         if (cudaMemsetAsync(ws_ptr<char>(ws, wb.part), 0, wb.tail - wb.part, st) != cudaSuccess) return DGP_ERR_LAUNCH;
     }
     DGP_CHECK_LAUNCH();

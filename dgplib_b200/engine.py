@@ -537,7 +537,8 @@ class Engine:
                             _cabi.ptr(gF) if gF is not None else None, gF.shape[1] if gF is not None else 0,
                             _cabi.ptr(buf["gX"][l]) if l > 0 else None, 1 if ci > 0 else 0, st), "dgp_cond_backward"))
                         self._timed(f"gram.l{l}", lambda: _cabi.check(lib.dgp_cond_backward_gram(
-                            c.ref(), _cabi.ptr(c.ws), _cabi.ptr(buf["A"][l][ci]), rows, st), "dgp_cond_backward_gram"))
+                            c.ref(), _cabi.ptr(c.ws), _cabi.ptr(buf["A"][l][ci]), rows, 1 if ck > 0 else 0, st),
+                            "dgp_cond_backward_gram"))
                     if ck == nchunks - 1:
                         run_tail(l)
             for ev in tail_events:

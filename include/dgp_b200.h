@@ -138,7 +138,8 @@ int dgp_cond_backward(const dgp_cond_desc* d, void* ws, const double* X, int64_t
                       const double* A_save, const double* mean, const double* var, const double* F, int32_t ldf,
                       const double* g_mean_in, const double* g_var_in, const double* g_F, int32_t ldgf,
                       double* gX, int32_t accumulate_gX, void* stream);
-int dgp_cond_backward_gram(const dgp_cond_desc* d, void* ws, const double* A_save, int64_t n_rows, void* stream);
+int dgp_cond_backward_gram(const dgp_cond_desc* d, void* ws, const double* A_save, int64_t n_rows, int32_t accumulate,
+                           void* stream);   /* accumulate: 0 for the first row chunk after dgp_cond_prepare, 1 after */
 /* Parameter-only tail: Cholesky / Kuu / KL reverse mode.  Outputs (device, this conditional's part OVERWRITTEN):
  *   gZ [M, Dx], gtheta [T, 2+D], gq_mu [M, ldr] (columns col0..), gq_sqrt [ldr, M, M] (rows col0..)
  *   kl_weight: this rank's share of the KL term (1/world_size) so that an all-reduce(sum) over ranks is exact */

@@ -95,7 +95,7 @@ def run_conditional(cuda, M, D, R, N, kind, S=1, white=1e-5, linear=True, backwa
         C.check(lib.dgp_cond_backward(ctypes.byref(d), C.ptr(ws), C.ptr(Xrep), n, n, C.ptr(Asave), C.ptr(mean),
                                       C.ptr(varo), C.ptr(F), R, C.ptr(gmd), C.ptr(gvd), C.ptr(gFd), R, C.ptr(gX), 0,
                                       st), "backward")
-        C.check(lib.dgp_cond_backward_gram(ctypes.byref(d), C.ptr(ws), C.ptr(Asave), n, st), "gram")
+        C.check(lib.dgp_cond_backward_gram(ctypes.byref(d), C.ptr(ws), C.ptr(Asave), n, 0, st), "gram")
         gZ = torch.zeros(M, D, dtype=torch.float64, device=dev)
         gth = torch.zeros(2 + D, dtype=torch.float64, device=dev)
         gqm = torch.zeros(M, R, dtype=torch.float64, device=dev)
@@ -216,7 +216,7 @@ def test_ragged_tiles_do_not_write_out_of_bounds(cuda):
     gm, gv = t(rng.randn(N, R)), t(rng.randn(N, R))
     C.check(lib.dgp_cond_backward(ctypes.byref(d), C.ptr(ws), C.ptr(X), N, N, C.ptr(A), C.ptr(mean), C.ptr(var), None, R,
                                   C.ptr(gm), C.ptr(gv), None, 0, C.ptr(gX), 0, st), "backward")
-    C.check(lib.dgp_cond_backward_gram(ctypes.byref(d), C.ptr(ws), C.ptr(A), N, st), "gram")
+    C.check(lib.dgp_cond_backward_gram(ctypes.byref(d), C.ptr(ws), C.ptr(A), N, 0, st), "gram")
     torch.cuda.synchronize()
     for name, buf in (("mean", mean), ("var", var), ("F", F), ("A", A), ("gX", gX)):
         assert bool((buf[N:] == SENT).all()), name

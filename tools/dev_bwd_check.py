@@ -45,7 +45,7 @@ def run(M, D, R, N, kind="rbf", white=1e-5, seed=0, linear=True, use_gF=True):
     gmd, gvd, gFd = gm_in.to(dev), gv_in.to(dev), gF.to(dev)
     C.check(lib.dgp_cond_backward(ctypes.byref(d), C.ptr(ws), C.ptr(Xd), N, N, C.ptr(Asave), C.ptr(mean), C.ptr(varo), C.ptr(F), R,
                                   C.ptr(gmd), C.ptr(gvd), C.ptr(gFd) if use_gF else None, R, C.ptr(gX), 0, C.stream_ptr()), "backward")
-    C.check(lib.dgp_cond_backward_gram(ctypes.byref(d), C.ptr(ws), C.ptr(Asave), N, C.stream_ptr()), "gram")
+    C.check(lib.dgp_cond_backward_gram(ctypes.byref(d), C.ptr(ws), C.ptr(Asave), N, 0, C.stream_ptr()), "gram")
     gZ = torch.zeros(M, D, dtype=torch.float64, device=dev); gth = torch.zeros(2 + D, dtype=torch.float64, device=dev)
     gqm = torch.zeros(M, R, dtype=torch.float64, device=dev); gqs = torch.zeros(R, M, M, dtype=torch.float64, device=dev)
     C.check(lib.dgp_cond_backward_params(ctypes.byref(d), C.ptr(ws), 1.0, C.ptr(gZ), C.ptr(gth), C.ptr(gqm), C.ptr(gqs), C.stream_ptr()), "params")

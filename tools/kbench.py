@@ -28,7 +28,7 @@ gm = t(rng.randn(N, R)); gv = t(rng.randn(N, R)); gF = t(rng.randn(N, R)); gX = 
 def fwd(): C.check(lib.dgp_cond_forward(ctypes.byref(d), C.ptr(ws), C.ptr(X), N, N, None, 1, None, 0, 0, 0, C.ptr(mean), C.ptr(var), C.ptr(F), R, C.ptr(A), st), "fwd")
 def fwd_nosave(): C.check(lib.dgp_cond_forward(ctypes.byref(d), C.ptr(ws), C.ptr(X), N, N, None, 1, None, 0, 0, 0, C.ptr(mean), C.ptr(var), C.ptr(F), R, None, st), "fwd")
 def bwd(): C.check(lib.dgp_cond_backward(ctypes.byref(d), C.ptr(ws), C.ptr(X), N, N, C.ptr(A), C.ptr(mean), C.ptr(var), C.ptr(F), R, C.ptr(gm), C.ptr(gv), C.ptr(gF), R, C.ptr(gX), 0, st), "bwd")
-def gram(): C.check(lib.dgp_cond_backward_gram(ctypes.byref(d), C.ptr(ws), C.ptr(A), N, st), "gram")
+def gram(): C.check(lib.dgp_cond_backward_gram(ctypes.byref(d), C.ptr(ws), C.ptr(A), N, 0, st), "gram")
 def prep(): C.check(lib.dgp_cond_prepare(ctypes.byref(d), C.ptr(ws), wsb, 1, None, st), "prepare")
 gZ = torch.zeros(M, D, dtype=torch.float64, device=dev); gth = torch.zeros(2 + D, dtype=torch.float64, device=dev)
 gqm = torch.zeros(M, R, dtype=torch.float64, device=dev); gqs = torch.zeros(R, M, M, dtype=torch.float64, device=dev)
