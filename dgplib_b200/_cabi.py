@@ -11,6 +11,7 @@ import torch
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("DGP_B200_LIB", os.path.join(_HERE, "libdgp_b200.so"))   # override: A/B builds only
 
+DGP_OK, DGP_ERR_ARG, DGP_ERR_LAUNCH, DGP_ERR_WORKSPACE, DGP_ERR_UNSUPPORTED = 0, -1, -2, -3, -4
 DGP_KIND_RBF = 0
 DGP_KIND_MATERN52 = 1
 DGP_MAX_TASKS = 16
@@ -56,6 +57,8 @@ SIGNATURES = {
     "dgp_chol_sample_ws_bytes": (_sz, [_i64, _i32]),
     "dgp_chol_sample": (ctypes.c_int, [_vp, _i64, _i64, _i64, _i64, _i32, _dbl, _vp, _i32, _vp, _i64, _i64, _vp, _vp, _sz,
                                        _vp, _vp]),
+    "dgp_pca_ws_bytes": (_sz, [_i64, _i32]),
+    "dgp_pca_weights": (ctypes.c_int, [_vp, _i64, _i32, _i32, _i32, _vp, _sz, _vp, _vp, _vp]),
     "dgp_kernel_K": (ctypes.c_int, [_P, _vp, _i64, _vp, _i64, _i32, _vp, _vp]),
     "dgp_kernel_Kdiag": (ctypes.c_int, [_P, _vp, _i64, _vp, _vp]),
     "dgp_mpad": (_i32, [_i32]),

@@ -737,3 +737,24 @@ def kernel_Kdiag(kernel, X):
     _cabi.check(_cabi.lib().dgp_kernel_Kdiag(ctypes.byref(d), _cabi.ptr(X), X.shape[0], _cabi.ptr(out),
                                              _cabi.stream_ptr()), "dgp_kernel_Kdiag")
     return out
+
+
+def pca_weights(X, output_dim, return_singular_values=False):
+    """Leading `output_dim` right-singular vectors of X [N, D] as a NumPy [D, output_dim] matrix, computed on the GPU
+    (dgp_pca_weights, csrc/pca.cu) -- the SVD step of find_weights (dgplib/layers.py:104-109)."""
+    _cabi.require_cuda()
+    lib = _cabi.lib()
+    dev = torch.device("cuda", torch.cuda.current_device())
+    Xd = X if isinstance(X, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(X, dtype=np.float64))
+    Xd = Xd.to(device=dev, dtype=torch.float64).contiguous()
+    n, D = Xd.shape
+    wsb = lib.dgp_pca_ws_bytes(n, D)
+    if wsb == 0:
+        raise _cabi.DgpError(f"dgp_pca_ws_bytes: unsupported shape N={n}, D={D} (D <= {_cabi.DGP_MAX_D})")
+    ws = torch.empty(wsb, dtype=torch.uint8, device=dev)
+    W = torch.empty(D, output_dim, dtype=torch.float64, device=dev)
+    sing = torch.empty(D, dtype=torch.float64, device=dev)
+    _cabi.check(lib.dgp_pca_weights(_cabi.ptr(Xd), n, D, D, output_dim, _cabi.ptr(ws), wsb, _cabi.ptr(W), _cabi.ptr(sing), _cabi.stream_ptr()),
+            "dgp_pca_weights")
+    out = W.cpu().numpy()
+    return (out, sing.cpu().numpy()) if return_singular_values else out

@@ -8,6 +8,7 @@ initialisation (dgplib/layers.py:97-218), NumPy in / NumPy out, exactly as in th
 """
 import numpy as np
 
+from . import settings
 from .features import inducingpoint_wrapper
 from .mean_functions import Linear, Zero
 from .params import Param, ParamList, Parameterized
@@ -54,16 +55,24 @@ class Layer(Parameterized):
 SVGP_Layer = Layer   # the name BASELINE.json's north_star uses for this class
 
 
-def find_weights(input_dim, output_dim, X, multitask=False):
+def find_weights(input_dim, output_dim, X, multitask=False, backend=None):
     """Initial weights of a layer's Linear mean function (dgplib/layers.py:97-121): identity when the widths agree,
     the leading right-singular vectors of X when the layer narrows, identity padded with zero columns when it widens;
-    multitask appends a zero row so that the task-id column does not leak into the mean."""
+    multitask appends a zero row so that the task-id column does not leak into the mean.
+    backend (default settings.pca_backend): "numpy" = host LAPACK SVD as in the reference, "cuda" = dgp_pca_weights."""
     if input_dim == output_dim:
         W = np.identity(input_dim)
     elif input_dim > output_dim:
         data = X[:, :-1] if multitask else X
-        _, _, Vt = np.linalg.svd(data, full_matrices=False)
-        W = Vt[:output_dim].T
+        backend = backend or settings.pca_backend
+        if backend == "cuda":
+            from .engine import pca_weights
+            W = pca_weights(data, output_dim)
+        elif backend == "numpy":
+            _, _, Vt = np.linalg.svd(data, full_matrices=False)
+            W = Vt[:output_dim].T
+        else:
+            raise ValueError(f"unknown pca backend {backend!r} (numpy | cuda)")
     else:
         W = np.zeros((input_dim, output_dim))
         W[:, :input_dim] = np.identity(input_dim)

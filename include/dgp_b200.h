@@ -164,6 +164,17 @@ int dgp_chol_sample(const double* var, int64_t stride_b, int64_t stride_i, int64
                     int64_t mean_stride_i, double* out, void* scratch, size_t scratch_bytes, int32_t* status_dev,
                     void* stream);
 
+/* ---- layer initialisation: PCA weights of a narrowing layer ------------------------------------------------------
+ * dgp_pca_weights replaces the `np.linalg.svd(X)` of find_weights (dgplib/layers.py:104-109, input_dim > output_dim):
+ *   W [D, R] (row-major) = the R leading right-singular vectors of X [n_rows, D] (row pitch ldx; the caller drops the
+ *   task-id column of a multitask X by passing D = columns - 1), computed as eigenvectors of X^T X (one pass over X,
+ *   then a D x D Jacobi).  sing (nullable) [D]: the singular values, descending.  Sign convention: the component of
+ *   largest magnitude of each vector is negative (an SVD leaves the sign open; this choice reproduces the reference's
+ *   golden vector, tests/test_layer.py:33-38).  D <= DGP_MAX_D. */
+size_t dgp_pca_ws_bytes(int64_t n_rows, int32_t D);
+int dgp_pca_weights(const double* X, int64_t n_rows, int32_t ldx, int32_t D, int32_t R, void* ws, size_t ws_bytes,
+                    double* W, double* sing, void* stream);
+
 /* ---- stand-alone kernel-matrix entry points (dgplib_b200.specialized_kernels; gpflow Kernel.K / Kdiag) -------
  *   K [n1, n2] = k(X1, X2) (White contributes nothing, as in gpflow when X2 is given);  symmetric != 0 computes
  *   k(X1, X1) + White on the diagonal.  Kdiag [n1]. */
