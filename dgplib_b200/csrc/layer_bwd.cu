@@ -697,7 +697,6 @@ extern "C" int dgp_cond_backward(const dgp_cond_desc* d, void* ws, const double*
     if (!g_F && !g_mean_in && !g_var_in) return DGP_ERR_ARG;
     if (n_rows == 0) return DGP_OK;
     const WsLayout w = ws_layout(*d, n_rows, 1);
-    if (w.Mpad > 512) return DGP_ERR_UNSUPPORTED;  // backward tiles for M > 512 are not instantiated
     cudaStream_t st = (cudaStream_t)stream;
     BwdArgs a{};
     a.d = *d;
@@ -724,6 +723,7 @@ extern "C" int dgp_cond_backward(const dgp_cond_desc* d, void* ws, const double*
         DGP_TRY_BWD(DGP_BWD_WN, 32, 4) DGP_TRY_BWD(DGP_BWD_WN, 32, 3) DGP_TRY_BWD(DGP_BWD_WN, 32, 2)
     } else {
         DGP_TRY_BWD(2, 16, 4) DGP_TRY_BWD(2, 16, 3) DGP_TRY_BWD(2, 16, 2)
+        DGP_TRY_BWD(1, 8, 3) DGP_TRY_BWD(1, 8, 2)   // Mpad > 512: two 8-row tiles are all that fits
     }
 #undef DGP_TRY_BWD
     rc = DGP_ERR_UNSUPPORTED;

@@ -376,7 +376,7 @@ using namespace dgp;
 extern "C" int32_t dgp_mpad(int32_t M) { return (M + 63) / 64 * 64; }
 
 extern "C" size_t dgp_cond_ws_bytes(const dgp_cond_desc* d, int64_t n_rows, int need_bwd) {
-    if (!d || d->M < 1 || d->R < 1 || n_rows < 0) return 0;
+    if (!d || d->M < 1 || d->M > 1024 || d->R < 1 || n_rows < 0) return 0;
     return ws_layout(*d, n_rows, need_bwd).total;
 }
 

@@ -121,6 +121,8 @@ CASES = [
     (500, 16, 16, 700, "matern52", 1),
     (7, 2, 1, 1, "rbf", 1),             # a single row
     (33, 5, 3, 63, "matern52", 3),
+    (600, 8, 3, 150, "rbf", 1),         # M > 512: 8-row backward tiles
+    (1024, 8, 2, 100, "matern52", 1),   # the largest supported inducing set
 ]
 
 
@@ -241,8 +243,9 @@ def test_empty_and_unsupported_inputs(cuda):
     assert lib.dgp_philox_normal(C.ptr(one), 0, 1, 1, 0, 0, 0, 0, C.stream_ptr()) == 0
     # too small a workspace is refused, not overrun
     assert lib.dgp_cond_prepare(ctypes.byref(d), C.ptr(ws), 1024, 0, None, C.stream_ptr()) == -3
-    # backward tiles are instantiated for M <= 512 only
-    d.M = 600
+    # inducing sets beyond 1024 points are refused by every entry point
+    d.M = 1025
+    assert lib.dgp_cond_ws_bytes(ctypes.byref(d), 8, 1) == 0
     assert lib.dgp_cond_backward(ctypes.byref(d), C.ptr(ws), C.ptr(one), 1, 1, C.ptr(one), C.ptr(one), C.ptr(one), None, 1,
                                  C.ptr(one), C.ptr(one), None, 0, None, 0, C.stream_ptr()) == -4
     torch.cuda.synchronize()
