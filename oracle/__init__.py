@@ -27,5 +27,7 @@ Pinning status
   They are pinned instead by (i) the init-state identities that follow from ``dgplib/layers.py:52-56``
   (q_mu=0, q_sqrt=I => mean = mean_fn(X), var = Kdiag, KL = 0), (ii) the closed-form single-layer SVGP bound,
   (iii) an independent 50-digit mpmath evaluation on tiny cases (``oracle/mp_arbiter.py``, fixtures in
-  ``tests/golden/``), and (iv) finite differences for the autograd gradients.
+  ``tests/golden/``), (iv) finite differences for the autograd gradients, and (v) an independent third-party
+  library: scikit-learn's RBF / Matern(nu=2.5) gram matrices (1e-12) and its exact-GP log marginal likelihood, which
+  the single-layer ELBO must equal when Z = X and q(u) is the exact posterior (1e-8 relative; ``tests/_exact_gp.py``).
 """

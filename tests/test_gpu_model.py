@@ -416,3 +416,29 @@ def test_trainable_linear_mean_is_refused(cuda):
     ol.mean_function.set_trainable(False)
     v, _ = model.elbo_and_grad()
     assert torch.isfinite(v)
+
+
+def test_exact_gp_limit_matches_scikit_learn(cuda, monkeypatch):
+    """Third-party anchor: Z = X with the optimal q(u) makes the single-layer bound tight, so the CUDA path's ELBO must
+    equal scikit-learn's exact-GP log marginal likelihood (jitter lowered so that Kuu = Kff to rounding)."""
+    from _exact_gp import exact_gp_case
+    from dgplib_b200 import settings
+    monkeypatch.setattr(settings, "jitter_level", 1e-12)
+    for kind in ("rbf", "matern52"):
+        c = exact_gp_case(kind)
+        N, D = c["X"].shape
+        kern = (RBF if kind == "rbf" else Matern52)(D, variance=c["variance"], lengthscales=c["ls"], ARD=True)
+        layer = InputLayer(D, 1, N, kern)
+        model = dg.DSDGP(c["X"], c["Y"], c["X"].copy(), Sequential([layer]), Gaussian(variance=c["noise"]), num_samples=1)
+        layer.q_mu.assign(c["q_mu"])
+        layer.q_sqrt.assign(c["q_sqrt"])
+        model.compile()
+        val = float(model.compute_log_likelihood())
+        assert abs(val - c["lml"]) < 1e-8 * abs(c["lml"]), (kind, val, c["lml"])
+        # and the stand-alone kernel-matrix entry points against scikit-learn's
+        K = kern.K(c["X"])
+        K = K.cpu().numpy() if isinstance(K, torch.Tensor) else np.asarray(K)
+        assert np.max(np.abs(K - c["K"])) < 5e-12
+        Kx = kern.K(c["X"][:7], c["X"][5:])
+        Kx = Kx.cpu().numpy() if isinstance(Kx, torch.Tensor) else np.asarray(Kx)
+        assert np.max(np.abs(Kx - c["kernel"](c["X"][:7], c["X"][5:]))) < 5e-12

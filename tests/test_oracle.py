@@ -7,6 +7,7 @@ import numpy as np
 import torch
 
 from oracle import dsdgp_oracle as O
+from _exact_gp import exact_gp_case, sk_kernel
 
 T64 = torch.float64
 HERE = os.path.dirname(os.path.abspath(__file__))
@@ -181,3 +182,28 @@ def test_multitask_predict_y_shape_quirk():
     lik = {"kind": "switched", "variances": [t(0.1), t(0.2)]}
     mu, var = O.predict_y([layer], lik, Xs, [torch.zeros(1, 10, 1, dtype=T64)], multitask=True)
     assert mu.shape == (1, 20, 1) and var.shape == (1, 20, 1)
+
+
+# ------------------------------------------------------------------ independent third-party anchor (scikit-learn)
+def test_kernels_match_scikit_learn():
+    rng = np.random.RandomState(2)
+    X, X2, ls = rng.randn(9, 3), rng.randn(5, 3), np.array([0.7, 1.3, 2.1])
+    for kind in ("rbf", "matern52"):
+        kern = {"kind": kind, "input_dim": 3, "variance": t(1.9), "lengthscales": t(ls), "white": None}
+        skk = sk_kernel(kind, 1.9, ls)
+        assert np.max(np.abs(O.kern_K(kern, t(X), t(X2)).numpy() - skk(X, X2))) < 1e-12
+        assert np.max(np.abs(O.kern_Kdiag(kern, t(X)).numpy() - skk.diag(X))) < 1e-12
+        # gpflow's Matern52 takes sqrt(r2 + 1e-12): worth up to 5/6 variance 1e-12 near r = 0
+        assert np.max(np.abs(O.kern_K(kern, t(X)).numpy() - skk(X))) < 5e-12
+
+
+def test_exact_gp_limit_matches_scikit_learn(monkeypatch):
+    monkeypatch.setattr(O, "JITTER", 1e-12)
+    for kind in ("rbf", "matern52"):
+        c = exact_gp_case(kind)
+        N, D = c["X"].shape
+        kern = {"kind": kind, "input_dim": D, "variance": t(c["variance"]), "lengthscales": t(c["ls"]), "white": None}
+        layer = {"groups": [{"kernel": kern, "Z": t(c["X"])}], "q_mu": t(c["q_mu"]), "q_sqrt": t(c["q_sqrt"]), "mean": None}
+        lik = {"kind": "gaussian", "variance": t(c["noise"])}
+        val = float(O.elbo([layer], lik, t(c["X"]), t(c["Y"]), 1, [torch.zeros(1, N, 1, dtype=T64)]))
+        assert abs(val - c["lml"]) < 1e-8 * abs(c["lml"]), (kind, val, c["lml"])
