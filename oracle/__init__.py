@@ -29,5 +29,6 @@ Pinning status
   (iii) an independent 50-digit mpmath evaluation on tiny cases (``oracle/mp_arbiter.py``, fixtures in
   ``tests/golden/``), (iv) finite differences for the autograd gradients, and (v) an independent third-party
   library: scikit-learn's RBF / Matern(nu=2.5) gram matrices (1e-12) and its exact-GP log marginal likelihood, which
-  the single-layer ELBO must equal when Z = X and q(u) is the exact posterior (1e-8 relative; ``tests/_exact_gp.py``).
+  the single-layer ELBO must equal when Z = X and q(u) is the exact posterior (1e-8 relative), with its hyper-parameter
+  gradients equal to scikit-learn's d lml / d theta and zero gradient in q (envelope theorem; ``tests/_exact_gp.py``).
 """

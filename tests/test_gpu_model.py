@@ -435,6 +435,19 @@ def test_exact_gp_limit_matches_scikit_learn(cuda, monkeypatch):
         model.compile()
         val = float(model.compute_log_likelihood())
         assert abs(val - c["lml"]) < 1e-8 * abs(c["lml"]), (kind, val, c["lml"])
+        # gradients: stationary in q, equal to scikit-learn's d lml / d theta in the hyper-parameters (envelope theorem)
+        val2, grads = model.elbo_and_grad(X=torch.from_numpy(c["X"]), Y=torch.from_numpy(c["Y"]),
+                                          eps=[np.zeros((1, N, 1))])
+        gp = oracle_grads_by_param(model, grads)
+        sk = c["grad"]
+        scale = max(abs(sk["variance"]), np.abs(sk["lengthscales"]).max(), abs(sk["noise"]))
+        assert abs(float(val2) - c["lml"]) < 1e-8 * abs(c["lml"])
+        assert float(gp["l0.q_mu"].abs().max()) < 1e-7 * scale
+        assert float(torch.tril(gp["l0.q_sqrt"]).abs().max()) < 1e-7 * scale
+        th = gp["l0.g0.theta"].cpu().numpy()
+        assert abs(th[0, 0] - sk["variance"]) < 1e-7 * scale
+        assert np.max(np.abs(th[0, 2:] - sk["lengthscales"])) < 1e-7 * scale
+        assert abs(float(gp["lik"].cpu()[0]) - sk["noise"]) < 1e-7 * scale
         # and the stand-alone kernel-matrix entry points against scikit-learn's
         K = kern.K(c["X"])
         K = K.cpu().numpy() if isinstance(K, torch.Tensor) else np.asarray(K)

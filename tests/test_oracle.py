@@ -205,5 +205,12 @@ def test_exact_gp_limit_matches_scikit_learn(monkeypatch):
         kern = {"kind": kind, "input_dim": D, "variance": t(c["variance"]), "lengthscales": t(c["ls"]), "white": None}
         layer = {"groups": [{"kernel": kern, "Z": t(c["X"])}], "q_mu": t(c["q_mu"]), "q_sqrt": t(c["q_sqrt"]), "mean": None}
         lik = {"kind": "gaussian", "variance": t(c["noise"])}
-        val = float(O.elbo([layer], lik, t(c["X"]), t(c["Y"]), 1, [torch.zeros(1, N, 1, dtype=T64)]))
-        assert abs(val - c["lml"]) < 1e-8 * abs(c["lml"]), (kind, val, c["lml"])
+        val, g = O.elbo_and_grad([layer], lik, t(c["X"]), t(c["Y"]), 1, [torch.zeros(1, N, 1, dtype=T64)])
+        assert abs(float(val) - c["lml"]) < 1e-8 * abs(c["lml"]), (kind, float(val), c["lml"])
+        # gradients: stationary in q, and equal to scikit-learn's d lml / d theta in the hyper-parameters
+        scale = max(abs(c["grad"]["variance"]), np.abs(c["grad"]["lengthscales"]).max(), abs(c["grad"]["noise"]))
+        assert float(g["l0.q_mu"].abs().max()) < 1e-7 * scale
+        assert float(torch.tril(g["l0.q_sqrt"]).abs().max()) < 1e-7 * scale
+        assert abs(float(g["l0.g0.kern.variance"]) - c["grad"]["variance"]) < 1e-7 * scale
+        assert np.max(np.abs(g["l0.g0.kern.lengthscales"].numpy() - c["grad"]["lengthscales"])) < 1e-7 * scale
+        assert abs(float(g["lik.variance"]) - c["grad"]["noise"]) < 1e-7 * scale
