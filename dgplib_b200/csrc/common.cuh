@@ -122,7 +122,8 @@ static inline const T* ws_ptr(const void* ws, size_t off) { return reinterpret_c
 
 int check_desc(const dgp_cond_desc* d);
 // batched in-place lower Cholesky of `batch` Mpad x Mpad matrices (Mpad multiple of 64, <= 1024); status[b] = failing pivot + 1
-int cholesky_batched(double* K, int Mpad, int batch, int32_t* status, cudaStream_t st);
+// Linv (nullable): receives the inverses of the 32 x 32 diagonal blocks of the factor (input of k_tri_inv_cols)
+int cholesky_batched(double* K, int Mpad, int batch, int32_t* status, cudaStream_t st, double* Linv = nullptr);
 
 #ifdef __CUDACC__
 // ------------------------------------------------------------------------------------------------ PTX wrappers

@@ -7,6 +7,10 @@
 // tensor-core GEMM by forming Lm^-1 once (O(M^3), parameter-only) so that the per-row stage is A = Linv * Kuf with
 // block skipping; measured against 50-digit arithmetic the explicit inverse stays within 3x of LAPACK's substitution
 // error on the worst-conditioned reference configuration (D=1, M=50).
+#include <atomic>
+#include <cstdlib>
+#include <mutex>
+
 #include "common.cuh"
 #define DGP_GEMM_SMALL_IMPL
 #include "gemm_small.cuh"
@@ -212,75 +216,244 @@ k_cholesky(double* __restrict__ K, int Mpad, int NB, int32_t* __restrict__ statu
     if (tid == 0) status[0] = s_fail;
 }
 
-int cholesky_batched(double* K, int Mpad, int batch, int32_t* status, cudaStream_t st) {
-    const int NB = (Mpad <= 512) ? 32 : 16;
-    const size_t chol_smem = (32 * 33 + 32 + (size_t)(Mpad - NB) * (NB + 1)) * sizeof(double);
-    static bool attr_set = false;
-    if (!attr_set) {
-        if (cudaFuncSetAttribute(k_cholesky, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess) return DGP_ERR_LAUNCH;
-        attr_set = true;
+// Same factorisation for Mpad <= 512 with the three stages of a 32-column panel laid out for latency, the quantity that
+// matters here (the factorisation is a serial chain at the head of every evaluation):
+//   1. warp 0 factors the 32 x 32 diagonal block in registers (lane = row, column broadcasts by shuffle) with no CTA
+//      barrier inside, while the other 480 threads already fetch their panel rows;
+//   2. one thread per row below the block solves x L_jj^T = a by substitution (L_jj broadcast from shared memory);
+//   3. the trailing update runs on DMMA.8x8x4, 8 x 8 tiles of the lower triangle dealt to the 16 warps.
+// Inverse of the factored 32 x 32 diagonal block in sD (pitch 33, reciprocal pivots in sDinv) by one warp: lane = column
+// of the inverse, held in registers; forward substitution with the rows of the block broadcast from shared memory.
+__device__ __noinline__ void diag_block_inverse(const double* sD, const double* sDinv, double* __restrict__ out,
+                                                   int ld, int lane) {
+    double x[32];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) x[i] = (i == lane) ? 1.0 : 0.0;
+#pragma unroll
+    for (int k = 0; k < 32; ++k) {              // column-oriented: independent updates once x[k] is final
+        x[k] *= sDinv[k];                       // rows above the lane's column stay exactly zero
+        out[(size_t)k * ld + lane] = x[k];
+#pragma unroll
+        for (int i = k + 1; i < 32; ++i) x[i] = fma(-sD[i * 33 + k], x[k], x[i]);
     }
-    k_cholesky<<<batch, CHOL_THREADS, chol_smem, st>>>(K, Mpad, NB, status);
-    DGP_COUNT_LAUNCH();
-    return cudaGetLastError() == cudaSuccess ? DGP_OK : DGP_ERR_LAUNCH;
+}
+
+constexpr int CHOL_LDP = 36;   // panel pitch in shared memory: 36 mod 16 = 4 keeps the DMMA fragment loads conflict-free
+
+__global__ void __launch_bounds__(CHOL_THREADS, 1)
+k_cholesky32(double* __restrict__ K, int Mpad, int32_t* __restrict__ status, double* __restrict__ Linv) {
+    K += (size_t)blockIdx.x * Mpad * Mpad;      // batched: one CTA per matrix
+    status += blockIdx.x;
+    if (Linv) Linv += (size_t)blockIdx.x * Mpad * Mpad;
+    extern __shared__ double sm[];
+    double* sD = sm;                 // [32][33] factored diagonal block
+    double* sDinv = sD + 32 * 33;    // [32] reciprocal pivots
+    double* sP = sDinv + 32;         // [Mpad - 32][CHOL_LDP] panel below the block
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
+    int fail = 0;                    // warp 0 only
+
+    for (int j0 = 0; j0 < Mpad; j0 += 32) {
+        const int rem = Mpad - j0 - 32;          // rows below the diagonal block (<= 480)
+        const int ri = tid - 32;                 // panel row of this thread (warps 1..15)
+        double x[32];
+        if (warp == 0) {
+            const double* src = K + (size_t)(j0 + lane) * Mpad + j0;
+#pragma unroll
+            for (int k = 0; k < 32; ++k) x[k] = src[k];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+                double dj = __shfl_sync(0xffffffffu, x[j], j);
+                if (!(dj > 0.0)) {
+                    if (fail == 0) fail = j0 + j + 1;
+                    dj = 1.0;
+                }
+                // reciprocal square root (<= 1 ulp) instead of sqrt followed by a division: this chain of 32 dependent
+                // pivots is the critical path of the whole evaluation's parameter stage
+                const double inv = rsqrt(dj), dk = dj * inv;
+                x[j] = (lane == j) ? dk : (lane > j ? x[j] * inv : 0.0);
+                if (lane == j) sDinv[j] = inv;
+#pragma unroll
+                for (int k = j + 1; k < 32; ++k) {
+                    const double lkj = __shfl_sync(0xffffffffu, x[j], k);
+                    x[k] = fma(-x[j], lkj, x[k]);     // rows above k carry don't-care values until column k zeroes them
+                }
+            }
+            double* dst = K + (size_t)(j0 + lane) * Mpad + j0;
+#pragma unroll
+            for (int k = 0; k < 32; ++k) {
+                sD[lane * 33 + k] = x[k];
+                dst[k] = x[k];
+            }
+        } else if (ri < rem) {
+            const double* src = K + (size_t)(j0 + 32 + ri) * Mpad + j0;
+#pragma unroll
+            for (int k = 0; k < 32; ++k) x[k] = src[k];
+        }
+        if (rem == 0) {
+            if (warp == 0 && Linv) {
+                __syncwarp();
+                diag_block_inverse(sD, sDinv, Linv + (size_t)j0 * Mpad + j0, Mpad, lane);
+            }
+            break;
+        }
+        // zero the strict upper part right of the diagonal block
+        for (int e = tid; e < 32 * rem; e += CHOL_THREADS) {
+            const int i = e / rem, j = e % rem;
+            K[(size_t)(j0 + i) * Mpad + j0 + 32 + j] = 0.0;
+        }
+        __syncthreads();
+        if (warp == 0 && Linv) diag_block_inverse(sD, sDinv, Linv + (size_t)j0 * Mpad + j0, Mpad, lane);
+        if (warp > 0 && ri < rem) {
+            // column-oriented substitution: once x[k] is final, the updates of x[k+1 ..] are independent FMAs (the
+            // row-oriented form is one dependent chain per entry and ran 3x slower)
+#pragma unroll
+            for (int k = 0; k < 32; ++k) {
+                x[k] *= sDinv[k];
+#pragma unroll
+                for (int j = k + 1; j < 32; ++j) x[j] = fma(-x[k], sD[j * 33 + k], x[j]);
+            }
+            double* dst = K + (size_t)(j0 + 32 + ri) * Mpad + j0;
+#pragma unroll
+            for (int k = 0; k < 32; ++k) {
+                dst[k] = x[k];
+                sP[ri * CHOL_LDP + k] = x[k];
+            }
+        }
+        __syncthreads();
+        // trailing update of the lower triangle: C(ti, tj) -= P(ti) P(tj)^T on 8 x 8 tiles
+        const int nt = rem / 8;
+        const int ntile = nt * (nt + 1) / 2;
+        // four tiles per warp and pass, so that four read-modify-write round trips to L2 are in flight at once
+        constexpr int TU = 4;
+        for (int p0 = warp * TU; p0 < ntile; p0 += (CHOL_THREADS / 32) * TU) {
+            double* cptr[TU];
+            double2 c0[TU];
+            const double *pa[TU], *pb[TU];
+            bool lo[TU], hi[TU];
+#pragma unroll
+            for (int u = 0; u < TU; ++u) {
+                const int p = (p0 + u < ntile) ? p0 + u : ntile - 1;   // the clamped duplicates are not stored
+                int ti = (int)((sqrt(8.0 * (double)p + 1.0) - 1.0) * 0.5);
+                while ((ti + 1) * (ti + 2) / 2 <= p) ++ti;
+                while (ti * (ti + 1) / 2 > p) --ti;
+                const int tj = p - ti * (ti + 1) / 2;
+                const int row = j0 + 32 + ti * 8 + g, col = j0 + 32 + tj * 8 + 2 * t;
+                cptr[u] = K + (size_t)row * Mpad + col;
+                c0[u] = *reinterpret_cast<const double2*>(cptr[u]);
+                pa[u] = sP + (ti * 8 + g) * CHOL_LDP + t;
+                pb[u] = sP + (tj * 8 + g) * CHOL_LDP + t;
+                lo[u] = (p0 + u < ntile) && col <= row;
+                hi[u] = (p0 + u < ntile) && col + 1 <= row;
+            }
+            double c[TU][2];
+#pragma unroll
+            for (int u = 0; u < TU; ++u) c[u][0] = c[u][1] = 0.0;
+#pragma unroll
+            for (int kk = 0; kk < 8; ++kk)
+#pragma unroll
+                for (int u = 0; u < TU; ++u) dmma884(c[u], pa[u][kk * 4], pb[u][kk * 4]);
+#pragma unroll
+            for (int u = 0; u < TU; ++u) {
+                if (lo[u]) cptr[u][0] = c0[u].x - c[u][0];
+                if (hi[u]) cptr[u][1] = c0[u].y - c[u][1];
+            }
+        }
+        __syncthreads();
+    }
+    if (tid == 0) status[0] = fail;
 }
 
 // ------------------------------------------------------------------------------------------------ triangular inverse
-// (a) inverses of the 32x32 diagonal blocks of Lm, one CTA (32 threads) per block, written into Linv's diagonal blocks;
-//     everything else in Linv's block row is zeroed here.
+// Linv = Lm^-1 by block forward substitution on 32 x 32 blocks.  The inverses of the diagonal blocks come out of the
+// Cholesky kernel (k_diag_inv does the same for the legacy path); k_tri_inv_cols fills the blocks below them, one CTA
+// per 32-wide column block c:   X_Ic = -Linv_II * sum_{K=c}^{I-1} L_IK X_Kc,   I = c+1 .. nb-1,
+// both products on DMMA.8x8x4 with the fragments of the long one read straight from global memory (L1 / L2 resident).
+// The blocks above the diagonal are zeroed here (the workspace arrives uninitialised).
+__global__ void __launch_bounds__(256)
+k_tri_inv_cols(const double* __restrict__ L, double* __restrict__ Linv, int Mpad) {
+    __shared__ double sT[32 * 36];
+    __shared__ double sDi[32 * 36];
+    const int c = blockIdx.x, nb = Mpad / 32, tid = threadIdx.x;
+    const int warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
+    const int c0 = c * 32;
+    const int ta = warp >> 1, tb = (warp & 1) * 2;       // this warp's tiles: (ta, tb) and (ta, tb + 1) of the 4 x 4 grid
+    for (int e = tid; e < c0 * 32; e += 256) Linv[(size_t)(e >> 5) * Mpad + c0 + (e & 31)] = 0.0;
+    for (int I = c + 1; I < nb; ++I) {
+        const int i0 = I * 32;
+        for (int e = tid; e < 32 * 32; e += 256)
+            sDi[(e >> 5) * 36 + (e & 31)] = Linv[(size_t)(i0 + (e >> 5)) * Mpad + i0 + (e & 31)];
+        // T = L[I rows][c0 .. i0) * X[c0 .. i0)[c block]
+        double acc0[2] = {0.0, 0.0}, acc1[2] = {0.0, 0.0};
+        const double* pa = L + (size_t)(i0 + ta * 8 + g) * Mpad + t;
+        const double* pb = Linv + (size_t)t * Mpad + c0 + tb * 8 + g;
+        for (int kb = c0; kb < i0; kb += 32) {      // one 32-deep block per pass: 24 loads in flight, then 16 DMMAs
+            double a[8], b0[8], b1[8];
+#pragma unroll
+            for (int kk = 0; kk < 8; ++kk) {
+                const int k = kb + 4 * kk;
+                a[kk] = pa[k];
+                b0[kk] = pb[(size_t)k * Mpad];
+                b1[kk] = pb[(size_t)k * Mpad + 8];
+            }
+#pragma unroll
+            for (int kk = 0; kk < 8; ++kk) {
+                dmma884(acc0, a[kk], b0[kk]);
+                dmma884(acc1, a[kk], b1[kk]);
+            }
+        }
+        sT[(ta * 8 + g) * 36 + tb * 8 + 2 * t] = acc0[0];
+        sT[(ta * 8 + g) * 36 + tb * 8 + 2 * t + 1] = acc0[1];
+        sT[(ta * 8 + g) * 36 + tb * 8 + 8 + 2 * t] = acc1[0];
+        sT[(ta * 8 + g) * 36 + tb * 8 + 8 + 2 * t + 1] = acc1[1];
+        __syncthreads();
+        // X_Ic = -Linv_II * T
+        double o0[2] = {0.0, 0.0}, o1[2] = {0.0, 0.0};
+#pragma unroll
+        for (int kk = 0; kk < 8; ++kk) {
+            const double a = sDi[(ta * 8 + g) * 36 + kk * 4 + t];
+            dmma884(o0, a, sT[(kk * 4 + t) * 36 + tb * 8 + g]);
+            dmma884(o1, a, sT[(kk * 4 + t) * 36 + tb * 8 + 8 + g]);
+        }
+        double* dst = Linv + (size_t)(i0 + ta * 8 + g) * Mpad + c0 + tb * 8 + 2 * t;
+        dst[0] = -o0[0]; dst[1] = -o0[1];
+        dst[8] = -o1[0]; dst[9] = -o1[1];
+        __syncthreads();  // X_Ic visible to the whole CTA before the next block row reads it (global, same CTA)
+    }
+}
+
+// Legacy path (Mpad > 512): inverses of the 32 x 32 diagonal blocks, one warp per block.
 __global__ void k_diag_inv(const double* __restrict__ L, double* __restrict__ Linv, int Mpad) {
     __shared__ double sL[32 * 33];
-    __shared__ double sX[32 * 33];
+    __shared__ double sInv[32];
+    L += (size_t)blockIdx.y * Mpad * Mpad;
+    Linv += (size_t)blockIdx.y * Mpad * Mpad;
     const int b0 = blockIdx.x * 32, lane = threadIdx.x;
     for (int i = 0; i < 32; ++i) sL[i * 33 + lane] = L[(size_t)(b0 + i) * Mpad + b0 + lane];
     __syncwarp();
-    // lane = column j of the inverse: forward substitution L x = e_j
-    for (int i = 0; i < 32; ++i) {
-        double s = (i == lane) ? 1.0 : 0.0;
-        for (int k = lane; k < i; ++k) s = fma(-sL[i * 33 + k], sX[k * 33 + lane], s);
-        sX[i * 33 + lane] = (i >= lane) ? s / sL[i * 33 + i] : 0.0;
-    }
+    sInv[lane] = 1.0 / sL[lane * 33 + lane];
     __syncwarp();
-    for (int i = 0; i < 32; ++i) {
-        for (int j = lane; j < Mpad; j += 32) {
-            const bool in = (j >= b0 && j < b0 + 32);
-            Linv[(size_t)(b0 + i) * Mpad + j] = in ? sX[i * 33 + (j - b0)] : 0.0;
-        }
-    }
+    diag_block_inverse(sL, sInv, Linv + (size_t)b0 * Mpad + b0, Mpad, lane);
 }
-// (b) block forward substitution, one CTA per 32-wide column block c:  X_Ic = -Linv_II * sum_{K=c}^{I-1} L_IK X_Kc.
-__global__ void __launch_bounds__(256)
-k_tri_inv_cols(const double* __restrict__ L, double* __restrict__ Linv, int Mpad) {
-    __shared__ double sT[32 * 33];
-    __shared__ double sDi[32 * 33];
-    const int c = blockIdx.x, nb = Mpad / 32, tid = threadIdx.x;
-    const int c0 = c * 32;
-    for (int I = c + 1; I < nb; ++I) {
-        const int i0 = I * 32;
-        // T = sum_K L[I-block rows][K-block cols] * X[K-block rows][c-block cols], K = c .. I-1
-        // thread -> 4 consecutive columns of one row
-        const int ti = tid >> 3, tj = (tid & 7) * 4;
-        double acc[4] = {0.0, 0.0, 0.0, 0.0};
-        for (int k = c0; k < i0; ++k) {
-            const double l = L[(size_t)(i0 + ti) * Mpad + k];
-            const double* x = Linv + (size_t)k * Mpad + c0 + tj;
-#pragma unroll
-            for (int b = 0; b < 4; ++b) acc[b] = fma(l, x[b], acc[b]);
-        }
-#pragma unroll
-        for (int b = 0; b < 4; ++b) sT[ti * 33 + tj + b] = acc[b];
-        for (int e = tid; e < 32 * 32; e += 256) sDi[(e >> 5) * 33 + (e & 31)] = Linv[(size_t)(i0 + (e >> 5)) * Mpad + i0 + (e & 31)];
-        __syncthreads();
-        double out[4] = {0.0, 0.0, 0.0, 0.0};
-        for (int k = 0; k <= ti; ++k) {
-            const double di = sDi[ti * 33 + k];
-#pragma unroll
-            for (int b = 0; b < 4; ++b) out[b] = fma(di, sT[k * 33 + tj + b], out[b]);
-        }
-#pragma unroll
-        for (int b = 0; b < 4; ++b) Linv[(size_t)(i0 + ti) * Mpad + c0 + tj + b] = -out[b];
-        __syncthreads();  // X_Ic visible to the whole CTA before the next block row reads it (global, same CTA)
+
+int cholesky_batched(double* K, int Mpad, int batch, int32_t* status, cudaStream_t st, double* Linv) {
+    static bool attr_set = false;
+    if (!attr_set) {
+        if (cudaFuncSetAttribute(k_cholesky, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess) return DGP_ERR_LAUNCH;
+        if (cudaFuncSetAttribute(k_cholesky32, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess) return DGP_ERR_LAUNCH;
+        attr_set = true;
     }
+    static const bool legacy = getenv("DGP_CHOL_LEGACY") != nullptr;   // A/B switch for tools/kbench.py
+    if (Mpad <= 512 && !legacy) {
+        const size_t smem = (32 * 33 + 32 + (size_t)(Mpad - 32) * CHOL_LDP) * sizeof(double);
+        k_cholesky32<<<batch, CHOL_THREADS, smem, st>>>(K, Mpad, status, Linv);
+    } else {
+        const int NB = (Mpad <= 512) ? 32 : 16;
+        const size_t chol_smem = (32 * 33 + 32 + (size_t)(Mpad - NB) * (NB + 1)) * sizeof(double);
+        k_cholesky<<<batch, CHOL_THREADS, chol_smem, st>>>(K, Mpad, NB, status);
+        if (Linv) { k_diag_inv<<<dim3(Mpad / 32, batch), 32, 0, st>>>(K, Linv, Mpad); DGP_COUNT_LAUNCH(); }
+    }
+    DGP_COUNT_LAUNCH();
+    return cudaGetLastError() == cudaSuccess ? DGP_OK : DGP_ERR_LAUNCH;
 }
 
 // ------------------------------------------------------------------------------------------------ q_sqrt, KL
@@ -373,6 +546,51 @@ __global__ void k_sub_identity(double* __restrict__ S, int Mpad, int M) {
 
 using namespace dgp;
 
+// ------------------------------------------------------------------------------------------------ helper streams
+// dgp_cond_prepare forks its q_sqrt-only chain onto a helper stream.  A small pool per process, created on first use
+// outside any stream capture; a lane (stream + fork/join events) is held under its mutex from fork to join, so that
+// concurrent callers never share a pair of events.  No lane available (first call arrives inside a capture, or stream
+// creation fails): the caller runs both chains on its own stream.
+namespace dgp {
+struct SideLane {
+    cudaStream_t stream = nullptr;
+    cudaEvent_t fork = nullptr, join = nullptr;
+    std::mutex mu;
+};
+constexpr int N_SIDE_LANES = 16;
+static SideLane g_lanes[N_SIDE_LANES];
+static std::once_flag g_lanes_once;
+static std::atomic<bool> g_lanes_ok{false};
+static std::atomic<unsigned> g_lane_next{0};
+
+static SideLane* side_lane_acquire(cudaStream_t caller) {
+    static const bool disabled = getenv("DGP_NO_SIDE_STREAM") != nullptr;   // A/B switch
+    if (disabled) return nullptr;
+    if (!g_lanes_ok.load(std::memory_order_acquire)) {
+        cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+        if (cudaStreamIsCapturing(caller, &cs) != cudaSuccess || cs != cudaStreamCaptureStatusNone) {
+            cudaGetLastError();
+            return nullptr;                       // never create streams while a capture is in progress
+        }
+        std::call_once(g_lanes_once, [] {
+            bool ok = true;
+            for (int i = 0; i < N_SIDE_LANES && ok; ++i) {
+                ok = cudaStreamCreateWithFlags(&g_lanes[i].stream, cudaStreamNonBlocking) == cudaSuccess &&
+                     cudaEventCreateWithFlags(&g_lanes[i].fork, cudaEventDisableTiming) == cudaSuccess &&
+                     cudaEventCreateWithFlags(&g_lanes[i].join, cudaEventDisableTiming) == cudaSuccess;
+            }
+            if (!ok) cudaGetLastError();
+            g_lanes_ok.store(ok, std::memory_order_release);
+        });
+        if (!g_lanes_ok.load(std::memory_order_acquire)) return nullptr;
+    }
+    SideLane* l = &g_lanes[g_lane_next.fetch_add(1) % N_SIDE_LANES];
+    l->mu.lock();
+    return l;
+}
+static void side_lane_release(SideLane* l) { l->mu.unlock(); }
+}  // namespace dgp
+
 extern "C" int32_t dgp_mpad(int32_t M) { return (M + 63) / 64 * 64; }
 
 extern "C" size_t dgp_cond_ws_bytes(const dgp_cond_desc* d, int64_t n_rows, int need_bwd) {
@@ -397,22 +615,25 @@ extern "C" int dgp_cond_prepare(const dgp_cond_desc* d, void* ws, size_t ws_byte
     double* LqT = ws_ptr<double>(ws, w.LqT);
     int32_t* status = ws_ptr<int32_t>(ws, w.status);
 
-    k_prep_z<<<(Mpad + 127) / 128, 128, 0, st>>>(*d, Mpad, Dp, Zs, zn, ztask); DGP_COUNT_LAUNCH();
-    k_kuu<<<dim3((Mpad + 127) / 128, Mpad), 128, 0, st>>>(*d, Mpad, Dp, Zs, zn, ztask, Lm); DGP_COUNT_LAUNCH();
-    if ((rc = cholesky_batched(Lm, Mpad, 1, status, st)) != DGP_OK) return rc;
-    k_diag_inv<<<Mpad / 32, 32, 0, st>>>(Lm, Linv, Mpad); DGP_COUNT_LAUNCH();
-    k_tri_inv_cols<<<Mpad / 32, 256, 0, st>>>(Lm, Linv, Mpad); DGP_COUNT_LAUNCH();
+    // Two independent chains: (A) Z -> Kuu -> Cholesky -> Linv (one SM, a serial chain) and (B) everything that depends
+    // on q_sqrt only (LqT, KL, S_r - I and their tiled copies).  B runs on a helper stream forked from and joined back
+    // into `st` with events, so that it overlaps the Cholesky instead of queueing behind it on the critical path of the
+    // forward pass.  (Inside a stream capture the helper stream simply becomes a parallel branch of the graph.)
+    const WsLayout wb = ws_layout(*d, 0, 1);      // LinvT and SmI offsets do not depend on n_rows
+    if (need_bwd && ws_bytes < wb.tail) return DGP_ERR_WORKSPACE;
+    SideLane* lane = side_lane_acquire(st);
+    cudaStream_t sb = lane ? lane->stream : st;
+    if (lane) {
+        cudaEventRecord(lane->fork, st);
+        cudaStreamWaitEvent(sb, lane->fork, 0);
+    }
+    // ---- chain B
     double* klpart = ws_ptr<double>(ws, w.klpart);
-    k_lq_prep<<<dim3(Mpad / 32, Mpad / 32, d->R), dim3(32, 8), 0, st>>>(*d, Mpad, LqT, klpart); DGP_COUNT_LAUNCH();
-    if (kl_out) { k_kl<<<1, 256, 0, st>>>(*d, klpart, d->R * (Mpad / 32) * (Mpad / 32), kl_out); DGP_COUNT_LAUNCH(); }
-    if ((rc = retile(Linv, ws_ptr<double>(ws, w.LinvTl), Mpad, 1, st)) != DGP_OK) return rc;
-    if ((rc = retile(LqT, ws_ptr<double>(ws, w.LqTTl), Mpad, d->R, st)) != DGP_OK) return rc;
-    if (need_bwd) {
-        const WsLayout wb = ws_layout(*d, 0, 1);  // LinvT and SmI offsets do not depend on n_rows
-        if (ws_bytes < wb.tail) return DGP_ERR_WORKSPACE;
-        double* LinvT = ws_ptr<double>(ws, wb.LinvT);
+    k_lq_prep<<<dim3(Mpad / 32, Mpad / 32, d->R), dim3(32, 8), 0, sb>>>(*d, Mpad, LqT, klpart); DGP_COUNT_LAUNCH();
+    if (kl_out) { k_kl<<<1, 256, 0, sb>>>(*d, klpart, d->R * (Mpad / 32) * (Mpad / 32), kl_out); DGP_COUNT_LAUNCH(); }
+    rc = retile(LqT, ws_ptr<double>(ws, w.LqTTl), Mpad, d->R, sb);
+    if (rc == DGP_OK && need_bwd) {
         double* SmI = ws_ptr<double>(ws, wb.SmI);
-        k_transpose<<<dim3(Mpad / 32, Mpad / 32), dim3(32, 8), 0, st>>>(Linv, LinvT, Mpad); DGP_COUNT_LAUNCH();
         // S_r = Lq_r Lq_r^T = LqT_r^T LqT_r :  A(i,k) = LqT[k][i], B(k,j) = LqT[k][j]
         GemmArgs g{};
         g.A = LqT; g.B = LqT; g.C = SmI;
@@ -420,16 +641,36 @@ extern "C" int dgp_cond_prepare(const dgp_cond_desc* d, void* ws, size_t ws_byte
         g.sAi = 1; g.sAk = Mpad; g.sBk = Mpad; g.sBj = 1; g.sCi = Mpad; g.sCj = 1;
         g.bA = g.bB = g.bC = (long long)Mpad * Mpad;
         g.alpha = 1.0; g.beta = 0.0; g.batch = d->R;
-        rc = gemm_small(g, st);
-        if (rc != DGP_OK) return rc;
-        k_sub_identity<<<dim3((d->M + 127) / 128, d->R), 128, 0, st>>>(SmI, Mpad, d->M); DGP_COUNT_LAUNCH();
-        if ((rc = retile(LinvT, ws_ptr<double>(ws, wb.LinvTTl), Mpad, 1, st)) != DGP_OK) return rc;
-        if ((rc = retile(SmI, ws_ptr<double>(ws, wb.SmITl), Mpad, d->R, st)) != DGP_OK) return rc;
+        rc = gemm_small(g, sb);
+        if (rc == DGP_OK) {
+            k_sub_identity<<<dim3((d->M + 127) / 128, d->R), 128, 0, sb>>>(SmI, Mpad, d->M); DGP_COUNT_LAUNCH();
+            rc = retile(SmI, ws_ptr<double>(ws, wb.SmITl), Mpad, d->R, sb);
+        }
         // the per-CTA row-sum partials of the backward pass start from zero; dgp_cond_backward adds to them (row chunks).
         // (The Gram partials are not cleared: the first dgp_cond_backward_gram call of an evaluation stores into them.)
-        if (ws_bytes < wb.tail) return DGP_ERR_WORKSPACE;
-        if (cudaMemsetAsync(ws_ptr<char>(ws, wb.part), 0, wb.tail - wb.part, st) != cudaSuccess) return DGP_ERR_LAUNCH;
+        if (rc == DGP_OK && cudaMemsetAsync(ws_ptr<char>(ws, wb.part), 0, wb.tail - wb.part, sb) != cudaSuccess) rc = DGP_ERR_LAUNCH;
     }
+    if (lane) cudaEventRecord(lane->join, sb);
+    // ---- chain A
+    if (rc == DGP_OK) {
+        k_prep_z<<<(Mpad + 127) / 128, 128, 0, st>>>(*d, Mpad, Dp, Zs, zn, ztask); DGP_COUNT_LAUNCH();
+        k_kuu<<<dim3((Mpad + 127) / 128, Mpad), 128, 0, st>>>(*d, Mpad, Dp, Zs, zn, ztask, Lm); DGP_COUNT_LAUNCH();
+        rc = cholesky_batched(Lm, Mpad, 1, status, st, Linv);
+    }
+    if (rc == DGP_OK) {
+        k_tri_inv_cols<<<Mpad / 32, 256, 0, st>>>(Lm, Linv, Mpad); DGP_COUNT_LAUNCH();
+        rc = retile(Linv, ws_ptr<double>(ws, w.LinvTl), Mpad, 1, st);
+    }
+    if (rc == DGP_OK && need_bwd) {
+        double* LinvT = ws_ptr<double>(ws, wb.LinvT);
+        k_transpose<<<dim3(Mpad / 32, Mpad / 32), dim3(32, 8), 0, st>>>(Linv, LinvT, Mpad); DGP_COUNT_LAUNCH();
+        rc = retile(LinvT, ws_ptr<double>(ws, wb.LinvTTl), Mpad, 1, st);
+    }
+    if (lane) {                                   // join, also on the error paths (a capture must not be left forked)
+        cudaStreamWaitEvent(st, lane->join, 0);
+        side_lane_release(lane);
+    }
+    if (rc != DGP_OK) return rc;
     DGP_CHECK_LAUNCH();
     return DGP_OK;
 }
