@@ -1,5 +1,6 @@
 // Shared device/host helpers for libdgp_b200 (sm_100a only).
 #pragma once
+#include <mutex>
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <math.h>
@@ -63,6 +64,17 @@ struct WsLayout {
 };
 
 int device_sm_count();
+
+// Helper stream + fork/join events for the independent chains of the parameter stages (defined in prep.cu).  acquire
+// returns nullptr when no lane can be had (then the caller keeps everything on its own stream); a lane is held under its
+// mutex from fork to join.
+struct SideLane {
+    cudaStream_t stream = nullptr;
+    cudaEvent_t fork = nullptr, join = nullptr;
+    std::mutex mu;
+};
+SideLane* side_lane_acquire(cudaStream_t caller);
+void side_lane_release(SideLane* lane);
 
 static inline WsLayout ws_layout(const dgp_cond_desc& d, int64_t n_rows, int need_bwd) {
     WsLayout w{};

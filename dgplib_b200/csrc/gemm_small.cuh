@@ -30,25 +30,42 @@ __global__ void __launch_bounds__(256) k_gemm_small(GemmArgs g) {
     for (int a = 0; a < 4; ++a)
 #pragma unroll
         for (int c = 0; c < 4; ++c) acc[a][c] = 0.0;
+    // the next 16-deep chunk travels global -> registers while the current one is multiplied out of shared memory:
+    // these GEMMs sit on the serial parameter chains, where the exposed load latency of every chunk was the whole cost
+    double ra[4], rb[4];
+    auto fetch = [&](int k0) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int e = tid + q * 256;
+            int i, k;
+            if (g.sAk == 1) { k = e & 15; i = e >> 4; } else { i = e & 63; k = e >> 6; }
+            ra[q] = A[(long long)i * g.sAi + (long long)(k0 + k) * g.sAk];
+            int j, kb;
+            if (g.sBk == 1) { kb = e & 15; j = e >> 4; } else { j = e & 63; kb = e >> 6; }
+            rb[q] = B[(long long)(k0 + kb) * g.sBk + (long long)j * g.sBj];
+        }
+    };
+    fetch(0);
     for (int k0 = 0; k0 < g.K; k0 += 16) {
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
             const int e = tid + q * 256;
             int i, k;
             if (g.sAk == 1) { k = e & 15; i = e >> 4; } else { i = e & 63; k = e >> 6; }
-            As[k][i] = A[(long long)i * g.sAi + (long long)(k0 + k) * g.sAk];
+            As[k][i] = ra[q];
             int j, kb;
             if (g.sBk == 1) { kb = e & 15; j = e >> 4; } else { j = e & 63; kb = e >> 6; }
-            Bs[kb][j] = B[(long long)(k0 + kb) * g.sBk + (long long)j * g.sBj];
+            Bs[kb][j] = rb[q];
         }
         __syncthreads();
+        if (k0 + 16 < g.K) fetch(k0 + 16);
 #pragma unroll
         for (int k = 0; k < 16; ++k) {
             double a[4], c[4];
 #pragma unroll
             for (int q = 0; q < 4; ++q) a[q] = As[k][ty * 4 + q];
 #pragma unroll
-            for (int q = 0; q < 4; ++q) c[q] = Bs[k][tx * 4 + q];
+            for (int q = 0; q < 4; ++q) c[q] = Bs[k][tx + 16 * q];   // interleaved columns: conflict-free across tx
 #pragma unroll
             for (int p = 0; p < 4; ++p)
 #pragma unroll
@@ -61,7 +78,7 @@ __global__ void __launch_bounds__(256) k_gemm_small(GemmArgs g) {
     for (int p = 0; p < 4; ++p)
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
-            const long long off = (long long)(bi * 64 + ty * 4 + p) * g.sCi + (long long)(bj * 64 + tx * 4 + q) * g.sCj;
+            const long long off = (long long)(bi * 64 + ty * 4 + p) * g.sCi + (long long)(bj * 64 + tx + 16 * q) * g.sCj;
             double v = g.alpha * acc[p][q];
             if (g.beta != 0.0) v = fma(g.beta, C[off], v);
             C[off] = v;

@@ -10,9 +10,10 @@
 namespace dgp {
 
 // (a) reduce the split-K Gram partials.  mat < R: full symmetric G (lower tiles mirrored); mat == R: Lbar = -tril(P).
-__global__ void k_gram_reduce(const double* __restrict__ gram, int nsplit, int R, int Mpad, double* __restrict__ Gfull,
-                              double* __restrict__ Lbar) {
-    const int j = blockIdx.x * blockDim.x + threadIdx.x, i = blockIdx.y, mat = blockIdx.z;
+//     blockIdx.z + mat0 = matrix index, so that the G_r and the Lbar parts can be launched separately.
+__global__ void k_gram_reduce(const double* __restrict__ gram, int nsplit, int R, int Mpad, int mat0,
+                              double* __restrict__ Gfull, double* __restrict__ Lbar) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x, i = blockIdx.y, mat = mat0 + blockIdx.z;
     if (j >= Mpad) return;
     const size_t mm = (size_t)Mpad * Mpad;
     if (mat < R) {
@@ -191,31 +192,57 @@ extern "C" int dgp_cond_backward_params(const dgp_cond_desc* d, void* ws, double
     double* scal = ws_ptr<double>(ws, w.scal);  // unused here; small vectors live at the front of T2 after it is consumed
     (void)scal;
 
-    k_gram_reduce<<<dim3((Mpad + 127) / 128, Mpad, R + 1), 128, 0, st>>>(gram, w.nsplit, R, Mpad, Gfull, Lbar); DGP_COUNT_LAUNCH();
+    // Two chains that share only the Gram partials: (A, on `st`) Lbar -> Cholesky reverse mode -> Kuu reverse mode -> gZ,
+    // gtheta, a serial chain of small GEMMs; (B, helper stream) G_r -> gq_sqrt and the row-sum partials -> gq_mu.  B joins
+    // before the finishing kernels, which read the reduced partials.
+    double* psum = ws_ptr<double>(ws, w.psum);
+    SideLane* lane = side_lane_acquire(st);
+    cudaStream_t sb = lane ? lane->stream : st;
+    if (lane) {
+        cudaEventRecord(lane->fork, st);
+        cudaStreamWaitEvent(sb, lane->fork, 0);
+    }
+    // ---- chain B
+    k_gram_reduce<<<dim3((Mpad + 127) / 128, Mpad, R), 128, 0, sb>>>(gram, w.nsplit, R, Mpad, 0, Gfull, Lbar); DGP_COUNT_LAUNCH();
     // Tq_r = G_r Lq_r ;  B(k,j) = Lq_r[k][j] = LqT_r[j][k]
     GemmArgs g{};
     g.A = Gfull; g.B = LqT; g.C = Tq; g.I = g.J = g.K = Mpad; g.batch = R;
     g.sAi = Mpad; g.sAk = 1; g.sBk = 1; g.sBj = Mpad; g.sCi = Mpad; g.sCj = 1;
     g.bA = g.bB = g.bC = (long long)mm; g.alpha = 1.0; g.beta = 0.0; g.lower_tiles_only = 1;
-    if ((rc = gemm_small(g, st)) != DGP_OK) return rc;
-    k_gq_sqrt<<<dim3((d->M + 127) / 128, d->M, R), 128, 0, st>>>(*d, Mpad, Tq, kl_weight, gq_sqrt); DGP_COUNT_LAUNCH();
-    double* psum = ws_ptr<double>(ws, w.psum);
-    k_part_reduce<<<(w.npart + 127) / 128, 128, 0, st>>>(part, w.ncta, w.npart, psum); DGP_COUNT_LAUNCH();
-    k_gq_mu<<<(d->M * R + 127) / 128, 128, 0, st>>>(*d, Mpad, Dp, psum, kl_weight, gq_mu); DGP_COUNT_LAUNCH();
-    // T1 = Lm^T Lbar ; Phi ; T2 = Linv^T T1 ; T3 = T2 Linv
-    g = GemmArgs{};
-    g.A = Lm; g.B = Lbar; g.C = T1; g.I = g.J = g.K = Mpad; g.batch = 1;
-    g.sAi = 1; g.sAk = Mpad; g.sBk = Mpad; g.sBj = 1; g.sCi = Mpad; g.sCj = 1; g.alpha = 1.0;
-    if ((rc = gemm_small(g, st)) != DGP_OK) return rc;
-    k_phi<<<dim3((Mpad + 127) / 128, Mpad), 128, 0, st>>>(T1, Mpad); DGP_COUNT_LAUNCH();
-    g.A = LinvT; g.B = T1; g.C = T2; g.sAi = Mpad; g.sAk = 1;
-    if ((rc = gemm_small(g, st)) != DGP_OK) return rc;
-    g.A = T2; g.B = Linv; g.C = T3;
-    if ((rc = gemm_small(g, st)) != DGP_OK) return rc;
-    // Kuu reverse mode; rowp / dzs / cs_sum reuse the (now free) T1 buffer
-    double* rowp = T1;
+    rc = gemm_small(g, sb);
+    if (rc == DGP_OK) {
+        k_gq_sqrt<<<dim3((d->M + 127) / 128, d->M, R), 128, 0, sb>>>(*d, Mpad, Tq, kl_weight, gq_sqrt); DGP_COUNT_LAUNCH();
+        k_part_reduce<<<(w.npart + 127) / 128, 128, 0, sb>>>(part, w.ncta, w.npart, psum); DGP_COUNT_LAUNCH();
+        k_gq_mu<<<(d->M * R + 127) / 128, 128, 0, sb>>>(*d, Mpad, Dp, psum, kl_weight, gq_mu); DGP_COUNT_LAUNCH();
+    }
+    if (lane) cudaEventRecord(lane->join, sb);
+    // ---- chain A:  T1 = Lm^T Lbar ; Phi ; T2 = Linv^T T1 ; T3 = T2 Linv
+    double* rowp = T1;                    // rowp / dzs reuse the T1 buffer once T2 has been formed
     double* dzs = rowp + (size_t)Mpad * (2 + Dp);
-    k_kuu_bwd<<<d->M, 128, 0, st>>>(*d, Mpad, Dp, Zs, zn, ztask, T3, rowp, dzs); DGP_COUNT_LAUNCH();
+    if (rc == DGP_OK) {
+        k_gram_reduce<<<dim3((Mpad + 127) / 128, Mpad, 1), 128, 0, st>>>(gram, w.nsplit, R, Mpad, R, Gfull, Lbar); DGP_COUNT_LAUNCH();
+        g = GemmArgs{};
+        g.A = Lm; g.B = Lbar; g.C = T1; g.I = g.J = g.K = Mpad; g.batch = 1;
+        g.sAi = 1; g.sAk = Mpad; g.sBk = Mpad; g.sBj = 1; g.sCi = Mpad; g.sCj = 1; g.alpha = 1.0;
+        rc = gemm_small(g, st);
+    }
+    if (rc == DGP_OK) {
+        k_phi<<<dim3((Mpad + 127) / 128, Mpad), 128, 0, st>>>(T1, Mpad); DGP_COUNT_LAUNCH();
+        g.A = LinvT; g.B = T1; g.C = T2; g.sAi = Mpad; g.sAk = 1;
+        rc = gemm_small(g, st);
+    }
+    if (rc == DGP_OK) {
+        g.A = T2; g.B = Linv; g.C = T3;
+        rc = gemm_small(g, st);
+    }
+    if (rc == DGP_OK) {   // Kuu reverse mode
+        k_kuu_bwd<<<d->M, 128, 0, st>>>(*d, Mpad, Dp, Zs, zn, ztask, T3, rowp, dzs); DGP_COUNT_LAUNCH();
+    }
+    if (lane) {                                   // join, also on the error paths (a capture must not be left forked)
+        cudaStreamWaitEvent(st, lane->join, 0);
+        side_lane_release(lane);
+    }
+    if (rc != DGP_OK) return rc;
     k_finish_Z<<<(d->M * d->Dx + 127) / 128, 128, 0, st>>>(*d, Mpad, Dp, Zs, ztask, psum, dzs, gZ); DGP_COUNT_LAUNCH();
     k_finish_theta<<<d->T * (2 + d->D), 32, 0, st>>>(*d, Mpad, Dp, Zs, ztask, psum, rowp, gtheta); DGP_COUNT_LAUNCH();
     DGP_CHECK_LAUNCH();

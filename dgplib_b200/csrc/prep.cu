@@ -9,7 +9,6 @@
 // error on the worst-conditioned reference configuration (D=1, M=50).
 #include <atomic>
 #include <cstdlib>
-#include <mutex>
 
 #include "common.cuh"
 #define DGP_GEMM_SMALL_IMPL
@@ -547,23 +546,18 @@ __global__ void k_sub_identity(double* __restrict__ S, int Mpad, int M) {
 using namespace dgp;
 
 // ------------------------------------------------------------------------------------------------ helper streams
-// dgp_cond_prepare forks its q_sqrt-only chain onto a helper stream.  A small pool per process, created on first use
+// dgp_cond_prepare and dgp_cond_backward_params fork an independent chain onto a helper stream.  A small pool per process, created on first use
 // outside any stream capture; a lane (stream + fork/join events) is held under its mutex from fork to join, so that
 // concurrent callers never share a pair of events.  No lane available (first call arrives inside a capture, or stream
 // creation fails): the caller runs both chains on its own stream.
 namespace dgp {
-struct SideLane {
-    cudaStream_t stream = nullptr;
-    cudaEvent_t fork = nullptr, join = nullptr;
-    std::mutex mu;
-};
 constexpr int N_SIDE_LANES = 16;
 static SideLane g_lanes[N_SIDE_LANES];
 static std::once_flag g_lanes_once;
 static std::atomic<bool> g_lanes_ok{false};
 static std::atomic<unsigned> g_lane_next{0};
 
-static SideLane* side_lane_acquire(cudaStream_t caller) {
+SideLane* side_lane_acquire(cudaStream_t caller) {
     static const bool disabled = getenv("DGP_NO_SIDE_STREAM") != nullptr;   // A/B switch
     if (disabled) return nullptr;
     if (!g_lanes_ok.load(std::memory_order_acquire)) {
@@ -588,7 +582,7 @@ static SideLane* side_lane_acquire(cudaStream_t caller) {
     l->mu.lock();
     return l;
 }
-static void side_lane_release(SideLane* l) { l->mu.unlock(); }
+void side_lane_release(SideLane* l) { l->mu.unlock(); }
 }  // namespace dgp
 
 extern "C" int32_t dgp_mpad(int32_t M) { return (M + 63) / 64 * 64; }
