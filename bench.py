@@ -467,7 +467,9 @@ def main():
         sync_all()
         ms_train = t0.elapsed_time(t1) / args.steps
         train = {"ms_per_step": ms_train, "rows_per_s": rows_per_step / (ms_train * 1e-3),
-                 "what": "DSDGP._build_likelihood().backward() + torch fused Adam, minibatch from pinned host memory"}
+                 "what": "AdamOptimizer.minimize: positive transforms + fused ELBO/grad + chain rule + torch fused Adam"
+                         + (" replayed as one CUDA graph per step" if model.use_cuda_graph and dist is None else "")
+                         + ", minibatch from pinned host memory"}
     Dx, ldy = model.X.shape[1], model.Y.shape[1]
     h2d = B * (Dx + ldy) * 8       # per rank, the rows it copies
     d2h = 8
