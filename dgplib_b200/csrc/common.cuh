@@ -63,6 +63,10 @@ struct WsLayout {
     size_t total;
 };
 
+// Host-side caches (shared-memory opt-ins, SM counts, helper streams) are kept per device, so that one process may
+// drive several GPUs through the library (the usual deployment is still one process per GPU).
+constexpr int DGP_MAX_DEVICES = 16;
+int current_device();   // cudaGetDevice, clamped to [0, DGP_MAX_DEVICES)
 int device_sm_count();
 
 // Helper stream + fork/join events for the independent chains of the parameter stages (defined in prep.cu).  acquire

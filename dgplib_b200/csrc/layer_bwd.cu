@@ -494,7 +494,8 @@ static int launch_bwd(const BwdArgs& a, cudaStream_t st) {
     const BwdSmem<C> L(a.Mpad, a.Dp, a.d.R);
     const size_t bytes = (size_t)L.total_doubles * sizeof(double);
     if (bytes > 227 * 1024) return DGP_ERR_UNSUPPORTED;
-    static size_t configured = 0;
+    static size_t configured_dev[DGP_MAX_DEVICES] = {};
+    size_t& configured = configured_dev[current_device()];
     if (bytes > configured) {
         if (cudaFuncSetAttribute(k_cond_bwd<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes) != cudaSuccess) return DGP_ERR_LAUNCH;
         configured = bytes;
@@ -747,7 +748,8 @@ extern "C" int dgp_cond_backward_gram(const dgp_cond_desc* d, void* ws, const do
     ga.accumulate = accumulate;
     const int nbt = w.Mpad / 64;
     const size_t gsm_bytes = (size_t)(2 * GR_STAGES * GR_KC * GR_LD + GR_STAGES * GR_KC) * sizeof(double);
-    static bool gram_attr = false;
+    static bool gram_attr_dev[DGP_MAX_DEVICES] = {};
+    bool& gram_attr = gram_attr_dev[current_device()];
     if (!gram_attr) {
         if (cudaFuncSetAttribute(k_gram, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gsm_bytes) != cudaSuccess) return DGP_ERR_LAUNCH;
         gram_attr = true;

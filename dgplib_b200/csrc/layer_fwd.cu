@@ -338,7 +338,8 @@ static int launch_fwd(const FwdArgs& a, cudaStream_t st) {
     const FwdSmem<C> L(a.Mpad, a.Dp);
     const size_t bytes = (size_t)L.total_doubles * sizeof(double);
     if (bytes > 227 * 1024) return DGP_ERR_UNSUPPORTED;
-    static size_t configured = 0;
+    static size_t configured_dev[DGP_MAX_DEVICES] = {};
+    size_t& configured = configured_dev[current_device()];
     if (bytes > configured) {
         if (cudaFuncSetAttribute(k_cond_fwd<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes) != cudaSuccess) return DGP_ERR_LAUNCH;
         configured = bytes;

@@ -221,7 +221,8 @@ extern "C" int dgp_pca_weights(const double* X, int64_t n_rows, int32_t ldx, int
     DGP_CHECK_LAUNCH();
     const size_t smem = (size_t)(2 * D * (D + 1) + 2 * (D / 2 + 1) + 32) * sizeof(double) +
                         (size_t)(2 * (D / 2 + 1) + D) * sizeof(int);
-    static bool configured = false;
+    static bool configured_dev[DGP_MAX_DEVICES] = {};
+    bool& configured = configured_dev[current_device()];
     if (!configured) {
         if (cudaFuncSetAttribute(k_pca_eig, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024) != cudaSuccess) return DGP_ERR_LAUNCH;
         configured = true;

@@ -19,14 +19,24 @@ namespace dgp {
 
 long long g_launches = 0;
 
+int current_device() {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) { cudaGetLastError(); dev = 0; }
+    return dev < 0 ? 0 : (dev >= DGP_MAX_DEVICES ? DGP_MAX_DEVICES - 1 : dev);
+}
+
 int device_sm_count() {
-    static int n = 0;
-    if (n == 0) {
-        int dev = 0;
-        if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0)
-            n = 148;  // B200; also used when cross-checking layouts on a GPU-less host
+    static int n[DGP_MAX_DEVICES] = {};
+    const int dev = current_device();
+    if (n[dev] == 0) {
+        int v = 0;
+        if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || v <= 0) {
+            cudaGetLastError();
+            v = 148;  // B200; also used when cross-checking layouts on a GPU-less host
+        }
+        n[dev] = v;
     }
-    return n;
+    return n[dev];
 }
 
 int check_desc(const dgp_cond_desc* d) {
@@ -435,11 +445,12 @@ __global__ void k_diag_inv(const double* __restrict__ L, double* __restrict__ Li
 }
 
 int cholesky_batched(double* K, int Mpad, int batch, int32_t* status, cudaStream_t st, double* Linv) {
-    static bool attr_set = false;
-    if (!attr_set) {
+    static bool attr_set[DGP_MAX_DEVICES] = {};
+    const int dev = current_device();
+    if (!attr_set[dev]) {
         if (cudaFuncSetAttribute(k_cholesky, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess) return DGP_ERR_LAUNCH;
         if (cudaFuncSetAttribute(k_cholesky32, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess) return DGP_ERR_LAUNCH;
-        attr_set = true;
+        attr_set[dev] = true;
     }
     static const bool legacy = getenv("DGP_CHOL_LEGACY") != nullptr;   // A/B switch for tools/kbench.py
     if (Mpad <= 512 && !legacy) {
@@ -552,33 +563,34 @@ using namespace dgp;
 // creation fails): the caller runs both chains on its own stream.
 namespace dgp {
 constexpr int N_SIDE_LANES = 16;
-static SideLane g_lanes[N_SIDE_LANES];
-static std::once_flag g_lanes_once;
-static std::atomic<bool> g_lanes_ok{false};
+static SideLane g_lanes[DGP_MAX_DEVICES][N_SIDE_LANES];
+static std::once_flag g_lanes_once[DGP_MAX_DEVICES];
+static std::atomic<bool> g_lanes_ok[DGP_MAX_DEVICES];
 static std::atomic<unsigned> g_lane_next{0};
 
 SideLane* side_lane_acquire(cudaStream_t caller) {
     static const bool disabled = getenv("DGP_NO_SIDE_STREAM") != nullptr;   // A/B switch
     if (disabled) return nullptr;
-    if (!g_lanes_ok.load(std::memory_order_acquire)) {
+    const int dev = current_device();
+    if (!g_lanes_ok[dev].load(std::memory_order_acquire)) {
         cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
         if (cudaStreamIsCapturing(caller, &cs) != cudaSuccess || cs != cudaStreamCaptureStatusNone) {
             cudaGetLastError();
             return nullptr;                       // never create streams while a capture is in progress
         }
-        std::call_once(g_lanes_once, [] {
+        std::call_once(g_lanes_once[dev], [dev] {
             bool ok = true;
             for (int i = 0; i < N_SIDE_LANES && ok; ++i) {
-                ok = cudaStreamCreateWithFlags(&g_lanes[i].stream, cudaStreamNonBlocking) == cudaSuccess &&
-                     cudaEventCreateWithFlags(&g_lanes[i].fork, cudaEventDisableTiming) == cudaSuccess &&
-                     cudaEventCreateWithFlags(&g_lanes[i].join, cudaEventDisableTiming) == cudaSuccess;
+                ok = cudaStreamCreateWithFlags(&g_lanes[dev][i].stream, cudaStreamNonBlocking) == cudaSuccess &&
+                     cudaEventCreateWithFlags(&g_lanes[dev][i].fork, cudaEventDisableTiming) == cudaSuccess &&
+                     cudaEventCreateWithFlags(&g_lanes[dev][i].join, cudaEventDisableTiming) == cudaSuccess;
             }
             if (!ok) cudaGetLastError();
-            g_lanes_ok.store(ok, std::memory_order_release);
+            g_lanes_ok[dev].store(ok, std::memory_order_release);
         });
-        if (!g_lanes_ok.load(std::memory_order_acquire)) return nullptr;
+        if (!g_lanes_ok[dev].load(std::memory_order_acquire)) return nullptr;
     }
-    SideLane* l = &g_lanes[g_lane_next.fetch_add(1) % N_SIDE_LANES];
+    SideLane* l = &g_lanes[dev][g_lane_next.fetch_add(1) % N_SIDE_LANES];
     l->mu.lock();
     return l;
 }

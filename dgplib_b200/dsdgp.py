@@ -40,6 +40,21 @@ class _Minibatch:
         return np.concatenate(idx)
 
 
+def _on_model_device(fn):
+    """Run a model method with the model's GPU as the current CUDA device (streams, events and the staging copies below
+    are taken from the current device)."""
+    import functools
+
+    @functools.wraps(fn)
+    def wrapper(self, *args, **kwargs):
+        dev = self.engine.device
+        if torch.cuda.current_device() == dev.index:
+            return fn(self, *args, **kwargs)
+        with torch.cuda.device(dev):
+            return fn(self, *args, **kwargs)
+    return wrapper
+
+
 class DSDGP(Parameterized):
     """Doubly Stochastic Deep Gaussian Process Model."""
 
@@ -185,6 +200,7 @@ class DSDGP(Parameterized):
                                                  chunk_rows=self.predict_chunk_rows, last_only=True)
         return Fmeans[-1], Fvars[-1]
 
+    @_on_model_device
     def _build_likelihood(self, eps=None, seed=None, X=None, Y=None):
         """Variational bound on the marginal likelihood (dgplib/dsdgp.py:107-130) of the next minibatch, as a CUDA
         scalar attached to torch.autograd (call .backward() or hand it to a torch optimiser).  The node's forward runs
@@ -202,6 +218,7 @@ class DSDGP(Parameterized):
         with torch.no_grad():
             return float(self._build_likelihood(eps=eps, seed=seed))
 
+    @_on_model_device
     def elbo_and_grad(self, X=None, Y=None, eps=None, seed=None):
         """One fused ELBO + gradient evaluation; returns (elbo tensor, grads of engine.params()).  With X=None the next
         minibatch comes from the model's own host data through the pinned, double-buffered staging path."""

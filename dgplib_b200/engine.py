@@ -25,6 +25,20 @@ def _dev_tensor(x, device):
     return x.detach().to(device=device, dtype=_F64).contiguous()
 
 
+def _on_device(fn):
+    """Run an Engine method with the engine's GPU as the current CUDA device: the C-ABI launches on the current device, so
+    a model compiled for cuda:1 must not run its kernels under another device's context."""
+    import functools
+
+    @functools.wraps(fn)
+    def wrapper(self, *args, **kwargs):
+        if torch.cuda.current_device() == self.device.index:
+            return fn(self, *args, **kwargs)
+        with torch.cuda.device(self.device):
+            return fn(self, *args, **kwargs)
+    return wrapper
+
+
 class _Cond:
     """One whitened conditional (kernel + inducing points + a column slice of q_mu / q_sqrt): descriptor + workspace."""
 
@@ -227,6 +241,7 @@ class Engine:
             events.append(evs)
         return events
 
+    @_on_device
     def check_status(self):
         """Raises if a Cholesky factorisation failed (the reference surfaces this as TF's InvalidArgumentError)."""
         lib, st = _cabi.lib(), _cabi.stream_ptr()
@@ -278,6 +293,7 @@ class Engine:
                     _cabi.ptr(Fbuf), Fbuf.shape[1], _cabi.ptr(X), X.shape[1], st), "dgp_sample_expand"))
             inp, x_rows = Fbuf, n
 
+    @_on_device
     def propagate(self, X, S, eps=None, seed=0, params=None, chunk_rows=None, last_only=False):
         """Fs, Fmeans, Fvars as lists of [S, B, .] CUDA tensors (DSDGP._propagate, dgplib/dsdgp.py:84-99).
         chunk_rows bounds the data rows pushed through the cascade per pass (memory: S * chunk_rows rows are live per
@@ -347,6 +363,7 @@ class Engine:
                         "dgp_cond_fullcov")
         return mean, fvar
 
+    @_on_device
     def chol_sample(self, var, z, mean=None, jitter=None):
         """mean + chol(var + jitter I) z for a batch: var [Bt, N, N], z [Bt, N, nz], mean [Bt, N] or None -> [Bt, N, nz]
         (normal_sample's full-covariance branch, dgplib/utils.py:28-36)."""
@@ -370,6 +387,7 @@ class Engine:
             raise _cabi.DgpError(f"Cholesky of a predictive covariance failed at pivot {bad - 1}")
         return out
 
+    @_on_device
     def propagate_full_cov(self, X, S, z=None, seed=0, params=None):
         """DSDGP._propagate(full_cov=True) (dgplib/dsdgp.py:84-99): Fs [S,N,R(+1)], Fmeans [S,N,R], Fvars [S,N,N,R] per
         layer.  z[l] [S, R_l, N] are the N(0,1) draws of normal_sample's full-covariance branch (Philox when None)."""
@@ -414,6 +432,7 @@ class Engine:
             o += p.numel()
         return offs, o
 
+    @_on_device
     def elbo(self, params, X, Y, S, eps=None, seed=0, num_data=None, need_grad=True, row_offset=0,
              global_batch=None, world_size=1, all_reduce=None, chunk_rows=None, check=True):
         """ELBO (dgplib/dsdgp.py:107-130) of the minibatch rows X [B, Dx], Y [B, ldy] held by THIS rank, and -- if
@@ -563,6 +582,12 @@ class GraphedElbo:
 
     def __init__(self, engine, params, X, Y, S, num_data=None, row_offset=0, global_batch=None, world_size=1,
                  chunk_rows=None, need_grad=True, base_seed=0):
+        with torch.cuda.device(engine.device):
+            self._build(engine, params, X, Y, S, num_data, row_offset, global_batch, world_size, chunk_rows, need_grad,
+                        base_seed)
+
+    def _build(self, engine, params, X, Y, S, num_data, row_offset, global_batch, world_size, chunk_rows, need_grad,
+               base_seed):
         self.eng = engine
         dev = engine.device
         self.key = (tuple(X.shape), tuple(Y.shape), S, num_data, row_offset, global_batch, world_size, chunk_rows)
@@ -594,7 +619,7 @@ class GraphedElbo:
 
     def run(self, params, X, Y, seed, all_reduce=None):
         """Replay with the given parameters, minibatch and (full) Philox seed; returns views of static buffers."""
-        with torch.no_grad():
+        with torch.no_grad(), torch.cuda.device(self.eng.device):
             torch._foreach_copy_(self.ps, [p.detach() for p in params])
             self.Xs.copy_(X, non_blocking=True)
             self.Ys.copy_(Y, non_blocking=True)

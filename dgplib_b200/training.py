@@ -19,6 +19,10 @@ class GraphedTrainStep:
     captured run takes exactly the steps an eager run takes."""
 
     def __init__(self, model, opt, X, Y):
+        with torch.cuda.device(model.engine.device):
+            self._build(model, opt, X, Y)
+
+    def _build(self, model, opt, X, Y):
         eng = model.engine
         dev = eng.device
         self.model, self.eng, self.opt = model, eng, opt
@@ -65,10 +69,11 @@ class GraphedTrainStep:
     def run(self, X, Y, seed):
         """One training step on the staged minibatch (X, Y device tensors) with the given full Philox seed; returns the
         step's ELBO (a view of a static buffer, overwritten by the next replay)."""
-        self.Xs.copy_(X, non_blocking=True)
-        self.Ys.copy_(Y, non_blocking=True)
-        self.seed_host[0] = (int(seed) - self.base_seed) & 0x7FFFFFFFFFFFFFFF     # added to base_seed on the device
-        self.graph.replay()
+        with torch.cuda.device(self.eng.device):
+            self.Xs.copy_(X, non_blocking=True)
+            self.Ys.copy_(Y, non_blocking=True)
+            self.seed_host[0] = (int(seed) - self.base_seed) & 0x7FFFFFFFFFFFFFFF     # added to base_seed on the device
+            self.graph.replay()
         return self.elbo
 
 
@@ -112,7 +117,12 @@ class AdamOptimizer:
         """Run `maxiter` Adam steps on -ELBO; returns the list of per-step ELBO values (CUDA scalars, read lazily)."""
         opt = self._optimizer(model)
         history = []
-        for it in range(int(maxiter)):
+        with torch.cuda.device(model.engine.device):
+            self._loop(model, opt, int(maxiter), callback, history)
+        return history
+
+    def _loop(self, model, opt, maxiter, callback, history):
+        for it in range(maxiter):
             if self._graphable(model):
                 elbo = self._graphed_step(model, opt)
             else:
@@ -124,4 +134,3 @@ class AdamOptimizer:
             history.append(elbo)
             if callback is not None:
                 callback(it, elbo)
-        return history

@@ -425,6 +425,24 @@ def test_graphed_training_step_matches_eager(cuda):
         assert float((a - b).abs().max()) <= 1e-12 * max(1.0, float(a.abs().max()))
 
 
+def test_second_device_in_one_process(cuda):
+    """A model compiled for cuda:1 while cuda:0 is the current device gives the same ELBO and gradients as on cuda:0
+    (host-side caches of the library are per device; the engine switches the current device around its launches)."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    outs = []
+    for dev in ("cuda:0", "cuda:1"):
+        model, X, Y = build_dsdgp(L=2, M=24, D=3, N=120, S=2)
+        model.compile(dev)
+        eps = make_eps(model, 2, 120)
+        v, g = model.elbo_and_grad(X=torch.from_numpy(X), Y=torch.from_numpy(Y), eps=eps)
+        assert v.device == torch.device(dev)
+        outs.append((v.cpu(), [x.cpu() for x in g]))
+    assert torch.equal(outs[0][0], outs[1][0])
+    for a, b in zip(outs[0][1], outs[1][1]):
+        assert torch.equal(a, b)
+
+
 def test_trainable_linear_mean_is_refused(cuda):
     rng = np.random.RandomState(0)
     X, Y, Z = rng.randn(40, 2), rng.randn(40, 1), rng.randn(8, 2)
