@@ -64,6 +64,16 @@ struct BwdSmem {
     }
 };
 
+// K splits of the T1 product: the consumer warps form NWARPS / (NT / 8) groups, each taking a slice of the inducing index;
+// their partial [NT][Dp + 1] tiles are parked in the A-tile buffer (NT x ldb doubles), so wide inputs (Dp + 1 > ldb / 4)
+// use fewer splits.  ldb = Mpad + 4 >= 68 > Dp + 1 always leaves room for one.
+template <class C>
+__device__ __forceinline__ int t1_splits(int Dp, int ldb) {
+    int kqe = C::NWARPS / (C::NT / 8);
+    while (kqe > 1 && kqe * (Dp + 1) > ldb) kqe >>= 1;
+    return kqe;
+}
+
 template <class C>
 __global__ void __launch_bounds__(C::NTHREADS, 1) k_cond_bwd(const __grid_constant__ BwdArgs a) {
     extern __shared__ __align__(128) double smem[];
@@ -377,11 +387,11 @@ __global__ void __launch_bounds__(C::NTHREADS, 1) k_cond_bwd(const __grid_consta
         //      KQ warp groups whose partial tiles are summed in fixed order through the (now free) A-tile buffer.
         {
             constexpr int NTT = C::NT / 8;                 // 8-row tiles of the row tile
-            constexpr int KQ = C::NWARPS / NTT;            // K splits
             const int nt4 = warp % NTT, kq = warp / NTT;
-            const int kspan = Mpad / KQ;                   // Mpad is a multiple of 64, KQ of {2, 4}
-            double* t1p = Bt;                              // scratch [KQ][NT][Dp + 1]; column Dp = row sums of Gr2
-            for (int d0 = 0; d0 < Dp + 1; d0 += 8) {
+            const int kqe = t1_splits<C>(Dp, ldb);         // splits whose partials fit in the A-tile buffer
+            const int kspan = Mpad / kqe;                  // Mpad is a multiple of 64, kqe of {1, 2, 4}
+            double* t1p = Bt;                              // scratch [kqe][NT][Dp + 1]; column Dp = row sums of Gr2
+            for (int d0 = 0; d0 < Dp + 1 && kq < kqe; d0 += 8) {
                 double c[2] = {0.0, 0.0};
                 for (int ks = 0; ks < kspan / 4; ++ks) {
                     const int m = kq * kspan + ks * 4 + t;
@@ -421,11 +431,10 @@ __global__ void __launch_bounds__(C::NTHREADS, 1) k_cond_bwd(const __grid_consta
         PH(8);
         // ---- row sums of Gr2 from the ones column (fast path; the general path computed them above)
         if (d.T == 1) {
-            constexpr int KQ = C::NWARPS / (C::NT / 8);
+            const int kqe = t1_splits<C>(Dp, ldb);
             if (tid < C::NT) {
                 double r = 0.0;
-#pragma unroll
-                for (int q = 0; q < KQ; ++q) r += Bt[(q * C::NT + tid) * (Dp + 1) + Dp];
+                for (int q = 0; q < kqe; ++q) r += Bt[(q * C::NT + tid) * (Dp + 1) + Dp];
                 rs[tid] = r;
             }
             consumer_sync<C>();
@@ -433,10 +442,9 @@ __global__ void __launch_bounds__(C::NTHREADS, 1) k_cond_bwd(const __grid_consta
         // ---- finish T1 -> gX and the lengthscale row terms
         for (int idx = tid; idx < C::NT * Dp; idx += C::NCONS) {
             const int n = idx / Dp, k = idx % Dp;
-            constexpr int KQ = C::NWARPS / (C::NT / 8);
+            const int kqe = t1_splits<C>(Dp, ldb);
             double t1 = 0.0;
-#pragma unroll
-            for (int q = 0; q < KQ; ++q) t1 += Bt[(q * C::NT + n) * (Dp + 1) + k];
+            for (int q = 0; q < kqe; ++q) t1 += Bt[(q * C::NT + n) * (Dp + 1) + k];
             const double xv = xs[n * xld + k];
             rowq[n * nq + 2 + k] = xv * xv * rs[n] - 2.0 * xv * t1;
             const long long gn = n0 + n;

@@ -121,6 +121,12 @@ CASES = [
     (500, 16, 16, 700, "matern52", 1),
     (7, 2, 1, 1, "rbf", 1),             # a single row
     (33, 5, 3, 63, "matern52", 3),
+    (70, 64, 3, 150, "rbf", 1),         # the widest supported input (DGP_MAX_D)
+    (50, 20, 2, 100, "rbf", 1),         # small Mpad with a wide input: fewer K splits of the T1 product fit
+    (64, 33, 1, 64, "matern52", 1),
+    (1, 1, 1, 5, "rbf", 1),             # a single inducing point
+    (40, 4, 64, 90, "matern52", 1),     # the largest number of outputs per conditional (DGP_MAX_R)
+    (256, 61, 33, 130, "rbf", 2),       # odd D and R together with full-width row tiles
     (600, 8, 3, 150, "rbf", 1),         # M > 512: 8-row backward tiles
     (1024, 8, 2, 100, "matern52", 1),   # the largest supported inducing set
 ]

@@ -206,6 +206,25 @@ def test_multitask_switched_kernels_match_oracle(cuda):
     compare_elbo_and_grads(model, X, Y, S, multitask=True)
 
 
+def test_multitask_sixteen_tasks(cuda):
+    """The largest supported task count (DGP_MAX_TASKS = 16) through a SwitchedKernel layer and a SwitchedLikelihood,
+    with a task that owns no inducing point and one that owns no data row."""
+    T, D, M, N, S = 16, 2, 40, 160, 2
+    X, Y, Z = _multitask_data(N, M, D, T, seed=7)
+    Z[Z[:, -1] == 3, -1] = 4            # task 3: no inducing point
+    X[X[:, -1] == 9, -1] = 10           # task 9: no data row
+    Y[:, -1] = X[:, -1]
+    il = InputLayer(D, 2, M, RBF(D) + White(D, 1e-3), mean_function=Linear(A=np.zeros((D + 1, 2))), multitask=True)
+    sw = SwitchedKernel([(RBF if k % 2 else Matern52)(2, variance=0.7 + 0.05 * k, lengthscales=1.5 + 0.1 * k)
+                         for k in range(T)], T)
+    ol = OutputLayer(2, 1, M, sw, multitask=True)
+    model = dg.MultitaskDSDGP(X, Y, Z, MultitaskSequential([il, ol]),
+                              SwitchedLikelihood([Gaussian(0.05 * (k + 1)) for k in range(T)]), num_latent=1,
+                              num_samples=S)
+    randomize_q(model)
+    compare_elbo_and_grads(model, X, Y, S, multitask=True)
+
+
 def test_multitask_predictions(cuda):
     X, Y, Z = _multitask_data(100, 10, 2, 2, seed=42)
     il = InputLayer(2, 1, 10, RBF(2) + White(2), mean_function=Linear(A=np.ones((3, 1))), multitask=True)
