@@ -82,3 +82,41 @@ def test_normal_sample_full_cov_util(cuda):
     got = normal_sample(mean, var, full_cov=True, eps=z)
     want = O.normal_sample_full_cov(mean.cpu(), var.cpu(), z.cpu())
     assert got.shape == (S, N, D) and rel_err(got, want) < 1e-10
+
+
+@pytest.mark.parametrize("N", [1, 64, 130, 1024])
+def test_full_cov_sizes(cuda, N):
+    """Single points, exact tile multiples, ragged sizes and the largest supported point count (1024)."""
+    model, X, Y = build_dsdgp(L=2, M=20, D=2, N=60, S=1, white=1e-3)
+    model.compile()
+    rng = np.random.RandomState(N)
+    Xs = rng.randn(N, 2)
+    dims = [l.output_dim for l in model.layers.layers]
+    z = [rng.randn(1, R, N) for R in dims]
+    ol = oracle_layers(model.layers.layers)
+    oF, oM, oV = O.propagate_full_cov(ol, t(Xs), 1, [t(a) for a in z])
+    F, M, V = model.predict_all_layers_full_cov(Xs, 1, eps=z)
+    for l in range(2):
+        assert M[l].shape == tuple(oM[l].shape) and V[l].shape == tuple(oV[l].shape)
+        assert rel_err(M[l], oM[l]) < TOL and rel_err(V[l], oV[l]) < TOL and rel_err(F[l], oF[l]) < 1e-7
+
+
+def test_full_cov_refuses_more_than_1024_points(cuda):
+    model, X, Y = build_dsdgp(L=2, M=20, D=2, N=60, S=1)
+    model.compile()
+    with pytest.raises(Exception):
+        model.predict_f_full_cov(np.random.RandomState(0).randn(1025, 2), 1)
+
+
+def test_multikernel_full_cov_matches_oracle(cuda):
+    rng = np.random.RandomState(3)
+    layer = MultikernelInputLayer(2, 4, 12, [RBF(2, lengthscales=0.9) + White(2, 1e-3), Matern52(2, lengthscales=1.4)],
+                                  share_Z=False, mean_function=Linear(A=rng.randn(2, 4)))
+    layer.initialize_forward(rng.randn(30, 2), rng.randn(12, 2))
+    layer.q_mu.assign(0.2 * rng.randn(12, 4))
+    layer.q_sqrt.assign(np.eye(12)[None] + 0.1 * np.tril(rng.randn(4, 12, 12)))
+    Xs = rng.randn(2, 21, 2)
+    m, v = layer._build_predict(Xs, full_cov=True)
+    om, ov = O.layer_build_predict_full_cov(oracle_layers([layer])[0], t(Xs))
+    assert m.shape == (2, 21, 4) and v.shape == (2, 21, 21, 4)
+    assert rel_err(m, om) < TOL and rel_err(v, ov) < TOL
