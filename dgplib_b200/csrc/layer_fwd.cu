@@ -226,14 +226,23 @@ __global__ void __launch_bounds__(C::NTHREADS, 1) k_cond_fwd(const __grid_consta
         // K = inducing index (q_mu fragments straight from global / L1), then + mean_fn(x)
         for (int nt = warp; nt < C::NT / 8; nt += C::NWARPS) {
             for (int r0 = 0; r0 < d.R; r0 += 8) {
-                double c[2] = {0.0, 0.0};
+                // four independent accumulators over interleaved k-steps: one dependent DMMA chain of Mpad / 4 steps with
+                // a global load in front of each was the whole cost of this phase
+                double c4[4][2] = {{0.0, 0.0}, {0.0, 0.0}, {0.0, 0.0}, {0.0, 0.0}};
                 const bool rok = (r0 + g < d.R);
                 const double* qcol = d.q_mu + d.col0 + r0 + g;
-                for (int m = 0; m < Mpad; m += 4) {
-                    const int mk = m + t;
-                    const double bv = (rok && mk < d.M) ? qcol[(size_t)mk * d.ldr] : 0.0;
-                    dmma884(c, Bt[(nt * 8 + g) * ldb + mk], bv);
+                const double* arow = Bt + (nt * 8 + g) * ldb + t;
+                for (int m = 0; m < Mpad; m += 16) {          // Mpad is a multiple of 64
+                    double bv[4];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const int mk = m + 4 * u + t;
+                        bv[u] = (rok && mk < d.M) ? qcol[(size_t)mk * d.ldr] : 0.0;
+                    }
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) dmma884(c4[u], arow[m + 4 * u], bv[u]);
                 }
+                double c[2] = {(c4[0][0] + c4[1][0]) + (c4[2][0] + c4[3][0]), (c4[0][1] + c4[1][1]) + (c4[2][1] + c4[3][1])};
 #pragma unroll
                 for (int e = 0; e < 2; ++e) {
                     const int r = r0 + 2 * t + e;
