@@ -229,7 +229,7 @@ class DSDGP(Parameterized):
         kw, finish = self._staged_step(eps, seed)
         graph = kw.pop("_graph", None)
         if graph is not None:
-            out = graph.run(eng.params(), kw["X"], kw["Y"], kw["seed"], all_reduce=kw.get("all_reduce"))
+            out = graph.run(None, kw["X"], kw["Y"], kw["seed"], all_reduce=kw.get("all_reduce"))
             if kw.get("check"):
                 eng.check_status()
         else:
@@ -265,10 +265,12 @@ class DSDGP(Parameterized):
     def _graph_for(self, xd, yd, kw):
         from .engine import GraphedElbo
         eng = self.engine
-        key = (tuple(xd.shape), tuple(yd.shape), kw["row_offset"], kw["global_batch"], kw.get("world_size", 1))
+        key = (tuple(xd.shape), tuple(yd.shape), kw["row_offset"], kw["global_batch"], kw.get("world_size", 1),
+               GraphedElbo.storage_key(eng))
         g = self._graphs.get(key)
         if g is None:
-            g = GraphedElbo(eng, eng.params(), xd, yd, self.num_samples, num_data=self.num_data,
+            # live parameters: the positive transforms are captured with the evaluation and read the model's own tensors
+            g = GraphedElbo(eng, None, xd, yd, self.num_samples, num_data=self.num_data,
                             row_offset=kw["row_offset"], global_batch=kw["global_batch"],
                             world_size=kw.get("world_size", 1), chunk_rows=self.chunk_rows, base_seed=self.seed)
             self._graphs[key] = g

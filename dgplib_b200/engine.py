@@ -141,6 +141,15 @@ class Engine:
             return torch.stack([l.variance.constrained() for l in lik.likelihood_list])
         return lik.variance.constrained().reshape(1)
 
+    def raw_parameters(self):
+        """The unconstrained torch Parameters behind params() (every Param of the layers and the likelihood)."""
+        out = []
+        for layer in self.layers:
+            out.extend(layer.parameters())
+        if self.likelihood is not None:
+            out.extend(self.likelihood.parameters())
+        return out
+
     def params(self):
         """Constrained, autograd-attached parameter tensors in the flat order used by the gradient buffer:
         per layer [Z_c, theta_c for each conditional c] + [q_mu, q_sqrt]; then the likelihood variances."""
@@ -582,18 +591,31 @@ class GraphedElbo:
 
     def __init__(self, engine, params, X, Y, S, num_data=None, row_offset=0, global_batch=None, world_size=1,
                  chunk_rows=None, need_grad=True, base_seed=0):
+        """params: list of constrained parameter tensors copied into static buffers before every replay, or None to read
+        the model's own parameters inside the graph (the positive transforms are then part of the capture; valid while
+        the parameter tensors keep their storage, i.e. in-place optimiser updates)."""
         with torch.cuda.device(engine.device):
             self._build(engine, params, X, Y, S, num_data, row_offset, global_batch, world_size, chunk_rows, need_grad,
                         base_seed)
 
+    @staticmethod
+    def storage_key(engine):
+        """Identity of the parameter storages a live-parameter graph reads (a re-assigned tensor needs a new capture)."""
+        return tuple(p.data_ptr() for p in engine.raw_parameters())
+
     def _build(self, engine, params, X, Y, S, num_data, row_offset, global_batch, world_size, chunk_rows, need_grad,
                base_seed):
         self.eng = engine
+        self.live = params is None
+        if self.live:
+            with torch.no_grad():
+                params = engine.params()
         dev = engine.device
         self.key = (tuple(X.shape), tuple(Y.shape), S, num_data, row_offset, global_batch, world_size, chunk_rows)
         self.Xs = _dev_tensor(X, dev).clone()
         self.Ys = _dev_tensor(Y, dev).clone()
-        self.ps = [_dev_tensor(p, dev).clone() for p in params]
+        self.ps = None if self.live else [_dev_tensor(p, dev).clone() for p in params]
+        live_ps = lambda: [p.detach() for p in engine.params()]
         self.seed_host = torch.zeros(1, dtype=torch.int64).pin_memory()
         self.seed_dev = torch.zeros(1, dtype=torch.int64, device=dev)
         self.base_seed = int(base_seed)
@@ -604,7 +626,8 @@ class GraphedElbo:
         warm.wait_stream(cur)
         with torch.cuda.stream(warm):                      # allocate every cached buffer before capture
             for _ in range(2):
-                engine.elbo(self.ps, self.Xs, self.Ys, **kw)
+                with torch.no_grad():
+                    engine.elbo(live_ps() if self.live else self.ps, self.Xs, self.Ys, **kw)
         cur.wait_stream(warm)
         torch.cuda.synchronize(dev)
         self.graph = torch.cuda.CUDAGraph()
@@ -612,7 +635,8 @@ class GraphedElbo:
         try:
             with torch.cuda.graph(self.graph):
                 self.seed_dev.copy_(self.seed_host, non_blocking=True)
-                self.val, self.grads = engine.elbo(self.ps, self.Xs, self.Ys, **kw)
+                with torch.no_grad():
+                    self.val, self.grads = engine.elbo(live_ps() if self.live else self.ps, self.Xs, self.Ys, **kw)
                 self.flat = engine._last_flat
         finally:
             engine._seed_dev = None
@@ -620,7 +644,8 @@ class GraphedElbo:
     def run(self, params, X, Y, seed, all_reduce=None):
         """Replay with the given parameters, minibatch and (full) Philox seed; returns views of static buffers."""
         with torch.no_grad(), torch.cuda.device(self.eng.device):
-            torch._foreach_copy_(self.ps, [p.detach() for p in params])
+            if not self.live:
+                torch._foreach_copy_(self.ps, [p.detach() for p in params])
             self.Xs.copy_(X, non_blocking=True)
             self.Ys.copy_(Y, non_blocking=True)
             self.seed_host[0] = (int(seed) - self.base_seed) & 0x7FFFFFFFFFFFFFFF   # added to base_seed on the device
