@@ -492,8 +492,9 @@ def main():
     roofline = {"bound": "tensor", "kernel": dom, "achieved": achieved, "peak": FP64_PEAK_TFLOPS, "unit": "TFLOP/s",
                 "frac": achieved / FP64_PEAK_TFLOPS,
                 # dram__bytes_read.sum + dram__bytes_write.sum per launch of k_cond_bwd at the T hidden-layer shape, from the
-                # committed capture profiles/r01c_metrics.txt (algorithmic bytes: A in 205 MB + dKuf out 205 MB + ~50 MB rows)
-                "traffic": 4.50e8 if (args.workload == "T" and dom == "bwd.l1") else None,
+                # committed capture profiles/r01g_metrics.txt: 248.3 MB read + 188.4 MB written (algorithmic bytes: A in
+                # 205 MB + dKuf out 205 MB + ~25 MB of row vectors; part of dKuf is still in L2 when the capture ends)
+                "traffic": 4.37e8 if (args.workload == "T" and dom == "bwd.l1") else None,
                 "peak_source": "fp64 DMMA.8x8x4 issue-rate microbenchmark on this pool's B200 (profiles/fp64_peak_r01.txt); "
                                "MEASURED_PEAKS.json has no fp64 entry (its bf16 tcgen05 peak does not apply: there is "
                                "no fp64 tcgen05 kind)",
