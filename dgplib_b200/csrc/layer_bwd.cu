@@ -728,7 +728,11 @@ extern "C" int dgp_cond_backward(const dgp_cond_desc* d, void* ws, const double*
     if (w.Mpad <= 256) {
         // 40-row tiles with a 4 x 5 consumer-warp grid and a 2-slot ring when they fit (R <= ~16): 25 % more rows per
         // streamed operand byte and per fixed tile cost than 32-row tiles (bwd 4.26 -> 4.10 ms at the T layer shape)
-        DGP_TRY_BWD(5, 40, 2)
+        // (unless 32-row tiles fill the last wave so much better that they win despite ~4 % more time per row)
+        const long long sms = device_sm_count();
+        const long long w40 = ((n_rows + 39) / 40 + sms - 1) / sms * 40;
+        const long long w32 = ((n_rows + 31) / 32 + sms - 1) / sms * 32;
+        if (w40 * 100 <= w32 * 104) { DGP_TRY_BWD(5, 40, 2) }
         DGP_TRY_BWD(DGP_BWD_WN, 32, 4) DGP_TRY_BWD(DGP_BWD_WN, 32, 3) DGP_TRY_BWD(DGP_BWD_WN, 32, 2)
     } else {
         DGP_TRY_BWD(2, 16, 4) DGP_TRY_BWD(2, 16, 3) DGP_TRY_BWD(2, 16, 2)
