@@ -63,3 +63,21 @@ def test_no_cpu_fallback():
         pytest.skip("CUDA present")
     with pytest.raises(_cabi.DgpError):
         _cabi.require_cuda()
+
+
+def test_product_and_tools_never_touch_the_oracle():
+    """oracle/ is test infrastructure: nothing shipped (the package, the C sources, tools/) may import or mention it as a
+    code path; bench.py and __graft_entry__.py may, as the checker / timed CPU baseline only."""
+    import os
+    import re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    pat = re.compile(r"^\s*(from|import)\s+oracle\b", re.M)
+    offenders = []
+    for sub in ("dgplib_b200", "tools", "include"):
+        for dirpath, _, files in os.walk(os.path.join(root, sub)):
+            for f in files:
+                if f.endswith((".py", ".cu", ".cuh", ".h")):
+                    text = open(os.path.join(dirpath, f), encoding="utf-8", errors="replace").read()
+                    if pat.search(text):
+                        offenders.append(os.path.join(dirpath, f))
+    assert not offenders, offenders
