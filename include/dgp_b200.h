@@ -67,7 +67,12 @@ typedef struct dgp_cond_desc {
  * number of rows (S*B) of any forward/backward call made with this workspace */
 size_t dgp_cond_ws_bytes(const dgp_cond_desc* d, int64_t n_rows, int need_bwd);
 /* Replaces: features.Kuu + tf.cholesky inside base_conditional, band_part(q_sqrt), and gauss_kl(q_mu, q_sqrt,
- * K=None) of dgplib/layers.py:58-60.  kl_out (device, 1 double) receives this conditional's KL if not NULL. */
+ * K=None) of dgplib/layers.py:58-60.  kl_out (device, 1 double) receives this conditional's KL if not NULL.
+ * Stream semantics (also dgp_cond_backward_params): everything is ordered after the work already queued on `stream`
+ * and complete, in stream order, for whatever is queued on it afterwards; internally the q_sqrt-only chain may run on
+ * a library-owned helper stream that is forked from and joined back into `stream` with events before the call returns
+ * (a capture on `stream` simply gains a parallel branch).  DGP_NO_SIDE_STREAM=1 in the environment keeps it all on
+ * `stream`. */
 int dgp_cond_prepare(const dgp_cond_desc* d, void* ws, size_t ws_bytes, int need_bwd, double* kl_out, void* stream);
 /* copies the Cholesky status word to the host (synchronises the stream) */
 int dgp_cond_status(const void* ws, void* stream, int32_t* status_host);
