@@ -217,7 +217,9 @@ extern "C" int dgp_cond_backward_params(const dgp_cond_desc* d, void* ws, double
     }
     if (lane) cudaEventRecord(lane->join, sb);
     // ---- chain A:  T1 = Lm^T Lbar ; Phi ; T2 = Linv^T T1 ; T3 = T2 Linv
-    double* rowp = T1;                    // rowp / dzs reuse the T1 buffer once T2 has been formed
+    // rowp [Mpad][2 + Dp] and dzs [Mpad][Dp] reuse Lbar | T1 | T2 (contiguous, 3 Mpad^2 doubles, all consumed before the Kuu
+    // reverse mode runs); 2 + 2 Dp <= 130 <= 3 Mpad always fits -- T1 | T2 alone would not for M <= 64 with D > 60
+    double* rowp = Lbar;
     double* dzs = rowp + (size_t)Mpad * (2 + Dp);
     if (rc == DGP_OK) {
         k_gram_reduce<<<dim3((Mpad + 127) / 128, Mpad, 1), 128, 0, st>>>(gram, w.nsplit, R, Mpad, R, Gfull, Lbar); DGP_COUNT_LAUNCH();

@@ -124,6 +124,7 @@ CASES = [
     (70, 64, 3, 150, "rbf", 1),         # the widest supported input (DGP_MAX_D)
     (50, 20, 2, 100, "rbf", 1),         # small Mpad with a wide input: fewer K splits of the T1 product fit
     (64, 33, 1, 64, "matern52", 1),
+    (60, 64, 2, 50, "rbf", 1),          # Mpad = 64 with the widest input: tail scratch needs more than two M x M buffers
     (1, 1, 1, 5, "rbf", 1),             # a single inducing point
     (40, 4, 64, 90, "matern52", 1),     # the largest number of outputs per conditional (DGP_MAX_R)
     (256, 61, 33, 130, "rbf", 2),       # odd D and R together with full-width row tiles
