@@ -430,6 +430,94 @@ k_tri_inv_cols(const double* __restrict__ L, double* __restrict__ Linv, int Mpad
     }
 }
 
+// Same substitution for Mpad <= 256 with everything the long product touches staged in shared memory: the column panel
+// X_Kc stays resident (this CTA produces it), the block row of L and Linv_II arrive by cp.async in one batch per step, so
+// a step costs one L2 round trip instead of one per 32-deep slice (53 -> ~16 us at M = 256 on the serial parameter chain).
+constexpr int TRI_LDX = 36;     // pitch of the 32-wide panels: 36 mod 16 = 4 keeps the DMMA fragment loads conflict-free
+__global__ void __launch_bounds__(256)
+k_tri_inv_cols_smem(const double* __restrict__ L, double* __restrict__ Linv, int Mpad) {
+    extern __shared__ __align__(16) double tsm[];
+    const int ldl = Mpad + 4;
+    double* sL = tsm;                       // [32][ldl]      block row I of L, columns c0 .. i0
+    double* sX = sL + 32 * ldl;             // [Mpad][TRI_LDX] rows k - c0 of the column panel X[., c block]
+    double* sDi = sX + Mpad * TRI_LDX;      // [32][TRI_LDX]  Linv_II
+    double* sT = sDi + 32 * TRI_LDX;        // [32][TRI_LDX]  T = L_I. X
+    const int c = blockIdx.x, nb = Mpad / 32, tid = threadIdx.x;
+    const int warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
+    const int c0 = c * 32;
+    const int ta = warp >> 1, tb = (warp & 1) * 2;
+    for (int e = tid; e < c0 * 32; e += 256) Linv[(size_t)(e >> 5) * Mpad + c0 + (e & 31)] = 0.0;
+    for (int e = tid; e < 32 * 32; e += 256)   // X_cc: the diagonal block's inverse (written by the Cholesky kernel)
+        sX[(e >> 5) * TRI_LDX + (e & 31)] = Linv[(size_t)(c0 + (e >> 5)) * Mpad + c0 + (e & 31)];
+    for (int I = c + 1; I < nb; ++I) {
+        const int i0 = I * 32, kw = i0 - c0;             // kw = depth of the long product
+        // stage L[i0 .. i0+32)[c0 .. i0) and Linv_II: 16-byte cp.async, all in flight at once
+        const int per_row = kw / 2;                      // 16-byte pieces per row
+        for (int e = tid; e < 32 * per_row; e += 256) {
+            const int r = e / per_row, q = e % per_row;
+            cp_async16(sL + r * ldl + 2 * q, L + (size_t)(i0 + r) * Mpad + c0 + 2 * q);
+        }
+        for (int e = tid; e < 32 * 16; e += 256) {
+            const int r = e >> 4, q = e & 15;
+            cp_async16(sDi + r * TRI_LDX + 2 * q, Linv + (size_t)(i0 + r) * Mpad + i0 + 2 * q);
+        }
+        cp_async_commit();
+        cp_async_wait<0>();
+        __syncthreads();
+        double acc0[2] = {0.0, 0.0}, acc1[2] = {0.0, 0.0};
+        const double* pa = sL + (ta * 8 + g) * ldl + t;
+        const double* pb = sX + t * TRI_LDX + tb * 8 + g;
+#pragma unroll 4
+        for (int k = 0; k < kw; k += 4) {
+            const double a = pa[k];
+            dmma884(acc0, a, pb[k * TRI_LDX]);
+            dmma884(acc1, a, pb[k * TRI_LDX + 8]);
+        }
+        sT[(ta * 8 + g) * TRI_LDX + tb * 8 + 2 * t] = acc0[0];
+        sT[(ta * 8 + g) * TRI_LDX + tb * 8 + 2 * t + 1] = acc0[1];
+        sT[(ta * 8 + g) * TRI_LDX + tb * 8 + 8 + 2 * t] = acc1[0];
+        sT[(ta * 8 + g) * TRI_LDX + tb * 8 + 8 + 2 * t + 1] = acc1[1];
+        __syncthreads();
+        // X_Ic = -Linv_II * T  -> global and the resident panel
+        double o0[2] = {0.0, 0.0}, o1[2] = {0.0, 0.0};
+#pragma unroll
+        for (int kk = 0; kk < 8; ++kk) {
+            const double a = sDi[(ta * 8 + g) * TRI_LDX + kk * 4 + t];
+            dmma884(o0, a, sT[(kk * 4 + t) * TRI_LDX + tb * 8 + g]);
+            dmma884(o1, a, sT[(kk * 4 + t) * TRI_LDX + tb * 8 + 8 + g]);
+        }
+        double* dst = Linv + (size_t)(i0 + ta * 8 + g) * Mpad + c0 + tb * 8 + 2 * t;
+        dst[0] = -o0[0]; dst[1] = -o0[1];
+        dst[8] = -o1[0]; dst[9] = -o1[1];
+        double* xs = sX + (kw + ta * 8 + g) * TRI_LDX + tb * 8 + 2 * t;
+        xs[0] = -o0[0]; xs[1] = -o0[1];
+        xs[8] = -o1[0]; xs[9] = -o1[1];
+        __syncthreads();   // panel rows of block I and the reuse of sL / sDi / sT by the next step
+    }
+}
+
+static size_t tri_inv_smem_bytes(int Mpad) {
+    return (size_t)(32 * (Mpad + 4) + Mpad * TRI_LDX + 2 * 32 * TRI_LDX) * sizeof(double);
+}
+
+int tri_inv_cols(const double* L, double* Linv, int Mpad, cudaStream_t st) {
+    static const bool legacy = getenv("DGP_TRIINV_GLOBAL") != nullptr;   // A/B switch for tools/kbench.py
+    if (Mpad <= 256 && !legacy) {
+        static bool attr_dev[DGP_MAX_DEVICES] = {};
+        bool& attr = attr_dev[current_device()];
+        if (!attr) {
+            if (cudaFuncSetAttribute(k_tri_inv_cols_smem, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)tri_inv_smem_bytes(256)) != cudaSuccess) return DGP_ERR_LAUNCH;
+            attr = true;
+        }
+        k_tri_inv_cols_smem<<<Mpad / 32, 256, tri_inv_smem_bytes(Mpad), st>>>(L, Linv, Mpad);
+    } else {
+        k_tri_inv_cols<<<Mpad / 32, 256, 0, st>>>(L, Linv, Mpad);
+    }
+    DGP_COUNT_LAUNCH();
+    return cudaGetLastError() == cudaSuccess ? DGP_OK : DGP_ERR_LAUNCH;
+}
+
 // Legacy path (Mpad > 512): inverses of the 32 x 32 diagonal blocks, one warp per block.
 __global__ void k_diag_inv(const double* __restrict__ L, double* __restrict__ Linv, int Mpad) {
     __shared__ double sL[32 * 33];
@@ -664,8 +752,8 @@ extern "C" int dgp_cond_prepare(const dgp_cond_desc* d, void* ws, size_t ws_byte
         rc = cholesky_batched(Lm, Mpad, 1, status, st, Linv);
     }
     if (rc == DGP_OK) {
-        k_tri_inv_cols<<<Mpad / 32, 256, 0, st>>>(Lm, Linv, Mpad); DGP_COUNT_LAUNCH();
-        rc = retile(Linv, ws_ptr<double>(ws, w.LinvTl), Mpad, 1, st);
+        rc = tri_inv_cols(Lm, Linv, Mpad, st);
+        if (rc == DGP_OK) rc = retile(Linv, ws_ptr<double>(ws, w.LinvTl), Mpad, 1, st);
     }
     if (rc == DGP_OK && need_bwd) {
         double* LinvT = ws_ptr<double>(ws, wb.LinvT);
