@@ -360,6 +360,58 @@ def test_full_size_properties_config2(cuda):
         assert rel_err(a, c) < 1e-10
 
 
+def _shard_and_chunk_properties(model, X, Y, S, num_data, split, chunk, multitask=False):
+    """Size-independent checks: finite values; ELBO and every gradient add up over two row shards evaluated as two ranks
+    (KL weight 1/2 each, global Philox row ids); a row-chunked evaluation equals the one-pass evaluation."""
+    model.compile()
+    eng = model.engine
+    params = [p.detach() for p in eng.params()]
+    Xd, Yd = torch.from_numpy(X).cuda(), torch.from_numpy(Y).cuda()
+    B = X.shape[0]
+    kw = dict(S=S, seed=5, num_data=num_data, need_grad=True)
+    v, g = eng.elbo(params, Xd, Yd, **kw)
+    v, g = v.clone(), [x.clone() for x in g]
+    assert torch.isfinite(v) and all(torch.isfinite(x).all() for x in g)
+    parts = []
+    for lo, hi in ((0, split), (split, B)):
+        pv, pg = eng.elbo(params, Xd[lo:hi], Yd[lo:hi], row_offset=lo, global_batch=B, world_size=2, **kw)
+        parts.append((pv.clone(), [x.clone() for x in pg]))
+    assert abs(float(parts[0][0] + parts[1][0]) - float(v)) < 1e-11 * abs(float(v))
+    for a, b, c in zip(parts[0][1], parts[1][1], g):
+        assert rel_err(a + b, c) < 1e-10
+    v2, g2 = eng.elbo(params, Xd, Yd, chunk_rows=chunk, **kw)
+    assert abs(float(v2) - float(v)) < 1e-11 * abs(float(v))
+    for a, c in zip(g2, g):
+        assert rel_err(a, c) < 1e-10
+
+
+def test_full_size_properties_target_line(cuda):
+    """The north-star target configuration at full size: 3 layers, M=256, D=8, minibatch 10k, S=10."""
+    model, X, Y = build_dsdgp(L=3, M=256, D=8, N=10_000, S=10)
+    _shard_and_chunk_properties(model, X, Y, 10, 100_000, split=3700, chunk=4096)
+
+
+def test_full_size_properties_config3_shard(cuda):
+    """BASELINE configs[2] shape (5 layers, Matern52, M=500, D=16, S=16) on a 1500-row slice of one GPU's shard."""
+    model, X, Y = build_dsdgp(L=5, M=500, D=16, N=1500, S=16, kind="matern52")
+    _shard_and_chunk_properties(model, X, Y, 16, 1_000_000, split=701, chunk=512)
+
+
+def test_full_size_properties_config4_multitask(cuda):
+    """BASELINE configs[3] shape: MultikernelInputLayer with 8 kernels + SwitchedKernel output over 8 tasks, M=256."""
+    T, D, M, N, S = 8, 8, 256, 3000, 4
+    X, Y, Z = _multitask_data(N, M, D, T, seed=11)
+    il = MultikernelInputLayer(D, 8, M, [RBF(D, lengthscales=np.sqrt(D) * (0.8 + 0.1 * k)) + White(D, 1e-5)
+                                         for k in range(8)],
+                               share_Z=False, mean_function=Linear(A=np.zeros((D + 1, 8))), multitask=True)
+    sw = SwitchedKernel([RBF(8, lengthscales=np.sqrt(8.0)) + White(8, 1e-5) for _ in range(T)], T)
+    ol = OutputLayer(8, 1, M, sw, multitask=True)
+    model = dg.MultitaskDSDGP(X, Y, Z, MultitaskSequential([il, ol]),
+                              SwitchedLikelihood([Gaussian(0.1) for _ in range(T)]), num_latent=1, num_samples=S)
+    randomize_q(model)
+    _shard_and_chunk_properties(model, X, Y, S, 200_000, split=1111, chunk=1000, multitask=True)
+
+
 def test_chunked_prediction_is_identical(cuda):
     """predict_* pushes test rows through the cascade in chunks; Philox draws are keyed by the global row id, so the
     result does not depend on the chunk size."""
