@@ -8,6 +8,7 @@ PyTorch is used for device memory, streams and (multi-GPU) the NCCL all-reduce o
 arithmetic step is a kernel of the extension.  There is no CPU / eager fallback.
 """
 import ctypes
+import os
 
 import numpy as np
 import torch
@@ -103,6 +104,7 @@ class Engine:
         _cabi.require_cuda()
         _cabi.lib()
         self.device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
+        self.gram_on_side_stream = os.environ.get("DGP_GRAM_MAIN_STREAM") is None
         self.layers = list(layers)
         self.likelihood = likelihood
         self.multitask = bool(multitask)
@@ -564,9 +566,19 @@ class Engine:
                             _cabi.ptr(g_var_in) if g_var_in is not None else None,
                             _cabi.ptr(gF) if gF is not None else None, gF.shape[1] if gF is not None else 0,
                             _cabi.ptr(buf["gX"][l]) if l > 0 else None, 1 if ci > 0 else 0, st), "dgp_cond_backward"))
-                        self._timed(f"gram.l{l}", lambda: _cabi.check(lib.dgp_cond_backward_gram(
-                            c.ref(), _cabi.ptr(c.ws), _cabi.ptr(buf["A"][l][ci]), rows, 1 if ck > 0 else 0, st),
-                            "dgp_cond_backward_gram"))
+                        if nchunks == 1 and l > 0 and self.gram_on_side_stream:
+                            # the Gram reduction of this layer is not needed by the next layer's backward kernel: on the
+                            # conditional's side stream it fills the SMs that kernel's last, partly empty wave leaves idle
+                            side = self._side_streams()[l][ci]
+                            side.wait_event(main.record_event())
+                            with torch.cuda.stream(side):
+                                self._timed(f"gram.l{l}", lambda: _cabi.check(lib.dgp_cond_backward_gram(
+                                    c.ref(), _cabi.ptr(c.ws), _cabi.ptr(buf["A"][l][ci]), rows, 0, _cabi.stream_ptr()),
+                                    "dgp_cond_backward_gram"))
+                        else:
+                            self._timed(f"gram.l{l}", lambda: _cabi.check(lib.dgp_cond_backward_gram(
+                                c.ref(), _cabi.ptr(c.ws), _cabi.ptr(buf["A"][l][ci]), rows, 1 if ck > 0 else 0, st),
+                                "dgp_cond_backward_gram"))
                     if ck == nchunks - 1:
                         run_tail(l)
             for ev in tail_events:
