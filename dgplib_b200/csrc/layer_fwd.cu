@@ -402,6 +402,13 @@ extern "C" int dgp_cond_forward(const dgp_cond_desc* d, const void* ws, const do
         const long long sms = device_sm_count();
         const long long w64 = ((n_rows + 63) / 64 + sms - 1) / sms * 64;
         const long long w32 = ((n_rows + 31) / 32 + sms - 1) / sms * 32;
+        const long long w72 = ((n_rows + 71) / 72 + sms - 1) / sms * 72;
+        // 72-row tiles (4 x 3 consumer warps, three column tiles per warp): one wave for the 10 000-row minibatch of the
+        // BASELINE configurations on 148 SMs, where 64-row tiles need two and 32-row tiles three
+        static const char* force_nt = getenv("DGP_FWD_NT");      // A/B switch for tools/kbench.py
+        if ((force_nt && atoi(force_nt) == 72) || (!force_nt && w72 * 104 < w64 * 100 && w72 * 100 <= w32 * 108)) {
+            DGP_TRY_FWD(3, 72, 3) DGP_TRY_FWD(3, 72, 2)
+        }
         if (w32 * 108 < w64 * 100) { DGP_TRY_FWD(DGP_FWD_WN, 32, 4) DGP_TRY_FWD(DGP_FWD_WN, 32, 3) }
         DGP_TRY_FWD(DGP_FWD_WN, 64, 4) DGP_TRY_FWD(DGP_FWD_WN, 64, 3) DGP_TRY_FWD(DGP_FWD_WN, 64, 2)
     } else if (w.Mpad <= 512) {
