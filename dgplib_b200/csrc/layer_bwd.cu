@@ -732,6 +732,9 @@ extern "C" int dgp_cond_backward(const dgp_cond_desc* d, void* ws, const double*
         const long long sms = device_sm_count();
         const long long w40 = ((n_rows + 39) / 40 + sms - 1) / sms * 40;
         const long long w32 = ((n_rows + 31) / 32 + sms - 1) / sms * 32;
+        // small inducing sets leave room for two 72-row tiles: taken when they save a wave (10 000 rows: one instead of two)
+        const long long w72 = ((n_rows + 71) / 72 + sms - 1) / sms * 72;
+        if (w.Mpad <= 128 && w72 * 104 < w40 * 100 && w72 * 104 < w32 * 104) { DGP_TRY_BWD(3, 72, 3) DGP_TRY_BWD(3, 72, 2) }
         if (w40 * 100 <= w32 * 104) { DGP_TRY_BWD(5, 40, 2) }
         DGP_TRY_BWD(DGP_BWD_WN, 32, 4) DGP_TRY_BWD(DGP_BWD_WN, 32, 3) DGP_TRY_BWD(DGP_BWD_WN, 32, 2)
     } else {
