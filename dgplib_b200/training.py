@@ -93,8 +93,9 @@ class AdamOptimizer:
         if self._opt is None or self._model is not model:
             model.engine            # compile: parameters live on the GPU from here on
             params = model.trainable_parameters()
-            self._opt = torch.optim.Adam(params, lr=self.lr, betas=self.betas, eps=self.eps, fused=True,
-                                         capturable=self._graphable(model))
+            # capturable always: the step counter lives on the device, so model.use_cuda_graph may be switched on
+            # between two minimize() calls without losing the optimiser state
+            self._opt = torch.optim.Adam(params, lr=self.lr, betas=self.betas, eps=self.eps, fused=True, capturable=True)
             self._model = model
             self._graphs = {}
         return self._opt

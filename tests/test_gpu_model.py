@@ -487,10 +487,13 @@ def test_graphed_training_step_matches_eager(cuda):
         opt = AdamOptimizer(0.01)
         hist = opt.minimize(model, maxiter=4)
         hist += opt.minimize(model, maxiter=2)                   # a second call keeps going with the same graph / state
+        if graph:                                                # switching the graph off keeps the optimiser state
+            model.use_cuda_graph = False
+        hist += opt.minimize(model, maxiter=1)
         return torch.stack([h.reshape(()) for h in hist]).cpu(), [p.detach().cpu().clone() for p in model.trainable_parameters()]
     he, pe = run(False)
     hg, pg = run(True)
-    assert len(he) == 6 and not torch.equal(he[0], he[1])
+    assert len(he) == 7 and not torch.equal(he[0], he[1])
     assert float((he - hg).abs().max()) <= 1e-12 * float(he.abs().max())
     for a, b in zip(pe, pg):
         assert float((a - b).abs().max()) <= 1e-12 * max(1.0, float(a.abs().max()))
