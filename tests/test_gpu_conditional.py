@@ -140,6 +140,25 @@ def test_conditional_forward_backward_parity(cuda, M, D, R, N, kind, S):
     assert not bad, (bad, errs)
 
 
+# The tile instantiations the benchmark runs are picked by the row count (one wave of wide tiles for ~10 k rows): these
+# cases have the BASELINE row counts / shapes, so that the production variants -- not only the small-launch ones -- are
+# compared with the oracle (T hidden and output layers, configs[1] hidden layer, configs[2] hidden layer).
+PRODUCTION_CASES = [
+    (256, 8, 8, 10_000, "rbf", 1),
+    (256, 8, 1, 10_000, "rbf", 1),
+    (128, 8, 8, 10_000, "rbf", 1),
+    (500, 16, 16, 10_000, "matern52", 1),
+    (256, 8, 8, 2_500, "rbf", 4),        # sample-tiled input (x_rows < n_rows) at the same launch size
+]
+
+
+@pytest.mark.parametrize("M,D,R,N,kind,S", PRODUCTION_CASES)
+def test_production_tile_variants_match_oracle(cuda, M, D, R, N, kind, S):
+    errs = run_conditional(cuda, M, D, R, N, kind, S=S)
+    bad = {k: v for k, v in errs.items() if not v < TOL}
+    assert not bad, (bad, errs)
+
+
 def test_forward_only_large_M(cuda):
     """M = 1000 (config 5's M=1024 class): forward tile width 16."""
     errs = run_conditional(cuda, 1000, 8, 2, 300, "rbf", linear=False, backward=False)
