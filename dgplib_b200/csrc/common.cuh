@@ -1,5 +1,6 @@
 // Shared device/host helpers for libdgp_b200 (sm_100a only).
 #pragma once
+#include <atomic>
 #include <mutex>
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -10,8 +11,27 @@
 namespace dgp {
 
 // ------------------------------------------------------------------------------------------------ launch counter
-extern long long g_launches;  // bench.py's gpu_launches (host-side count of our kernel launches)
-#define DGP_COUNT_LAUNCH() (++::dgp::g_launches)
+extern std::atomic<long long> g_launches;  // bench.py's gpu_launches (host-side count of our kernel launches)
+#define DGP_COUNT_LAUNCH() (::dgp::g_launches.fetch_add(1, std::memory_order_relaxed))
+
+// Per-device "already configured" flags of the launchers (dynamic shared-memory opt-ins): monotonic values behind
+// atomics, so that host threads driving the library concurrently never race on them (the attribute call itself is
+// idempotent, so two threads that both see "not yet" simply both make it).
+struct DevOnceSize {
+    std::atomic<size_t> v[16];
+    bool covers(int dev, size_t bytes) const { return v[dev].load(std::memory_order_acquire) >= bytes; }
+    void raise(int dev, size_t bytes) {
+        size_t cur = v[dev].load(std::memory_order_relaxed);
+        while (cur < bytes && !v[dev].compare_exchange_weak(cur, bytes, std::memory_order_release)) {}
+    }
+};
+
+#ifdef DGP_TEST_HOOKS
+// Test-only build (libdgp_b200_test.so, `make test_lib`): lets the parity tests force every row-tile instantiation
+// and the tuning experiments of tools/kbench.py override the Gram split count.  None of this exists in the product
+// library.
+extern int g_force_fwd_nt, g_force_bwd_nt, g_force_gram_splits, g_debug_mode;
+#endif
 
 #define DGP_CHECK_LAUNCH()                                   \
     do {                                                     \
@@ -20,11 +40,36 @@ extern long long g_launches;  // bench.py's gpu_launches (host-side count of our
 
 static inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
 
-// Tiled operand layout streamed by the row-tile kernels (stream_gemm.cuh): [block row][chunk][128 rows][20 doubles]
+// Tiled operand layout streamed by the row-tile kernels (stream_gemm.cuh): [block row][chunk][128 rows][16 doubles],
+// with the four 32-byte groups of a row permuted by (row & 3): element (row, k) of a chunk sits at
+// row * 16 + (((k >> 2) ^ (row & 3)) << 2) + (k & 3).  The eight rows x four columns a DMMA A fragment reads then
+// cover all 32 banks twice (conflict-free) without padding the 128-byte rows: a chunk is 16 KB instead of the 20 KB of
+// a padded pitch, which buys a deeper ring (or a wider row tile) out of the 227 KB of shared memory.
 constexpr int TILE_MB = 128;   // rows of a staged chunk
 constexpr int TILE_KC = 16;    // depth of a staged chunk
-constexpr int TILE_WLD = 20;   // padded row pitch of a staged chunk (doubles): conflict-free DMMA A-fragment loads
+constexpr int TILE_WLD = 16;   // row pitch of a staged chunk (doubles)
 constexpr int TILE_DOUBLES = TILE_MB * TILE_WLD;
+__host__ __device__ inline int tile_swizzle(int row, int k) { return (((k >> 2) ^ (row & 3)) << 2) | (k & 3); }
+
+// U_r = tril(q_sqrt_r)^T A kept from the forward pass for the backward pass (dgp_cond_forward's U_save):
+//   [r][16-deep chunk of the inducing index][group of 8 rows][16][8]
+// i.e. one (output, chunk) slab holds, for every group of 8 consecutive rows n, a 16 x 8 block U_r[16 kc + k][8 g + n]
+// of 1 KB.  A backward row tile of NT rows reads NT/8 consecutive blocks = ONE contiguous bulk copy per (output, chunk),
+// for any tile width that is a multiple of 8, and the forward kernel's accumulator fragments store into it as 512-byte
+// contiguous pieces per warp instruction.  Inside a block, element (k, n) sits at k * 8 + (n ^ (((k >> 1) & 1) << 2)):
+// the two 32-byte halves of rows 2, 3 (mod 4) are swapped, so that the 4 x 4 elements a half-warp reads as a DMMA B
+// fragment (k = 4 kk + t, n = g) fall into 16 distinct 8-byte bank pairs (unswizzled, rows t and t + 2 collide: measured
+// 35 % excess shared-memory wavefronts).
+constexpr int USAVE_BLOCK = 128;   // doubles of one 16 x 8 block
+#ifdef DGP_NO_USWZ
+__host__ __device__ inline int usave_swz(int k, int n) { return k * 8 + n; }
+#else
+__host__ __device__ inline int usave_swz(int k, int n) { return k * 8 + (n ^ (((k >> 1) & 1) << 2)); }
+#endif
+__host__ __device__ inline long long usave_groups(long long n_rows) { return (n_rows + 7) / 8; }
+__host__ __device__ inline size_t usave_doubles(int Mpad, int R, long long n_rows) {
+    return (size_t)R * (Mpad / TILE_KC) * (size_t)usave_groups(n_rows) * USAVE_BLOCK;
+}
 __host__ __device__ inline int tiled_mpad(int Mpad) { return (Mpad + TILE_MB - 1) / TILE_MB * TILE_MB; }
 __host__ __device__ inline size_t tiled_doubles(int Mpad) {
     const int mt = tiled_mpad(Mpad);
@@ -51,9 +96,9 @@ struct WsLayout {
     size_t klpart;     // [R][(Mpad/32)^2] per-tile partial sums of the KL term (written by k_lq_prep)
     // backward only
     size_t LinvT;      // [Mpad][Mpad]
-    size_t SmI;        // [R][Mpad][Mpad] tril(q_sqrt_r) tril(q_sqrt_r)^T - I
+    size_t Lq;         // [R][Mpad][Mpad] tril(q_sqrt_r) (lower), pad zero
     size_t LinvTTl;    // tiled copy of LinvT       (streamed by the backward kernel)
-    size_t SmITl;      // [R] tiled copies of SmI_r (streamed by the backward kernel)
+    size_t LqTl;       // [R] tiled copies of Lq_r  (streamed by the backward kernel)
     size_t dKuf;       // [n_rows][Mpad]
     size_t gmv;        // [n_rows][2R] combined g_mean | g_var of this conditional
     size_t gram;       // [nsplit][R+1][Mpad][Mpad]  split-K partials of G_r (r<R) and P (r==R)
@@ -113,13 +158,15 @@ static inline WsLayout ws_layout(const dgp_cond_desc& d, int64_t n_rows, int nee
         if ((size_t)ns * per_split > (size_t)512 << 20) ns = (int)(((size_t)512 << 20) / per_split);
         if (ns < 1) ns = 1;
         if (ns > 64) ns = 64;
-        if (const char* e = getenv("DGP_GRAM_SPLITS")) { int v = atoi(e); if (v >= 1 && v <= 64) ns = v; }   // tuning experiments
+#ifdef DGP_TEST_HOOKS
+        if (g_force_gram_splits >= 1 && g_force_gram_splits <= 64) ns = g_force_gram_splits;   // tuning experiments
+#endif
         w.nsplit = ns;
         w.npart = round_up(w.Mpad * w.Dp + w.Mpad + w.Mpad * d.R + d.T * (2 + w.Dp), 32);
         w.LinvT = o; o += align256(mm);
-        w.SmI = o;   o += align256(mm * d.R);
+        w.Lq = o;    o += align256(mm * d.R);
         w.LinvTTl = o; o += align256(w.tl * sizeof(double));
-        w.SmITl = o;   o += align256(w.tl * sizeof(double) * d.R);
+        w.LqTl = o;    o += align256(w.tl * sizeof(double) * d.R);
         w.gram = o;  o += align256(mm * (d.R + 1) * w.nsplit);
         w.part = o;  o += align256(size_t(w.ncta) * w.npart * sizeof(double));
         w.psum = o;  o += align256(size_t(w.npart) * sizeof(double));
@@ -185,6 +232,10 @@ __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gsrc, uint3
 __device__ __forceinline__ void bulk_s2g(void* gdst, const void* smem_src, uint32_t bytes) {
     asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;\n"
                  :: "l"(gdst), "r"(smem_u32(smem_src)), "r"(bytes) : "memory");
+}
+// L2 prefetch of a contiguous global range (no shared-memory destination, no completion tracking)
+__device__ __forceinline__ void bulk_prefetch_l2(const void* gsrc, uint32_t bytes) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;\n" :: "l"(gsrc), "r"(bytes) : "memory");
 }
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;\n" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;\n" ::: "memory"); }

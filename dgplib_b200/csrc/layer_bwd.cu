@@ -1,15 +1,22 @@
 // Reverse mode of the per-row stage of one whitened conditional (what tf.gradients emits for the graph of
 // gpflow's base_conditional(white=True) called at dgplib/layers.py:65-71, and for normal_sample, dgplib/utils.py:27).
-// Formulas: SURVEY.md Appendix B, rearranged so that only A = Lm^-1 Kuf has to be kept from the forward pass:
+// Formulas: SURVEY.md Appendix B, with A = Lm^-1 Kuf and U_r = tril(q_sqrt_r)^T A kept from the forward pass:
 //
 //   g_mean = g_mean_in + g_F ;  g_var = g_var_in + g_F (F - mean) / (2 var)
-//   dA   = q_mu g_mean^T + 2 sum_r (S_r - I) (A . g_var_r),   S_r = Lq_r Lq_r^T      [dense streamed GEMM, K = R M]
+//   dA   = q_mu g_mean^T - 2 A . (sum_r g_var_r) + 2 sum_r Lq_r (U_r . g_var_r)     [lower-triangular streamed GEMMs, K = R M / 2]
 //   dKuf = Lm^-T dA                                                                   [upper-triangular streamed GEMM]
 //   dX, dZ, d lengthscale, d variance from dKuf . k'(r2)                              [per tile, small]
 //   G_r  = sum_n g_var[n,r] a_n a_n^T  (-> d q_sqrt_r = 2 tril(G_r Lq_r)),  P = sum_n dKuf_n a_n^T (-> d Lm = -tril P)
 //                                                                                     [split-K Gram kernel over the rows]
-// k_cond_bwd : one CTA per SM walks row tiles; A tile arrives by bulk async copy (TMA engine), dA / dKuf live in
-//              shared memory, dKuf leaves by bulk async store; row-summed pieces go to per-CTA partial buffers
+// This executes the R M^2 + M^2 flops per row of the reference's own reverse mode (backward = 2 F with the
+// Gram kernel); the first version of this kernel recomputed through the dense S_r - I instead (2 R M^2 + M^2) in order to
+// keep only A.  U_r costs 8 R Mpad bytes per row each way in HBM, which the tensor-pipe-bound kernels hide.
+// k_cond_bwd : one CTA per SM walks row tiles.  BOTH operands of the dA phase are streamed through the same ring by the
+//              producer warp (TMA engine): the tiled tril(q_sqrt_r) chunk from L2 and the matching [NT/8][16][8] chunk of
+//              the saved U_r from HBM; only dA / dKuf (one row tile) is resident in shared memory, so the row tile is twice
+//              as wide as a design that also keeps the A tile resident (64-72 rows at Mpad <= 256, 32 at 512, 16 at 1024).
+//              A itself is needed only elementwise (epilogue of dA, d q_mu) and is read straight from L2 after a bulk L2
+//              prefetch of the tile.  dKuf leaves by bulk async store; row-summed pieces go to per-CTA partial buffers
 //              (no atomics: bitwise reproducible).
 // k_gram     : 64x64 output tiles x split-K over the rows, fp64 DMMA, partials per split (no atomics).
 #include "stream_gemm.cuh"
@@ -30,72 +37,65 @@ struct BwdArgs {
     dgp_cond_desc d;
     int Mpad, Dp;
     const double* Zs; const double* zn; const int32_t* ztask;
-    const double* LinvT; const double* SmI; size_t tl;   // tiled copies (stream_gemm.cuh)
+    const double* LinvT; const double* LqL; size_t tl;   // tiled copies (stream_gemm.cuh): Lm^-T and tril(q_sqrt_r)
     const double* X; long long x_rows, n_rows;
-    const double* A_save; const double* mean; const double* var; const double* F; int ldf;
+    const double* A_save; const double* U_save; long long NG;
+    const double* mean; const double* var; const double* F; int ldf;
     const double* g_mean_in; const double* g_var_in; const double* g_F; int ldgf;
     double* gX; int accumulate_gX;
     double* dKuf; double* gmv; double* part; int npart; double* scal;
+    long long row0;      // first row of this launch (a launch may cover a row range: tail tiles of another width)
     int ntiles;
+    int debug;           // test-hook builds only
 };
 
 template <class C>
 struct BwdSmem {
     int ldb, xld;
-    int Bt, Dt, Wst, xs, xn, gm, gv, rs, dv, rowq, xtask, bar, bars, total_doubles;
+    int Dt, Wst, xs, xn, gm, gv, gs, rs, dv, rowq, xtask, bars, total_doubles;
     __host__ __device__ BwdSmem(int Mpad, int Dp, int R) {
         ldb = Mpad + 4;
         xld = Dp + 4;
         int o = 0;
-        Bt = o; o += C::NT * ldb;
         Dt = o; o += C::NT * ldb;
         Wst = o; o += C::STAGES * C::STAGE_DOUBLES;
         xs = o; o += C::NT * xld;
         xn = o; o += C::NT;
         gm = o; o += C::NT * R;
         gv = o; o += C::NT * R;
+        gs = o; o += C::NT;
         rs = o; o += C::NT;
         dv = o; o += C::NT;
-        rowq = o; o += C::NT * (2 + Dp);
+        rowq = o; o += C::NT * (2 + Dp) > 32 ? C::NT * (2 + Dp) : 32;   // also: scratch of >= NWARPS doubles
         xtask = o; o += C::NT / 2 + 1;
-        bar = o; o += 2;
+        o += o & 1;
         bars = o; o += 2 * C::STAGES;
         total_doubles = o;
     }
 };
-
-// K splits of the T1 product: the consumer warps form NWARPS / (NT / 8) groups, each taking a slice of the inducing index;
-// their partial [NT][Dp + 1] tiles are parked in the A-tile buffer (NT x ldb doubles), so wide inputs (Dp + 1 > ldb / 4)
-// use fewer splits.  ldb = Mpad + 4 >= 68 > Dp + 1 always leaves room for one.
-template <class C>
-__device__ __forceinline__ int t1_splits(int Dp, int ldb) {
-    int kqe = C::NWARPS / (C::NT / 8);
-    while (kqe > 1 && kqe * (Dp + 1) > ldb) kqe >>= 1;
-    return kqe;
-}
 
 template <class C>
 __global__ void __launch_bounds__(C::NTHREADS, 1) k_cond_bwd(const __grid_constant__ BwdArgs a) {
     extern __shared__ __align__(128) double smem[];
     const dgp_cond_desc& d = a.d;
     const BwdSmem<C> L(a.Mpad, a.Dp, d.R);
-    double* Bt = smem + L.Bt;
     double* Dt = smem + L.Dt;
     double* Wst = smem + L.Wst;
     double* xs = smem + L.xs;
     double* xn = smem + L.xn;
     double* gm = smem + L.gm;
     double* gv = smem + L.gv;
+    double* gs = smem + L.gs;
     double* rs = smem + L.rs;
     double* dv = smem + L.dv;
     double* rowq = smem + L.rowq;
     int32_t* xtask = reinterpret_cast<int32_t*>(smem + L.xtask);
-    uint64_t* bar = reinterpret_cast<uint64_t*>(smem + L.bar);
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L.bars);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
     const int Mpad = a.Mpad, Dp = a.Dp, ldb = L.ldb, xld = L.xld, R = d.R;
     const int nb = (Mpad + C::MB - 1) / C::MB;
+    const int nkc = Mpad / C::KC;
     const int thd = 2 + d.D;
     const int nq = 2 + Dp;
 
@@ -106,14 +106,16 @@ __global__ void __launch_bounds__(C::NTHREADS, 1) k_cond_bwd(const __grid_consta
     double* pth = pqmu + (size_t)Mpad * R;                   // [T][2+Dp]
 
     // segment lists of the two streamed phases (shared by the producer warp and the consumers)
-    auto seg_dA = [&](int s) {      // dA block row i accumulates over all r: dense S_r - I
+    auto seg_dA = [&](int s) {      // dA block row i accumulates Lq_r (U_r . g_r) over all r: lower-triangular Lq_r
         Seg sg;
         sg.i = s / R;
         sg.r = s % R;
-        sg.W = a.SmI + (size_t)sg.r * a.tl;
+        sg.W = a.LqL + (size_t)sg.r * a.tl;
         sg.kc0 = 0;
-        sg.kc1 = Mpad / C::KC;
-        sg.flush = true;            // per-r flush: the column weights g_var[n, r] are applied to the accumulators
+        int kend = (sg.i + 1) * C::MB;
+        if (kend > Mpad) kend = Mpad;
+        sg.kc1 = kend / C::KC;
+        sg.flush = (sg.r == R - 1); // one accumulation over all r: the column weights g_var[n, r] scale the B fragments
         return sg;
     };
     auto seg_dK = [&](int s) {      // dKuf = LinvT * dA, block rows top-down, in place
@@ -129,40 +131,51 @@ __global__ void __launch_bounds__(C::NTHREADS, 1) k_cond_bwd(const __grid_consta
 
     Pipe pipe;
     pipe_init<C>(pipe, bars, Wst);
-    if (tid == 0) {
-        mbar_init(bar, 1);
-        mbar_fence_init();
-    }
+    // the U halves of the ring slots start as zeros: columns beyond the last row of a ragged tile are never copied and
+    // enter the GEMM with weight 0, which must not meet a NaN bit pattern left in shared memory by an earlier kernel
+    for (int e = tid; e < C::STAGES * C::UCH_DOUBLES; e += C::NTHREADS)
+        Wst[(e / C::UCH_DOUBLES) * C::STAGE_DOUBLES + TILE_DOUBLES + e % C::UCH_DOUBLES] = 0.0;
+    fence_async_smem();
     __syncthreads();   // the only CTA-wide barrier
     if (warp == C::NWARPS) {
+        // ---- producer warp: lane 0 issues the bulk copies of every ring slot (W chunk + the matching U chunk).
+        // (Pulling the next segment's U chunks into L2 ahead of the ring -- bulk prefetches by lane 0, or plain prefetch
+        // instructions by the idle lanes -- was measured slower both ways, 3.10 -> 3.31 / 3.25 ms at the T hidden-layer
+        // shape: the ring's look-ahead already covers the HBM latency.)
         if (lane == 0) {
             for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
-                produce_phase<C>(pipe, nb * R, seg_dA, Mpad);
+                const long long n0 = a.row0 + (long long)tile * C::NT;
+                const long long left = a.n_rows - n0;
+                const int nvalid = (int)(left < C::NT ? left : C::NT);
+                // the A tile is only read elementwise (dA epilogue, d q_mu): pull it into L2 ahead of those reads
+                bulk_prefetch_l2(a.A_save + (size_t)n0 * Mpad, (uint32_t)((size_t)nvalid * Mpad * sizeof(double)));
+                long long g0 = n0 / 8;
+                const long long gl = a.NG - g0;
+                uint32_t ubytes = (uint32_t)((gl < C::NT / 8 ? gl : C::NT / 8) * USAVE_BLOCK * sizeof(double));
+#ifdef DGP_TEST_HOOKS
+                if (a.debug == 1) ubytes = 0;          // timing experiments only: no U traffic / U always from L2
+                if (a.debug == 2) g0 = (long long)blockIdx.x * (C::NT / 8);
+#endif
+                auto ufn = [&](const Seg& sg, int kc, uint32_t& bytes) {
+                    bytes = ubytes;
+                    return a.U_save + (((size_t)sg.r * nkc + kc) * (size_t)a.NG + (size_t)g0) * USAVE_BLOCK;
+                };
+                produce_phase<C>(pipe, nb * R, seg_dA, Mpad, ufn);
                 produce_phase<C>(pipe, nb, seg_dK, Mpad);
             }
         }
         return;
     }
-    uint32_t parity = 0;
 #ifdef DGP_PROFILE_PHASES
     long long ph[12] = {0}; long long tlast = clock64();
 #endif
 
     for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
-        const long long n0 = (long long)tile * C::NT;
+        const long long n0 = a.row0 + (long long)tile * C::NT;
         const int nvalid = (int)((a.n_rows - n0 < C::NT) ? (a.n_rows - n0) : C::NT);
         bulk_wait_read0();   // previous tile's dKuf store has finished reading Dt
         consumer_sync<C>();  // every warp is done with the previous tile
         PH(0);
-
-        // ---- A tile: HBM -> Bt by bulk async copies, completion on the mbarrier
-        if (tid == 0) {
-            mbar_expect_tx(bar, (uint32_t)(nvalid * Mpad * sizeof(double)));
-            for (int n = 0; n < nvalid; ++n)
-                bulk_g2s(Bt + n * ldb, a.A_save + (size_t)(n0 + n) * Mpad, (uint32_t)(Mpad * sizeof(double)), bar);
-        }
-        for (int e = tid; e < (C::NT - nvalid) * Mpad; e += C::NCONS)   // ragged tile: zero rows
-            Bt[(nvalid + e / Mpad) * ldb + e % Mpad] = 0.0;
 
         // ---- per-row setup: scaled inputs, combined upstream gradients
         for (int n = tid; n < C::NT; n += C::NCONS) {
@@ -204,40 +217,43 @@ __global__ void __launch_bounds__(C::NTHREADS, 1) k_cond_bwd(const __grid_consta
             gm[idx] = gmean;
             gv[idx] = gvar;
         }
+        consumer_sync<C>();
+        for (int n = tid; n < C::NT; n += C::NCONS) {      // sum_r g_var[n, r]: weight of the -2 A term (and of Kdiag)
+            double s = 0.0;
+            for (int r = 0; r < R; ++r) s += gv[n * R + r];
+            gs[n] = s;
+        }
         PH(1);
-        mbar_wait(bar, parity);
-        parity ^= 1;
-        PH(2);
         // (run_phase starts with a consumer barrier)
 
-        // ---- phase dA: Dt = q_mu g_mean^T + 2 sum_r (S_r - I) (A . g_var_r)
+        // ---- phase dA: Dt = q_mu g_mean^T - 2 A . gs + 2 sum_r Lq_r (U_r . g_var_r)
         {
-            // (S_r - I)(A . g_r) = ((S_r - I) A) . g_r: the weight belongs to the OUTPUT column, so the streamed GEMM runs
-            // unweighted and g_var[n, r] scales the accumulators once per (block row, r).  (Multiplying the B fragments
-            // inside the loop put a DMUL in front of every DMMA group; both share the fp64 pipe, and ncu showed 24 % of
-            // all warp stalls on those DMULs.)
-            Acc<C> tot;
-            tot.clear();
+            // The weights g_var[n, r] scale the streamed U fragments (one DMUL per B fragment, placed behind the previous
+            // DMMA group: chunk_mma), so that ONE accumulator set runs over all r of a block row.  Keeping the GEMM
+            // unweighted and folding w * acc into a second register set per (block row, r) left too few of the 96 registers
+            // of a 17-warp CTA for the software pipeline of the streamed loop (ptxas put every LDS right in front of its
+            // DMMA: DMMA pipe 59 % active); accumulating that sum in the shared-memory tile was slower still.
+            // Columns beyond the last valid row get weight 0; their ring bytes are stale but finite (zeroed at start).
             auto epi = [&](Acc<C>& acc, const Seg& sg) {
-#pragma unroll
-                for (int j = 0; j < C::NJ; ++j)
-#pragma unroll
-                    for (int e = 0; e < 2; ++e) {
-                        const double w = gv[acc_col<C>(j, e) * R + sg.r];
-#pragma unroll
-                        for (int q = 0; q < 4; ++q) tot.v[q][j][e] = fma(w, acc.v[q][j][e], tot.v[q][j][e]);
-                    }
-                if (sg.r != R - 1) return;
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
                     const int row = acc_row<C>(sg.i, q);
                     if (row < Mpad) {
+                        // A[n][row] for this thread's columns, from L2 (prefetched by the producer warp)
+                        double av[C::NJ][2];
 #pragma unroll
                         for (int j = 0; j < C::NJ; ++j)
 #pragma unroll
                             for (int e = 0; e < 2; ++e) {
                                 const int n = acc_col<C>(j, e);
-                                double v = 2.0 * tot.v[q][j][e];
+                                av[j][e] = (n < nvalid) ? a.A_save[(size_t)(n0 + n) * Mpad + row] : 0.0;
+                            }
+#pragma unroll
+                        for (int j = 0; j < C::NJ; ++j)
+#pragma unroll
+                            for (int e = 0; e < 2; ++e) {
+                                const int n = acc_col<C>(j, e);
+                                double v = 2.0 * (acc.v[q][j][e] - av[j][e] * gs[n]);
                                 if (row < d.M) {
                                     const double* qm = d.q_mu + (size_t)row * d.ldr + d.col0;
                                     for (int r = 0; r < R; ++r) v = fma(qm[r], gm[n * R + r], v);
@@ -246,9 +262,8 @@ __global__ void __launch_bounds__(C::NTHREADS, 1) k_cond_bwd(const __grid_consta
                             }
                     }
                 }
-                tot.clear();
             };
-            run_phase<C, MASK_DENSE, false>(pipe, nb * R, seg_dA, epi, Bt, ldb, Mpad, nullptr, 0);
+            run_phase<C, MASK_LOWER, true, true>(pipe, nb * R, seg_dA, epi, nullptr, 0, Mpad, gv, R, nvalid);
         }
         PH(3);
 
@@ -268,7 +283,7 @@ __global__ void __launch_bounds__(C::NTHREADS, 1) k_cond_bwd(const __grid_consta
                     }
                 }
             };
-            run_phase<C, MASK_UPPER, false>(pipe, nb, seg_dK, epi, Dt, ldb, Mpad, nullptr, 0);
+            run_phase<C, MASK_UPPER, false>(pipe, nb, seg_dK, epi, Dt, ldb, Mpad);
         }
         consumer_sync<C>();
         PH(4);
@@ -279,22 +294,28 @@ __global__ void __launch_bounds__(C::NTHREADS, 1) k_cond_bwd(const __grid_consta
             bulk_s2g(a.dKuf + (size_t)(n0 + tid) * Mpad, Dt + tid * ldb, (uint32_t)(Mpad * sizeof(double)));
             bulk_commit();
         }
-        // ---- d q_mu partial: sum_n A[n][m] g_mean[n][r] on the tensor cores (reads Bt while the store drains).
-        //      Output tile rows = inducing index m, columns = output r, K = the NT rows of the tile.
+        // ---- d q_mu partial: sum_n A[n][m] g_mean[n][r] on the tensor cores while the store drains.  Output tile rows =
+        //      inducing index m, columns = output r, K = the NT rows of the tile; the A fragments come straight from L2.
         for (int mt = warp; mt < Mpad / 8; mt += C::NWARPS) {
             const int m0 = mt * 8;
+            double af[C::NT / 4];
+#pragma unroll
+            for (int ks = 0; ks < C::NT / 4; ++ks) {
+                const int n = ks * 4 + t;
+                af[ks] = (n < nvalid) ? a.A_save[(size_t)(n0 + n) * Mpad + m0 + g] : 0.0;
+            }
             for (int r0 = 0; r0 < R; r0 += 8) {
-                double c[2] = {0.0, 0.0};
+                double c0[2] = {0.0, 0.0}, c1[2] = {0.0, 0.0};
 #pragma unroll
                 for (int ks = 0; ks < C::NT / 4; ++ks) {
                     const int n = ks * 4 + t;
                     const double bv = (r0 + g < R) ? gm[n * R + r0 + g] : 0.0;
-                    dmma884(c, Bt[n * ldb + m0 + g], bv);
+                    if (ks & 1) dmma884(c1, af[ks], bv); else dmma884(c0, af[ks], bv);
                 }
 #pragma unroll
                 for (int e = 0; e < 2; ++e) {
                     const int m = m0 + g, r = r0 + 2 * t + e;
-                    if (m < d.M && r < R) pqmu[m * R + r] += c[e];
+                    if (m < d.M && r < R) pqmu[m * R + r] += c0[e] + c1[e];
                 }
             }
         }
@@ -383,25 +404,29 @@ __global__ void __launch_bounds__(C::NTHREADS, 1) k_cond_bwd(const __grid_consta
         consumer_sync<C>();
 
         PH(7);
-        // ---- T1[n][k] = sum_m Gr2[n][m] zs[m][k] on the tensor cores; the K range (inducing index) is split over
-        //      KQ warp groups whose partial tiles are summed in fixed order through the (now free) A-tile buffer.
-        {
-            constexpr int NTT = C::NT / 8;                 // 8-row tiles of the row tile
-            const int nt4 = warp % NTT, kq = warp / NTT;
-            const int kqe = t1_splits<C>(Dp, ldb);         // splits whose partials fit in the A-tile buffer
-            const int kspan = Mpad / kqe;                  // Mpad is a multiple of 64, kqe of {1, 2, 4}
-            double* t1p = Bt;                              // scratch [kqe][NT][Dp + 1]; column Dp = row sums of Gr2
-            for (int d0 = 0; d0 < Dp + 1 && kq < kqe; d0 += 8) {
-                double c[2] = {0.0, 0.0};
-                for (int ks = 0; ks < kspan / 4; ++ks) {
-                    const int m = kq * kspan + ks * 4 + t;
-                    const double bv = (d0 + g < Dp) ? a.Zs[(size_t)m * Dp + d0 + g] : (d0 + g == Dp ? 1.0 : 0.0);
-                    dmma884(c, Dt[(nt4 * 8 + g) * ldb + m], bv);
+        // ---- T1[n][k] = sum_m Gr2[n][m] zs[m][k] on the tensor cores, one 8-row tile of the row tile per warp, four
+        //      interleaved accumulators over the inducing index; parked in rowq[n][2 + k].  Column Dp of the product is a
+        //      column of ones: the row sums of Gr2, parked in rowq[n][0].
+        for (int nt4 = warp; nt4 < C::NT / 8; nt4 += C::NWARPS) {
+            for (int d0 = 0; d0 < Dp + 1; d0 += 8) {
+                double c4[4][2] = {{0.0, 0.0}, {0.0, 0.0}, {0.0, 0.0}, {0.0, 0.0}};
+                const int kcol = d0 + g;
+                for (int m = 0; m < Mpad; m += 16) {          // Mpad is a multiple of 64
+                    double bv[4];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const int mk = m + 4 * u + t;
+                        bv[u] = (kcol < Dp) ? a.Zs[(size_t)mk * Dp + kcol] : (kcol == Dp ? 1.0 : 0.0);
+                    }
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) dmma884(c4[u], Dt[(nt4 * 8 + g) * ldb + m + 4 * u + t], bv[u]);
                 }
 #pragma unroll
                 for (int e = 0; e < 2; ++e) {
                     const int k = d0 + 2 * t + e;
-                    if (k <= Dp) t1p[(kq * C::NT + nt4 * 8 + g) * (Dp + 1) + k] = c[e];
+                    const double v = (c4[0][e] + c4[1][e]) + (c4[2][e] + c4[3][e]);
+                    if (k < Dp) rowq[(nt4 * 8 + g) * nq + 2 + k] = v;
+                    else if (k == Dp) rowq[(nt4 * 8 + g) * nq] = v;
                 }
             }
         }
@@ -431,20 +456,13 @@ __global__ void __launch_bounds__(C::NTHREADS, 1) k_cond_bwd(const __grid_consta
         PH(8);
         // ---- row sums of Gr2 from the ones column (fast path; the general path computed them above)
         if (d.T == 1) {
-            const int kqe = t1_splits<C>(Dp, ldb);
-            if (tid < C::NT) {
-                double r = 0.0;
-                for (int q = 0; q < kqe; ++q) r += Bt[(q * C::NT + tid) * (Dp + 1) + Dp];
-                rs[tid] = r;
-            }
+            if (tid < C::NT) rs[tid] = rowq[tid * nq];
             consumer_sync<C>();
         }
-        // ---- finish T1 -> gX and the lengthscale row terms
+        // ---- finish T1 -> gX and the lengthscale row terms (in place in rowq[n][2 + k])
         for (int idx = tid; idx < C::NT * Dp; idx += C::NCONS) {
             const int n = idx / Dp, k = idx % Dp;
-            const int kqe = t1_splits<C>(Dp, ldb);
-            double t1 = 0.0;
-            for (int q = 0; q < kqe; ++q) t1 += Bt[(q * C::NT + n) * (Dp + 1) + k];
+            const double t1 = rowq[n * nq + 2 + k];
             const double xv = xs[n * xld + k];
             rowq[n * nq + 2 + k] = xv * xv * rs[n] - 2.0 * xv * t1;
             const long long gn = n0 + n;
@@ -474,8 +492,7 @@ __global__ void __launch_bounds__(C::NTHREADS, 1) k_cond_bwd(const __grid_consta
         }
         // Kdiag terms: d variance += sum_r g_var, d white += sum_r g_var
         for (int n = tid; n < C::NT; n += C::NCONS) {
-            double s = 0.0;
-            if (n < nvalid) for (int r = 0; r < R; ++r) s += gv[n * R + r];
+            const double s = (n < nvalid) ? gs[n] : 0.0;
             rowq[n * nq + 0] = dv[n] + s;
             rowq[n * nq + 1] = s;
         }
@@ -502,13 +519,14 @@ static int launch_bwd(const BwdArgs& a, cudaStream_t st) {
     const BwdSmem<C> L(a.Mpad, a.Dp, a.d.R);
     const size_t bytes = (size_t)L.total_doubles * sizeof(double);
     if (bytes > 227 * 1024) return DGP_ERR_UNSUPPORTED;
-    static size_t configured_dev[DGP_MAX_DEVICES] = {};
-    size_t& configured = configured_dev[current_device()];
-    if (bytes > configured) {
+    static DevOnceSize configured;
+    const int dev = current_device();
+    if (!configured.covers(dev, bytes)) {
         if (cudaFuncSetAttribute(k_cond_bwd<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes) != cudaSuccess) return DGP_ERR_LAUNCH;
-        configured = bytes;
+        configured.raise(dev, bytes);
     }
-    k_cond_bwd<C><<<device_sm_count(), C::NTHREADS, bytes, st>>>(a);
+    const int grid = a.ntiles < device_sm_count() ? a.ntiles : device_sm_count();
+    k_cond_bwd<C><<<grid, C::NTHREADS, bytes, st>>>(a);
     DGP_COUNT_LAUNCH();
     return cudaGetLastError() == cudaSuccess ? DGP_OK : DGP_ERR_LAUNCH;
 }
@@ -696,12 +714,12 @@ __global__ void __launch_bounds__(GR_THREADS, 4) k_gram(GramArgs a) {
 using namespace dgp;
 
 extern "C" int dgp_cond_backward(const dgp_cond_desc* d, void* ws, const double* X, int64_t x_rows, int64_t n_rows,
-                                 const double* A_save, const double* mean, const double* var, const double* F, int32_t ldf,
-                                 const double* g_mean_in, const double* g_var_in, const double* g_F, int32_t ldgf,
-                                 double* gX, int32_t accumulate_gX, void* stream) {
+                                 const double* A_save, const double* U_save, const double* mean, const double* var,
+                                 const double* F, int32_t ldf, const double* g_mean_in, const double* g_var_in,
+                                 const double* g_F, int32_t ldgf, double* gX, int32_t accumulate_gX, void* stream) {
     int rc = check_desc(d);
     if (rc != DGP_OK) return rc;
-    if (!ws || !X || !A_save || x_rows < 1 || n_rows < 0) return DGP_ERR_ARG;
+    if (!ws || !X || !A_save || !U_save || x_rows < 1 || n_rows < 0) return DGP_ERR_ARG;
     if (g_F && (!F || !mean || !var || ldgf < d->ldr || ldf < d->ldr)) return DGP_ERR_ARG;
     if (!g_F && !g_mean_in && !g_var_in) return DGP_ERR_ARG;
     if (n_rows == 0) return DGP_OK;
@@ -711,35 +729,54 @@ extern "C" int dgp_cond_backward(const dgp_cond_desc* d, void* ws, const double*
     a.d = *d;
     a.Mpad = w.Mpad; a.Dp = w.Dp;
     a.Zs = ws_ptr<double>(ws, w.Zs); a.zn = ws_ptr<double>(ws, w.zn); a.ztask = ws_ptr<int32_t>(ws, w.ztask);
-    a.LinvT = ws_ptr<double>(ws, w.LinvTTl); a.SmI = ws_ptr<double>(ws, w.SmITl); a.tl = w.tl;
+    a.LinvT = ws_ptr<double>(ws, w.LinvTTl); a.LqL = ws_ptr<double>(ws, w.LqTl); a.tl = w.tl;
     a.X = X; a.x_rows = x_rows; a.n_rows = n_rows;
-    a.A_save = A_save; a.mean = mean; a.var = var; a.F = F; a.ldf = ldf;
+    a.A_save = A_save; a.U_save = U_save; a.NG = usave_groups(n_rows);
+    a.mean = mean; a.var = var; a.F = F; a.ldf = ldf;
     a.g_mean_in = g_mean_in; a.g_var_in = g_var_in; a.g_F = g_F; a.ldgf = ldgf;
     a.gX = gX; a.accumulate_gX = accumulate_gX;
     a.dKuf = ws_ptr<double>(ws, w.dKuf); a.gmv = ws_ptr<double>(ws, w.gmv);
     a.part = ws_ptr<double>(ws, w.part); a.npart = w.npart; a.scal = ws_ptr<double>(ws, w.scal);
+    a.row0 = 0;
+#ifdef DGP_TEST_HOOKS
+    a.debug = g_debug_mode;
+#endif
 #define DGP_TRY_BWD(WNV, NTV, STG)                                                        \
     {                                                                                 \
-        using C = TileCfg<4, WNV, NTV, STG>;                                              \
-        a.ntiles = (int)((n_rows + C::NT - 1) / C::NT);                               \
+        using C = TileCfg<4, WNV, NTV, STG, true>;                                        \
+        a.ntiles = (int)((n_rows - a.row0 + C::NT - 1) / C::NT);                      \
         rc = launch_bwd<C>(a, st);                                                    \
         if (rc != DGP_ERR_UNSUPPORTED) return rc;                                     \
     }
+#ifdef DGP_TEST_HOOKS
+    switch (g_force_bwd_nt) {      // parity tests pin every instantiation (tests/test_gpu_conditional.py)
+        case 72: DGP_TRY_BWD(3, 72, 2) return DGP_ERR_UNSUPPORTED;
+        case 64: DGP_TRY_BWD(DGP_BWD_WN, 64, 3) DGP_TRY_BWD(DGP_BWD_WN, 64, 2) return DGP_ERR_UNSUPPORTED;
+        case 32: DGP_TRY_BWD(DGP_BWD_WN, 32, 4) DGP_TRY_BWD(DGP_BWD_WN, 32, 3) DGP_TRY_BWD(DGP_BWD_WN, 32, 2) return DGP_ERR_UNSUPPORTED;
+        case 16: DGP_TRY_BWD(2, 16, 4) DGP_TRY_BWD(2, 16, 3) DGP_TRY_BWD(2, 16, 2) return DGP_ERR_UNSUPPORTED;
+        case 8: DGP_TRY_BWD(1, 8, 3) DGP_TRY_BWD(1, 8, 2) return DGP_ERR_UNSUPPORTED;
+        default: break;
+    }
+#endif
     if (w.Mpad <= 256) {
-        // 40-row tiles with a 4 x 5 consumer-warp grid and a 2-slot ring when they fit (R <= ~16): 25 % more rows per
-        // streamed operand byte and per fixed tile cost than 32-row tiles (bwd 4.26 -> 4.10 ms at the T layer shape)
-        // (unless 32-row tiles fill the last wave so much better that they win despite ~4 % more time per row)
+        // Only dA / dKuf is resident, so the row tile is as wide as the forward kernel's: 64 rows (4 x 4 consumer warps,
+        // two column tiles per warp, 3-slot ring), 72 rows (4 x 3 warps, three column tiles) when that saves a wave --
+        // 10 000 rows are one wave of 72-row tiles on 148 SMs -- and 32 rows when those fill the last wave much better.
         const long long sms = device_sm_count();
-        const long long w40 = ((n_rows + 39) / 40 + sms - 1) / sms * 40;
+        const long long w64 = ((n_rows + 63) / 64 + sms - 1) / sms * 64;
         const long long w32 = ((n_rows + 31) / 32 + sms - 1) / sms * 32;
-        // small inducing sets leave room for two 72-row tiles: taken when they save a wave (10 000 rows: one instead of two)
         const long long w72 = ((n_rows + 71) / 72 + sms - 1) / sms * 72;
-        if (w.Mpad <= 128 && w72 * 104 < w40 * 100 && w72 * 104 < w32 * 104) { DGP_TRY_BWD(3, 72, 3) DGP_TRY_BWD(3, 72, 2) }
-        if (w40 * 100 <= w32 * 104) { DGP_TRY_BWD(5, 40, 2) }
+        if (w72 * 104 < w64 * 100 && w72 * 100 <= w32 * 108) { DGP_TRY_BWD(3, 72, 2) }
+        if (w32 * 108 < w64 * 100) { DGP_TRY_BWD(DGP_BWD_WN, 32, 4) DGP_TRY_BWD(DGP_BWD_WN, 32, 3) }
+        DGP_TRY_BWD(DGP_BWD_WN, 64, 3) DGP_TRY_BWD(DGP_BWD_WN, 64, 2)
         DGP_TRY_BWD(DGP_BWD_WN, 32, 4) DGP_TRY_BWD(DGP_BWD_WN, 32, 3) DGP_TRY_BWD(DGP_BWD_WN, 32, 2)
+        DGP_TRY_BWD(2, 16, 3) DGP_TRY_BWD(2, 16, 2)
+    } else if (w.Mpad <= 512) {
+        DGP_TRY_BWD(DGP_BWD_WN, 32, 4) DGP_TRY_BWD(DGP_BWD_WN, 32, 3) DGP_TRY_BWD(DGP_BWD_WN, 32, 2)
+        DGP_TRY_BWD(2, 16, 4) DGP_TRY_BWD(2, 16, 3) DGP_TRY_BWD(2, 16, 2)
     } else {
         DGP_TRY_BWD(2, 16, 4) DGP_TRY_BWD(2, 16, 3) DGP_TRY_BWD(2, 16, 2)
-        DGP_TRY_BWD(1, 8, 3) DGP_TRY_BWD(1, 8, 2)   // Mpad > 512: two 8-row tiles are all that fits
+        DGP_TRY_BWD(1, 8, 3) DGP_TRY_BWD(1, 8, 2)   // very wide inputs / many outputs next to Mpad = 1024
     }
 #undef DGP_TRY_BWD
     rc = DGP_ERR_UNSUPPORTED;
@@ -763,11 +800,11 @@ extern "C" int dgp_cond_backward_gram(const dgp_cond_desc* d, void* ws, const do
     ga.accumulate = accumulate;
     const int nbt = w.Mpad / 64;
     const size_t gsm_bytes = (size_t)(2 * GR_STAGES * GR_KC * GR_LD + GR_STAGES * GR_KC) * sizeof(double);
-    static bool gram_attr_dev[DGP_MAX_DEVICES] = {};
-    bool& gram_attr = gram_attr_dev[current_device()];
-    if (!gram_attr) {
+    static DevOnceSize gram_attr;
+    const int gdev = current_device();
+    if (!gram_attr.covers(gdev, gsm_bytes)) {
         if (cudaFuncSetAttribute(k_gram, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gsm_bytes) != cudaSuccess) return DGP_ERR_LAUNCH;
-        gram_attr = true;
+        gram_attr.raise(gdev, gsm_bytes);
     }
     k_gram<<<dim3(nbt * (nbt + 1) / 2, d->R + 1, w.nsplit), GR_THREADS, gsm_bytes, st>>>(ga);
     DGP_COUNT_LAUNCH();

@@ -6,6 +6,8 @@
 //   E1  mean = A^T q_mu + mean_fn(x), sum_m A^2 ; A tile -> HBM (bulk async store) for the backward pass
 //   U   sum_m (tril(q_sqrt_r)^T A)^2, r < R     streamed upper-triangular GEMMs, squared-column-sum epilogue;
 //                                               the reference's [R, M, N'] LTA tensor is never materialised
+//                                               (training: U_r is also stored for the backward pass, straight from the
+//                                               accumulator fragments, in the block layout of common.cuh)
 //   E2  var = Kdiag - sum A^2 + sum U^2 ; F = mean + eps sqrt(var)   (eps given, or Philox4x32-10)
 // Replaces the TF sub-graph of gpflow's base_conditional(white=True) as called from dgplib/layers.py:65-71 on the
 // flattened samples (dgplib/layers.py:84-87), and normal_sample's diag branch (dgplib/utils.py:25-27).
@@ -33,6 +35,7 @@ struct FwdArgs {
     const double* eps; unsigned long long seed, row_offset; const unsigned long long* seed_dev;
     long long rows_per_sample, sample_stride;
     double* mean; double* var; double* F; int ldf; double* A_save; double* scal;
+    double* U_save; long long NG;     // saved U_r blocks (common.cuh usave_*), NG = groups of 8 rows; nullptr: not kept
     int ntiles;
 };
 
@@ -209,7 +212,7 @@ __global__ void __launch_bounds__(C::NTHREADS, 1) k_cond_fwd(const __grid_consta
                     }
                 }
             };
-            run_phase<C, MASK_LOWER, false>(pipe, nb, seg_T, epi, Bt, ldb, Mpad, nullptr, 0);
+            run_phase<C, MASK_LOWER, false>(pipe, nb, seg_T, epi, Bt, ldb, Mpad);
         }
         consumer_sync<C>();
         PH(3);
@@ -275,6 +278,8 @@ __global__ void __launch_bounds__(C::NTHREADS, 1) k_cond_fwd(const __grid_consta
             double colsq[C::NJ][2];
 #pragma unroll
             for (int j = 0; j < C::NJ; ++j) { colsq[j][0] = 0.0; colsq[j][1] = 0.0; }
+            const int wn = warp % C::WN;
+            const int nkc = Mpad / C::KC;
             auto epi = [&](Acc<C>& acc, const Seg& sg) {
 #pragma unroll
                 for (int q = 0; q < 4; ++q)
@@ -283,6 +288,24 @@ __global__ void __launch_bounds__(C::NTHREADS, 1) k_cond_fwd(const __grid_consta
                         colsq[j][0] = fma(acc.v[q][j][0], acc.v[q][j][0], colsq[j][0]);
                         colsq[j][1] = fma(acc.v[q][j][1], acc.v[q][j][1], colsq[j][1]);
                     }
+                if (a.U_save) {
+                    // U_r rows of this block row -> HBM for the backward pass: thread (g, t) holds U[k0 + g][8 grp + 2t, +1],
+                    // a warp instruction stores eight 64-byte runs = one contiguous 512-byte piece of a 16 x 8 block
+                    const long long grp0 = n0 / 8 + wn * C::NJ;
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        const int krow = acc_row<C>(sg.i, q);
+                        if (krow < Mpad) {
+                            double* ub = a.U_save + ((size_t)sg.r * nkc + (krow >> 4)) * (size_t)a.NG * USAVE_BLOCK +
+                                         usave_swz(krow & 15, 2 * t);
+#pragma unroll
+                            for (int j = 0; j < C::NJ; ++j)
+                                if (grp0 + j < a.NG)
+                                    *reinterpret_cast<double2*>(ub + (size_t)(grp0 + j) * USAVE_BLOCK) =
+                                        make_double2(acc.v[q][j][0], acc.v[q][j][1]);
+                        }
+                    }
+                }
                 if (sg.i != nb - 1) return;
                 // ---- E2 for output r: reduce the column sums over the 8 row groups of the warp; the cross-warp sum and
                 //      the variance / sample of up to E2_GROUP outputs are done together behind one barrier
@@ -332,7 +355,7 @@ __global__ void __launch_bounds__(C::NTHREADS, 1) k_cond_fwd(const __grid_consta
                 // the next group's partials reuse the slots: order them after this group's reads
                 if (!last) consumer_sync<C>();
             };
-            run_phase<C, MASK_UPPER, false>(pipe, nb * d.R, seg_U, epi, Bt, ldb, Mpad, nullptr, 0);
+            run_phase<C, MASK_UPPER, false>(pipe, nb * d.R, seg_U, epi, Bt, ldb, Mpad);
         }
         PH(5);
     }
@@ -347,11 +370,11 @@ static int launch_fwd(const FwdArgs& a, cudaStream_t st) {
     const FwdSmem<C> L(a.Mpad, a.Dp);
     const size_t bytes = (size_t)L.total_doubles * sizeof(double);
     if (bytes > 227 * 1024) return DGP_ERR_UNSUPPORTED;
-    static size_t configured_dev[DGP_MAX_DEVICES] = {};
-    size_t& configured = configured_dev[current_device()];
-    if (bytes > configured) {
+    static DevOnceSize configured;
+    const int dev = current_device();
+    if (!configured.covers(dev, bytes)) {
         if (cudaFuncSetAttribute(k_cond_fwd<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes) != cudaSuccess) return DGP_ERR_LAUNCH;
-        configured = bytes;
+        configured.raise(dev, bytes);
     }
     int grid = a.ntiles < device_sm_count() ? a.ntiles : device_sm_count();
     k_cond_fwd<C><<<grid, C::NTHREADS, bytes, st>>>(a);
@@ -366,7 +389,7 @@ using namespace dgp;
 extern "C" int dgp_cond_forward(const dgp_cond_desc* d, const void* ws, const double* X, int64_t x_rows, int64_t n_rows,
                                 const double* eps, uint64_t seed, const uint64_t* seed_dev, uint64_t row_offset,
                                 int64_t rows_per_sample, int64_t sample_stride, double* mean, double* var, double* F,
-                                int32_t ldf, double* A_save, void* stream) {
+                                int32_t ldf, double* A_save, double* U_save, void* stream) {
     int rc = check_desc(d);
     if (rc != DGP_OK) return rc;
     if (!ws || !X || !mean || !var || x_rows < 1 || n_rows < 0) return DGP_ERR_ARG;
@@ -384,6 +407,7 @@ extern "C" int dgp_cond_forward(const dgp_cond_desc* d, const void* ws, const do
     a.rows_per_sample = rows_per_sample > 0 ? rows_per_sample : n_rows;
     a.sample_stride = sample_stride > 0 ? sample_stride : a.rows_per_sample;
     a.mean = mean; a.var = var; a.F = F; a.ldf = ldf; a.A_save = A_save;
+    a.U_save = U_save; a.NG = usave_groups(n_rows);
     a.scal = const_cast<double*>(ws_ptr<double>(ws, w.scal));
     cudaStream_t st = (cudaStream_t)stream;
     // row-tile width by inducing count (the A tile must fit in shared memory); ring depth 4, or 3 / 2 when the
@@ -395,6 +419,15 @@ extern "C" int dgp_cond_forward(const dgp_cond_desc* d, const void* ws, const do
         rc = launch_fwd<C>(a, st);                                                    \
         if (rc != DGP_ERR_UNSUPPORTED) return rc;                                     \
     }
+#ifdef DGP_TEST_HOOKS
+    switch (g_force_fwd_nt) {      // parity tests pin every instantiation (tests/test_gpu_conditional.py)
+        case 72: DGP_TRY_FWD(3, 72, 3) DGP_TRY_FWD(3, 72, 2) return DGP_ERR_UNSUPPORTED;
+        case 64: DGP_TRY_FWD(DGP_FWD_WN, 64, 4) DGP_TRY_FWD(DGP_FWD_WN, 64, 3) DGP_TRY_FWD(DGP_FWD_WN, 64, 2) return DGP_ERR_UNSUPPORTED;
+        case 32: DGP_TRY_FWD(DGP_FWD_WN, 32, 4) DGP_TRY_FWD(DGP_FWD_WN, 32, 3) DGP_TRY_FWD(DGP_FWD_WN, 32, 2) return DGP_ERR_UNSUPPORTED;
+        case 16: DGP_TRY_FWD(2, 16, 4) DGP_TRY_FWD(2, 16, 3) DGP_TRY_FWD(2, 16, 2) return DGP_ERR_UNSUPPORTED;
+        default: break;
+    }
+#endif
     if (w.Mpad <= 256) {
         // wave quantisation: a grid of ceil(n / 64) tiles that just spills into another wave (10 000 rows = 157 tiles on
         // 148 SMs: two waves, the second almost empty) is cheaper as 32-row tiles, although those stream every operand
@@ -405,8 +438,7 @@ extern "C" int dgp_cond_forward(const dgp_cond_desc* d, const void* ws, const do
         const long long w72 = ((n_rows + 71) / 72 + sms - 1) / sms * 72;
         // 72-row tiles (4 x 3 consumer warps, three column tiles per warp): one wave for the 10 000-row minibatch of the
         // BASELINE configurations on 148 SMs, where 64-row tiles need two and 32-row tiles three
-        static const char* force_nt = getenv("DGP_FWD_NT");      // A/B switch for tools/kbench.py
-        if ((force_nt && atoi(force_nt) == 72) || (!force_nt && w72 * 104 < w64 * 100 && w72 * 100 <= w32 * 108)) {
+        if (w72 * 104 < w64 * 100 && w72 * 100 <= w32 * 108) {
             DGP_TRY_FWD(3, 72, 3) DGP_TRY_FWD(3, 72, 2)
         }
         if (w32 * 108 < w64 * 100) { DGP_TRY_FWD(DGP_FWD_WN, 32, 4) DGP_TRY_FWD(DGP_FWD_WN, 32, 3) }

@@ -17,7 +17,10 @@
 
 namespace dgp {
 
-long long g_launches = 0;
+std::atomic<long long> g_launches{0};
+#ifdef DGP_TEST_HOOKS
+int g_force_fwd_nt = 0, g_force_bwd_nt = 0, g_force_gram_splits = 0, g_debug_mode = 0;
+#endif
 
 int current_device() {
     int dev = 0;
@@ -26,17 +29,17 @@ int current_device() {
 }
 
 int device_sm_count() {
-    static int n[DGP_MAX_DEVICES] = {};
+    static std::atomic<int> n[DGP_MAX_DEVICES];
     const int dev = current_device();
-    if (n[dev] == 0) {
-        int v = 0;
+    int v = n[dev].load(std::memory_order_relaxed);
+    if (v == 0) {
         if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || v <= 0) {
             cudaGetLastError();
             v = 148;  // B200; also used when cross-checking layouts on a GPU-less host
         }
-        n[dev] = v;
+        n[dev].store(v, std::memory_order_relaxed);
     }
-    return n[dev];
+    return v;
 }
 
 int check_desc(const dgp_cond_desc* d) {
@@ -501,14 +504,13 @@ static size_t tri_inv_smem_bytes(int Mpad) {
 }
 
 int tri_inv_cols(const double* L, double* Linv, int Mpad, cudaStream_t st) {
-    static const bool legacy = getenv("DGP_TRIINV_GLOBAL") != nullptr;   // A/B switch for tools/kbench.py
-    if (Mpad <= 256 && !legacy) {
-        static bool attr_dev[DGP_MAX_DEVICES] = {};
-        bool& attr = attr_dev[current_device()];
-        if (!attr) {
+    if (Mpad <= 256) {
+        static DevOnceSize attr;
+        const int dev = current_device();
+        if (!attr.covers(dev, 1)) {
             if (cudaFuncSetAttribute(k_tri_inv_cols_smem, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      (int)tri_inv_smem_bytes(256)) != cudaSuccess) return DGP_ERR_LAUNCH;
-            attr = true;
+            attr.raise(dev, 1);
         }
         k_tri_inv_cols_smem<<<Mpad / 32, 256, tri_inv_smem_bytes(Mpad), st>>>(L, Linv, Mpad);
     } else {
@@ -533,15 +535,14 @@ __global__ void k_diag_inv(const double* __restrict__ L, double* __restrict__ Li
 }
 
 int cholesky_batched(double* K, int Mpad, int batch, int32_t* status, cudaStream_t st, double* Linv) {
-    static bool attr_set[DGP_MAX_DEVICES] = {};
+    static DevOnceSize attr_set;
     const int dev = current_device();
-    if (!attr_set[dev]) {
+    if (!attr_set.covers(dev, 1)) {
         if (cudaFuncSetAttribute(k_cholesky, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess) return DGP_ERR_LAUNCH;
         if (cudaFuncSetAttribute(k_cholesky32, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess) return DGP_ERR_LAUNCH;
-        attr_set[dev] = true;
+        attr_set.raise(dev, 1);
     }
-    static const bool legacy = getenv("DGP_CHOL_LEGACY") != nullptr;   // A/B switch for tools/kbench.py
-    if (Mpad <= 512 && !legacy) {
+    if (Mpad <= 512) {
         const size_t smem = (32 * 33 + 32 + (size_t)(Mpad - 32) * CHOL_LDP) * sizeof(double);
         k_cholesky32<<<batch, CHOL_THREADS, smem, st>>>(K, Mpad, status, Linv);
     } else {
@@ -557,7 +558,9 @@ int cholesky_batched(double* K, int Mpad, int batch, int32_t* status, cudaStream
 // ------------------------------------------------------------------------------------------------ q_sqrt, KL
 // LqT[r][i][j] = tril(q_sqrt[col0+r])[j][i]  (upper triangular), zero padded.  The same pass accumulates this tile's
 // share of the whitened KL term: sum over the lower triangle of q^2, minus log(q_ii^2) on the diagonal.
-__global__ void k_lq_prep(dgp_cond_desc d, int Mpad, double* __restrict__ LqT, double* __restrict__ klpart) {
+// Lq (nullable, backward pass only) receives the untransposed lower factor [r][j][i], zero padded.
+__global__ void k_lq_prep(dgp_cond_desc d, int Mpad, double* __restrict__ LqT, double* __restrict__ Lq,
+                          double* __restrict__ klpart) {
     __shared__ double tile[32][33];
     __shared__ double red[32];
     const int r = blockIdx.z;
@@ -574,6 +577,7 @@ __global__ void k_lq_prep(dgp_cond_desc d, int Mpad, double* __restrict__ LqT, d
             if (i == j) s -= log(v * v);
         }
         tile[jj][threadIdx.x] = v;
+        if (Lq) Lq[((size_t)r * Mpad + j) * Mpad + i] = v;
     }
     __syncthreads();
     for (int ii = threadIdx.y; ii < 32; ii += blockDim.y)
@@ -613,18 +617,19 @@ __global__ void k_transpose(const double* __restrict__ in, double* __restrict__ 
     for (int jj = threadIdx.y; jj < 32; jj += blockDim.y) out[(size_t)(j0 + jj) * n + i0 + threadIdx.x] = tile[threadIdx.x][jj];
 }
 
-// row-major [batch][Mpad][Mpad] -> tiled [batch][block row][chunk][128][20] (zero padded)
+// row-major [batch][Mpad][Mpad] -> tiled [batch][block row][chunk][128][16], 32-byte groups of a row permuted by
+// (row & 3) (common.cuh tile_swizzle); rows / columns beyond Mpad are zero
 __global__ void k_retile(const double* __restrict__ src, double* __restrict__ dst, int Mpad, size_t tl) {
     const size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= tl) return;
-    const int c = (int)(e % TILE_WLD);
     const int row = (int)((e / TILE_WLD) % TILE_MB);
+    const int c = tile_swizzle(row, (int)(e % TILE_WLD));    // the permutation is an involution: stored slot -> column
     const size_t tile = e / TILE_DOUBLES;
     const int nch = tiled_mpad(Mpad) / TILE_KC;
     const int kc = (int)(tile % nch), bi = (int)(tile / nch);
     const int i = bi * TILE_MB + row, k = kc * TILE_KC + c;
     double v = 0.0;
-    if (c < TILE_KC && i < Mpad && k < Mpad) v = src[(size_t)blockIdx.y * Mpad * Mpad + (size_t)i * Mpad + k];
+    if (i < Mpad && k < Mpad) v = src[(size_t)blockIdx.y * Mpad * Mpad + (size_t)i * Mpad + k];
     dst[(size_t)blockIdx.y * tl + e] = v;
 }
 int retile(const double* src, double* dst, int Mpad, int batch, cudaStream_t st) {
@@ -632,12 +637,6 @@ int retile(const double* src, double* dst, int Mpad, int batch, cudaStream_t st)
     k_retile<<<dim3((unsigned)((tl + 255) / 256), batch), 256, 0, st>>>(src, dst, Mpad, tl);
     DGP_COUNT_LAUNCH();
     return cudaGetLastError() == cudaSuccess ? DGP_OK : DGP_ERR_LAUNCH;
-}
-
-// SmI[r] -= I on the leading M x M block
-__global__ void k_sub_identity(double* __restrict__ S, int Mpad, int M) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < M) S[((size_t)blockIdx.y * Mpad + i) * Mpad + i] -= 1.0;
 }
 
 }  // namespace dgp
@@ -657,8 +656,6 @@ static std::atomic<bool> g_lanes_ok[DGP_MAX_DEVICES];
 static std::atomic<unsigned> g_lane_next{0};
 
 SideLane* side_lane_acquire(cudaStream_t caller) {
-    static const bool disabled = getenv("DGP_NO_SIDE_STREAM") != nullptr;   // A/B switch
-    if (disabled) return nullptr;
     const int dev = current_device();
     if (!g_lanes_ok[dev].load(std::memory_order_acquire)) {
         cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
@@ -710,7 +707,7 @@ extern "C" int dgp_cond_prepare(const dgp_cond_desc* d, void* ws, size_t ws_byte
     int32_t* status = ws_ptr<int32_t>(ws, w.status);
 
     // Two independent chains: (A) Z -> Kuu -> Cholesky -> Linv (one SM, a serial chain) and (B) everything that depends
-    // on q_sqrt only (LqT, KL, S_r - I and their tiled copies).  B runs on a helper stream forked from and joined back
+    // on q_sqrt only (LqT, Lq, KL and their tiled copies).  B runs on a helper stream forked from and joined back
     // into `st` with events, so that it overlaps the Cholesky instead of queueing behind it on the critical path of the
     // forward pass.  (Inside a stream capture the helper stream simply becomes a parallel branch of the graph.)
     const WsLayout wb = ws_layout(*d, 0, 1);      // LinvT and SmI offsets do not depend on n_rows
@@ -723,23 +720,14 @@ extern "C" int dgp_cond_prepare(const dgp_cond_desc* d, void* ws, size_t ws_byte
     }
     // ---- chain B
     double* klpart = ws_ptr<double>(ws, w.klpart);
-    k_lq_prep<<<dim3(Mpad / 32, Mpad / 32, d->R), dim3(32, 8), 0, sb>>>(*d, Mpad, LqT, klpart); DGP_COUNT_LAUNCH();
+    double* Lq = need_bwd ? ws_ptr<double>(ws, wb.Lq) : nullptr;
+    k_lq_prep<<<dim3(Mpad / 32, Mpad / 32, d->R), dim3(32, 8), 0, sb>>>(*d, Mpad, LqT, Lq, klpart); DGP_COUNT_LAUNCH();
     if (kl_out) { k_kl<<<1, 256, 0, sb>>>(*d, klpart, d->R * (Mpad / 32) * (Mpad / 32), kl_out); DGP_COUNT_LAUNCH(); }
     rc = retile(LqT, ws_ptr<double>(ws, w.LqTTl), Mpad, d->R, sb);
     if (rc == DGP_OK && need_bwd) {
-        double* SmI = ws_ptr<double>(ws, wb.SmI);
-        // S_r = Lq_r Lq_r^T = LqT_r^T LqT_r :  A(i,k) = LqT[k][i], B(k,j) = LqT[k][j]
-        GemmArgs g{};
-        g.A = LqT; g.B = LqT; g.C = SmI;
-        g.I = Mpad; g.J = Mpad; g.K = Mpad;
-        g.sAi = 1; g.sAk = Mpad; g.sBk = Mpad; g.sBj = 1; g.sCi = Mpad; g.sCj = 1;
-        g.bA = g.bB = g.bC = (long long)Mpad * Mpad;
-        g.alpha = 1.0; g.beta = 0.0; g.batch = d->R;
-        rc = gemm_small(g, sb);
-        if (rc == DGP_OK) {
-            k_sub_identity<<<dim3((d->M + 127) / 128, d->R), 128, 0, sb>>>(SmI, Mpad, d->M); DGP_COUNT_LAUNCH();
-            rc = retile(SmI, ws_ptr<double>(ws, wb.SmITl), Mpad, d->R, sb);
-        }
+        // the backward kernel streams tril(q_sqrt_r) itself: d A = ... + 2 sum_r Lq_r (U_r . g_var_r) with the U_r kept from
+        // the forward pass
+        rc = retile(Lq, ws_ptr<double>(ws, wb.LqTl), Mpad, d->R, sb);
         // the per-CTA row-sum partials of the backward pass start from zero; dgp_cond_backward adds to them (row chunks).
         // (The Gram partials are not cleared: the first dgp_cond_backward_gram call of an evaluation stores into them.)
         if (rc == DGP_OK && cudaMemsetAsync(ws_ptr<char>(ws, wb.part), 0, wb.tail - wb.part, sb) != cudaSuccess) rc = DGP_ERR_LAUNCH;
@@ -788,4 +776,13 @@ extern "C" const char* dgp_strerror(int code) {
     }
 }
 extern "C" const char* dgp_version(void) { return "dgp_b200 0.1 (sm_100a)"; }
-extern "C" int64_t dgp_launch_count(void) { return (int64_t)g_launches; }
+extern "C" int64_t dgp_launch_count(void) { return (int64_t)g_launches.load(); }
+extern "C" size_t dgp_usave_bytes(const dgp_cond_desc* d, int64_t n_rows) {
+    if (!d || d->M < 1 || d->M > 1024 || d->R < 1 || n_rows < 0) return 0;
+    return usave_doubles(dgp_mpad(d->M), d->R, n_rows) * sizeof(double);
+}
+#ifdef DGP_TEST_HOOKS
+extern "C" void dgp_test_force_tiles(int fwd_nt, int bwd_nt) { g_force_fwd_nt = fwd_nt; g_force_bwd_nt = bwd_nt; }
+extern "C" void dgp_test_force_gram_splits(int n) { g_force_gram_splits = n; }
+extern "C" void dgp_test_debug_mode(int m) { g_debug_mode = m; }
+#endif

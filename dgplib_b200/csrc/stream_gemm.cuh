@@ -2,12 +2,14 @@
 //
 //     C[block-row i][NT columns]  (+)=  W[block-row i][k-range]  x  Bt[NT columns][k-range]^T
 //
-// W  : an Mpad x Mpad parameter matrix (Lm^-1, tril(q_sqrt_r)^T, S_r - I, Lm^-T), pre-tiled in global memory by the
-//      parameter stage as [block row][16-deep chunk][128 rows][20 doubles] (dgp::retile), so that one chunk is ONE
-//      contiguous 20 KB block.  A dedicated producer warp streams the chunks with bulk async copies (TMA engine,
-//      cp.async.bulk + mbarrier complete_tx) into a STAGES-deep shared-memory ring; the 20-double pitch makes the
-//      DMMA A-fragment loads conflict-free.
-// Bt : the resident row tile in shared memory, stored [n][k] with pitch Mpad+4 (conflict-free B-fragment loads);
+// W  : an Mpad x Mpad parameter matrix (Lm^-1, tril(q_sqrt_r)^T, tril(q_sqrt_r), Lm^-T), pre-tiled in global memory by
+//      the parameter stage as [block row][16-deep chunk][128 rows][16 doubles] with the 32-byte groups of a row
+//      XOR-permuted by (row & 3) (dgp::retile, common.cuh), so that one chunk is ONE contiguous 16 KB block and the
+//      DMMA A-fragment loads are conflict-free without padding.  A dedicated producer warp streams the chunks with bulk
+//      async copies (TMA engine, cp.async.bulk + mbarrier complete_tx) into a STAGES-deep shared-memory ring.
+// Bt : the resident row tile in shared memory, stored [n][k] with pitch Mpad+4 (conflict-free B-fragment loads) -- or,
+//      for the backward pass's dA phase (BSTAGE), a second streamed operand: the chunk [NT/8][16][8] of the saved
+//      U_r = tril(q_sqrt_r)^T A that travels in the same ring slot as the W chunk it is multiplied with;
 // C  : fp64 tensor-core accumulators (DMMA.8x8x4) in registers.  Consumer warp grid WM x WN; a warp owns 4
 //      interleaved 8-row tiles (rows (q*WM+wm)*8 ..) so that triangular skipping stays balanced across warps, and
 //      NJ = NT/(8 WN) column tiles.
@@ -26,16 +28,18 @@ enum { MASK_LOWER = 0, MASK_UPPER = 1, MASK_DENSE = 2 };
 // host: row-major [Mpad][Mpad] (batched) -> tiled layout (defined in prep.cu)
 int retile(const double* src, double* dst, int Mpad, int batch, cudaStream_t st);
 
-template <int WM_, int WN_, int NT_, int STAGES_>
+template <int WM_, int WN_, int NT_, int STAGES_, bool USTREAM_ = false>
 struct TileCfg {
     static constexpr int WM = WM_, WN = WN_, NT = NT_, STAGES = STAGES_;
+    static constexpr bool USTREAM = USTREAM_;            // ring slots carry a [NT/8][16][8] chunk of the second operand
     static constexpr int NWARPS = WM * WN;              // consumer warps
     static constexpr int NCONS = NWARPS * 32;           // consumer threads
     static constexpr int NTHREADS = NCONS + 32;         // + one producer warp
     static constexpr int MB = 32 * WM;                  // rows per block row
     static constexpr int NJ = NT / (8 * WN);            // 8-column tiles per warp
     static constexpr int KC = TILE_KC, WLD = TILE_WLD;
-    static constexpr int STAGE_DOUBLES = TILE_DOUBLES;
+    static constexpr int UCH_DOUBLES = USTREAM ? NT * TILE_KC : 0;
+    static constexpr int STAGE_DOUBLES = TILE_DOUBLES + UCH_DOUBLES;
     static_assert(MB == TILE_MB, "the tiled operand layout assumes 128-row block rows (WM = 4)");
     static_assert(NT % (8 * WN) == 0, "NT must be a multiple of 8*WN");
 };
@@ -97,43 +101,61 @@ __device__ __forceinline__ void consumer_sync() {
     asm volatile("bar.sync 1, %0;\n" :: "n"(C::NCONS) : "memory");
 }
 
-// ---- producer side: one elected lane enqueues every chunk of the phase
-template <class C, class SegFn>
-__device__ __forceinline__ void produce_phase(Pipe& p, int nseg, SegFn segfn, int Mpad) {
+// ---- producer side: one elected lane enqueues every chunk of the phase.  ufn(seg, kc, bytes&) returns the global
+//      address of the second operand's chunk that shares the slot (bytes = 0: none).
+struct NoU {
+    __device__ __forceinline__ const double* operator()(const Seg&, int, uint32_t& bytes) const { bytes = 0; return nullptr; }
+};
+template <class C, class SegFn, class UFn = NoU>
+__device__ __forceinline__ void produce_phase(Pipe& p, int nseg, SegFn segfn, int Mpad, UFn ufn = UFn()) {
     const int nch = tiled_mpad(Mpad) / C::KC;   // chunks per block row in the tiled layout
     for (int s = 0; s < nseg; ++s) {
         const Seg sg = segfn(s);
         for (int kc = sg.kc0; kc < sg.kc1; ++kc) {
             if (p.round > 0) mbar_wait(&p.empty[p.stage], (p.round - 1) & 1);
-            mbar_expect_tx(&p.full[p.stage], (uint32_t)(C::STAGE_DOUBLES * sizeof(double)));
-            bulk_g2s(p.stages + (size_t)p.stage * C::STAGE_DOUBLES,
-                     sg.W + ((size_t)sg.i * nch + kc) * C::STAGE_DOUBLES,
-                     (uint32_t)(C::STAGE_DOUBLES * sizeof(double)), &p.full[p.stage]);
+            uint32_t ub = 0;
+            const double* usrc = ufn(sg, kc, ub);
+            double* slot = p.stages + (size_t)p.stage * C::STAGE_DOUBLES;
+            mbar_expect_tx(&p.full[p.stage], (uint32_t)(TILE_DOUBLES * sizeof(double)) + ub);
+            bulk_g2s(slot, sg.W + ((size_t)sg.i * nch + kc) * TILE_DOUBLES, (uint32_t)(TILE_DOUBLES * sizeof(double)),
+                     &p.full[p.stage]);
+            if (ub) bulk_g2s(slot + TILE_DOUBLES, usrc, ub, &p.full[p.stage]);
             pipe_advance<C>(p);
         }
     }
 }
 
-// One staged W chunk (16 deep) against the resident tile for the warp's tiles q in [QLO, QHI).
-//   Aw = &Ws[(wm*8 + g) * WLD + t]          tile q adds q*WM*8 rows
-//   Bw = &Bt[(wn*NJ*8 + g) * ldb + k0 + t]  column tile j adds j*8 rows of Bt
-template <class C, int QLO, int QHI, bool WEIGHTED>
+// One staged W chunk (16 deep) against the B operand for the warp's tiles q in [QLO, QHI).
+//   Aw = &Ws[(wm*8 + g) * 16 + t]            tile q adds q*WM*8 rows; k-step kk sits at column group kk ^ (g & 3) (ko[kk])
+//   resident B : Bw = &Bt[(wn*NJ*8 + g) * ldb + k0 + t]     column tile j adds j*8 rows of Bt, k-step kk 4 columns
+//   streamed B : Bw = &Us[wn*NJ*128 + usave_swz(t, g)]      column tile j adds one 16 x 8 block, k-step kk 4 rows of it
+// WEIGHTED: the B fragment of column n is multiplied by wv[j] (the backward pass's g_var[n, r]).  The multiply is a DMUL
+// on the same fp64 pipe as the DMMAs and warps issue in order, so it is placed AFTER the DMMA group of the previous
+// k-step (as volatile asm, which keeps its place between the volatile DMMAs): by then the LDS it depends on has long
+// returned.  (Multiplying right at the load put a stalled DMUL in front of every DMMA group: 24 % of all warp stalls.)
+__device__ __forceinline__ void dmul_inplace(double& x, double w) {
+    asm volatile("mul.f64 %0, %0, %1;\n" : "+d"(x) : "d"(w));
+}
+template <class C, int QLO, int QHI, bool BSTAGE, bool WEIGHTED>
 __device__ __forceinline__ void chunk_mma(Acc<C>& acc, const double* __restrict__ Aw, const double* __restrict__ Bw,
-                                          int ldb, const double (&wv)[C::NJ]) {
+                                          int ldb, const int (&ko)[4], const double (&wv)[C::NJ]) {
     // Software-pipelined over the four k-steps of the chunk: the fragments of step kk+1 are loaded (into their own
     // registers) before the DMMAs of step kk are issued.  Left to itself ptxas reused one register pair for every A
     // fragment and put each LDS directly in front of its DMMA (30 % short-scoreboard stalls on the DMMAs in ncu).
     double af[2][4], bf[2][C::NJ];
     auto load = [&](int kk, int buf) {
 #pragma unroll
-        for (int j = 0; j < C::NJ; ++j) {
-            bf[buf][j] = Bw[j * 8 * ldb + kk * 4];
-            if (WEIGHTED) bf[buf][j] *= wv[j];
-        }
+        for (int j = 0; j < C::NJ; ++j)
+            bf[buf][j] = BSTAGE ? Bw[j * USAVE_BLOCK + kk * 32] : Bw[j * 8 * ldb + kk * 4];
 #pragma unroll
-        for (int q = QLO; q < QHI; ++q) af[buf][q] = Aw[q * C::WM * 8 * C::WLD + kk * 4];
+        for (int q = QLO; q < QHI; ++q) af[buf][q] = Aw[q * C::WM * 8 * C::WLD + ko[kk]];
+    };
+    auto scale = [&](int buf) {
+#pragma unroll
+        for (int j = 0; j < C::NJ; ++j) dmul_inplace(bf[buf][j], wv[j]);
     };
     load(0, 0);
+    if (WEIGHTED) scale(0);
 #pragma unroll
     for (int kk = 0; kk < 4; ++kk) {
         if (kk + 1 < 4) load(kk + 1, (kk + 1) & 1);
@@ -142,17 +164,22 @@ __device__ __forceinline__ void chunk_mma(Acc<C>& acc, const double* __restrict_
         for (int q = QLO; q < QHI; ++q)
 #pragma unroll
             for (int j = 0; j < C::NJ; ++j) dmma884(acc.v[q][j], af[kk & 1][q], bf[kk & 1][j]);
+        if (WEIGHTED && kk + 1 < 4) scale((kk + 1) & 1);
     }
 }
 
-// ---- consumer side.  WEIGHTED: the B fragment of column n is multiplied by wts[n * wld + seg.r] (backward pass).
+// ---- consumer side.  BSTAGE: the B operand is the chunk streamed in the same ring slot (Bt / ldb unused).
+// WEIGHTED: B column n is scaled by wts[n * wld + seg.r] for n < nvalid and by 0 beyond (backward pass).
 // Starts with a consumer barrier (Bt is complete, previous phase's epilogue writes are visible).
-template <class C, int MASK, bool WEIGHTED, class SegFn, class EpiFn>
+template <class C, int MASK, bool BSTAGE, bool WEIGHTED = false, class SegFn, class EpiFn>
 __device__ __forceinline__ void run_phase(Pipe& p, int nseg, SegFn segfn, EpiFn epi, const double* __restrict__ Bt,
-                                          int ldb, int Mpad, const double* __restrict__ wts, int wld) {
+                                          int ldb, int Mpad, const double* __restrict__ wts = nullptr, int wld = 0,
+                                          int nvalid = 0) {
+    static_assert(!BSTAGE || C::USTREAM, "BSTAGE needs a tile configuration whose ring slots carry the second operand");
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int g = lane >> 2, t = lane & 3;
     const int wm = warp / C::WN, wn = warp % C::WN;
+    const int ko[4] = {((0 ^ (g & 3)) << 2), ((1 ^ (g & 3)) << 2), ((2 ^ (g & 3)) << 2), ((3 ^ (g & 3)) << 2)};
 
     Acc<C> acc;
     acc.clear();
@@ -164,7 +191,10 @@ __device__ __forceinline__ void run_phase(Pipe& p, int nseg, SegFn segfn, EpiFn 
         double wv[C::NJ] = {};
         if (WEIGHTED) {
 #pragma unroll
-            for (int j = 0; j < C::NJ; ++j) wv[j] = wts[(wn * C::NJ * 8 + j * 8 + g) * wld + seg.r];
+            for (int j = 0; j < C::NJ; ++j) {
+                const int n = wn * C::NJ * 8 + j * 8 + g;      // B-fragment column of this lane
+                wv[j] = n < nvalid ? wts[n * wld + seg.r] : 0.0;
+            }
         }
         // Active 8-row tiles of this warp per chunk: a contiguous range [qlo, qhi) of its 4 interleaved tiles (tile q
         // starts at row rbase + 32 q).  Skipping uses real (warp-uniform) branches: a predicated-off DMMA still occupies
@@ -172,16 +202,18 @@ __device__ __forceinline__ void run_phase(Pipe& p, int nseg, SegFn segfn, EpiFn 
         const int rbase = row0 + wm * 8;
         int qmax = (Mpad - rbase + 31) >> 5;          // tiles with first row < Mpad
         qmax = qmax < 0 ? 0 : (qmax > 4 ? 4 : qmax);
-        const double* Bw0 = Bt + (wn * C::NJ * 8 + g) * ldb + t;
+        const double* Bw0 = BSTAGE ? (const double*)nullptr : Bt + (wn * C::NJ * 8 + g) * ldb + t;
+        const int boff = TILE_DOUBLES + wn * C::NJ * USAVE_BLOCK + usave_swz(t, g);   // + kk * 32: same swizzle bit
         const int aoff = (wm * 8 + g) * C::WLD + t;
         for (int kc = seg.kc0; kc < seg.kc1; ++kc) {
             const int k0 = kc * C::KC;
-            const double* Bw = Bw0 + k0;
-            const double* Aw = p.stages + (size_t)p.stage * C::STAGE_DOUBLES + aoff;
+            const double* slot = p.stages + (size_t)p.stage * C::STAGE_DOUBLES;
+            const double* Bw = BSTAGE ? slot + boff : Bw0 + k0;
+            const double* Aw = slot + aoff;
             if (MASK == MASK_DENSE && qmax == 4) {
                 // dense phase, full block row: no range bookkeeping at all
                 mbar_wait(&p.full[p.stage], p.round & 1);
-                chunk_mma<C, 0, 4, WEIGHTED>(acc, Aw, Bw, ldb, wv);
+                chunk_mma<C, 0, 4, BSTAGE, WEIGHTED>(acc, Aw, Bw, ldb, ko, wv);
             } else {
                 int qlo = 0, qhi = qmax;
                 if (MASK == MASK_LOWER) {                 // tile active iff rbase + 32 q + 7 >= k0
@@ -194,17 +226,17 @@ __device__ __forceinline__ void run_phase(Pipe& p, int nseg, SegFn segfn, EpiFn 
                 }
                 mbar_wait(&p.full[p.stage], p.round & 1);
                 if (qlo == 0 && qhi == 4) {
-                    chunk_mma<C, 0, 4, WEIGHTED>(acc, Aw, Bw, ldb, wv);
+                    chunk_mma<C, 0, 4, BSTAGE, WEIGHTED>(acc, Aw, Bw, ldb, ko, wv);
                 } else if (qlo < qhi) switch ((qlo << 3) | qhi) {
-                    case (1 << 3) | 4: chunk_mma<C, 1, 4, WEIGHTED>(acc, Aw, Bw, ldb, wv); break;
-                    case (2 << 3) | 4: chunk_mma<C, 2, 4, WEIGHTED>(acc, Aw, Bw, ldb, wv); break;
-                    case (3 << 3) | 4: chunk_mma<C, 3, 4, WEIGHTED>(acc, Aw, Bw, ldb, wv); break;
-                    case (0 << 3) | 3: chunk_mma<C, 0, 3, WEIGHTED>(acc, Aw, Bw, ldb, wv); break;
-                    case (0 << 3) | 2: chunk_mma<C, 0, 2, WEIGHTED>(acc, Aw, Bw, ldb, wv); break;
-                    case (0 << 3) | 1: chunk_mma<C, 0, 1, WEIGHTED>(acc, Aw, Bw, ldb, wv); break;
-                    case (1 << 3) | 3: chunk_mma<C, 1, 3, WEIGHTED>(acc, Aw, Bw, ldb, wv); break;
-                    case (1 << 3) | 2: chunk_mma<C, 1, 2, WEIGHTED>(acc, Aw, Bw, ldb, wv); break;
-                    case (2 << 3) | 3: chunk_mma<C, 2, 3, WEIGHTED>(acc, Aw, Bw, ldb, wv); break;
+                    case (1 << 3) | 4: chunk_mma<C, 1, 4, BSTAGE, WEIGHTED>(acc, Aw, Bw, ldb, ko, wv); break;
+                    case (2 << 3) | 4: chunk_mma<C, 2, 4, BSTAGE, WEIGHTED>(acc, Aw, Bw, ldb, ko, wv); break;
+                    case (3 << 3) | 4: chunk_mma<C, 3, 4, BSTAGE, WEIGHTED>(acc, Aw, Bw, ldb, ko, wv); break;
+                    case (0 << 3) | 3: chunk_mma<C, 0, 3, BSTAGE, WEIGHTED>(acc, Aw, Bw, ldb, ko, wv); break;
+                    case (0 << 3) | 2: chunk_mma<C, 0, 2, BSTAGE, WEIGHTED>(acc, Aw, Bw, ldb, ko, wv); break;
+                    case (0 << 3) | 1: chunk_mma<C, 0, 1, BSTAGE, WEIGHTED>(acc, Aw, Bw, ldb, ko, wv); break;
+                    case (1 << 3) | 3: chunk_mma<C, 1, 3, BSTAGE, WEIGHTED>(acc, Aw, Bw, ldb, ko, wv); break;
+                    case (1 << 3) | 2: chunk_mma<C, 1, 2, BSTAGE, WEIGHTED>(acc, Aw, Bw, ldb, ko, wv); break;
+                    case (2 << 3) | 3: chunk_mma<C, 2, 3, BSTAGE, WEIGHTED>(acc, Aw, Bw, ldb, ko, wv); break;
                     default: break;
                 }
             }

@@ -71,8 +71,7 @@ size_t dgp_cond_ws_bytes(const dgp_cond_desc* d, int64_t n_rows, int need_bwd);
  * Stream semantics (also dgp_cond_backward_params): everything is ordered after the work already queued on `stream`
  * and complete, in stream order, for whatever is queued on it afterwards; internally the q_sqrt-only chain may run on
  * a library-owned helper stream that is forked from and joined back into `stream` with events before the call returns
- * (a capture on `stream` simply gains a parallel branch).  DGP_NO_SIDE_STREAM=1 in the environment keeps it all on
- * `stream`. */
+ * (a capture on `stream` simply gains a parallel branch). */
 int dgp_cond_prepare(const dgp_cond_desc* d, void* ws, size_t ws_bytes, int need_bwd, double* kl_out, void* stream);
 /* copies the Cholesky status word to the host (synchronises the stream) */
 int dgp_cond_status(const void* ws, void* stream, int32_t* status_host);
@@ -94,11 +93,16 @@ int dgp_cond_status(const void* ws, void* stream, int32_t* status_host);
  *   F       [n_rows, ldf] sample mean + eps*sqrt(var) (NULL: skip).  When ldf > ldr the trailing column Dx-1 of X
  *           is copied into column ldf-1 (task-label propagation, dgplib/multitask_dsdgp.py:20)
  *   A_save  [n_rows, Mpad] Lm^-1 Kuf per row, kept for the backward pass (NULL: skip)
+ *   U_save  dgp_usave_bytes(d, n_rows) bytes: U_r = tril(q_sqrt_r)^T A for every output r, kept for the backward pass
+ *           (the reference's [R, M, N'] LTA tensor of base_conditional, which TF keeps for its own reverse mode) in
+ *           16 x 8 blocks [r][m / 16][n / 8][m % 16][n % 8]; NULL: not kept (prediction)
  */
 int dgp_cond_forward(const dgp_cond_desc* d, const void* ws, const double* X, int64_t x_rows, int64_t n_rows,
                      const double* eps, uint64_t seed, const uint64_t* seed_dev, uint64_t row_offset,
                      int64_t rows_per_sample, int64_t sample_stride, double* mean, double* var, double* F, int32_t ldf,
-                     double* A_save, void* stream);
+                     double* A_save, double* U_save, void* stream);
+/* bytes of the U_save buffer for n_rows rows of this conditional (R * Mpad * 8 * ceil(n_rows / 8) * 8) */
+size_t dgp_usave_bytes(const dgp_cond_desc* d, int64_t n_rows);
 
 /* ---- first-layer sample sharing -------------------------------------------------------------------------------
  * tile_over_samples (dgplib/utils.py:15-18, used at dgplib/dsdgp.py:89) hands the first layer S identical copies of
@@ -133,6 +137,7 @@ size_t dgp_lik_ws_bytes(int64_t n_rows, int32_t R);
  *   g_mean_in, g_var_in [n_rows, ldr]  direct gradients of mean / var (last layer: from the likelihood), or NULL
  *   g_F       [n_rows, ldgf] gradient of the sample F (from the next layer's gX), or NULL;  then
  *             g_mean = g_mean_in + g_F,  g_var = g_var_in + g_F * (F - mean) / (2 var)
+ *   A_save, U_save  what dgp_cond_forward kept for these rows
  *   gX        [n_rows, Dx] gradient w.r.t. the input rows (NULL for the data layer); accumulate != 0 adds to it
  * dgp_cond_backward leaves dKuf and the combined g_mean / g_var in the workspace; dgp_cond_backward_gram (call it next,
  * same n_rows / A_save) reduces them over the rows into the Gram accumulators G_r = sum_n g_var[n,r] a_n a_n^T and
@@ -140,8 +145,8 @@ size_t dgp_lik_ws_bytes(int64_t n_rows, int32_t R);
  * may be pushed between one dgp_cond_prepare and dgp_cond_backward_params, which finishes them).
  */
 int dgp_cond_backward(const dgp_cond_desc* d, void* ws, const double* X, int64_t x_rows, int64_t n_rows,
-                      const double* A_save, const double* mean, const double* var, const double* F, int32_t ldf,
-                      const double* g_mean_in, const double* g_var_in, const double* g_F, int32_t ldgf,
+                      const double* A_save, const double* U_save, const double* mean, const double* var, const double* F,
+                      int32_t ldf, const double* g_mean_in, const double* g_var_in, const double* g_F, int32_t ldgf,
                       double* gX, int32_t accumulate_gX, void* stream);
 int dgp_cond_backward_gram(const dgp_cond_desc* d, void* ws, const double* A_save, int64_t n_rows, int32_t accumulate,
                            void* stream);   /* accumulate: 0 for the first row chunk after dgp_cond_prepare, 1 after */

@@ -77,9 +77,10 @@ def run_conditional(cuda, M, D, R, N, kind, S=1, white=1e-5, linear=True, backwa
     mean = torch.zeros(n, R, dtype=torch.float64, device=dev)
     varo, F = torch.zeros_like(mean), torch.zeros_like(mean)
     Asave = torch.full((n, Mp), float("nan"), dtype=torch.float64, device=dev)
+    Usave = torch.full((lib.dgp_usave_bytes(ctypes.byref(d), n) // 8,), float("nan"), dtype=torch.float64, device=dev)
     # the S copies of X are addressed by index arithmetic (x_rows = N), never materialised
     C.check(lib.dgp_cond_forward(ctypes.byref(d), C.ptr(ws), C.ptr(Xd), N, n, C.ptr(epsd), 0, None, 0, 0, 0, C.ptr(mean),
-                                 C.ptr(varo), C.ptr(F), R, C.ptr(Asave), st), "forward")
+                                 C.ptr(varo), C.ptr(F), R, C.ptr(Asave), C.ptr(Usave) if backward else None, st), "forward")
     torch.cuda.synchronize()
     errs = {"kl": abs(kl.item() - kl_ref.item()) / max(abs(kl_ref.item()), 1e-12), "mean": rel(mean, m_ref),
             "var": rel(varo, v_ref), "F": rel(F, F_ref)}
@@ -92,7 +93,7 @@ def run_conditional(cuda, M, D, R, N, kind, S=1, white=1e-5, linear=True, backwa
         gX = torch.zeros(N * S, D, dtype=torch.float64, device=dev)
         Xrep = Xd.repeat(S, 1).contiguous()                  # d/dX per flattened row: give every row its own X row
         gmd, gvd, gFd = gm_in.to(dev), gv_in.to(dev), gF.to(dev)   # keep the device copies alive across the call
-        C.check(lib.dgp_cond_backward(ctypes.byref(d), C.ptr(ws), C.ptr(Xrep), n, n, C.ptr(Asave), C.ptr(mean),
+        C.check(lib.dgp_cond_backward(ctypes.byref(d), C.ptr(ws), C.ptr(Xrep), n, n, C.ptr(Asave), C.ptr(Usave), C.ptr(mean),
                                       C.ptr(varo), C.ptr(F), R, C.ptr(gmd), C.ptr(gvd), C.ptr(gFd), R, C.ptr(gX), 0,
                                       st), "backward")
         C.check(lib.dgp_cond_backward_gram(ctypes.byref(d), C.ptr(ws), C.ptr(Asave), n, 0, st), "gram")
@@ -239,13 +240,16 @@ def test_ragged_tiles_do_not_write_out_of_bounds(cuda):
     Mp = C.mpad(M)
     full = lambda cols: torch.full((N + PAD, cols), SENT, dtype=torch.float64, device=cuda)
     mean, var, F, A, gX = full(R), full(R), full(R), full(Mp), full(D)
+    nU = lib.dgp_usave_bytes(ctypes.byref(d), N) // 8
+    U = torch.full((nU + 4096,), SENT, dtype=torch.float64, device=cuda)
     C.check(lib.dgp_cond_forward(ctypes.byref(d), C.ptr(ws), C.ptr(X), N, N, None, 5, None, 0, 0, 0, C.ptr(mean), C.ptr(var),
-                                 C.ptr(F), R, C.ptr(A), st), "forward")
+                                 C.ptr(F), R, C.ptr(A), C.ptr(U), st), "forward")
     gm, gv = t(rng.randn(N, R)), t(rng.randn(N, R))
-    C.check(lib.dgp_cond_backward(ctypes.byref(d), C.ptr(ws), C.ptr(X), N, N, C.ptr(A), C.ptr(mean), C.ptr(var), None, R,
+    C.check(lib.dgp_cond_backward(ctypes.byref(d), C.ptr(ws), C.ptr(X), N, N, C.ptr(A), C.ptr(U), C.ptr(mean), C.ptr(var), None, R,
                                   C.ptr(gm), C.ptr(gv), None, 0, C.ptr(gX), 0, st), "backward")
     C.check(lib.dgp_cond_backward_gram(ctypes.byref(d), C.ptr(ws), C.ptr(A), N, 0, st), "gram")
     torch.cuda.synchronize()
+    assert bool((U[nU:] == SENT).all()) and bool(torch.isfinite(U[:nU]).all()) and not bool((U[:nU] == SENT).any()), "U"
     for name, buf in (("mean", mean), ("var", var), ("F", F), ("A", A), ("gX", gX)):
         assert bool((buf[N:] == SENT).all()), name
         assert bool(torch.isfinite(buf[:N]).all()) and not bool((buf[:N] == SENT).any()), name
@@ -265,13 +269,13 @@ def test_empty_and_unsupported_inputs(cuda):
     one = torch.zeros(8, 2, dtype=torch.float64, device=cuda)
     # zero rows: a no-op that succeeds
     assert lib.dgp_cond_forward(ctypes.byref(d), C.ptr(ws), C.ptr(one), 1, 0, None, 0, None, 0, 0, 0, C.ptr(one), C.ptr(one),
-                                None, 1, None, C.stream_ptr()) == 0
+                                None, 1, None, None, C.stream_ptr()) == 0
     assert lib.dgp_philox_normal(C.ptr(one), 0, 1, 1, 0, 0, 0, 0, C.stream_ptr()) == 0
     # too small a workspace is refused, not overrun
     assert lib.dgp_cond_prepare(ctypes.byref(d), C.ptr(ws), 1024, 0, None, C.stream_ptr()) == -3
     # inducing sets beyond 1024 points are refused by every entry point
     d.M = 1025
     assert lib.dgp_cond_ws_bytes(ctypes.byref(d), 8, 1) == 0
-    assert lib.dgp_cond_backward(ctypes.byref(d), C.ptr(ws), C.ptr(one), 1, 1, C.ptr(one), C.ptr(one), C.ptr(one), None, 1,
+    assert lib.dgp_cond_backward(ctypes.byref(d), C.ptr(ws), C.ptr(one), 1, 1, C.ptr(one), C.ptr(one), C.ptr(one), C.ptr(one), None, 1,
                                  C.ptr(one), C.ptr(one), None, 0, None, 0, C.stream_ptr()) == -4
     torch.cuda.synchronize()

@@ -214,3 +214,26 @@ def test_exact_gp_limit_matches_scikit_learn(monkeypatch):
         assert abs(float(g["l0.g0.kern.variance"]) - c["grad"]["variance"]) < 1e-7 * scale
         assert np.max(np.abs(g["l0.g0.kern.lengthscales"].numpy() - c["grad"]["lengthscales"])) < 1e-7 * scale
         assert abs(float(g["lik.variance"]) - c["grad"]["noise"]) < 1e-7 * scale
+
+
+def test_oracle_c1_gradients_against_50_digit_arbiter():
+    """BASELINE configs[0] with White(1e-5) (cond(Kuu) ~ 4e6): the oracle's ELBO and hyper-parameter gradients against
+    the committed 50-digit values (oracle/mp_c1_grad.py -> tests/golden/c1_white_grad_mp.json).  The White-variance
+    gradient is the ill-conditioned entry; the oracle is 2.4e-10 off there, inside the 1e-9 bar."""
+    import json, os
+    from _models import build_dsdgp, make_eps, oracle_layers, oracle_lik, t
+    gold = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "c1_white_grad_mp.json")))
+    N = gold["N"]
+    model, X, Y = build_dsdgp(L=2, M=50, D=1, N=N, S=1, white=1e-5)
+    eps = make_eps(model, 1, N)
+    oval, og = O.elbo_and_grad(oracle_layers(model.layers.layers), oracle_lik(model.likelihood), t(X), t(Y), 1,
+                               [t(e) for e in eps], num_data=N)
+    assert abs(float(oval) - float(gold["elbo_mp"])) < 1e-12 * abs(float(gold["elbo_mp"]))
+    names = {"white": "white", "variance": "variance", "lengthscale": "lengthscales"}
+    for key, exact in gold["grad_mp"].items():
+        if key == "lik_variance":
+            got = float(og["lik.variance"])
+        else:
+            l, nm = key.split(".")
+            got = float(og[f"{l}.g0.kern.{names[nm]}"].sum())
+        assert abs(got - float(exact)) < 1e-9 * abs(float(exact)), (key, got, exact)
