@@ -50,9 +50,9 @@ SIGNATURES = {
                                         _vp, _sz, _vp]),
     "dgp_lik_ws_bytes": (_sz, [_i64, _i32]),
     "dgp_cond_backward": (ctypes.c_int, [_P, _vp, _vp, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _i32, _vp, _vp, _vp, _i32,
-                                         _vp, _i32, _vp]),
+                                         _vp, _i32, _i32, _vp]),
     "dgp_cond_backward_gram": (ctypes.c_int, [_P, _vp, _vp, _i64, _i32, _vp]),
-    "dgp_cond_backward_params": (ctypes.c_int, [_P, _vp, _dbl, _vp, _vp, _vp, _vp, _vp]),
+    "dgp_cond_backward_params": (ctypes.c_int, [_P, _vp, _dbl, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "dgp_cond_fullcov_ws_bytes": (_sz, [_P, _i64]),
     "dgp_cond_fullcov": (ctypes.c_int, [_P, _vp, _vp, _i64, _vp, _vp, _vp, _sz, _vp]),
     "dgp_chol_sample_ws_bytes": (_sz, [_i64, _i32]),
@@ -60,6 +60,11 @@ SIGNATURES = {
                                        _vp, _vp]),
     "dgp_pca_ws_bytes": (_sz, [_i64, _i32]),
     "dgp_pca_weights": (ctypes.c_int, [_vp, _i64, _i32, _i32, _i32, _vp, _sz, _vp, _vp, _vp]),
+    "dgp_transform_params": (ctypes.c_int, [_vp, _vp, _vp, _vp, _i32, _dbl, _vp, _vp]),
+    "dgp_adam_step": (ctypes.c_int, [_vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _dbl, _dbl, _dbl, _dbl, _vp, _vp]),
+    "dgp_set_u64": (ctypes.c_int, [_vp, _u64, _vp]),
+    "dgp_finish_elbo": (ctypes.c_int, [_vp, _vp, _i32, _dbl, _vp]),
+    "dgp_zero": (ctypes.c_int, [_vp, _sz, _vp]),
     "dgp_kernel_K": (ctypes.c_int, [_P, _vp, _i64, _vp, _i64, _i32, _vp, _vp]),
     "dgp_kernel_Kdiag": (ctypes.c_int, [_P, _vp, _i64, _vp, _vp]),
     "dgp_mpad": (_i32, [_i32]),

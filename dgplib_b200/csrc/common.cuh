@@ -102,7 +102,7 @@ struct WsLayout {
     size_t dKuf;       // [n_rows][Mpad]
     size_t gmv;        // [n_rows][2R] combined g_mean | g_var of this conditional
     size_t gram;       // [nsplit][R+1][Mpad][Mpad]  split-K partials of G_r (r<R) and P (r==R)
-    size_t part;       // [ncta][npart] per-CTA partials: T2z[Mpad][Dp], cs[Mpad], dq_mu[Mpad][R], th[T][2+Dp]
+    size_t part;       // [ncta][npart] per-CTA partials: T2z[Mpad][Dp], cs[Mpad], dq_mu[Mpad][R], th[T][2+Dp], dA_lin[Dx][R], db[R]
     size_t psum;       // [npart] the per-CTA partials summed over CTAs (fixed order)
     size_t tail;       // [2R+4][Mpad][Mpad] scratch of the parameter tail (Gfull, Tq, Lbar, T1, T2, T3)
     size_t total;
@@ -162,7 +162,7 @@ static inline WsLayout ws_layout(const dgp_cond_desc& d, int64_t n_rows, int nee
         if (g_force_gram_splits >= 1 && g_force_gram_splits <= 64) ns = g_force_gram_splits;   // tuning experiments
 #endif
         w.nsplit = ns;
-        w.npart = round_up(w.Mpad * w.Dp + w.Mpad + w.Mpad * d.R + d.T * (2 + w.Dp), 32);
+        w.npart = round_up(w.Mpad * w.Dp + w.Mpad + w.Mpad * d.R + d.T * (2 + w.Dp) + d.Dx * d.R + d.R, 32);
         w.LinvT = o; o += align256(mm);
         w.Lq = o;    o += align256(mm * d.R);
         w.LinvTTl = o; o += align256(w.tl * sizeof(double));

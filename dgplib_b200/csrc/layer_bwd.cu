@@ -43,6 +43,7 @@ struct BwdArgs {
     const double* mean; const double* var; const double* F; int ldf;
     const double* g_mean_in; const double* g_var_in; const double* g_F; int ldgf;
     double* gX; int accumulate_gX;
+    int mean_grad;       // != 0: also accumulate the gradient of a trainable Linear mean (A, b) in the per-CTA partials
     double* dKuf; double* gmv; double* part; int npart; double* scal;
     long long row0;      // first row of this launch (a launch may cover a row range: tail tiles of another width)
     int ntiles;
@@ -104,6 +105,8 @@ __global__ void __launch_bounds__(C::NTHREADS, 1) k_cond_bwd(const __grid_consta
     double* pcs = pT2z + (size_t)Mpad * Dp;                  // [Mpad]
     double* pqmu = pcs + Mpad;                               // [Mpad][R]
     double* pth = pqmu + (size_t)Mpad * R;                   // [T][2+Dp]
+    double* pmA = pth + (size_t)d.T * (2 + Dp);              // [Dx][R] Linear mean weights: X^T g_mean
+    double* pmb = pmA + (size_t)d.Dx * R;                    // [R]     Linear mean offset: sum_n g_mean
 
     // segment lists of the two streamed phases (shared by the producer warp and the consumers)
     auto seg_dA = [&](int s) {      // dA block row i accumulates Lq_r (U_r . g_r) over all r: lower-triangular Lq_r
@@ -490,6 +493,20 @@ __global__ void __launch_bounds__(C::NTHREADS, 1) k_cond_bwd(const __grid_consta
                 }
             }
         }
+        // trainable Linear mean (an OutputLayer built with its own Linear mean, dgplib/layers.py:211-218): mean += X A + b, so
+        // dA = X^T g_mean over the raw input columns and db = sum_n g_mean; a few thousand FMAs per tile, rows in order
+        if (a.mean_grad) {
+            for (int idx = tid; idx < (d.Dx + 1) * R; idx += C::NCONS) {
+                const int k = idx / R, r = idx % R;
+                double s2 = 0.0;
+                for (int n = 0; n < nvalid; ++n) {
+                    const double xv = (k < d.Dx) ? a.X[(size_t)((n0 + n) % a.x_rows) * d.Dx + k] : 1.0;
+                    s2 = fma(xv, gm[n * R + r], s2);
+                }
+                if (k < d.Dx) pmA[k * R + r] += s2;
+                else pmb[r] += s2;
+            }
+        }
         // Kdiag terms: d variance += sum_r g_var, d white += sum_r g_var
         for (int n = tid; n < C::NT; n += C::NCONS) {
             const double s = (n < nvalid) ? gs[n] : 0.0;
@@ -716,7 +733,8 @@ using namespace dgp;
 extern "C" int dgp_cond_backward(const dgp_cond_desc* d, void* ws, const double* X, int64_t x_rows, int64_t n_rows,
                                  const double* A_save, const double* U_save, const double* mean, const double* var,
                                  const double* F, int32_t ldf, const double* g_mean_in, const double* g_var_in,
-                                 const double* g_F, int32_t ldgf, double* gX, int32_t accumulate_gX, void* stream) {
+                                 const double* g_F, int32_t ldgf, double* gX, int32_t accumulate_gX, int32_t mean_grad,
+                                 void* stream) {
     int rc = check_desc(d);
     if (rc != DGP_OK) return rc;
     if (!ws || !X || !A_save || !U_save || x_rows < 1 || n_rows < 0) return DGP_ERR_ARG;
@@ -735,6 +753,7 @@ extern "C" int dgp_cond_backward(const dgp_cond_desc* d, void* ws, const double*
     a.mean = mean; a.var = var; a.F = F; a.ldf = ldf;
     a.g_mean_in = g_mean_in; a.g_var_in = g_var_in; a.g_F = g_F; a.ldgf = ldgf;
     a.gX = gX; a.accumulate_gX = accumulate_gX;
+    a.mean_grad = (mean_grad && d->mean_A) ? 1 : 0;
     a.dKuf = ws_ptr<double>(ws, w.dKuf); a.gmv = ws_ptr<double>(ws, w.gmv);
     a.part = ws_ptr<double>(ws, w.part); a.npart = w.npart; a.scal = ws_ptr<double>(ws, w.scal);
     a.row0 = 0;

@@ -27,7 +27,15 @@ k_lik_gaussian(const double* __restrict__ Fmu, const double* __restrict__ Fvar, 
             const long long n = e / R;
             const int r = (int)(e % R);
             const double* yr = Y + (size_t)(n % y_rows) * ldy;
-            if (T > 1 && (int)yr[ldy - 1] != tk) continue;
+            if (T > 1) {
+                const int id = (int)yr[ldy - 1];
+                if (id != tk) {
+                    // a task id outside [0, T) matches no likelihood (the reference's dynamic_partition would raise): the
+                    // row contributes nothing, and its gradient slots are written (zeros) rather than left stale
+                    if (tk == 0 && (id < 0 || id >= T) && g_mu) { g_mu[e] = 0.0; g_var[e] = 0.0; }
+                    continue;
+                }
+            }
             const double dlt = yr[r] - Fmu[e];
             const double q = fma(dlt, dlt, Fvar[e]);
             ve += c0 - 0.5 * q * inv;

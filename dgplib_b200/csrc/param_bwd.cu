@@ -61,6 +61,15 @@ __global__ void k_gq_mu(dgp_cond_desc d, int Mpad, int Dp, const double* __restr
     gq_mu[o] = psum[(size_t)Mpad * Dp + Mpad + idx] - klw * d.q_mu[o];
 }
 
+// (c') gradient of a trainable Linear mean: this conditional's columns of dA [Dx, ldr] and db [ldr]
+__global__ void k_gmean(dgp_cond_desc d, const double* __restrict__ pm, double* __restrict__ gA, double* __restrict__ gb) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (d.Dx + 1) * d.R) return;
+    const int k = idx / d.R, r = idx % d.R;
+    if (k < d.Dx) gA[(size_t)k * d.ldr + d.col0 + r] = pm[idx];
+    else if (gb) gb[d.col0 + r] = pm[idx];
+}
+
 // Phi: lower triangle with halved diagonal, in place
 __global__ void k_phi(double* __restrict__ T, int Mpad) {
     const int j = blockIdx.x * blockDim.x + threadIdx.x, i = blockIdx.y;
@@ -165,7 +174,7 @@ __global__ void k_finish_theta(dgp_cond_desc d, int Mpad, int Dp, const double* 
 using namespace dgp;
 
 extern "C" int dgp_cond_backward_params(const dgp_cond_desc* d, void* ws, double kl_weight, double* gZ, double* gtheta,
-                                        double* gq_mu, double* gq_sqrt, void* stream) {
+                                        double* gq_mu, double* gq_sqrt, double* gmean_A, double* gmean_b, void* stream) {
     int rc = check_desc(d);
     if (rc != DGP_OK) return rc;
     if (!ws || !gZ || !gtheta || !gq_mu || !gq_sqrt) return DGP_ERR_ARG;
@@ -214,6 +223,10 @@ extern "C" int dgp_cond_backward_params(const dgp_cond_desc* d, void* ws, double
         k_gq_sqrt<<<dim3((d->M + 127) / 128, d->M, R), 128, 0, sb>>>(*d, Mpad, Tq, kl_weight, gq_sqrt); DGP_COUNT_LAUNCH();
         k_part_reduce<<<(w.npart + 127) / 128, 128, 0, sb>>>(part, w.ncta, w.npart, psum); DGP_COUNT_LAUNCH();
         k_gq_mu<<<(d->M * R + 127) / 128, 128, 0, sb>>>(*d, Mpad, Dp, psum, kl_weight, gq_mu); DGP_COUNT_LAUNCH();
+        if (gmean_A) {
+            const double* pm = psum + (size_t)Mpad * Dp + Mpad + (size_t)Mpad * R + (size_t)d->T * (2 + Dp);
+            k_gmean<<<((d->Dx + 1) * R + 127) / 128, 128, 0, sb>>>(*d, pm, gmean_A, gmean_b); DGP_COUNT_LAUNCH();
+        }
     }
     if (lane) cudaEventRecord(lane->join, sb);
     // ---- chain A:  T1 = Lm^T Lbar ; Phi ; T2 = Linv^T T1 ; T3 = T2 Linv

@@ -104,6 +104,8 @@ class DSDGP(Parameterized):
         self.check_status_every = 1
         # replay each evaluation of elbo_and_grad() as one CUDA graph (fixed minibatch shape; Philox noise only)
         self.use_cuda_graph = False
+        # under distribute(): capture the NCCL all-reduce inside the training-step graph (training.py)
+        self.graph_collectives = False
         self._graphs = {}
 
     # ------------------------------------------------------------------------------------------------ plumbing
@@ -225,7 +227,8 @@ class DSDGP(Parameterized):
         eng = self.engine
         if X is not None:
             self._step += 1
-            return eng.elbo(eng.params(), need_grad=True, **self._eval_kwargs(X, Y, eps, seed))
+            with torch.no_grad():
+                return eng.elbo(eng.native_params(), need_grad=True, **self._eval_kwargs(X, Y, eps, seed))
         kw, finish = self._staged_step(eps, seed)
         graph = kw.pop("_graph", None)
         if graph is not None:
@@ -233,7 +236,8 @@ class DSDGP(Parameterized):
             if kw.get("check"):
                 eng.check_status()
         else:
-            out = eng.elbo(eng.params(), need_grad=True, **kw)
+            with torch.no_grad():
+                out = eng.elbo(eng.native_params(), need_grad=True, **kw)
         finish()
         return out
 
@@ -253,6 +257,8 @@ class DSDGP(Parameterized):
         if self._dist is not None:
             dist, group = self._dist
             kw.update(world_size=dist.get_world_size(group), all_reduce=lambda t: dist.all_reduce(t, group=group))
+            if eps is not None:        # injected noise is given for the whole minibatch: this rank's rows of it
+                kw["eps"] = [torch.as_tensor(e)[:, lo:lo + xd.shape[0]] for e in eps]
         if self.use_cuda_graph and eps is None and seed is None:
             kw["_graph"] = self._graph_for(xd, yd, kw)
 
@@ -266,7 +272,7 @@ class DSDGP(Parameterized):
         from .engine import GraphedElbo
         eng = self.engine
         key = (tuple(xd.shape), tuple(yd.shape), kw["row_offset"], kw["global_batch"], kw.get("world_size", 1),
-               GraphedElbo.storage_key(eng))
+               self.num_samples, self.num_data, self.chunk_rows, self.seed, GraphedElbo.storage_key(eng))
         g = self._graphs.get(key)
         if g is None:
             # live parameters: the positive transforms are captured with the evaluation and read the model's own tensors

@@ -8,7 +8,6 @@ PyTorch is used for device memory, streams and (multi-GPU) the NCCL all-reduce o
 arithmetic step is a kernel of the extension.  There is no CPU / eager fallback.
 """
 import ctypes
-import os
 
 import numpy as np
 import torch
@@ -85,7 +84,10 @@ class _Cond:
         d.mean_b = mean_b.data_ptr() if mean_b is not None else None
 
     def ensure_ws(self, n_rows, need_bwd, device):
-        if self.ws is not None and self.ws_rows >= n_rows and (self.ws_bwd or not need_bwd):
+        # the forward layout does not depend on n_rows (only the backward pass keeps row-sized buffers in the workspace):
+        # any existing workspace serves a forward-only call, so a predict between two training steps never replaces the
+        # backward-capable workspace a captured CUDA graph may point into
+        if self.ws is not None and (not need_bwd or (self.ws_bwd and self.ws_rows >= n_rows)):
             return
         nbytes = _cabi.lib().dgp_cond_ws_bytes(ctypes.byref(self.desc), n_rows, 1 if need_bwd else 0)
         if nbytes == 0:
@@ -104,7 +106,7 @@ class Engine:
         _cabi.require_cuda()
         _cabi.lib()
         self.device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
-        self.gram_on_side_stream = os.environ.get("DGP_GRAM_MAIN_STREAM") is None
+        self.gram_on_side_stream = True     # bench.py turns it off to time the Gram kernels alone
         self.layers = list(layers)
         self.likelihood = likelihood
         self.multitask = bool(multitask)
@@ -114,6 +116,7 @@ class Engine:
             self.conds.append([_Cond(k, f, c0, R, layer, Dx) for (k, f, c0, R) in layer.conditionals()])
         self._rows = {}
         self._lik_ws = None
+        self._flat = None
         self.last_status = None
         self.timers = None         # set to {} to collect CUDA-event timings per kernel class (bench.py)
 
@@ -152,9 +155,18 @@ class Engine:
             out.extend(self.likelihood.parameters())
         return out
 
+    @staticmethod
+    def mean_trainable(layer):
+        """A Linear mean whose A or b is trainable: only an OutputLayer built with its own Linear mean (the reference
+        freezes the mean of Input / Hidden layers in initialize_forward, dgplib/layers.py:184-186, :202-204, but not of an
+        OutputLayer, :211-218)."""
+        mf = layer.mean_function
+        return isinstance(mf, Linear) and (mf.A.trainable or mf.b.trainable)
+
     def params(self):
         """Constrained, autograd-attached parameter tensors in the flat order used by the gradient buffer:
-        per layer [Z_c, theta_c for each conditional c] + [q_mu, q_sqrt]; then the likelihood variances."""
+        per layer [Z_c, theta_c for each conditional c] + [q_mu, q_sqrt] (+ [mean A, mean b] of a trainable Linear mean);
+        then the likelihood variances."""
         out = []
         for layer, conds in zip(self.layers, self.conds):
             for c in conds:
@@ -162,9 +174,28 @@ class Engine:
                 out.append(c.theta())
             out.append(layer.q_mu.constrained())
             out.append(layer.q_sqrt.constrained())
+            if self.mean_trainable(layer):
+                out.append(layer.mean_function.A.constrained())
+                out.append(layer.mean_function.b.constrained())
         if self.likelihood is not None:
             out.append(self._lik_variances())
         return out
+
+    def flatten(self):
+        """The model's parameters as one flat unconstrained buffer + transform / chain-rule tables (flatparams.py);
+        rebuilt when a parameter tensor was re-assigned or its trainable flag changed."""
+        from .flatparams import FlatParams
+        if self._flat is None or self._flat.key != FlatParams.storage_key(self):
+            with torch.cuda.device(self.device):
+                self._flat = FlatParams(self)
+        return self._flat
+
+    def native_params(self):
+        """params() without torch arithmetic: one dgp_transform_params launch on the current stream, then views of the
+        flat buffers (detached; what the non-autograd entry points and the captured graphs use)."""
+        flat = self.flatten()
+        flat.transform()
+        return flat.views()
 
     def _bind(self, params):
         """params: detached contiguous CUDA tensors in params() order."""
@@ -173,7 +204,9 @@ class Engine:
             zt = [(next(it), next(it)) for _ in conds]
             q_mu, q_sqrt = next(it), next(it)
             mA = mb = None
-            if isinstance(layer.mean_function, Linear):
+            if self.mean_trainable(layer):
+                mA, mb = next(it), next(it)
+            elif isinstance(layer.mean_function, Linear):
                 mA = _dev_tensor(layer.mean_function.A.constrained(), self.device)
                 mb = _dev_tensor(layer.mean_function.b.constrained(), self.device)
                 if mA.shape != (conds[0].desc.Dx, layer.output_dim):
@@ -457,15 +490,6 @@ class Engine:
         shard's first row in it, and `all_reduce(flat)` sums the flat buffer over ranks (NCCL).  The KL term enters
         with weight 1/world_size on every rank so the sum is exact."""
         lib, st = _cabi.lib(), _cabi.stream_ptr()
-        if need_grad:
-            for layer in self.layers:
-                mf = layer.mean_function
-                if isinstance(mf, Linear) and (mf.A.trainable or mf.b.trainable):
-                    # the reference freezes the Linear mean in initialize_forward (dgplib/layers.py:184-186); only an
-                    # OutputLayer built with its own Linear mean keeps it trainable -- there is no gradient kernel for it
-                    raise NotImplementedError("a trainable Linear mean function is not supported on the B200 path: call "
-                                              "mean_function.set_trainable(False), as the reference does for "
-                                              "Input/Hidden layers")
         with torch.no_grad():
             dev = self.device
             main = torch.cuda.current_stream()
@@ -481,7 +505,8 @@ class Engine:
             weight = (float(num_data) / float(Bg)) / float(S_lik)
             ncond = sum(len(c) for c in self.conds)
             offs, total = self.grad_layout(params)
-            flat = torch.zeros(total + ncond, dtype=_F64, device=dev)   # [elbo | grads | kl per conditional]
+            flat = torch.empty(total + ncond, dtype=_F64, device=dev)   # [elbo | grads | kl per conditional]
+            _cabi.check(lib.dgp_zero(ctypes.c_void_p(flat.data_ptr()), flat.numel() * 8, st), "dgp_zero")
             kl = flat[total:]
             Bc = B if not chunk_rows else max(1, min(B, int(chunk_rows)))
             events = self._prepare(S, Bc, need_grad, kl)
@@ -504,20 +529,25 @@ class Engine:
                     side.wait_event(done)
                     with torch.cuda.stream(side):
                         base = flat.data_ptr()
-                        o_mu, o_sqrt = self._q_offsets[l]
+                        o_mu, o_sqrt, o_mA, o_mb = self._q_offsets[l]
                         self._timed("params_bwd", lambda: _cabi.check(lib.dgp_cond_backward_params(
                             c.ref(), _cabi.ptr(c.ws), klw, ctypes.c_void_p(base + 8 * oZ), ctypes.c_void_p(base + 8 * oT),
-                            ctypes.c_void_p(base + 8 * o_mu), ctypes.c_void_p(base + 8 * o_sqrt), _cabi.stream_ptr()),
+                            ctypes.c_void_p(base + 8 * o_mu), ctypes.c_void_p(base + 8 * o_sqrt),
+                            ctypes.c_void_p(base + 8 * o_mA) if o_mA is not None else None,
+                            ctypes.c_void_p(base + 8 * o_mb) if o_mb is not None else None, _cabi.stream_ptr()),
                             "dgp_cond_backward_params"))
                         tail_events.append(side.record_event())
 
             # offsets of each layer's gradient slots
             it = iter(zip(params, offs))
             self._zt_offsets, self._q_offsets = [], []
-            for conds in self.conds:
+            for layer, conds in zip(self.layers, self.conds):
                 self._zt_offsets.append([(next(it), next(it)) for _ in conds])
                 (_, o_mu), (_, o_sqrt) = next(it), next(it)
-                self._q_offsets.append((o_mu, o_sqrt))
+                o_mA = o_mb = None
+                if self.mean_trainable(layer):
+                    (_, o_mA), (_, o_mb) = next(it), next(it)
+                self._q_offsets.append((o_mu, o_sqrt, o_mA, o_mb))
 
             nchunks = (B + Bc - 1) // Bc
             for ck, b0 in enumerate(range(0, B, Bc)):
@@ -569,7 +599,8 @@ class Engine:
                             _cabi.ptr(g_mean_in) if g_mean_in is not None else None,
                             _cabi.ptr(g_var_in) if g_var_in is not None else None,
                             _cabi.ptr(gF) if gF is not None else None, gF.shape[1] if gF is not None else 0,
-                            _cabi.ptr(buf["gX"][l]) if l > 0 else None, 1 if ci > 0 else 0, st), "dgp_cond_backward"))
+                            _cabi.ptr(buf["gX"][l]) if l > 0 else None, 1 if ci > 0 else 0,
+                            1 if self.mean_trainable(layer) else 0, st), "dgp_cond_backward"))
                         if nchunks == 1 and l > 0 and self.gram_on_side_stream:
                             # the Gram reduction of this layer is not needed by the next layer's backward kernel: on the
                             # conditional's side stream it fills the SMs that kernel's last, partly empty wave leaves idle
@@ -587,7 +618,8 @@ class Engine:
                         run_tail(l)
             for ev in tail_events:
                 main.wait_event(ev)
-            flat[0] -= klw * kl.sum()
+            _cabi.check(lib.dgp_finish_elbo(ctypes.c_void_p(flat.data_ptr()), ctypes.c_void_p(kl.data_ptr()), ncond, klw,
+                                            st), "dgp_finish_elbo")
             if all_reduce is not None and world_size > 1:
                 all_reduce(flat[:total])
             if check:
@@ -617,7 +649,9 @@ class GraphedElbo:
     @staticmethod
     def storage_key(engine):
         """Identity of the parameter storages a live-parameter graph reads (a re-assigned tensor needs a new capture)."""
-        return tuple(p.data_ptr() for p in engine.raw_parameters())
+        from .flatparams import FlatParams
+        engine.flatten()
+        return FlatParams.storage_key(engine)
 
     def _build(self, engine, params, X, Y, S, num_data, row_offset, global_batch, world_size, chunk_rows, need_grad,
                base_seed):
@@ -631,13 +665,14 @@ class GraphedElbo:
         self.Xs = _dev_tensor(X, dev).clone()
         self.Ys = _dev_tensor(Y, dev).clone()
         self.ps = None if self.live else [_dev_tensor(p, dev).clone() for p in params]
-        live_ps = lambda: [p.detach() for p in engine.params()]
-        self.seed_host = torch.zeros(1, dtype=torch.int64).pin_memory()
+        live_ps = engine.native_params        # one transform launch (captured), then views of the model's own storage
         self.seed_dev = torch.zeros(1, dtype=torch.int64, device=dev)
         self.base_seed = int(base_seed)
         kw = dict(S=S, eps=None, seed=base_seed, num_data=num_data, need_grad=need_grad, row_offset=row_offset,
                   global_batch=global_batch, world_size=world_size, all_reduce=None, chunk_rows=chunk_rows, check=False)
         cur = torch.cuda.current_stream()
+        if self.live:
+            engine.flatten()                               # build the tables (allocations, H2D copies) outside the capture
         warm = torch.cuda.Stream(device=dev)
         warm.wait_stream(cur)
         with torch.cuda.stream(warm):                      # allocate every cached buffer before capture
@@ -650,12 +685,14 @@ class GraphedElbo:
         engine._seed_dev = self.seed_dev
         try:
             with torch.cuda.graph(self.graph):
-                self.seed_dev.copy_(self.seed_host, non_blocking=True)
                 with torch.no_grad():
                     self.val, self.grads = engine.elbo(live_ps() if self.live else self.ps, self.Xs, self.Ys, **kw)
                 self.flat = engine._last_flat
         finally:
             engine._seed_dev = None
+        # the capture holds raw device pointers into the engine's workspaces and row buffers: keep them alive for as long
+        # as this graph lives, whatever the engine allocates (or drops from its caches) for later calls
+        self._pins = ([c.ws for conds in engine.conds for c in conds], dict(engine._rows), engine._lik_ws, engine._flat)
 
     def run(self, params, X, Y, seed, all_reduce=None):
         """Replay with the given parameters, minibatch and (full) Philox seed; returns views of static buffers."""
@@ -664,7 +701,11 @@ class GraphedElbo:
                 torch._foreach_copy_(self.ps, [p.detach() for p in params])
             self.Xs.copy_(X, non_blocking=True)
             self.Ys.copy_(Y, non_blocking=True)
-            self.seed_host[0] = (int(seed) - self.base_seed) & 0x7FFFFFFFFFFFFFFF   # added to base_seed on the device
+            # Philox seed offset (added to base_seed on the device): a stream-ordered device write in front of the replay,
+            # so that back-to-back replays each see their own seed
+            _cabi.check(_cabi.lib().dgp_set_u64(ctypes.c_void_p(self.seed_dev.data_ptr()),
+                                                (int(seed) - self.base_seed) & 0x7FFFFFFFFFFFFFFF, _cabi.stream_ptr()),
+                        "dgp_set_u64")
             self.graph.replay()
             if all_reduce is not None:
                 all_reduce(self.flat)

@@ -26,6 +26,14 @@ class Kernel(Parameterized):
         """List of per-task (kind, variance, white, lengthscales) tuples; one entry for a non-switched kernel."""
         return [self.stationary_parts()]
 
+    # -- the Param objects behind stationary_parts(): (variance Param, [White variance Params], lengthscales Param);
+    #    flatparams.py builds the transform / chain-rule tables of the native training step from them
+    def param_refs(self):
+        raise NotImplementedError(f"{type(self).__name__} is not supported by the B200 DSDGP path")
+
+    def task_param_refs(self):
+        return [self.param_refs()]
+
     @property
     def switched(self):
         return False
@@ -57,6 +65,9 @@ class Stationary(Kernel):
         ls = self.lengthscales.constrained()
         ls = ls.expand(self.input_dim) if ls.dim() == 0 else ls
         return (self.KIND, self.variance.constrained(), None, ls)
+
+    def param_refs(self):
+        return (self.variance, [], self.lengthscales)
 
 
 class RBF(Stationary):
@@ -97,6 +108,11 @@ class Sum(Combination):
         for k in white:
             w = k.variance.constrained() if w is None else w + k.variance.constrained()
         return (kind, var, w, ls)
+
+    def param_refs(self):
+        self.stationary_parts()      # raises for unsupported sums
+        stat = [k for k in self.kernels if isinstance(k, Stationary)][0]
+        return (stat.variance, [k.variance for k in self.kernels if isinstance(k, White)], stat.lengthscales)
 
     @property
     def input_dim_active(self):

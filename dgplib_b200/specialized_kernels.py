@@ -22,6 +22,9 @@ class SwitchedKernel(Combination):
     def task_kernels(self):
         return [k.stationary_parts() for k in self.kernels]
 
+    def task_param_refs(self):
+        return [k.param_refs() for k in self.kernels]
+
 
 def kuf(kernel, Z, X):
     """Kuf = k(Z, X) [M, N] (gpflow features.Kuf): CUDA, through dgp_kernel_K."""

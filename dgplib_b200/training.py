@@ -1,43 +1,50 @@
 """Training step around the hot path: the reference trains with
-`gpflow.train.AdamOptimizer(lr).minimize(model, maxiter=n)` (tests/test_dsdgp.py:56-60, notebooks cell 16), i.e. Adam on the
-unconstrained variables of -ELBO, one minibatch per step.  Here the ELBO + gradient of every step is one fused evaluation
-(`DSDGP._build_likelihood`, a single autograd node), the softplus chain runs in torch, and the update is torch's fused
-multi-tensor Adam.  With `model.use_cuda_graph` on one GPU the WHOLE step -- positive transforms, the fused evaluation,
-the chain rule back to the unconstrained variables and the Adam update -- is captured once as a CUDA graph and replayed
-per minibatch (`GraphedTrainStep`), which removes the ~60 small launches around the evaluation from every step."""
+`gpflow.train.AdamOptimizer(lr).minimize(model, maxiter=n)` (tests/test_dsdgp.py:56-60, notebooks cell 16), i.e.
+tf.train.AdamOptimizer on the unconstrained variables of -ELBO, one minibatch per step.
+
+Here a step is a handful of launches of the extension and nothing else: `dgp_transform_params` (Log1pe transforms of the
+hyper-parameters), the fused ELBO + gradient evaluation, and `dgp_adam_step` (softplus chain factor + TF's Adam update on
+the flat unconstrained buffer, csrc/optim.cu).  With `model.use_cuda_graph` the whole step is captured once per minibatch
+shape and replayed with one launch (`GraphedTrainStep`); under `model.distribute()` the flat gradient buffer is
+all-reduced between the evaluation and the update, so every rank takes the same step."""
+import ctypes
+
 import torch
 
-from .engine import elbo_autograd
+from . import _cabi
 
 
 class GraphedTrainStep:
-    """One Adam step on -ELBO as a CUDA graph (fixed minibatch shape, Philox noise, one GPU).
+    """One Adam step on -ELBO as a CUDA graph (fixed minibatch shape, Philox noise).
 
     Static inputs: the minibatch (copied from the model's staged device buffers before each replay) and the per-step
-    Philox seed offset (added on the device).  Parameters and the optimiser state are updated in place by the replay.
-    The three eager warm-up steps PyTorch needs before a capture are undone (parameters restored, Adam state zeroed), so a
-    captured run takes exactly the steps an eager run takes."""
+    Philox seed offset (a stream-ordered device write in front of the replay).  Parameters and the optimiser state are
+    updated in place by the replay.  The eager warm-up steps a capture needs are undone completely: parameters, both Adam
+    moments and the step counter are snapshotted before and restored after, so a captured run takes exactly the steps an
+    eager run takes, whatever state the optimiser was in when the graph was built."""
 
-    def __init__(self, model, opt, X, Y):
+    def __init__(self, model, opt, X, Y, kw):
         with torch.cuda.device(model.engine.device):
-            self._build(model, opt, X, Y)
+            self._build(model, opt, X, Y, kw)
 
-    def _build(self, model, opt, X, Y):
+    def _build(self, model, opt, X, Y, kw):
         eng = model.engine
         dev = eng.device
         self.model, self.eng, self.opt = model, eng, opt
         self.Xs, self.Ys = X.clone(), Y.clone()
-        self.seed_host = torch.zeros(1, dtype=torch.int64).pin_memory()
         self.seed_dev = torch.zeros(1, dtype=torch.int64, device=dev)
         self.base_seed = int(model.seed)
-        self.key = (tuple(X.shape), tuple(Y.shape))
-        params = [p for group in opt.param_groups for p in group["params"]]
-        saved = [p.detach().clone() for p in params]
+        self.kw = dict(S=model.num_samples, eps=None, seed=self.base_seed, num_data=model.num_data,
+                       chunk_rows=model.chunk_rows, row_offset=kw.get("row_offset", 0),
+                       global_batch=kw.get("global_batch", X.shape[0]), world_size=kw.get("world_size", 1),
+                       all_reduce=kw.get("all_reduce"), check=False)
+        flat, st = eng.flatten(), opt._state_for(eng)
+        saved = [flat.u.clone(), st["m"].clone(), st["v"].clone(), st["step"].clone()]
         cur = torch.cuda.current_stream()
         warm = torch.cuda.Stream(device=dev)
         warm.wait_stream(cur)
         with torch.cuda.stream(warm):
-            for _ in range(3):
+            for _ in range(2):
                 self._step_body()
         cur.wait_stream(warm)
         torch.cuda.synchronize(dev)
@@ -45,26 +52,20 @@ class GraphedTrainStep:
         eng._seed_dev = self.seed_dev
         try:
             with torch.cuda.graph(self.graph):
-                self.seed_dev.copy_(self.seed_host, non_blocking=True)
                 self.elbo = self._step_body()
         finally:
             eng._seed_dev = None
         with torch.no_grad():                                   # undo the warm-up steps
-            torch._foreach_copy_(params, saved)
-            for state in opt.state.values():
-                for v in state.values():
-                    if torch.is_tensor(v):
-                        v.zero_()
+            for dst, src in zip([flat.u, st["m"], st["v"], st["step"]], saved):
+                dst.copy_(src)
+        self._pins = ([c.ws for conds in eng.conds for c in conds], dict(eng._rows), eng._lik_ws, flat, st)
 
     def _step_body(self):
-        m = self.model
-        self.opt.zero_grad(set_to_none=True)
-        elbo = elbo_autograd(self.eng, X=self.Xs, Y=self.Ys, S=m.num_samples, eps=None, seed=self.base_seed,
-                             num_data=m.num_data, chunk_rows=m.chunk_rows, row_offset=0, global_batch=self.Xs.shape[0],
-                             check=False)
-        (-elbo).backward()
-        self.opt.step()
-        return elbo.detach()
+        eng = self.eng
+        with torch.no_grad():
+            val, _ = eng.elbo(eng.native_params(), self.Xs, self.Ys, need_grad=True, **self.kw)
+            self.opt._apply(eng)
+        return val
 
     def run(self, X, Y, seed):
         """One training step on the staged minibatch (X, Y device tensors) with the given full Philox seed; returns the
@@ -72,66 +73,75 @@ class GraphedTrainStep:
         with torch.cuda.device(self.eng.device):
             self.Xs.copy_(X, non_blocking=True)
             self.Ys.copy_(Y, non_blocking=True)
-            self.seed_host[0] = (int(seed) - self.base_seed) & 0x7FFFFFFFFFFFFFFF     # added to base_seed on the device
+            _cabi.check(_cabi.lib().dgp_set_u64(ctypes.c_void_p(self.seed_dev.data_ptr()),
+                                                (int(seed) - self.base_seed) & 0x7FFFFFFFFFFFFFFF, _cabi.stream_ptr()),
+                        "dgp_set_u64")
             self.graph.replay()
         return self.elbo
 
 
 class AdamOptimizer:
-    """gpflow.train.AdamOptimizer stand-in: `AdamOptimizer(0.01).minimize(model, maxiter=100)`."""
+    """gpflow.train.AdamOptimizer stand-in: `AdamOptimizer(0.01).minimize(model, maxiter=100)`.  The update rule is
+    tf.train.AdamOptimizer's (lr_t = lr sqrt(1 - beta2^t) / (1 - beta1^t); u -= lr_t m / (sqrt(v) + epsilon)), applied to
+    the unconstrained variables by one kernel launch over the model's flat parameter buffer."""
 
     def __init__(self, learning_rate=0.001, beta1=0.9, beta2=0.999, epsilon=1e-8):
-        self.lr, self.betas, self.eps = learning_rate, (beta1, beta2), epsilon
-        self._opt = None
-        self._model = None
+        self.lr, self.betas, self.eps = float(learning_rate), (float(beta1), float(beta2)), float(epsilon)
+        self._state = None
         self._graphs = {}
 
-    def _graphable(self, model):
-        return bool(model.use_cuda_graph) and model._dist is None
-
-    def _optimizer(self, model):
-        if self._opt is None or self._model is not model:
-            model.engine            # compile: parameters live on the GPU from here on
-            params = model.trainable_parameters()
-            # capturable always: the step counter lives on the device, so model.use_cuda_graph may be switched on
-            # between two minimize() calls without losing the optimiser state
-            self._opt = torch.optim.Adam(params, lr=self.lr, betas=self.betas, eps=self.eps, fused=True, capturable=True)
-            self._model = model
+    def _state_for(self, eng):
+        """Adam moments + step counter (device) for the engine's flat buffer; created on first use and whenever the flat
+        buffer was rebuilt (a parameter re-assigned or its trainable flag changed)."""
+        flat = eng.flatten()
+        if self._state is None or self._state["key"] != flat.key:
+            self._state = flat.new_adam_state()
             self._graphs = {}
-        return self._opt
+        return self._state
 
-    def _graphed_step(self, model, opt):
+    def _apply(self, eng):
+        """The update from the evaluation that just ran (its flat [elbo | gradients] buffer, already all-reduced)."""
+        flat = eng.flatten()
+        flat.adam_step(self._state_for(eng), eng._last_flat, self.lr, self.betas[0], self.betas[1], self.eps)
+
+    def _graphed_step(self, model):
         kw, finish = model._staged_step(None, None)
         kw.pop("_graph", None)
         X, Y = kw["X"], kw["Y"]
-        key = (tuple(X.shape), tuple(Y.shape))
+        eng = model.engine
+        self._state_for(eng)
+        key = (tuple(X.shape), tuple(Y.shape), kw.get("row_offset", 0), kw.get("global_batch"), kw.get("world_size", 1),
+               model.num_samples, model.num_data, model.chunk_rows, model.seed, eng.flatten().key)
         g = self._graphs.get(key)
         if g is None:
-            g = self._graphs[key] = GraphedTrainStep(model, opt, X, Y)
+            g = self._graphs[key] = GraphedTrainStep(model, self, X, Y, kw)
         elbo = g.run(X, Y, kw["seed"]).clone()
         if kw.get("check"):
-            model.engine.check_status()
+            eng.check_status()
         finish()
         return elbo
 
+    def _eager_step(self, model):
+        kw, finish = model._staged_step(None, None)
+        kw.pop("_graph", None)
+        eng = model.engine
+        with torch.no_grad():
+            val, _ = eng.elbo(eng.native_params(), need_grad=True, **kw)
+            self._apply(eng)
+        finish()
+        return val.clone()
+
     def minimize(self, model, maxiter=1000, callback=None):
         """Run `maxiter` Adam steps on -ELBO; returns the list of per-step ELBO values (CUDA scalars, read lazily)."""
-        opt = self._optimizer(model)
+        eng = model.engine
         history = []
-        with torch.cuda.device(model.engine.device):
-            self._loop(model, opt, int(maxiter), callback, history)
+        with torch.cuda.device(eng.device):
+            self._state_for(eng)
+            # NCCL collectives are captured with the step when the process group allows it (model.graph_collectives)
+            graphable = bool(model.use_cuda_graph) and (model._dist is None or getattr(model, "graph_collectives", False))
+            for it in range(int(maxiter)):
+                elbo = self._graphed_step(model) if graphable else self._eager_step(model)
+                history.append(elbo)
+                if callback is not None:
+                    callback(it, elbo)
         return history
-
-    def _loop(self, model, opt, maxiter, callback, history):
-        for it in range(maxiter):
-            if self._graphable(model):
-                elbo = self._graphed_step(model, opt)
-            else:
-                opt.zero_grad(set_to_none=True)
-                elbo = model._build_likelihood()
-                (-elbo).backward()
-                opt.step()
-                elbo = elbo.detach()
-            history.append(elbo)
-            if callback is not None:
-                callback(it, elbo)

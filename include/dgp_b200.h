@@ -139,6 +139,8 @@ size_t dgp_lik_ws_bytes(int64_t n_rows, int32_t R);
  *             g_mean = g_mean_in + g_F,  g_var = g_var_in + g_F * (F - mean) / (2 var)
  *   A_save, U_save  what dgp_cond_forward kept for these rows
  *   gX        [n_rows, Dx] gradient w.r.t. the input rows (NULL for the data layer); accumulate != 0 adds to it
+ *   mean_grad != 0: the Linear mean (d->mean_A, d->mean_b) is trainable -- an OutputLayer built with its own Linear mean,
+ *             which dgplib/layers.py:211-218 does not freeze: also accumulate dA = X^T g_mean, db = sum_n g_mean
  * dgp_cond_backward leaves dKuf and the combined g_mean / g_var in the workspace; dgp_cond_backward_gram (call it next,
  * same n_rows / A_save) reduces them over the rows into the Gram accumulators G_r = sum_n g_var[n,r] a_n a_n^T and
  * P = sum_n dKuf_n a_n^T.  Row-summed parameter gradients are accumulated inside the workspace (several row chunks
@@ -147,14 +149,15 @@ size_t dgp_lik_ws_bytes(int64_t n_rows, int32_t R);
 int dgp_cond_backward(const dgp_cond_desc* d, void* ws, const double* X, int64_t x_rows, int64_t n_rows,
                       const double* A_save, const double* U_save, const double* mean, const double* var, const double* F,
                       int32_t ldf, const double* g_mean_in, const double* g_var_in, const double* g_F, int32_t ldgf,
-                      double* gX, int32_t accumulate_gX, void* stream);
+                      double* gX, int32_t accumulate_gX, int32_t mean_grad, void* stream);
 int dgp_cond_backward_gram(const dgp_cond_desc* d, void* ws, const double* A_save, int64_t n_rows, int32_t accumulate,
                            void* stream);   /* accumulate: 0 for the first row chunk after dgp_cond_prepare, 1 after */
 /* Parameter-only tail: Cholesky / Kuu / KL reverse mode.  Outputs (device, this conditional's part OVERWRITTEN):
- *   gZ [M, Dx], gtheta [T, 2+D], gq_mu [M, ldr] (columns col0..), gq_sqrt [ldr, M, M] (rows col0..)
+ *   gZ [M, Dx], gtheta [T, 2+D], gq_mu [M, ldr] (columns col0..), gq_sqrt [ldr, M, M] (rows col0..),
+ *   gmean_A [Dx, ldr], gmean_b [ldr] (columns col0..; NULL unless dgp_cond_backward ran with mean_grad)
  *   kl_weight: this rank's share of the KL term (1/world_size) so that an all-reduce(sum) over ranks is exact */
 int dgp_cond_backward_params(const dgp_cond_desc* d, void* ws, double kl_weight, double* gZ, double* gtheta,
-                             double* gq_mu, double* gq_sqrt, void* stream);
+                             double* gq_mu, double* gq_sqrt, double* gmean_A, double* gmean_b, void* stream);
 
 /* ---- full-covariance branch (small N: plots, posterior draws) ---------------------------------------------------
  * dgp_cond_fullcov replaces base_conditional(full_cov=True) as called from dgplib/layers.py:74-81:
@@ -184,6 +187,30 @@ int dgp_chol_sample(const double* var, int64_t stride_b, int64_t stride_i, int64
 size_t dgp_pca_ws_bytes(int64_t n_rows, int32_t D);
 int dgp_pca_weights(const double* X, int64_t n_rows, int32_t ldx, int32_t D, int32_t R, void* ws, size_t ws_bytes,
                     double* W, double* sing, void* stream);
+
+/* ---- training step around the evaluation ------------------------------------------------------
+ * The reference trains with gpflow.train.AdamOptimizer(lr).minimize(model, maxiter) (tests/test_dsdgp.py:56-60): TF's Adam
+ * on the unconstrained variables of -ELBO, positive parameters through gpflow's Log1pe transform softplus(u) + 1e-6.
+ * All of a model's unconstrained parameters live in one flat buffer u [n] (device).
+ * dgp_transform_params: the composite constrained arrays the kernels read (per conditional theta [T, 2+D], likelihood
+ *   variances) as c[i] = sum_{e in crow[i] .. crow[i+1]} (cpos[e] ? softplus(u[cidx[e]]) + lower : u[cidx[e]]).
+ * dgp_adam_step: for every trainable element j (flags bit 1; bit 0: positive transform)
+ *   g = -(gidx[j] >= 0 ? grad[gidx[j]] : sum_{e in grow[r] .. grow[r+1]} grad[gimg[e]], r = -2 - gidx[j]; -1: none)
+ *       * (positive ? sigmoid(u[j]) : 1);   t = *step_dev + 1;   lr_t = lr sqrt(1 - beta2^t) / (1 - beta1^t)
+ *   m = beta1 m + (1 - beta1) g;  v = beta2 v + (1 - beta2) g^2;  u -= lr_t m / (sqrt(v) + eps)      (tf.train.AdamOptimizer)
+ *   then *step_dev += 1 (device counter: the launch pair can be replayed from a CUDA graph).  grad is the flat
+ *   [elbo | gradients] buffer the evaluation filled (dgp_cond_backward_params / dgp_lik_gaussian outputs).
+ * dgp_set_u64: stream-ordered device write of one 64-bit word (the Philox seed offset of a graph replay). */
+int dgp_transform_params(const double* u, const int32_t* crow, const int32_t* cidx, const uint8_t* cpos, int32_t n_c,
+                         double lower, double* c, void* stream);
+int dgp_adam_step(double* u, double* m, double* v, int64_t n, const double* grad, const int32_t* gidx,
+                  const int32_t* grow, const int32_t* gimg, const uint8_t* flags, double lr, double beta1, double beta2,
+                  double eps, int64_t* step_dev, void* stream);
+int dgp_set_u64(uint64_t* dst, uint64_t value, void* stream);
+/* closes an evaluation (dgplib/dsdgp.py:124-130): *elbo -= kl_weight * sum_c kl[c] over the ncond per-conditional KL terms
+ * dgp_cond_prepare wrote (summed in index order); dgp_zero: cudaMemsetAsync of the flat [elbo | gradients | kl] buffer */
+int dgp_finish_elbo(double* elbo, const double* kl, int32_t ncond, double kl_weight, void* stream);
+int dgp_zero(void* dst, size_t bytes, void* stream);
 
 /* ---- stand-alone kernel-matrix entry points (dgplib_b200.specialized_kernels; gpflow Kernel.K / Kdiag) -------
  *   K [n1, n2] = k(X1, X2) (White contributes nothing, as in gpflow when X2 is given);  symmetric != 0 computes

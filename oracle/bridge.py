@@ -33,7 +33,8 @@ def oracle_layers(model_layers):
             groups.append({"kernel": oracle_kernel(k), "Z": zcache[id(f)]})
         mean = None
         if type(layer.mean_function).__name__ == "Linear":
-            mean = {"A": t(layer.mean_function.A.value), "b": t(layer.mean_function.b.value)}
+            mf = layer.mean_function
+            mean = {"A": t(mf.A.value), "b": t(mf.b.value), "trainable": bool(mf.A.trainable or mf.b.trainable)}
         out.append({"groups": groups, "q_mu": t(layer.q_mu.value), "q_sqrt": t(layer.q_sqrt.value), "mean": mean})
     return out
 

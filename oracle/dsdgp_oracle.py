@@ -359,6 +359,11 @@ def leaves(layers, lik):
             kern_leaves(f"l{l}.g{g}.kern", grp["kernel"])
         out[f"l{l}.q_mu"] = layer["q_mu"]
         out[f"l{l}.q_sqrt"] = layer["q_sqrt"]
+        if layer.get("mean") is not None and layer["mean"].get("trainable"):
+            # only an OutputLayer built with its own Linear mean keeps it trainable (dgplib/layers.py:211-218 does not
+            # freeze it, unlike :184-186 and :202-204)
+            out[f"l{l}.mean.A"] = layer["mean"]["A"]
+            out[f"l{l}.mean.b"] = layer["mean"]["b"]
     if lik["kind"] == "gaussian":
         out["lik.variance"] = lik["variance"]
     else:

@@ -82,6 +82,10 @@ def oracle_grads_by_param(model, glist):
             out[f"l{l}.g{g}.theta"] = next(it)
         out[f"l{l}.q_mu"] = next(it)
         out[f"l{l}.q_sqrt"] = next(it)
+        mf = layer.mean_function
+        if type(mf).__name__ == "Linear" and (mf.A.trainable or mf.b.trainable):
+            out[f"l{l}.mean.A"] = next(it)
+            out[f"l{l}.mean.b"] = next(it)
     out["lik"] = next(it)
     return out
 

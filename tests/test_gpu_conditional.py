@@ -19,7 +19,7 @@ def rel(a, b):
     return float((a.detach().cpu() - b).abs().max() / max(float(b.abs().max()), 1e-300))
 
 
-def run_conditional(cuda, M, D, R, N, kind, S=1, white=1e-5, linear=True, backward=True, seed=0):
+def run_conditional(cuda, M, D, R, N, kind, S=1, white=1e-5, linear=True, backward=True, seed=0, mean_grad=False, lib=None):
     rng = np.random.RandomState(seed)
     X = torch.tensor(rng.randn(N, D))
     Z = torch.tensor(rng.randn(M, D))
@@ -36,7 +36,7 @@ def run_conditional(cuda, M, D, R, N, kind, S=1, white=1e-5, linear=True, backwa
     kern = {"kind": kind, "input_dim": D, "variance": var, "lengthscales": ls, "white": wh}
     layer = {"groups": [{"kernel": kern, "Z": Z}], "q_mu": q_mu, "q_sqrt": q_sqrt,
              "mean": {"A": A, "b": b} if linear else None}
-    leaves = [X, Z, var, ls, wh, q_mu, q_sqrt]
+    leaves = [X, Z, var, ls, wh, q_mu, q_sqrt] + ([A, b] if mean_grad else [])
     for p in leaves:
         p.requires_grad_(True)
     Xt = X[None].repeat(S, 1, 1)
@@ -47,11 +47,11 @@ def run_conditional(cuda, M, D, R, N, kind, S=1, white=1e-5, linear=True, backwa
     ref = None
     if backward:
         obj = (gm_in * m_ref).sum() + (gv_in * v_ref).sum() + (gF * F_ref).sum() - kl_ref
-        ref = dict(zip(["X", "Z", "var", "ls", "wh", "q_mu", "q_sqrt"], torch.autograd.grad(obj, leaves)))
+        ref = dict(zip(["X", "Z", "var", "ls", "wh", "q_mu", "q_sqrt", "mA", "mb"], torch.autograd.grad(obj, leaves)))
     for p in leaves:
         p.requires_grad_(False)
 
-    lib = C.lib()
+    lib = lib or C.lib()
     d = C.CondDesc()
     d.M, d.D, d.Dx, d.R, d.ldr, d.col0, d.T = M, D, D, R, R, 0, 1
     d.kind[0] = 0 if kind == "rbf" else 1
@@ -95,18 +95,22 @@ def run_conditional(cuda, M, D, R, N, kind, S=1, white=1e-5, linear=True, backwa
         gmd, gvd, gFd = gm_in.to(dev), gv_in.to(dev), gF.to(dev)   # keep the device copies alive across the call
         C.check(lib.dgp_cond_backward(ctypes.byref(d), C.ptr(ws), C.ptr(Xrep), n, n, C.ptr(Asave), C.ptr(Usave), C.ptr(mean),
                                       C.ptr(varo), C.ptr(F), R, C.ptr(gmd), C.ptr(gvd), C.ptr(gFd), R, C.ptr(gX), 0,
-                                      st), "backward")
+                                      1 if mean_grad else 0, st), "backward")
         C.check(lib.dgp_cond_backward_gram(ctypes.byref(d), C.ptr(ws), C.ptr(Asave), n, 0, st), "gram")
         gZ = torch.zeros(M, D, dtype=torch.float64, device=dev)
         gth = torch.zeros(2 + D, dtype=torch.float64, device=dev)
         gqm = torch.zeros(M, R, dtype=torch.float64, device=dev)
         gqs = torch.full((R, M, M), float("nan"), dtype=torch.float64, device=dev)
+        gmA = torch.full((D, R), float("nan"), dtype=torch.float64, device=dev) if mean_grad else None
+        gmb = torch.full((R,), float("nan"), dtype=torch.float64, device=dev) if mean_grad else None
         C.check(lib.dgp_cond_backward_params(ctypes.byref(d), C.ptr(ws), 1.0, C.ptr(gZ), C.ptr(gth), C.ptr(gqm),
-                                             C.ptr(gqs), st), "params")
+                                             C.ptr(gqs), C.ptr(gmA), C.ptr(gmb), st), "params")
         torch.cuda.synchronize()
         errs.update({"gX": rel(gX.reshape(S, N, D).sum(0), ref["X"]), "gZ": rel(gZ, ref["Z"]),
                      "gvar": rel(gth[0:1], ref["var"].reshape(1)), "gwhite": rel(gth[1:2], ref["wh"].reshape(1)),
                      "gls": rel(gth[2:], ref["ls"]), "gq_mu": rel(gqm, ref["q_mu"]), "gq_sqrt": rel(gqs, ref["q_sqrt"])})
+        if mean_grad:
+            errs.update({"gmean_A": rel(gmA, ref["mA"]), "gmean_b": rel(gmb, ref["mb"])})
         assert float(torch.triu(gqs, 1).abs().max()) == 0.0  # band_part: zero gradient above the diagonal
     return errs
 
@@ -158,6 +162,37 @@ def test_production_tile_variants_match_oracle(cuda, M, D, R, N, kind, S):
     errs = run_conditional(cuda, M, D, R, N, kind, S=S)
     bad = {k: v for k, v in errs.items() if not v < TOL}
     assert not bad, (bad, errs)
+
+
+# every row-tile instantiation of the forward and backward kernels, pinned through the test-hook build (the product
+# library picks the width from the shape and the row count): (forward NT, backward NT, M, D, R, N)
+FORCED = [
+    (72, 72, 256, 8, 8, 700), (72, 72, 128, 8, 1, 333),
+    (64, 64, 256, 8, 8, 700), (64, 64, 200, 5, 16, 130),
+    (32, 32, 256, 8, 8, 700), (32, 32, 500, 16, 16, 200), (32, 32, 64, 3, 2, 100),
+    (16, 16, 1024, 8, 2, 100), (16, 16, 500, 16, 4, 90), (16, 16, 100, 4, 3, 50),
+    (16, 8, 1024, 8, 8, 40), (32, 8, 300, 6, 5, 70),
+]
+
+
+@pytest.mark.parametrize("fnt,bnt,M,D,R,N", FORCED)
+def test_every_tile_instantiation_matches_oracle(cuda, hooked_lib, fnt, bnt, M, D, R, N):
+    hooked_lib.dgp_test_force_tiles(fnt, bnt)
+    try:
+        errs = run_conditional(cuda, M, D, R, N, "rbf" if M % 3 else "matern52", lib=hooked_lib)
+    finally:
+        hooked_lib.dgp_test_force_tiles(0, 0)
+    bad = {k: v for k, v in errs.items() if not v < TOL}
+    assert not bad, (bad, errs)
+
+
+def test_trainable_linear_mean_gradient(cuda):
+    """A Linear mean left trainable (an OutputLayer built with its own Linear mean, dgplib/layers.py:211-218): dA = X^T g_mean,
+    db = sum g_mean through the per-CTA partials, for a sample-tiled input and ragged tiles."""
+    for (M, D, R, N, kind, S) in [(40, 3, 2, 333, "rbf", 2), (256, 8, 8, 2050, "matern52", 1), (64, 5, 1, 100, "rbf", 1)]:
+        errs = run_conditional(cuda, M, D, R, N, kind, S=S, mean_grad=True)
+        bad = {k: v for k, v in errs.items() if not v < TOL}
+        assert not bad, (bad, errs)
 
 
 def test_forward_only_large_M(cuda):
@@ -246,7 +281,7 @@ def test_ragged_tiles_do_not_write_out_of_bounds(cuda):
                                  C.ptr(F), R, C.ptr(A), C.ptr(U), st), "forward")
     gm, gv = t(rng.randn(N, R)), t(rng.randn(N, R))
     C.check(lib.dgp_cond_backward(ctypes.byref(d), C.ptr(ws), C.ptr(X), N, N, C.ptr(A), C.ptr(U), C.ptr(mean), C.ptr(var), None, R,
-                                  C.ptr(gm), C.ptr(gv), None, 0, C.ptr(gX), 0, st), "backward")
+                                  C.ptr(gm), C.ptr(gv), None, 0, C.ptr(gX), 0, 0, st), "backward")
     C.check(lib.dgp_cond_backward_gram(ctypes.byref(d), C.ptr(ws), C.ptr(A), N, 0, st), "gram")
     torch.cuda.synchronize()
     assert bool((U[nU:] == SENT).all()) and bool(torch.isfinite(U[:nU]).all()) and not bool((U[:nU] == SENT).any()), "U"
@@ -277,5 +312,5 @@ def test_empty_and_unsupported_inputs(cuda):
     d.M = 1025
     assert lib.dgp_cond_ws_bytes(ctypes.byref(d), 8, 1) == 0
     assert lib.dgp_cond_backward(ctypes.byref(d), C.ptr(ws), C.ptr(one), 1, 1, C.ptr(one), C.ptr(one), C.ptr(one), C.ptr(one), None, 1,
-                                 C.ptr(one), C.ptr(one), None, 0, None, 0, C.stream_ptr()) == -4
+                                 C.ptr(one), C.ptr(one), None, 0, None, 0, 0, C.stream_ptr()) == -4
     torch.cuda.synchronize()

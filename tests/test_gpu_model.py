@@ -52,6 +52,9 @@ def compare_elbo_and_grads(model, X, Y, S, multitask=False, tol=TOL):
                 errs[pre + ".ls"] = rel_err(th[tk, 2:].sum() if ols.dim() == 0 else th[tk, 2:], ols)
         for zkey, gz in seen.values():
             errs[zkey] = rel_err(gz, og[zkey])
+        for nm in ("A", "b"):
+            if f"l{l}.mean.{nm}" in og:
+                errs[f"l{l}.mean.{nm}"] = rel_err(gp[f"l{l}.mean.{nm}"], og[f"l{l}.mean.{nm}"])
     lik_g = gp["lik"].cpu()
     if olik["kind"] == "gaussian":
         errs["lik"] = rel_err(lik_g[0], og["lik.variance"])
@@ -463,7 +466,7 @@ def test_adam_optimizer_api_and_moment_matched_prediction(cuda):
     model, X, Y = build_dsdgp(L=2, M=20, D=2, N=200, S=4, minibatch=50)
     model.compile()
     Xd, Yd = torch.from_numpy(X), torch.from_numpy(Y)
-    fixed = lambda: float(model.engine.elbo(model.engine.params(), Xd, Yd, 4, seed=1, num_data=200, need_grad=False)[0])
+    fixed = lambda: float(model.engine.elbo(model.engine.native_params(), Xd, Yd, 4, seed=1, num_data=200, need_grad=False)[0])
     before = fixed()
     hist = AdamOptimizer(0.01).minimize(model, maxiter=60)
     after = fixed()
@@ -524,6 +527,118 @@ def test_graphed_training_step_matches_eager(cuda):
         assert float((a - b).abs().max()) <= 1e-12 * max(1.0, float(a.abs().max()))
 
 
+def _tf_adam_reference_trajectory(model_kwargs, steps, lr, seed0):
+    """The reference's training loop restated on the host: oracle ELBO + autograd gradients w.r.t. the constrained
+    parameters, gpflow's Log1pe chain factor, tf.train.AdamOptimizer's update on the unconstrained variables (NumPy), with
+    the very noise draws the kernels make (Philox, extracted through dgp_philox_normal).  Returns (elbo history, model)."""
+    import ctypes
+    from dgplib_b200 import _cabi as C
+    ref, X, Y = build_dsdgp(**model_kwargs)          # parameter container of the reference trajectory (never compiled)
+    N, S = X.shape[0], ref.num_samples
+    layers = ref.layers.layers
+    targets = {}                                      # oracle leaf name -> [Param, ...]
+    for l, layer in enumerate(layers):
+        for g, (k, f, c0, R) in enumerate(layer.conditionals()):
+            targets[f"l{l}.g{g}.Z"] = [f.Z]
+            (var, whites, ls), = k.task_param_refs()
+            targets[f"l{l}.g{g}.kern.variance"] = [var]
+            targets[f"l{l}.g{g}.kern.lengthscales"] = [ls]
+            targets[f"l{l}.g{g}.kern.white"] = whites
+        targets[f"l{l}.q_mu"], targets[f"l{l}.q_sqrt"] = [layer.q_mu], [layer.q_sqrt]
+    targets["lik.variance"] = [ref.likelihood.variance]
+    state = {}
+    b1, b2, eps_hat = 0.9, 0.999, 1e-8
+    hist = []
+    lib = C.lib()
+    eng_seed = lambda seed, l: (seed + 0x9E3779B97F4A7C15 * (l + 1)) & 0xFFFFFFFFFFFFFFFF
+    for k in range(steps):
+        seed = seed0 + k + 1                          # DSDGP._staged_step: self._step += 1; seed = self.seed + self._step
+        eps = []
+        for l, layer in enumerate(layers):
+            z = torch.empty(S * N, layer.output_dim, dtype=torch.float64, device="cuda")
+            C.check(lib.dgp_philox_normal(C.ptr(z), S * N, layer.output_dim, layer.output_dim, eng_seed(seed, l), 0, N, N,
+                                          C.stream_ptr()), "philox")
+            eps.append(z.cpu().reshape(S, N, -1))
+        val, og = O.elbo_and_grad(oracle_layers(layers), oracle_lik(ref.likelihood), t(X), t(Y), S, eps, num_data=N)
+        hist.append(float(val))
+        tt = k + 1
+        lr_t = lr * np.sqrt(1.0 - b2 ** tt) / (1.0 - b1 ** tt)
+        for name, params in targets.items():
+            for p in params:
+                u = p.raw.detach().numpy().astype(np.float64)
+                g = np.broadcast_to(og[name].numpy(), u.shape).copy() if og[name].numel() == u.size else \
+                    np.full(u.shape, float(og[name].sum()))
+                if p.positive:
+                    g = g / (1.0 + np.exp(-u))            # d softplus(u) / du
+                g = -g                                     # minimise -ELBO
+                m, v = state.get(id(p), (np.zeros_like(u), np.zeros_like(u)))
+                m = b1 * m + (1 - b1) * g
+                v = b2 * v + (1 - b2) * g * g
+                state[id(p)] = (m, v)
+                with torch.no_grad():
+                    p.raw.copy_(torch.from_numpy(np.asarray(u - lr_t * m / (np.sqrt(v) + eps_hat))).reshape(p.raw.shape))
+    return hist, ref
+
+
+@pytest.mark.parametrize("graph", [False, True])
+def test_adam_trajectory_matches_oracle_reference(cuda, graph):
+    """f1 parity: `AdamOptimizer(lr).minimize(model, maxiter)` (reference tests/test_dsdgp.py:56-60) against the reference
+    loop restated on the host (oracle gradients + NumPy tf.train.AdamOptimizer): the ELBO history of 10 steps and every
+    parameter after them, eager and as a replayed CUDA graph."""
+    from dgplib_b200.training import AdamOptimizer
+    kw = dict(L=2, M=16, D=2, N=60, S=2)
+    model, X, Y = build_dsdgp(**kw)
+    model.compile()
+    model.use_cuda_graph = graph
+    hist = AdamOptimizer(0.01).minimize(model, maxiter=10)
+    hist = [float(h) for h in hist]
+    ref_hist, ref = _tf_adam_reference_trajectory(kw, 10, 0.01, model.seed)
+    assert max(abs(a - b) / abs(b) for a, b in zip(hist, ref_hist)) < TOL, (hist, ref_hist)
+    for (name, p), (_, q) in zip(model.named_parameters(), ref.named_parameters()):
+        a, b = p.detach().cpu(), q.detach()
+        assert float((a - b).abs().max()) <= 1e-8 * max(1.0, float(b.abs().max())), name
+
+
+def test_optimizer_state_survives_eager_to_graph_switch(cuda):
+    """Eager steps first, then `use_cuda_graph = True`: building the graph (which runs warm-up steps) must not disturb the
+    parameters, the Adam moments or the step counter -- the mixed run equals an all-eager run."""
+    from dgplib_b200.training import AdamOptimizer
+    def run(switch):
+        model, X, Y = build_dsdgp(L=2, M=24, D=3, N=128, S=2, minibatch=32)
+        model.compile()
+        opt = AdamOptimizer(0.02)
+        hist = opt.minimize(model, maxiter=3)
+        model.use_cuda_graph = switch
+        hist += opt.minimize(model, maxiter=3)
+        return torch.stack([h.reshape(()) for h in hist]).cpu(), [p.detach().cpu().clone() for p in model.parameters()]
+    he, pe = run(False)
+    hg, pg = run(True)
+    assert float((he - hg).abs().max()) <= 1e-12 * float(he.abs().max())
+    for a, b in zip(pe, pg):
+        assert float((a - b).abs().max()) <= 1e-12 * max(1.0, float(a.abs().max()))
+
+
+def test_predict_between_graph_replays(cuda):
+    """A prediction on more rows than the training minibatch between two graph replays must neither invalidate the
+    captured workspaces / row buffers nor disturb the training trajectory (the graph owns what it captured)."""
+    from dgplib_b200.training import AdamOptimizer
+    def run(predict):
+        model, X, Y = build_dsdgp(L=3, M=32, D=4, N=256, S=3, minibatch=64)
+        model.compile()
+        model.use_cuda_graph = True
+        opt = AdamOptimizer(0.01)
+        hist = opt.minimize(model, maxiter=2)
+        if predict:
+            for n in (300, 77, 1000, 5, 513, 64, 129, 2000, 31, 640):     # many shapes: the row-buffer cache turns over
+                model.predict_f(np.random.RandomState(n).randn(n, 4), 5)
+            torch.cuda.empty_cache()
+        hist += opt.minimize(model, maxiter=3)
+        v, g = model.elbo_and_grad()
+        return torch.stack([h.reshape(()) for h in hist] + [v.reshape(())]).cpu()
+    a, b = run(False), run(True)
+    assert torch.equal(a, b)
+
+
 def test_second_device_in_one_process(cuda):
     """A model compiled for cuda:1 while cuda:0 is the current device gives the same ELBO and gradients as on cuda:0
     (host-side caches of the library are per device; the engine switches the current device around its launches)."""
@@ -542,18 +657,27 @@ def test_second_device_in_one_process(cuda):
         assert torch.equal(a, b)
 
 
-def test_trainable_linear_mean_is_refused(cuda):
+def test_trainable_linear_mean_of_an_output_layer(cuda):
+    """The reference freezes the Linear mean of Input / Hidden layers in initialize_forward (dgplib/layers.py:184-186,
+    :202-204) but not of an OutputLayer (:211-218): a user-supplied Linear mean there trains.  ELBO and every gradient,
+    including d/dA and d/db of that mean, against the oracle; then the mean actually moves under Adam."""
+    from dgplib_b200.training import AdamOptimizer
     rng = np.random.RandomState(0)
-    X, Y, Z = rng.randn(40, 2), rng.randn(40, 1), rng.randn(8, 2)
-    il = InputLayer(2, 2, 8, RBF(2), mean_function=Linear(A=np.zeros((2, 2))))
-    ol = OutputLayer(2, 1, 8, RBF(2), mean_function=Linear(A=np.ones((2, 1))))     # stays trainable (layers.py:211-218)
-    model = dg.DSDGP(X, Y, Z, Sequential([il, ol]), Gaussian())
-    model.compile()
-    with pytest.raises(NotImplementedError):
-        model.elbo_and_grad()
-    ol.mean_function.set_trainable(False)
-    v, _ = model.elbo_and_grad()
-    assert torch.isfinite(v)
+    X, Y, Z = rng.randn(90, 3), rng.randn(90, 2), rng.randn(12, 3)
+    il = InputLayer(3, 3, 12, RBF(3, lengthscales=1.3) + White(3, 1e-4), mean_function=Linear(A=np.zeros((3, 3))))
+    ol = OutputLayer(3, 2, 12, Matern52(3, lengthscales=1.7) + White(3, 1e-4),
+                     mean_function=Linear(A=0.3 * rng.randn(3, 2), b=0.1 * rng.randn(2)))
+    model = dg.DSDGP(X, Y, Z, Sequential([il, ol]), Gaussian(0.2), num_samples=3)
+    randomize_q(model)
+    assert not il.mean_function.A.trainable and ol.mean_function.A.trainable and ol.mean_function.b.trainable
+    errs = compare_elbo_and_grads(model, X, Y, 3)
+    assert "l1.mean.A" in errs and "l1.mean.b" in errs
+    A0, b0 = ol.mean_function.A.value, ol.mean_function.b.value
+    AdamOptimizer(0.01).minimize(model, maxiter=5)
+    assert np.abs(ol.mean_function.A.value - A0).max() > 1e-3 and np.abs(ol.mean_function.b.value - b0).max() > 1e-3
+    ol.mean_function.set_trainable(False)          # freezing it afterwards drops the slots again
+    v, g = model.elbo_and_grad()
+    assert torch.isfinite(v) and len(g) == len(model.engine.params())
 
 
 def test_exact_gp_limit_matches_scikit_learn(cuda, monkeypatch):

@@ -33,12 +33,12 @@ U = torch.zeros(lib.dgp_usave_bytes(ctypes.byref(d), N) // 8, dtype=torch.float6
 gm = t(rng.randn(N, R)); gv = t(rng.randn(N, R)); gF = t(rng.randn(N, R)); gX = torch.zeros(N, D, dtype=torch.float64, device=dev)
 def fwd(): C.check(lib.dgp_cond_forward(ctypes.byref(d), C.ptr(ws), C.ptr(X), N, N, None, 1, None, 0, 0, 0, C.ptr(mean), C.ptr(var), C.ptr(F), R, C.ptr(A), C.ptr(U), st), "fwd")
 def fwd_nosave(): C.check(lib.dgp_cond_forward(ctypes.byref(d), C.ptr(ws), C.ptr(X), N, N, None, 1, None, 0, 0, 0, C.ptr(mean), C.ptr(var), C.ptr(F), R, None, None, st), "fwd")
-def bwd(): C.check(lib.dgp_cond_backward(ctypes.byref(d), C.ptr(ws), C.ptr(X), N, N, C.ptr(A), C.ptr(U), C.ptr(mean), C.ptr(var), C.ptr(F), R, C.ptr(gm), C.ptr(gv), C.ptr(gF), R, C.ptr(gX), 0, st), "bwd")
+def bwd(): C.check(lib.dgp_cond_backward(ctypes.byref(d), C.ptr(ws), C.ptr(X), N, N, C.ptr(A), C.ptr(U), C.ptr(mean), C.ptr(var), C.ptr(F), R, C.ptr(gm), C.ptr(gv), C.ptr(gF), R, C.ptr(gX), 0, 0, st), "bwd")
 def gram(): C.check(lib.dgp_cond_backward_gram(ctypes.byref(d), C.ptr(ws), C.ptr(A), N, 0, st), "gram")
 def prep(): C.check(lib.dgp_cond_prepare(ctypes.byref(d), C.ptr(ws), wsb, 1, None, st), "prepare")
 gZ = torch.zeros(M, D, dtype=torch.float64, device=dev); gth = torch.zeros(2 + D, dtype=torch.float64, device=dev)
 gqm = torch.zeros(M, R, dtype=torch.float64, device=dev); gqs = torch.zeros(R, M, M, dtype=torch.float64, device=dev)
-def tail(): C.check(lib.dgp_cond_backward_params(ctypes.byref(d), C.ptr(ws), 1.0, C.ptr(gZ), C.ptr(gth), C.ptr(gqm), C.ptr(gqs), st), "tail")
+def tail(): C.check(lib.dgp_cond_backward_params(ctypes.byref(d), C.ptr(ws), 1.0, C.ptr(gZ), C.ptr(gth), C.ptr(gqm), C.ptr(gqs), None, None, st), "tail")
 fl = {"fwd_nosave": 0, "fwd": N * (2*M*D + M*M + 2*M*R + 2*M + R*(M*M + 2*M)), "bwd": N * (R*M*M + M*M + 2*M*R + 6*M*D), "gram": N * (R + 1) * M * M, "prep": 0, "tail": 0}
 out = []
 fl["fwd_nosave"] = fl["fwd"]
