@@ -40,6 +40,7 @@ SIGNATURES = {
     "dgp_cond_ws_bytes": (_sz, [_P, _i64, ctypes.c_int]),
     "dgp_cond_prepare": (ctypes.c_int, [_P, _vp, _sz, ctypes.c_int, _vp, _vp]),
     "dgp_cond_status": (ctypes.c_int, [_vp, _vp, ctypes.POINTER(_i32)]),
+    "dgp_cond_status_async": (ctypes.c_int, [_vp, _vp, _vp]),
     "dgp_cond_forward": (ctypes.c_int, [_P, _vp, _vp, _i64, _i64, _vp, _u64, _vp, _u64, _i64, _i64, _vp, _vp, _vp, _i32,
                                         _vp, _vp, _vp]),
     "dgp_usave_bytes": (_sz, [_P, _i64]),

@@ -765,6 +765,12 @@ extern "C" int dgp_cond_status(const void* ws, void* stream_, int32_t* status_ho
     return DGP_OK;
 }
 
+extern "C" int dgp_cond_status_async(const void* ws, void* stream_, int32_t* status_pinned) {
+    if (!ws || !status_pinned) return DGP_ERR_ARG;
+    return cudaMemcpyAsync(status_pinned, ws, sizeof(int32_t), cudaMemcpyDeviceToHost, (cudaStream_t)stream_) == cudaSuccess
+               ? DGP_OK : DGP_ERR_LAUNCH;
+}
+
 extern "C" const char* dgp_strerror(int code) {
     switch (code) {
         case DGP_OK: return "ok";

@@ -12,7 +12,7 @@ import torch
 from . import settings
 from .engine import Engine, elbo_autograd, _dev_tensor
 from .mean_functions import Zero
-from .parallel import shard_range
+from .parallel import BucketReducer, shard_range
 from .params import Parameterized
 
 
@@ -99,13 +99,17 @@ class DSDGP(Parameterized):
         self._dist = None
         self._staging = None
         self._prefetched = None
-        # Cholesky status is read back (a 4-byte D2H + sync) every this many evaluations; 0 = only on demand
-        # through engine.check_status()
+        # Cholesky status words are read back every this many evaluations (0 = only on demand through
+        # engine.check_status()).  The read is asynchronous: the copy into pinned memory is queued behind the evaluation and
+        # looked at when the NEXT evaluation is being queued (or by engine.poll_status()), so a failed factorisation raises
+        # one call later and the host never stalls the stream -- the reference surfaces it as TF's InvalidArgumentError
         self.check_status_every = 1
         # replay each evaluation of elbo_and_grad() as one CUDA graph (fixed minibatch shape; Philox noise only)
         self.use_cuda_graph = False
-        # under distribute(): capture the NCCL all-reduce inside the training-step graph (training.py)
-        self.graph_collectives = False
+        # under distribute(): all-reduce each layer's gradients as soon as they are final (overlapping the backward pass of
+        # the earlier layers) and capture those NCCL collectives inside the step's CUDA graph
+        self.overlap_all_reduce = True
+        self.graph_collectives = True
         self._graphs = {}
 
     # ------------------------------------------------------------------------------------------------ plumbing
@@ -130,6 +134,22 @@ class DSDGP(Parameterized):
         import torch.distributed as dist
         self._dist = (dist, process_group)
         return self
+
+    def release_graphs(self):
+        """Drop every captured CUDA graph of this model.  Graphs that captured NCCL collectives must be gone before
+        torch.distributed.destroy_process_group() (NCCL waits for them when it tears the communicator down)."""
+        self._graphs.clear()
+        import gc
+        gc.collect()
+        torch.cuda.synchronize()
+
+    def _reducer(self):
+        """Per-layer bucketed all-reduce overlapping the backward pass (parallel.BucketReducer), or -- with
+        `overlap_all_reduce` off -- one collective over the whole flat buffer after the last kernel."""
+        dist, group = self._dist
+        if self.overlap_all_reduce:
+            return BucketReducer(dist, group)
+        return lambda t: dist.all_reduce(t, group=group)
 
     def _next_batch(self):
         """Host view of the next minibatch (aligned X, Y rows)."""
@@ -181,7 +201,7 @@ class DSDGP(Parameterized):
             B = X.shape[0]
             lo, hi = shard_range(B, r, W)
             kw.update(X=X[lo:hi], Y=Y[lo:hi], row_offset=lo, global_batch=B, world_size=W,
-                      all_reduce=lambda t: dist.all_reduce(t, group=group))
+                      all_reduce=self._reducer())
             if eps is not None:
                 kw["eps"] = [e[:, lo:hi] for e in eps]
         return kw
@@ -231,20 +251,22 @@ class DSDGP(Parameterized):
                 return eng.elbo(eng.native_params(), need_grad=True, **self._eval_kwargs(X, Y, eps, seed))
         kw, finish = self._staged_step(eps, seed)
         graph = kw.pop("_graph", None)
+        check = kw.pop("check", False)
         if graph is not None:
             out = graph.run(None, kw["X"], kw["Y"], kw["seed"], all_reduce=kw.get("all_reduce"))
-            if kw.get("check"):
-                eng.check_status()
         else:
             with torch.no_grad():
-                out = eng.elbo(eng.native_params(), need_grad=True, **kw)
+                out = eng.elbo(eng.native_params(), need_grad=True, check=False, **kw)
         finish()
+        if check:
+            eng.post_status_read()
         return out
 
     def _staged_step(self, eps, seed):
         """Arguments of Engine.elbo for the next minibatch taken from the model's own host data through the pinned,
         double-buffered staging path, plus a callback to run once the step's kernels are enqueued."""
         eng = self.engine
+        eng.poll_status()          # the previous evaluation's Cholesky status (posted asynchronously)
         staged = self._prefetched or self._stage_next()
         self._prefetched = None
         xd, yd, ready, lo, B, slot = staged
@@ -256,7 +278,7 @@ class DSDGP(Parameterized):
                   check=bool(self.check_status_every) and self._step % self.check_status_every == 0)
         if self._dist is not None:
             dist, group = self._dist
-            kw.update(world_size=dist.get_world_size(group), all_reduce=lambda t: dist.all_reduce(t, group=group))
+            kw.update(world_size=dist.get_world_size(group), all_reduce=self._reducer())
             if eps is not None:        # injected noise is given for the whole minibatch: this rank's rows of it
                 kw["eps"] = [torch.as_tensor(e)[:, lo:lo + xd.shape[0]] for e in eps]
         if self.use_cuda_graph and eps is None and seed is None:
@@ -276,9 +298,11 @@ class DSDGP(Parameterized):
         g = self._graphs.get(key)
         if g is None:
             # live parameters: the positive transforms are captured with the evaluation and read the model's own tensors
+            captured = kw.get("all_reduce") if (self.graph_collectives and self.overlap_all_reduce) else None
             g = GraphedElbo(eng, None, xd, yd, self.num_samples, num_data=self.num_data,
                             row_offset=kw["row_offset"], global_batch=kw["global_batch"],
-                            world_size=kw.get("world_size", 1), chunk_rows=self.chunk_rows, base_seed=self.seed)
+                            world_size=kw.get("world_size", 1), chunk_rows=self.chunk_rows, base_seed=self.seed,
+                            all_reduce=captured)
             self._graphs[key] = g
         return g
 

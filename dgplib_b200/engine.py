@@ -106,7 +106,11 @@ class Engine:
         _cabi.require_cuda()
         _cabi.lib()
         self.device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
-        self.gram_on_side_stream = True     # bench.py turns it off to time the Gram kernels alone
+        # stream placement of the parameter stages, Gram reductions and parameter tails; bench.py's per-kernel timing pass
+        # puts everything on the main stream so that an event pair times one kernel and not its wait for SMs
+        self.gram_on_side_stream = True
+        self.params_on_side_streams = True
+        self._prep_key = None      # parameter version the forward halves of the workspaces were prepared for
         self.layers = list(layers)
         self.likelihood = likelihood
         self.multitask = bool(multitask)
@@ -265,6 +269,11 @@ class Engine:
             self._streams = [[torch.cuda.Stream(device=self.device) for _ in conds] for conds in self.conds]
         return self._streams
 
+    def _comm_stream(self):
+        if getattr(self, "_comm", None) is None:
+            self._comm = torch.cuda.Stream(device=self.device)
+        return self._comm
+
     def _prepare(self, S, nb, need_bwd, kl):
         """Parameter-only stage of every conditional (Kuu, Cholesky, inverse factor, tiled operands, KL).  The
         conditionals are independent of each other and of the data, so each chain runs on its own stream; returns, per
@@ -276,17 +285,27 @@ class Engine:
         for l, (conds, sides) in enumerate(zip(self.conds, self._side_streams())):
             evs = []
             for c, side in zip(conds, sides):
-                side.wait_event(start)
+                if not self.params_on_side_streams:
+                    side = main
+                else:
+                    side.wait_event(start)
                 with torch.cuda.stream(side):
                     c.ensure_ws(self._rows_of(l, S, nb), need_bwd, self.device)
                     self._timed("prepare", lambda: _cabi.check(lib.dgp_cond_prepare(
                         c.ref(), _cabi.ptr(c.ws), c.ws.numel(), 1 if need_bwd else 0,
                         ctypes.c_void_p(kl[i:].data_ptr()) if kl is not None else None, _cabi.stream_ptr()),
                         "dgp_cond_prepare"))
-                    evs.append(side.record_event())
+                    if side is not main:
+                        evs.append(side.record_event())
                 i += 1
             events.append(evs)
         return events
+
+    def _param_version(self):
+        """Changes whenever a parameter of the model may have changed: torch bumps the flat buffer's version counter on
+        every in-place write through any parameter view, the library's own Adam launch bumps `native_version`."""
+        flat = self.flatten()
+        return (flat.key, flat.u._version, flat.native_version)
 
     @_on_device
     def check_status(self):
@@ -299,6 +318,37 @@ class Engine:
                 if s.value != 0:
                     raise _cabi.DgpError(f"Cholesky of Kuu failed in layer {l} at pivot {s.value - 1}: "
                                          "Kuu + jitter is not positive definite")
+
+    @_on_device
+    def post_status_read(self):
+        """Queue the copy of every conditional's Cholesky status word into pinned host memory behind the work already on
+        the current stream, without waiting for it; `poll_status()` looks at the result once that work has finished."""
+        lib, st = _cabi.lib(), _cabi.stream_ptr()
+        n = sum(len(c) for c in self.conds)
+        if getattr(self, "_status_host", None) is None or self._status_host.numel() != n:
+            self._status_host = torch.zeros(n, dtype=torch.int32).pin_memory()
+        i = 0
+        for conds in self.conds:
+            for c in conds:
+                _cabi.check(lib.dgp_cond_status_async(_cabi.ptr(c.ws), st,
+                                                      ctypes.c_void_p(self._status_host.data_ptr() + 4 * i)),
+                            "dgp_cond_status_async")
+                i += 1
+        self._status_event = torch.cuda.current_stream().record_event()
+
+    def poll_status(self):
+        """Raises if the evaluation whose status was posted by post_status_read() had a failed Cholesky factorisation
+        (waits for that evaluation only -- normally long finished when the next one is being queued)."""
+        ev = getattr(self, "_status_event", None)
+        if ev is None:
+            return
+        ev.synchronize()
+        self._status_event = None
+        bad = self._status_host.nonzero()
+        if bad.numel():
+            i = int(bad[0])
+            raise _cabi.DgpError(f"Cholesky of Kuu failed in conditional {i} at pivot {int(self._status_host[i]) - 1}: "
+                                 "Kuu + jitter is not positive definite")
 
     # ------------------------------------------------------------------------------------------ forward
     def _seed_dev_ptr(self):
@@ -348,10 +398,22 @@ class Engine:
         layer), last_only returns only the final layer's (mean, var) -- what predict_f / predict_y need."""
         with torch.no_grad():
             X = _dev_tensor(X, self.device)
-            self._bind(self._detached(params))
             B = X.shape[0]
             Bc = B if not chunk_rows else max(1, min(B, int(chunk_rows)))
-            events = self._prepare(S, Bc, False, None)
+            if params is None:
+                # the model's own parameters: the parameter stage (33 ms at M = 1024) is redone only when they changed
+                # since the workspaces were last prepared -- a prediction sweep pays for it once
+                self._bind(self.native_params())
+                key = self._param_version()
+                if key == self._prep_key and all(c.ws is not None for conds in self.conds for c in conds):
+                    events = [[] for _ in self.conds]
+                else:
+                    events = self._prepare(S, Bc, False, None)
+                    self._prep_key = key
+            else:
+                self._bind(self._detached(params))
+                self._prep_key = None
+                events = self._prepare(S, Bc, False, None)
             eps_full = None
             if eps is not None:
                 eps_full = [_dev_tensor(e, self.device).reshape(S, B, -1) for e in eps]
@@ -444,6 +506,7 @@ class Engine:
             dev = self.device
             X = _dev_tensor(X, dev)
             self._bind(self._detached(params))
+            self._prep_key = None
             N = X.shape[0]
             for evs in self._prepare(1, N, False, None):
                 for ev in evs:
@@ -509,6 +572,7 @@ class Engine:
             _cabi.check(lib.dgp_zero(ctypes.c_void_p(flat.data_ptr()), flat.numel() * 8, st), "dgp_zero")
             kl = flat[total:]
             Bc = B if not chunk_rows else max(1, min(B, int(chunk_rows)))
+            self._prep_key = None       # prepared for whatever `params` holds, which this method cannot identify
             events = self._prepare(S, Bc, need_grad, kl)
             if self._lik_ws is None:
                 self._lik_ws = torch.empty(lib.dgp_lik_ws_bytes(0, 1), dtype=torch.uint8, device=dev)
@@ -521,12 +585,30 @@ class Engine:
             if eps is not None:
                 eps_full = [_dev_tensor(e, dev).reshape(S, B, -1) for e in eps]
             tail_events = []
+            bucketed = need_grad and world_size > 1 and all_reduce is not None and hasattr(all_reduce, "bucket")
+
+            def reduce_bucket(l, events):
+                """All-reduce of layer l's gradient slots as soon as they are final: [layer l] for a middle layer, the last
+                layer's together with the likelihood gradient behind it, the first layer's together with the ELBO in front
+                of it.  Issued on the communication stream behind the events of the tails that wrote the slots."""
+                lo = 0 if l == 0 else self._zt_offsets[l][0][0][1]
+                hi = total if l == L - 1 else self._zt_offsets[l + 1][0][0][1]
+                comm = self._comm_stream()
+                comm.wait_event(main.record_event())
+                for ev in events:
+                    comm.wait_event(ev)
+                with torch.cuda.stream(comm):
+                    all_reduce.bucket(flat[lo:hi])
 
             def run_tail(l):
                 """Parameter-only backward tails of layer l on their side streams (overlap the earlier layers' rows)."""
+                n_before = len(tail_events)
                 done = main.record_event()
                 for c, side, ((Z, oZ), (th, oT)) in zip(self.conds[l], self._side_streams()[l], self._zt_offsets[l]):
-                    side.wait_event(done)
+                    if not self.params_on_side_streams:
+                        side = main
+                    else:
+                        side.wait_event(done)
                     with torch.cuda.stream(side):
                         base = flat.data_ptr()
                         o_mu, o_sqrt, o_mA, o_mb = self._q_offsets[l]
@@ -536,7 +618,10 @@ class Engine:
                             ctypes.c_void_p(base + 8 * o_mA) if o_mA is not None else None,
                             ctypes.c_void_p(base + 8 * o_mb) if o_mb is not None else None, _cabi.stream_ptr()),
                             "dgp_cond_backward_params"))
-                        tail_events.append(side.record_event())
+                        if side is not main:
+                            tail_events.append(side.record_event())
+                if bucketed:
+                    reduce_bucket(l, tail_events[n_before:])
 
             # offsets of each layer's gradient slots
             it = iter(zip(params, offs))
@@ -567,6 +652,12 @@ class Engine:
                     _cabi.ptr(buf["g_mu"]) if need_grad else None, _cabi.ptr(buf["g_var"]) if need_grad else None,
                     ctypes.c_void_p(g_lik.data_ptr()) if need_grad else None,
                     _cabi.ptr(self._lik_ws), self._lik_ws.numel(), st), "dgp_lik_gaussian"))
+                if ck == nchunks - 1:
+                    # ELBO = weighted variational expectations - sum of the KL terms (every parameter stage has been waited
+                    # for by the forward pass): final before the backward pass starts, so that the first layer's bucket
+                    # can carry it
+                    _cabi.check(lib.dgp_finish_elbo(ctypes.c_void_p(flat.data_ptr()), ctypes.c_void_p(kl.data_ptr()), ncond,
+                                                    klw, st), "dgp_finish_elbo")
                 if not need_grad:
                     continue
                 for l in range(L - 1, -1, -1):
@@ -618,9 +709,9 @@ class Engine:
                         run_tail(l)
             for ev in tail_events:
                 main.wait_event(ev)
-            _cabi.check(lib.dgp_finish_elbo(ctypes.c_void_p(flat.data_ptr()), ctypes.c_void_p(kl.data_ptr()), ncond, klw,
-                                            st), "dgp_finish_elbo")
-            if all_reduce is not None and world_size > 1:
+            if bucketed:
+                all_reduce.finish()
+            elif all_reduce is not None and world_size > 1:
                 all_reduce(flat[:total])
             if check:
                 self.check_status()
@@ -638,13 +729,15 @@ class GraphedElbo:
     copied into static buffers before each replay; the Philox seed is added on the device (dgp_cond_forward's seed_dev)."""
 
     def __init__(self, engine, params, X, Y, S, num_data=None, row_offset=0, global_batch=None, world_size=1,
-                 chunk_rows=None, need_grad=True, base_seed=0):
+                 chunk_rows=None, need_grad=True, base_seed=0, all_reduce=None):
         """params: list of constrained parameter tensors copied into static buffers before every replay, or None to read
         the model's own parameters inside the graph (the positive transforms are then part of the capture; valid while
         the parameter tensors keep their storage, i.e. in-place optimiser updates)."""
+        """all_reduce: a reducer (parallel.BucketReducer) whose NCCL collectives are captured INSIDE the graph, per-layer
+        buckets overlapping the backward pass; None: the caller reduces the flat buffer after each replay (run())."""
         with torch.cuda.device(engine.device):
             self._build(engine, params, X, Y, S, num_data, row_offset, global_batch, world_size, chunk_rows, need_grad,
-                        base_seed)
+                        base_seed, all_reduce)
 
     @staticmethod
     def storage_key(engine):
@@ -654,8 +747,9 @@ class GraphedElbo:
         return FlatParams.storage_key(engine)
 
     def _build(self, engine, params, X, Y, S, num_data, row_offset, global_batch, world_size, chunk_rows, need_grad,
-               base_seed):
+               base_seed, all_reduce):
         self.eng = engine
+        self.captured_collectives = all_reduce is not None
         self.live = params is None
         if self.live:
             with torch.no_grad():
@@ -669,7 +763,8 @@ class GraphedElbo:
         self.seed_dev = torch.zeros(1, dtype=torch.int64, device=dev)
         self.base_seed = int(base_seed)
         kw = dict(S=S, eps=None, seed=base_seed, num_data=num_data, need_grad=need_grad, row_offset=row_offset,
-                  global_batch=global_batch, world_size=world_size, all_reduce=None, chunk_rows=chunk_rows, check=False)
+                  global_batch=global_batch, world_size=world_size, all_reduce=all_reduce, chunk_rows=chunk_rows,
+                  check=False)
         cur = torch.cuda.current_stream()
         if self.live:
             engine.flatten()                               # build the tables (allocations, H2D copies) outside the capture
@@ -684,7 +779,8 @@ class GraphedElbo:
         self.graph = torch.cuda.CUDAGraph()
         engine._seed_dev = self.seed_dev
         try:
-            with torch.cuda.graph(self.graph):
+            # thread-local capture mode: NCCL's watchdog thread may touch the CUDA API while this thread captures
+            with torch.cuda.graph(self.graph, capture_error_mode="thread_local"):
                 with torch.no_grad():
                     self.val, self.grads = engine.elbo(live_ps() if self.live else self.ps, self.Xs, self.Ys, **kw)
                 self.flat = engine._last_flat
@@ -707,7 +803,7 @@ class GraphedElbo:
                                                 (int(seed) - self.base_seed) & 0x7FFFFFFFFFFFFFFF, _cabi.stream_ptr()),
                         "dgp_set_u64")
             self.graph.replay()
-            if all_reduce is not None:
+            if all_reduce is not None and not self.captured_collectives:
                 all_reduce(self.flat)
         return self.val, self.grads
 

@@ -51,6 +51,7 @@ class FlatParams:
                 p.raw.data = view                      # the nn.Parameter is now a view of the flat buffer
                 flags[s:s + n] = (1 if p.positive else 0) | (2 if p.raw.requires_grad else 0)
         self.key = self.storage_key(engine)
+        self.native_version = 0        # bumped by every in-place update the library's own kernels make (adam_step)
         self._build_tables(flags)
 
     @staticmethod
@@ -183,6 +184,7 @@ class FlatParams:
         """One tf.train.AdamOptimizer step on -ELBO from the evaluation's flat [elbo | gradients] buffer."""
         p = lambda t: ctypes.c_void_p(t.data_ptr())
         assert grad_flat.numel() >= self.grad_total
+        self.native_version += 1
         _cabi.check(_cabi.lib().dgp_adam_step(p(self.u), p(state["m"]), p(state["v"]), self.n, p(grad_flat), p(self.gidx),
                                               p(self.grow), p(self.gimg), p(self.flags), lr, beta1, beta2, eps,
                                               p(state["step"]), _cabi.stream_ptr()), "dgp_adam_step")

@@ -18,3 +18,26 @@ def kl_weight(world_size):
 def philox_row_id(row_offset, sample, local_row, sample_stride):
     """Global row id that keys the Philox draw of (sample, local row): identical for any sharding of the rows."""
     return row_offset + sample * sample_stride + local_row
+
+
+class BucketReducer:
+    """Sum-all-reduce of the flat [elbo | gradients] buffer in per-layer buckets, each issued as soon as that layer's
+    gradients are final (last layer first), so that the collectives run on NCCL's stream beside the backward kernels of
+    the earlier layers instead of after the whole evaluation.  `bucket()` is called with the stream that produced the slice
+    current (torch.distributed makes NCCL's stream wait for it); `finish()` makes the current stream wait for every
+    bucket.  Calling the object reduces a whole buffer in one collective (ELBO-only evaluations)."""
+
+    def __init__(self, dist, group=None):
+        self.dist, self.group = dist, group
+        self.works = []
+
+    def bucket(self, tensor):
+        self.works.append(self.dist.all_reduce(tensor, group=self.group, async_op=True))
+
+    def finish(self):
+        for w in self.works:
+            w.wait()
+        self.works.clear()
+
+    def __call__(self, tensor):
+        self.dist.all_reduce(tensor, group=self.group)

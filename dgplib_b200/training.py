@@ -51,7 +51,7 @@ class GraphedTrainStep:
         self.graph = torch.cuda.CUDAGraph()
         eng._seed_dev = self.seed_dev
         try:
-            with torch.cuda.graph(self.graph):
+            with torch.cuda.graph(self.graph, capture_error_mode="thread_local"):
                 self.elbo = self._step_body()
         finally:
             eng._seed_dev = None
@@ -77,6 +77,7 @@ class GraphedTrainStep:
                                                 (int(seed) - self.base_seed) & 0x7FFFFFFFFFFFFFFF, _cabi.stream_ptr()),
                         "dgp_set_u64")
             self.graph.replay()
+            self.eng.flatten().native_version += 1      # the replayed Adam launch changed the parameters
         return self.elbo
 
 
@@ -89,6 +90,11 @@ class AdamOptimizer:
         self.lr, self.betas, self.eps = float(learning_rate), (float(beta1), float(beta2)), float(epsilon)
         self._state = None
         self._graphs = {}
+
+    def release_graphs(self):
+        """Drop the captured training-step graphs (before torch.distributed.destroy_process_group(), see
+        DSDGP.release_graphs)."""
+        self._graphs.clear()
 
     def _state_for(self, eng):
         """Adam moments + step counter (device) for the engine's flat buffer; created on first use and whenever the flat
@@ -116,20 +122,24 @@ class AdamOptimizer:
         if g is None:
             g = self._graphs[key] = GraphedTrainStep(model, self, X, Y, kw)
         elbo = g.run(X, Y, kw["seed"]).clone()
-        if kw.get("check"):
-            eng.check_status()
         finish()
+        if kw.get("check"):
+            eng.post_status_read()     # looked at when the next step is queued (DSDGP._staged_step) / at the end of minimize
         return elbo
 
     def _eager_step(self, model):
         kw, finish = model._staged_step(None, None)
         kw.pop("_graph", None)
         eng = model.engine
+        check = kw.pop("check", False)
         with torch.no_grad():
-            val, _ = eng.elbo(eng.native_params(), need_grad=True, **kw)
+            val, _ = eng.elbo(eng.native_params(), need_grad=True, check=False, **kw)
             self._apply(eng)
+        val = val.clone()
         finish()
-        return val.clone()
+        if check:
+            eng.post_status_read()
+        return val
 
     def minimize(self, model, maxiter=1000, callback=None):
         """Run `maxiter` Adam steps on -ELBO; returns the list of per-step ELBO values (CUDA scalars, read lazily)."""
@@ -138,10 +148,12 @@ class AdamOptimizer:
         with torch.cuda.device(eng.device):
             self._state_for(eng)
             # NCCL collectives are captured with the step when the process group allows it (model.graph_collectives)
-            graphable = bool(model.use_cuda_graph) and (model._dist is None or getattr(model, "graph_collectives", False))
+            graphable = bool(model.use_cuda_graph) and (
+                model._dist is None or (model.graph_collectives and model.overlap_all_reduce))
             for it in range(int(maxiter)):
                 elbo = self._graphed_step(model) if graphable else self._eager_step(model)
                 history.append(elbo)
                 if callback is not None:
                     callback(it, elbo)
+            eng.poll_status()
         return history

@@ -75,6 +75,9 @@ size_t dgp_cond_ws_bytes(const dgp_cond_desc* d, int64_t n_rows, int need_bwd);
 int dgp_cond_prepare(const dgp_cond_desc* d, void* ws, size_t ws_bytes, int need_bwd, double* kl_out, void* stream);
 /* copies the Cholesky status word to the host (synchronises the stream) */
 int dgp_cond_status(const void* ws, void* stream, int32_t* status_host);
+/* the same copy without the synchronisation: status_pinned (page-locked host memory) is valid once the work queued on
+ * `stream` up to here has finished (the caller records an event behind it and looks one step later) */
+int dgp_cond_status_async(const void* ws, void* stream, int32_t* status_pinned);
 
 /* All per-row arrays below (eps, mean, var, F, g_*) are the LAYER's arrays with row stride ldr (F: ldf); a
  * conditional reads / writes only its own columns col0 .. col0+R-1. */

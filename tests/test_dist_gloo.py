@@ -60,6 +60,33 @@ def _worker(rank, world, port, out):
     dist.destroy_process_group()
 
 
+def _bucket_worker(rank, world, port, out):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from dgplib_b200.parallel import BucketReducer
+    g = torch.Generator().manual_seed(100 + rank)
+    flat = torch.randn(1000, dtype=torch.float64, generator=g)
+    whole = flat.clone()
+    red = BucketReducer(dist)
+    for lo, hi in [(700, 1000), (300, 700), (0, 300)]:        # last layer (+ likelihood) first, first layer (+ ELBO) last
+        red.bucket(flat[lo:hi])
+    red.finish()
+    red(whole)                                                 # the single-collective path
+    if rank == 0:
+        torch.save((flat, whole), out)
+    dist.destroy_process_group()
+
+
+def test_bucketed_all_reduce_equals_the_single_collective(tmp_path):
+    out = str(tmp_path / "b.pt")
+    mp.spawn(_bucket_worker, args=(2, _free_port(), out), nprocs=2, join=True)
+    flat, whole = torch.load(out)
+    assert torch.equal(flat, whole)
+    want = sum(torch.randn(1000, dtype=torch.float64, generator=torch.Generator().manual_seed(100 + r)) for r in range(2))
+    assert torch.equal(flat, want)
+
+
 def _free_port():
     s = socket.socket()
     s.bind(("127.0.0.1", 0))

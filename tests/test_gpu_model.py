@@ -639,6 +639,24 @@ def test_predict_between_graph_replays(cuda):
     assert torch.equal(a, b)
 
 
+def test_cholesky_failure_surfaces_through_the_model(cuda, monkeypatch):
+    """Numerical failure convention at the model level: the status words are read back asynchronously, so an indefinite
+    Kuu + jitter raises when the next evaluation is queued, or at once through engine.poll_status() / check_status()."""
+    from dgplib_b200 import settings
+    from dgplib_b200._cabi import DgpError
+    monkeypatch.setattr(settings, "jitter_level", -3.0)
+    model, X, Y = build_dsdgp(L=2, M=12, D=2, N=40, S=2, minibatch=20)
+    model.compile()
+    model.elbo_and_grad()                      # queued; the failure is found behind it
+    with pytest.raises(DgpError, match="not positive definite"):
+        model.elbo_and_grad()
+    model.elbo_and_grad()
+    with pytest.raises(DgpError):
+        model.engine.poll_status()
+    with pytest.raises(DgpError):
+        model.engine.check_status()
+
+
 def test_second_device_in_one_process(cuda):
     """A model compiled for cuda:1 while cuda:0 is the current device gives the same ELBO and gradients as on cuda:0
     (host-side caches of the library are per device; the engine switches the current device around its launches)."""
