@@ -30,7 +30,7 @@ struct DevOnceSize {
 // Test-only build (libdgp_b200_test.so, `make test_lib`): lets the parity tests force every row-tile instantiation
 // and the tuning experiments of tools/kbench.py override the Gram split count.  None of this exists in the product
 // library.
-extern int g_force_fwd_nt, g_force_bwd_nt, g_force_gram_splits, g_debug_mode;
+extern int g_force_fwd_nt, g_force_bwd_nt, g_force_gram_splits, g_debug_mode, g_force_stages;
 #endif
 
 #define DGP_CHECK_LAUNCH()                                   \
@@ -228,6 +228,18 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n"
                  :: "r"(smem_u32(smem_dst)), "l"(gsrc), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+// the same copy with an L2 eviction-priority hint (createpolicy): evict_last for lines that will be read again soon,
+// evict_first for streaming data that will not
+__device__ __forceinline__ uint64_t l2_policy(bool keep) {
+    uint64_t p;
+    if (keep) asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;\n" : "=l"(p));
+    else asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;\n" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ void bulk_g2s_hint(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar, uint64_t policy) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;\n"
+                 :: "r"(smem_u32(smem_dst)), "l"(gsrc), "r"(bytes), "r"(smem_u32(bar)), "l"(policy) : "memory");
 }
 __device__ __forceinline__ void bulk_s2g(void* gdst, const void* smem_src, uint32_t bytes) {
     asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;\n"

@@ -156,11 +156,17 @@ __global__ void __launch_bounds__(C::NTHREADS, 1) k_cond_bwd(const __grid_consta
                 const long long gl = a.NG - g0;
                 uint32_t ubytes = (uint32_t)((gl < C::NT / 8 ? gl : C::NT / 8) * USAVE_BLOCK * sizeof(double));
 #ifdef DGP_TEST_HOOKS
-                if (a.debug == 1) ubytes = 0;          // timing experiments only: no U traffic / U always from L2
+                if (a.debug == 1 || a.debug == 4) ubytes = 0;   // timing experiments only: no U traffic / U always from L2
                 if (a.debug == 2) g0 = (long long)blockIdx.x * (C::NT / 8);
 #endif
-                auto ufn = [&](const Seg& sg, int kc, uint32_t& bytes) {
+                // a U chunk is read once per block row that reaches it: every block row but the last leaves it behind for a
+                // later one (~1 MB of other chunks per CTA in between), so those reads ask L2 to keep the lines and the last
+                // read of each chunk lets them go first (without the hints the re-reads came from HBM: 3.2 GB per launch at
+                // the T hidden-layer shape against 2.1 GB algorithmic)
+                const uint64_t keep = l2_policy(true), drop = l2_policy(false);
+                auto ufn = [&](const Seg& sg, int kc, uint32_t& bytes, uint64_t& policy) {
                     bytes = ubytes;
+                    policy = (sg.i < nb - 1) ? keep : drop;
                     return a.U_save + (((size_t)sg.r * nkc + kc) * (size_t)a.NG + (size_t)g0) * USAVE_BLOCK;
                 };
                 produce_phase<C>(pipe, nb * R, seg_dA, Mpad, ufn);
@@ -266,6 +272,11 @@ __global__ void __launch_bounds__(C::NTHREADS, 1) k_cond_bwd(const __grid_consta
                     }
                 }
             };
+#ifdef DGP_TEST_HOOKS
+            if (a.debug == 4)        // timing experiment: B fragments from the resident tile (the forward kernel's pattern)
+                run_phase<C, MASK_LOWER, false, true>(pipe, nb * R, seg_dA, epi, Dt, ldb, Mpad, gv, R, nvalid);
+            else
+#endif
             run_phase<C, MASK_LOWER, true, true>(pipe, nb * R, seg_dA, epi, nullptr, 0, Mpad, gv, R, nvalid);
         }
         PH(3);
@@ -290,6 +301,9 @@ __global__ void __launch_bounds__(C::NTHREADS, 1) k_cond_bwd(const __grid_consta
         }
         consumer_sync<C>();
         PH(4);
+#ifdef DGP_TEST_HOOKS
+        if (a.debug == 3) continue;      // timing experiment: GEMM phases only
+#endif
 
         // ---- dKuf tile -> HBM (for the Gram kernel)
         fence_async_smem();
@@ -760,8 +774,13 @@ extern "C" int dgp_cond_backward(const dgp_cond_desc* d, void* ws, const double*
 #ifdef DGP_TEST_HOOKS
     a.debug = g_debug_mode;
 #endif
+#ifdef DGP_TEST_HOOKS
+#define DGP_STAGE_OK(STG) (g_force_stages == 0 || g_force_stages == (STG))
+#else
+#define DGP_STAGE_OK(STG) true
+#endif
 #define DGP_TRY_BWD(WNV, NTV, STG)                                                        \
-    {                                                                                 \
+    if (DGP_STAGE_OK(STG)) {                                                          \
         using C = TileCfg<4, WNV, NTV, STG, true>;                                        \
         a.ntiles = (int)((n_rows - a.row0 + C::NT - 1) / C::NT);                      \
         rc = launch_bwd<C>(a, st);                                                    \

@@ -412,8 +412,13 @@ extern "C" int dgp_cond_forward(const dgp_cond_desc* d, const void* ws, const do
     cudaStream_t st = (cudaStream_t)stream;
     // row-tile width by inducing count (the A tile must fit in shared memory); ring depth 4, or 3 / 2 when the
     // per-row side buffers (large D) leave less room
+#ifdef DGP_TEST_HOOKS
+#define DGP_STAGE_OK(STG) (g_force_stages == 0 || g_force_stages == (STG))
+#else
+#define DGP_STAGE_OK(STG) true
+#endif
 #define DGP_TRY_FWD(WNV, NTV, STG)                                                        \
-    {                                                                                 \
+    if (DGP_STAGE_OK(STG)) {                                                          \
         using C = TileCfg<4, WNV, NTV, STG>;                                              \
         a.ntiles = (int)((n_rows + C::NT - 1) / C::NT);                               \
         rc = launch_fwd<C>(a, st);                                                    \

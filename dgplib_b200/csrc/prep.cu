@@ -19,7 +19,7 @@ namespace dgp {
 
 std::atomic<long long> g_launches{0};
 #ifdef DGP_TEST_HOOKS
-int g_force_fwd_nt = 0, g_force_bwd_nt = 0, g_force_gram_splits = 0, g_debug_mode = 0;
+int g_force_fwd_nt = 0, g_force_bwd_nt = 0, g_force_gram_splits = 0, g_debug_mode = 0, g_force_stages = 0;
 #endif
 
 int current_device() {
@@ -791,4 +791,5 @@ extern "C" size_t dgp_usave_bytes(const dgp_cond_desc* d, int64_t n_rows) {
 extern "C" void dgp_test_force_tiles(int fwd_nt, int bwd_nt) { g_force_fwd_nt = fwd_nt; g_force_bwd_nt = bwd_nt; }
 extern "C" void dgp_test_force_gram_splits(int n) { g_force_gram_splits = n; }
 extern "C" void dgp_test_debug_mode(int m) { g_debug_mode = m; }
+extern "C" void dgp_test_force_stages(int n) { g_force_stages = n; }
 #endif

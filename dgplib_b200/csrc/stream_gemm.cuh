@@ -101,10 +101,13 @@ __device__ __forceinline__ void consumer_sync() {
     asm volatile("bar.sync 1, %0;\n" :: "n"(C::NCONS) : "memory");
 }
 
-// ---- producer side: one elected lane enqueues every chunk of the phase.  ufn(seg, kc, bytes&) returns the global
-//      address of the second operand's chunk that shares the slot (bytes = 0: none).
+// ---- producer side: one elected lane enqueues every chunk of the phase.  ufn(seg, kc, bytes&, policy&) returns the
+//      global address of the second operand's chunk that shares the slot (bytes = 0: none) and its L2 eviction policy.
 struct NoU {
-    __device__ __forceinline__ const double* operator()(const Seg&, int, uint32_t& bytes) const { bytes = 0; return nullptr; }
+    __device__ __forceinline__ const double* operator()(const Seg&, int, uint32_t& bytes, uint64_t&) const {
+        bytes = 0;
+        return nullptr;
+    }
 };
 template <class C, class SegFn, class UFn = NoU>
 __device__ __forceinline__ void produce_phase(Pipe& p, int nseg, SegFn segfn, int Mpad, UFn ufn = UFn()) {
@@ -114,12 +117,13 @@ __device__ __forceinline__ void produce_phase(Pipe& p, int nseg, SegFn segfn, in
         for (int kc = sg.kc0; kc < sg.kc1; ++kc) {
             if (p.round > 0) mbar_wait(&p.empty[p.stage], (p.round - 1) & 1);
             uint32_t ub = 0;
-            const double* usrc = ufn(sg, kc, ub);
+            uint64_t upol = 0;
+            const double* usrc = ufn(sg, kc, ub, upol);
             double* slot = p.stages + (size_t)p.stage * C::STAGE_DOUBLES;
             mbar_expect_tx(&p.full[p.stage], (uint32_t)(TILE_DOUBLES * sizeof(double)) + ub);
             bulk_g2s(slot, sg.W + ((size_t)sg.i * nch + kc) * TILE_DOUBLES, (uint32_t)(TILE_DOUBLES * sizeof(double)),
                      &p.full[p.stage]);
-            if (ub) bulk_g2s(slot + TILE_DOUBLES, usrc, ub, &p.full[p.stage]);
+            if (ub) bulk_g2s_hint(slot + TILE_DOUBLES, usrc, ub, &p.full[p.stage], upol);
             pipe_advance<C>(p);
         }
     }

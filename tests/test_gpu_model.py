@@ -269,6 +269,21 @@ def test_multitask_predictions(cuda):
         assert np.array_equal(f[0, :, -1], Xs[:, -1])                # label column propagated (reference :141, :157)
     mu, sigma = model.predict_y(Xs)
     assert mu.shape == sigma.shape == (1, 20, 1)                      # SwitchedLikelihood quirk (reference :165-173)
+    # values, not only shapes: predict_f / predict_all_layers / predict_y of the multitask model against the oracle with
+    # injected noise, SwitchedLikelihood.predict_mean_and_var's per-likelihood concatenation included
+    randomize_q(model)
+    model.likelihood.likelihood_list[1].variance.assign(0.37)
+    S = 3
+    eps = make_eps(model, S, 10, seed=31)
+    ol_, olik = oracle_layers(model.layers.layers), oracle_lik(model.likelihood)
+    oFs, oM, oV = O.predict_all_layers(ol_, t(Xs), S, [t(e) for e in eps], multitask=True)
+    Fs, Ms, Vs = model.predict_all_layers(Xs, S, eps=eps)
+    for a, b in zip(Fs + Ms + Vs, oFs + oM + oV):
+        assert a.shape == tuple(b.shape) and rel_err(a, b) < TOL
+    omu, ovar = O.predict_y(ol_, olik, t(Xs), [t(e) for e in eps], S=S, multitask=True)
+    mu, var = model.predict_y(Xs, num_samples=S, eps=eps)
+    assert mu.shape == tuple(omu.shape) == (S, 20, 1) and rel_err(mu, omu) < TOL and rel_err(var, ovar) < TOL
+    assert not np.allclose(var[:, :10], var[:, 10:])                  # the two likelihoods' variances differ
 
 
 # ------------------------------------------------------------------------------------------------ prediction

@@ -205,11 +205,16 @@ float time_ms(F f) {
     cudaEvent_t e0, e1;
     CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
     f();  // warm
+    if (cudaError_t e = cudaGetLastError(); e != cudaSuccess) {      // e.g. too many registers for 1024 threads: no number
+        printf("  (launch failed: %s -- configuration skipped)\n", cudaGetErrorString(e));
+        return -1.0f;
+    }
     CK(cudaDeviceSynchronize());
     float best = 1e30f;
     for (int r = 0; r < 5; ++r) {
         CK(cudaEventRecord(e0));
         f();
+        CK(cudaGetLastError());
         CK(cudaEventRecord(e1));
         CK(cudaEventSynchronize(e1));
         float ms; CK(cudaEventElapsedTime(&ms, e0, e1));
@@ -231,17 +236,17 @@ int main() {
             {
                 float ms = time_ms([&] { k_dmma<8><<<sms * ctas, threads>>>(out, iters, 1.0, 1.0); });
                 double fl = 2.0 * 256 * 8 * (double)iters * warps * sms;
-                printf("DMMA884 acc=8  warps/SM=%2d ctas/SM=%d : %.3f ms  %.2f TFLOP/s\n", warps, ctas, ms, fl / ms * 1e-9);
+                if (ms > 0) printf("DMMA884 acc=8  warps/SM=%2d ctas/SM=%d : %.3f ms  %.2f TFLOP/s\n", warps, ctas, ms, fl / ms * 1e-9);
             }
             {
                 float ms = time_ms([&] { k_dmma<16><<<sms * ctas, threads>>>(out, iters, 1.0, 1.0); });
                 double fl = 2.0 * 256 * 16 * (double)iters * warps * sms;
-                printf("DMMA884 acc=16 warps/SM=%2d ctas/SM=%d : %.3f ms  %.2f TFLOP/s\n", warps, ctas, ms, fl / ms * 1e-9);
+                if (ms > 0) printf("DMMA884 acc=16 warps/SM=%2d ctas/SM=%d : %.3f ms  %.2f TFLOP/s\n", warps, ctas, ms, fl / ms * 1e-9);
             }
             {
                 float ms = time_ms([&] { k_dfma<16><<<sms * ctas, threads>>>(out, iters, 1.0000001, 1e-9); });
                 double fl = 2.0 * 32 * 16 * (double)iters * warps * sms;
-                printf("DFMA    acc=16 warps/SM=%2d ctas/SM=%d : %.3f ms  %.2f TFLOP/s\n", warps, ctas, ms, fl / ms * 1e-9);
+                if (ms > 0) printf("DFMA    acc=16 warps/SM=%2d ctas/SM=%d : %.3f ms  %.2f TFLOP/s\n", warps, ctas, ms, fl / ms * 1e-9);
             }
         }
     }

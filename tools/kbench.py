@@ -9,7 +9,7 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--M", type=int, default=256); ap.add_argument("--D", type=int, default=8)
 ap.add_argument("--R", type=int, default=8); ap.add_argument("--N", type=int, default=100000)
 ap.add_argument("--reps", type=int, default=8); ap.add_argument("--kind", default="rbf")
-ap.add_argument("--debug", type=int, default=0); ap.add_argument("--force-fwd", type=int, default=0); ap.add_argument("--force-bwd", type=int, default=0)   # test-hook library only
+ap.add_argument("--debug", type=int, default=0); ap.add_argument("--stages", type=int, default=0); ap.add_argument("--force-fwd", type=int, default=0); ap.add_argument("--force-bwd", type=int, default=0)   # test-hook library only
 a = ap.parse_args()
 M, D, R, N = a.M, a.D, a.R, a.N
 dev = "cuda"; lib = C.lib(); rng = np.random.RandomState(0)
@@ -17,6 +17,8 @@ if a.force_fwd or a.force_bwd:
     lib.dgp_test_force_tiles(a.force_fwd, a.force_bwd)
 if a.debug:
     lib.dgp_test_debug_mode(a.debug)
+if a.stages:
+    lib.dgp_test_force_stages(a.stages)
 t = lambda x: torch.tensor(x, dtype=torch.float64, device=dev)
 X = t(rng.randn(N, D)); Z = t(rng.randn(M, D)); theta = t(np.concatenate([[1.0, 1e-5], np.sqrt(D) * np.ones(D)]))
 q_mu = t(0.1 * rng.randn(M, R)); q_sqrt = t(np.eye(M)[None] + 0.1 * np.tril(rng.randn(R, M, M)))
@@ -48,7 +50,7 @@ for name, fn in (("fwd", fwd), ("fwd_nosave", fwd_nosave), ("bwd", bwd), ("gram"
         e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
         e0.record(); fn(); e1.record(); e1.synchronize(); ts.append(e0.elapsed_time(e1))
     out.append(f"{name} {min(ts):.3f}ms ({fl[name] / min(ts) * 1e-9:.1f}TF)")
-print(os.environ.get("DGP_B200_LIB", "default").split("/")[-1], f"fwd{a.force_fwd} bwd{a.force_bwd} dbg{a.debug}", f"M={M} D={D} R={R} N={N}:", " | ".join(out), flush=True)
+print(os.environ.get("DGP_B200_LIB", "default").split("/")[-1], f"fwd{a.force_fwd} bwd{a.force_bwd} dbg{a.debug} stg{a.stages}", f"M={M} D={D} R={R} N={N}:", " | ".join(out), flush=True)
 if os.environ.get("DGP_PHASES"):
     def show(title, names):
         ph = ws[256:256 + 96].view(torch.float64).cpu().numpy()

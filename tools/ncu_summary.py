@@ -19,7 +19,10 @@ KEY = ["gpu__time_duration.sum", "sm__pipe_tensor_subpipe_dmma_cycles_active.avg
        "smsp__average_warps_issue_stalled_wait_per_issue_active.ratio",
        "smsp__average_warps_issue_stalled_barrier_per_issue_active.ratio",
        "smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio",
-       "smsp__average_warps_issue_stalled_short_scoreboard_per_issue_active.ratio"]
+       "smsp__average_warps_issue_stalled_short_scoreboard_per_issue_active.ratio",
+       "smsp__average_warps_issue_stalled_no_instruction_per_issue_active.ratio",
+       "lts__t_sector_hit_rate.pct", "lts__t_sectors_srcunit_tex_op_read.sum", "l1tex__t_sector_hit_rate.pct",
+       "sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active"]
 
 
 def launches(path):
@@ -45,7 +48,10 @@ def launches(path):
 
 
 def raw(path):
-    out = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    if path.endswith(".csv"):          # a raw page exported on the GPU box (the reports themselves are too big to travel)
+        out = open(path).read()
+    else:
+        out = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(out.splitlines()))
     h = rows[0]
     idx = {k: h.index(k) for k in KEY if k in h}
@@ -58,5 +64,27 @@ def raw(path):
                 print(f"   {k:82s} {r[idx[k]]:>18s} {rows[1][idx[k]]}")
 
 
+def traffic(path, key, out_json):
+    """Append dram__bytes_read.sum + dram__bytes_write.sum of the first captured launch in an `ncu --set full` report to
+    the JSON table bench.py reads (profiles/r02_traffic.json): key = "<kernel>|M..,D..,R..,N..".""" 
+    import json
+    import os
+    out = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(out.splitlines()))
+    h, units, r = rows[0], rows[1], rows[2]
+    scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    tot = 0.0
+    for name in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+        i = h.index(name)
+        tot += float(r[i].replace(",", "")) * scale[units[i]]
+    tbl = json.load(open(out_json)) if os.path.exists(out_json) else {}
+    tbl[key] = tot
+    json.dump(tbl, open(out_json, "w"), indent=1, sort_keys=True)
+    print(key, tot)
+
+
 if __name__ == "__main__":
-    {"launches": launches, "raw": raw}[sys.argv[1]](sys.argv[2])
+    if sys.argv[1] == "traffic":
+        traffic(sys.argv[2], sys.argv[3], sys.argv[4])
+    else:
+        {"launches": launches, "raw": raw}[sys.argv[1]](sys.argv[2])
