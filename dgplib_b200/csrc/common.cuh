@@ -187,6 +187,9 @@ int check_desc(const dgp_cond_desc* d);
 // batched in-place lower Cholesky of `batch` Mpad x Mpad matrices (Mpad multiple of 64, <= 1024); status[b] = failing pivot + 1
 // Linv (nullable): receives the inverses of the 32 x 32 diagonal blocks of the factor (input of k_tri_inv_cols)
 int cholesky_batched(double* K, int Mpad, int batch, int32_t* status, cudaStream_t st, double* Linv = nullptr);
+// Linv = L^-1 for one lower-triangular Mpad x Mpad factor whose 32 x 32 diagonal-block inverses are already in Linv
+// (written by cholesky_batched); prep.cu
+int tri_inv_cols(const double* L, double* Linv, int Mpad, cudaStream_t st);
 
 #ifdef __CUDACC__
 // ------------------------------------------------------------------------------------------------ PTX wrappers

@@ -3,7 +3,10 @@
 //     fvar_r = Knn - A^T A + (Lq_r^T A)^T (Lq_r^T A)          [R, N, N],  Knn = k(X, X) incl. White
 // and normal_sample's full-covariance branch (dgplib/utils.py:28-36) / predict_f_samples (dgplib/dsdgp.py:170-185)
 //     f = mean + chol(var + jitter I) z.
-// O(R N^2 M + R N^3) on N <= 1024 points: parameter-stage class work, done with the small strided GEMM.
+// O(R N^2 M + R N^3): parameter-stage class work, done with the small strided GEMM.  Up to 1024 points the covariance
+// is factored by the one-CTA Cholesky of the parameter stage; above (to FULLCOV_MAX_N points) by a blocked right-looking
+// factorisation whose 256-wide diagonal blocks go through that same kernel and whose panel solves and trailing updates
+// are GEMMs over all SMs.
 #include "common.cuh"
 #include "gemm_small.cuh"
 
@@ -63,6 +66,77 @@ __global__ void k_chol_apply(const double* __restrict__ L, int n, int np, const 
     out[((size_t)b * n + i) * nz + c] = s;
 }
 
+// ---- blocked Cholesky for np > 1024 (np a multiple of 64): K [batch][np][np] lower factor in place
+constexpr int CB = 256;            // diagonal block width
+constexpr int FULLCOV_MAX_N = 16384;
+
+// D[b] = the CB x CB block of K[b] at (j0, j0), cb <= CB wide; pad rows / columns of D form an identity
+__global__ void k_block_get(const double* __restrict__ K, int np, int j0, int cb, double* __restrict__ D) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x, i = blockIdx.y, b = blockIdx.z;
+    if (j >= CB) return;
+    double v = (i == j) ? 1.0 : 0.0;
+    if (i < cb && j < cb) v = K[((size_t)b * np + j0 + i) * np + j0 + j];
+    D[((size_t)b * CB + i) * CB + j] = v;
+}
+__global__ void k_block_put(double* __restrict__ K, int np, int j0, int cb, const double* __restrict__ D) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x, i = blockIdx.y, b = blockIdx.z;
+    if (j >= cb || i >= cb) return;
+    K[((size_t)b * np + j0 + i) * np + j0 + j] = (j <= i) ? D[((size_t)b * CB + i) * CB + j] : 0.0;
+}
+// the solved panel P [b][rows][CB] back into K[b][j0 + cb .., j0 .. j0 + cb)
+__global__ void k_panel_put(double* __restrict__ K, int np, int j0, int cb, int rows, const double* __restrict__ P,
+                            long long pstride) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x, i = blockIdx.y, b = blockIdx.z;
+    if (j >= cb || i >= rows) return;
+    K[((size_t)b * np + j0 + cb + i) * np + j0 + j] = P[(size_t)b * pstride + (size_t)i * CB + j];
+}
+__global__ void k_status_merge(const int32_t* __restrict__ blk, int j0, int batch, int32_t* __restrict__ status) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b < batch && status[b] == 0 && blk[b] != 0) status[b] = j0 + blk[b];
+}
+
+static size_t chol_blocked_scratch_doubles(int np, int batch) {
+    return (size_t)batch * (2 * CB * CB + (size_t)np * CB) + 64;        // D, Dinv, panel P (+ block status words)
+}
+
+static int cholesky_blocked(double* K, int np, int batch, int32_t* status, double* scratch, cudaStream_t st) {
+    double* D = scratch;
+    double* Dinv = D + (size_t)batch * CB * CB;
+    double* P = Dinv + (size_t)batch * CB * CB;
+    int32_t* blk = reinterpret_cast<int32_t*>(P + (size_t)batch * np * CB);
+    if (batch > 128) return DGP_ERR_UNSUPPORTED;                        // 64 doubles of status words
+    if (cudaMemsetAsync(status, 0, sizeof(int32_t) * batch, st) != cudaSuccess) return DGP_ERR_LAUNCH;
+    const long long pstride = (long long)np * CB;
+    for (int j0 = 0; j0 < np; j0 += CB) {
+        const int cb = (np - j0 < CB) ? np - j0 : CB;                    // np is a multiple of 64, so is cb
+        const int rows = np - j0 - cb;
+        k_block_get<<<dim3(CB / 128, CB, batch), 128, 0, st>>>(K, np, j0, cb, D); DGP_COUNT_LAUNCH();
+        int rc = cholesky_batched(D, CB, batch, blk, st, Dinv);
+        if (rc != DGP_OK) return rc;
+        k_status_merge<<<(batch + 127) / 128, 128, 0, st>>>(blk, j0, batch, status); DGP_COUNT_LAUNCH();
+        k_block_put<<<dim3((cb + 127) / 128, cb, batch), 128, 0, st>>>(K, np, j0, cb, D); DGP_COUNT_LAUNCH();
+        if (rows == 0) break;
+        for (int b = 0; b < batch; ++b)
+            if ((rc = tri_inv_cols(D + (size_t)b * CB * CB, Dinv + (size_t)b * CB * CB, CB, st)) != DGP_OK) return rc;
+        // panel: P = K[j0 + cb .., j0 .. j0 + cb) D^-T   (B(k, j) = Dinv[j][k]; the identity pad of D keeps cb < CB exact)
+        GemmArgs g{};
+        g.A = K + (size_t)(j0 + cb) * np + j0; g.B = Dinv; g.C = P;
+        g.I = rows; g.J = CB; g.K = cb; g.batch = batch;
+        g.sAi = np; g.sAk = 1; g.sBk = 1; g.sBj = CB; g.sCi = CB; g.sCj = 1;
+        g.bA = (long long)np * np; g.bB = (long long)CB * CB; g.bC = pstride; g.alpha = 1.0;
+        if ((rc = gemm_small(g, st)) != DGP_OK) return rc;
+        // trailing update (lower tiles): K[j0 + cb .., j0 + cb ..] -= P P^T
+        g = GemmArgs{};
+        g.A = P; g.B = P; g.C = K + (size_t)(j0 + cb) * np + j0 + cb;
+        g.I = rows; g.J = rows; g.K = cb; g.batch = batch;
+        g.sAi = CB; g.sAk = 1; g.sBk = 1; g.sBj = CB; g.sCi = np; g.sCj = 1;
+        g.bA = g.bB = pstride; g.bC = (long long)np * np; g.alpha = -1.0; g.beta = 1.0; g.lower_tiles_only = 1;
+        if ((rc = gemm_small(g, st)) != DGP_OK) return rc;
+        k_panel_put<<<dim3((cb + 127) / 128, rows, batch), 128, 0, st>>>(K, np, j0, cb, rows, P, pstride); DGP_COUNT_LAUNCH();
+    }
+    return cudaGetLastError() == cudaSuccess ? DGP_OK : DGP_ERR_LAUNCH;
+}
+
 }  // namespace dgp
 
 using namespace dgp;
@@ -70,7 +144,7 @@ using namespace dgp;
 static inline int np_of(int64_t n) { return (int)((n + 63) / 64 * 64); }
 
 extern "C" size_t dgp_cond_fullcov_ws_bytes(const dgp_cond_desc* d, int64_t n) {
-    if (!d || n < 1 || n > 1024) return 0;
+    if (!d || n < 1 || n > FULLCOV_MAX_N) return 0;
     const size_t np = np_of(n), Mp = dgp_mpad(d->M);
     return (np * Mp * (1 + d->R) + np * np * (1 + d->R)) * sizeof(double) + 256;
 }
@@ -80,7 +154,7 @@ extern "C" int dgp_cond_fullcov(const dgp_cond_desc* d, const void* ws, const do
     int rc = check_desc(d);
     if (rc != DGP_OK) return rc;
     if (!ws || !X || !A_save || !fvar || !scratch || n < 1) return DGP_ERR_ARG;
-    if (n > 1024) return DGP_ERR_UNSUPPORTED;
+    if (n > FULLCOV_MAX_N) return DGP_ERR_UNSUPPORTED;
     if (scratch_bytes < dgp_cond_fullcov_ws_bytes(d, n)) return DGP_ERR_WORKSPACE;
     cudaStream_t st = (cudaStream_t)stream;
     const WsLayout w = ws_layout(*d, 0, 0);
@@ -115,9 +189,11 @@ extern "C" int dgp_cond_fullcov(const dgp_cond_desc* d, const void* ws, const do
 }
 
 extern "C" size_t dgp_chol_sample_ws_bytes(int64_t n, int32_t batch) {
-    if (n < 1 || n > 1024 || batch < 1) return 0;
+    if (n < 1 || n > FULLCOV_MAX_N || batch < 1 || (n > 1024 && batch > 128)) return 0;
     const size_t np = np_of(n);
-    return (size_t)batch * np * np * sizeof(double) + (size_t)batch * sizeof(int32_t) + 256;
+    size_t doubles = (size_t)batch * np * np;
+    if (np > 1024) doubles += chol_blocked_scratch_doubles((int)np, batch);
+    return doubles * sizeof(double) + (size_t)batch * sizeof(int32_t) + 256;
 }
 
 extern "C" int dgp_chol_sample(const double* var, int64_t stride_b, int64_t stride_i, int64_t stride_j, int64_t n,
@@ -125,15 +201,18 @@ extern "C" int dgp_chol_sample(const double* var, int64_t stride_b, int64_t stri
                                int64_t mean_stride_b, int64_t mean_stride_i, double* out, void* scratch,
                                size_t scratch_bytes, int32_t* status_dev, void* stream) {
     if (!var || !z || !out || !scratch || n < 1 || batch < 1 || nz < 1) return DGP_ERR_ARG;
-    if (n > 1024) return DGP_ERR_UNSUPPORTED;
+    if (n > FULLCOV_MAX_N || (n > 1024 && batch > 128)) return DGP_ERR_UNSUPPORTED;
     if (scratch_bytes < dgp_chol_sample_ws_bytes(n, batch)) return DGP_ERR_WORKSPACE;
     cudaStream_t st = (cudaStream_t)stream;
     const int np = np_of(n);
     double* L = static_cast<double*>(scratch);
-    int32_t* status = status_dev ? status_dev : reinterpret_cast<int32_t*>(L + (size_t)batch * np * np);
+    double* extra = L + (size_t)batch * np * np;                      // blocked-factorisation scratch (np > 1024)
+    if (np > 1024) extra += chol_blocked_scratch_doubles(np, batch);
+    int32_t* status = status_dev ? status_dev : reinterpret_cast<int32_t*>(extra);
     k_pad_cov<<<dim3((np + 127) / 128, np, batch), 128, 0, st>>>(var, stride_b, stride_i, stride_j, (int)n, np, jitter, L);
     DGP_COUNT_LAUNCH();
-    int rc = cholesky_batched(L, np, batch, status, st);
+    int rc = (np <= 1024) ? cholesky_batched(L, np, batch, status, st)
+                          : cholesky_blocked(L, np, batch, status, L + (size_t)batch * np * np, st);
     if (rc != DGP_OK) return rc;
     k_chol_apply<<<dim3((nz + 31) / 32, (unsigned)n, batch), 32, 0, st>>>(L, (int)n, np, z, nz, mean, mean_stride_b,
                                                                           mean_stride_i, out);

@@ -318,7 +318,7 @@ class DSDGP(Parameterized):
 
     def predict_f_full_cov(self, Xnew, num_samples, eps=None, seed=None):
         """Mean [S,N,D_Y] and covariance [S,N,N,D_Y] of the final layer at Xnew (dgplib/dsdgp.py:142-148); samples are
-        propagated with the full covariance across the N points (N <= 1024).  eps: per layer [S, R_l, N] draws."""
+        propagated with the full covariance across the N points (N <= 16384).  eps: per layer [S, R_l, N] draws."""
         mean, var = self._build_predict(Xnew, True, num_samples, eps=eps, seed=seed)
         return mean.cpu().numpy(), var.cpu().numpy()
 

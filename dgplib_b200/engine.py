@@ -302,10 +302,11 @@ class Engine:
         return events
 
     def _param_version(self):
-        """Changes whenever a parameter of the model may have changed: torch bumps the flat buffer's version counter on
-        every in-place write through any parameter view, the library's own Adam launch bumps `native_version`."""
+        """Changes whenever a parameter of the model may have changed: torch bumps a parameter's version counter on every
+        in-place write to it (Param.assign, optimisers, user code; the counters are per parameter -- `p.data = view` does
+        not share the flat buffer's), the library's own Adam launch bumps `native_version`."""
         flat = self.flatten()
-        return (flat.key, flat.u._version, flat.native_version)
+        return (flat.key, sum(p._version for p in self.raw_parameters()), flat.native_version)
 
     @_on_device
     def check_status(self):
@@ -465,7 +466,7 @@ class Engine:
                         "dgp_cond_forward")
             nbytes = lib.dgp_cond_fullcov_ws_bytes(c.ref(), N)
             if nbytes == 0:
-                raise _cabi.DgpError("full-covariance prediction supports at most 1024 points per call")
+                raise _cabi.DgpError("full-covariance prediction supports at most 16384 points per call")
             scratch = torch.empty(nbytes, dtype=torch.uint8, device=dev)
             out = fvar[c.desc.col0:c.desc.col0 + c.desc.R]
             _cabi.check(lib.dgp_cond_fullcov(c.ref(), _cabi.ptr(c.ws), _cabi.ptr(X), N, _cabi.ptr(A),
@@ -484,7 +485,7 @@ class Engine:
         out = torch.empty(Bt, N, nz, dtype=_F64, device=self.device)
         nbytes = lib.dgp_chol_sample_ws_bytes(N, Bt)
         if nbytes == 0:
-            raise _cabi.DgpError("full-covariance sampling supports at most 1024 points per call")
+            raise _cabi.DgpError("full-covariance sampling supports at most 16384 points per call (128 covariance matrices per call above 1024)")
         scratch = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
         status = torch.zeros(Bt, dtype=torch.int32, device=self.device)
         _cabi.check(lib.dgp_chol_sample(_cabi.ptr(var), N * N, N, 1, N, Bt,

@@ -43,7 +43,7 @@ class Layer(Parameterized):
 
     def _build_predict(self, Xnew, full_cov=False, stochastic=True):
         """(mean, var) of the layer at Xnew.  stochastic=True: Xnew [S,N,D] -> [S,N,R] each (samples flattened into
-        one conditional, dgplib/layers.py:82-87); stochastic=False: [N,D] -> [N,R].  full_cov=True (N <= 1024):
+        one conditional, dgplib/layers.py:82-87); stochastic=False: [N,D] -> [N,R].  full_cov=True (N <= 16384):
         var is [S,N,N,R] (dgplib/layers.py:74-81), or gpflow's [R,N,N] when stochastic=False."""
         if full_cov:
             from .engine import layer_predict_full_cov

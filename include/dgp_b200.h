@@ -164,7 +164,8 @@ int dgp_cond_backward_params(const dgp_cond_desc* d, void* ws, double kl_weight,
 
 /* ---- full-covariance branch (small N: plots, posterior draws) ---------------------------------------------------
  * dgp_cond_fullcov replaces base_conditional(full_cov=True) as called from dgplib/layers.py:74-81:
- *   fvar[r] = k(X, X) - A^T A + (Lq_r^T A)^T (Lq_r^T A)   for the conditional's R outputs, fvar [R, n, n] (n <= 1024);
+ *   fvar[r] = k(X, X) - A^T A + (Lq_r^T A)^T (Lq_r^T A)   for the conditional's R outputs, fvar [R, n, n] (n <= 16384:
+ *   the *_ws_bytes calls return 0 beyond; above 1024 points the covariance is factored by a blocked multi-launch Cholesky);
  *   A_save [n, Mpad] comes from dgp_cond_forward on the same rows.
  * dgp_chol_sample replaces normal_sample's full-covariance branch (dgplib/utils.py:28-36) and the sampling step of
  * predict_f_samples (dgplib/dsdgp.py:170-185): for b < batch

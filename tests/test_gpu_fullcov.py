@@ -84,9 +84,10 @@ def test_normal_sample_full_cov_util(cuda):
     assert got.shape == (S, N, D) and rel_err(got, want) < 1e-10
 
 
-@pytest.mark.parametrize("N", [1, 64, 130, 1024])
+@pytest.mark.parametrize("N", [1, 64, 130, 1024, 1100, 1500])
 def test_full_cov_sizes(cuda, N):
-    """Single points, exact tile multiples, ragged sizes and the largest supported point count (1024)."""
+    """Single points, exact tile multiples, ragged sizes, the largest size the one-CTA Cholesky takes (1024) and sizes
+    above it (blocked multi-launch factorisation; 1100 pads to 1152 = four full 256-blocks and one of 128)."""
     model, X, Y = build_dsdgp(L=2, M=20, D=2, N=60, S=1, white=1e-3)
     model.compile()
     rng = np.random.RandomState(N)
@@ -101,11 +102,10 @@ def test_full_cov_sizes(cuda, N):
         assert rel_err(M[l], oM[l]) < TOL and rel_err(V[l], oV[l]) < TOL and rel_err(F[l], oF[l]) < 1e-7
 
 
-def test_full_cov_refuses_more_than_1024_points(cuda):
-    model, X, Y = build_dsdgp(L=2, M=20, D=2, N=60, S=1)
-    model.compile()
-    with pytest.raises(Exception):
-        model.predict_f_full_cov(np.random.RandomState(0).randn(1025, 2), 1)
+def test_full_cov_refuses_more_than_16384_points(cuda):
+    from dgplib_b200 import _cabi
+    assert _cabi.lib().dgp_chol_sample_ws_bytes(16385, 1) == 0 and _cabi.lib().dgp_chol_sample_ws_bytes(16384, 1) > 0
+    assert _cabi.lib().dgp_chol_sample_ws_bytes(2048, 129) == 0
 
 
 def test_multikernel_full_cov_matches_oracle(cuda):

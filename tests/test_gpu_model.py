@@ -654,6 +654,39 @@ def test_predict_between_graph_replays(cuda):
     assert torch.equal(a, b)
 
 
+def test_prediction_cache_sees_parameter_changes(cuda):
+    """The parameter stage is cached across predict_* calls and redone only when a parameter changed: every way a parameter
+    can change (Param.assign, an in-place write, the library's Adam kernel, a torch optimiser) must invalidate it."""
+    from dgplib_b200.training import AdamOptimizer
+    model, X, Y = build_dsdgp(L=2, M=16, D=2, N=80, S=2, minibatch=40)
+    model.compile()
+    Xs = np.random.RandomState(9).randn(21, 2)
+    eps = make_eps(model, 2, 21, seed=5)
+
+    def check():
+        mu, var = model.predict_f(Xs, 2, eps=eps)
+        omu, ovar = O.predict_f(oracle_layers(model.layers.layers), t(Xs), 2, [t(e) for e in eps])
+        assert rel_err(mu, omu) < TOL and rel_err(var, ovar) < TOL
+        return mu
+
+    a = check()
+    assert np.array_equal(a, check())                              # unchanged parameters: cached stage, same result
+    model.layers.layers[0].kernel.kernels[0].lengthscales.assign(2.5)
+    b = check()
+    assert not np.allclose(a, b)
+    with torch.no_grad():
+        model.layers.layers[1].q_mu.raw.add_(0.05)
+    c = check()
+    assert not np.allclose(b, c)
+    AdamOptimizer(0.05).minimize(model, maxiter=2)
+    d = check()
+    assert not np.allclose(c, d)
+    opt = torch.optim.SGD(model.trainable_parameters(), lr=1e-4)
+    (-model._build_likelihood()).backward()
+    opt.step()
+    assert not np.allclose(d, check())
+
+
 def test_cholesky_failure_surfaces_through_the_model(cuda, monkeypatch):
     """Numerical failure convention at the model level: the status words are read back asynchronously, so an indefinite
     Kuu + jitter raises when the next evaluation is queued, or at once through engine.poll_status() / check_status()."""
