@@ -42,7 +42,7 @@ SIGNATURES = {
     "dgp_cond_status": (ctypes.c_int, [_vp, _vp, ctypes.POINTER(_i32)]),
     "dgp_cond_status_async": (ctypes.c_int, [_vp, _vp, _vp]),
     "dgp_cond_forward": (ctypes.c_int, [_P, _vp, _vp, _i64, _i64, _vp, _u64, _vp, _u64, _i64, _i64, _vp, _vp, _vp, _i32,
-                                        _vp, _vp, _vp]),
+                                        _vp, _vp, _vp, _vp]),
     "dgp_usave_bytes": (_sz, [_P, _i64]),
     "dgp_sample_expand": (ctypes.c_int, [_vp, _vp, _vp, _u64, _vp, _u64, _i64, _i32, _i64, _i32, _i32, _vp, _i32, _vp,
                                          _i32, _vp]),
@@ -50,8 +50,8 @@ SIGNATURES = {
     "dgp_lik_gaussian": (ctypes.c_int, [_vp, _vp, _vp, _i64, _i32, _i64, _i32, _vp, _i32, _dbl, _vp, _vp, _vp, _vp,
                                         _vp, _sz, _vp]),
     "dgp_lik_ws_bytes": (_sz, [_i64, _i32]),
-    "dgp_cond_backward": (ctypes.c_int, [_P, _vp, _vp, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _i32, _vp, _vp, _vp, _i32,
-                                         _vp, _i32, _i32, _vp]),
+    "dgp_cond_backward": (ctypes.c_int, [_P, _vp, _vp, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _vp, _vp, _vp,
+                                         _i32, _vp, _i32, _i32, _vp]),
     "dgp_cond_backward_gram": (ctypes.c_int, [_P, _vp, _vp, _i64, _i32, _vp]),
     "dgp_cond_backward_params": (ctypes.c_int, [_P, _vp, _dbl, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "dgp_cond_fullcov_ws_bytes": (_sz, [_P, _i64]),

@@ -40,6 +40,7 @@ struct BwdArgs {
     const double* LinvT; const double* LqL; size_t tl;   // tiled copies (stream_gemm.cuh): Lm^-T and tril(q_sqrt_r)
     const double* X; long long x_rows, n_rows;
     const double* A_save; const double* U_save; long long NG;
+    const double* K_save;    // Kuf per row kept by the forward pass (nullptr: recompute the covariance function)
     const double* mean; const double* var; const double* F; int ldf;
     const double* g_mean_in; const double* g_var_in; const double* g_F; int ldgf;
     double* gX; int accumulate_gX;
@@ -232,6 +233,33 @@ __global__ void __launch_bounds__(C::NTHREADS, 1) k_cond_bwd(const __grid_consta
             for (int r = 0; r < R; ++r) s += gv[n * R + r];
             gs[n] = s;
         }
+        // ---- Dt <- q_mu g_mean^T (the mean path of dA) on the tensor cores, K = R: the dA tile is free until the epilogue
+        //      of the streamed phase adds the variance path to it.  (As a scalar loop in that epilogue -- q_mu rows from
+        //      global memory behind every shared-memory store -- this term cost 9 % of the kernel at R = 8, 13 % at R = 1.)
+        for (int mt = warp; mt < Mpad / 8; mt += C::NWARPS) {
+            const int m = mt * 8 + g;
+            const double* qrow = d.q_mu + (size_t)m * d.ldr + d.col0;
+            for (int r0 = 0; r0 < R; r0 += 16) {
+                double aq[4];
+#pragma unroll
+                for (int ks = 0; ks < 4; ++ks) {
+                    const int k = r0 + ks * 4 + t;
+                    aq[ks] = (m < d.M && k < R) ? qrow[k] : 0.0;
+                }
+#pragma unroll
+                for (int nt = 0; nt < C::NT / 8; ++nt) {
+                    double c[2] = {0.0, 0.0};
+#pragma unroll
+                    for (int ks = 0; ks < 4; ++ks) {
+                        const int k = r0 + ks * 4 + t;
+                        if (r0 + ks * 4 < R) dmma884(c, aq[ks], k < R ? gm[(nt * 8 + g) * R + k] : 0.0);
+                    }
+                    double* dst = Dt + (nt * 8 + 2 * t) * ldb + m;
+                    if (r0 == 0) { dst[0] = c[0]; dst[ldb] = c[1]; }
+                    else { dst[0] += c[0]; dst[ldb] += c[1]; }
+                }
+            }
+        }
         PH(1);
         // (run_phase starts with a consumer barrier)
 
@@ -244,34 +272,41 @@ __global__ void __launch_bounds__(C::NTHREADS, 1) k_cond_bwd(const __grid_consta
             // DMMA: DMMA pipe 59 % active); accumulating that sum in the shared-memory tile was slower still.
             // Columns beyond the last valid row get weight 0; their ring bytes are stale but finite (zeroed at start).
             auto epi = [&](Acc<C>& acc, const Seg& sg) {
+                PH(3);
+                // A[n][row] for every element this thread owns, straight from L2 (prefetched by the producer warp): all
+                // 8 NJ loads are issued before the first use, one exposed round trip per block row
+                double av[4][C::NJ][2];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const int row = acc_row<C>(sg.i, q);
+#pragma unroll
+                    for (int j = 0; j < C::NJ; ++j)
+#pragma unroll
+                        for (int e = 0; e < 2; ++e) {
+                            const int n = acc_col<C>(j, e);
+                            av[q][j][e] = (n < nvalid && row < Mpad) ? __ldg(a.A_save + (size_t)(n0 + n) * Mpad + row) : 0.0;
+                        }
+                }
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
                     const int row = acc_row<C>(sg.i, q);
                     if (row < Mpad) {
-                        // A[n][row] for this thread's columns, from L2 (prefetched by the producer warp)
-                        double av[C::NJ][2];
 #pragma unroll
                         for (int j = 0; j < C::NJ; ++j)
 #pragma unroll
                             for (int e = 0; e < 2; ++e) {
                                 const int n = acc_col<C>(j, e);
-                                av[j][e] = (n < nvalid) ? a.A_save[(size_t)(n0 + n) * Mpad + row] : 0.0;
-                            }
-#pragma unroll
-                        for (int j = 0; j < C::NJ; ++j)
-#pragma unroll
-                            for (int e = 0; e < 2; ++e) {
-                                const int n = acc_col<C>(j, e);
-                                double v = 2.0 * (acc.v[q][j][e] - av[j][e] * gs[n]);
-                                if (row < d.M) {
-                                    const double* qm = d.q_mu + (size_t)row * d.ldr + d.col0;
-                                    for (int r = 0; r < R; ++r) v = fma(qm[r], gm[n * R + r], v);
-                                }
-                                Dt[n * ldb + row] = v;
+                                double* dst = Dt + n * ldb + row;       // holds (q_mu g_mean^T)[row][n] from the prologue
+                                *dst = fma(2.0, acc.v[q][j][e] - av[q][j][e] * gs[n], *dst);
                             }
                     }
                 }
+                PH(10);
             };
+#ifdef DGP_PROFILE_PHASES
+            consumer_sync<C>();
+            PH(11);
+#endif
 #ifdef DGP_TEST_HOOKS
             if (a.debug == 4)        // timing experiment: B fragments from the resident tile (the forward kernel's pattern)
                 run_phase<C, MASK_LOWER, false, true>(pipe, nb * R, seg_dA, epi, Dt, ldb, Mpad, gv, R, nvalid);
@@ -342,7 +377,44 @@ __global__ void __launch_bounds__(C::NTHREADS, 1) k_cond_bwd(const __grid_consta
         PH(6);
 
         // ---- Dt <- Gr2 = dKuf . variance . k'(r2);  per-row sums: rs = sum_m Gr2, dv = sum_m dKuf k(r2)/variance
-        if (d.T == 1) {
+        const bool saved_k = (d.T == 1 && d.kind[0] == DGP_KIND_RBF && a.K_save != nullptr);
+        if (saved_k) {
+            // RBF with Kuf kept by the forward pass: k'(r2) = -k/2, so Gr2 = -dKuf Kuf / 2 and dv = sum dKuf Kuf / variance
+            // need no exp, no cross term and no inducing inputs: one coalesced pass, a warp per row, 32 independent loads
+            // per lane in flight.  (Recomputing exp(-r2/2) for the 16 k elements of a tile was 7 % of the kernel at R = 8
+            // and 17 % at R = 1: latency-bound chains, five times the fp64-pipe time of the arithmetic.)
+            const double ivar = 1.0 / d.theta[0];
+            for (int n = warp; n < C::NT; n += C::NWARPS) {
+                double srs = 0.0, sdv = 0.0;
+                if (n < nvalid) {
+                    const double* krow = a.K_save + (size_t)(n0 + n) * Mpad;
+                    for (int m0 = 0; m0 < Mpad; m0 += 256) {
+                        double kv[8];
+#pragma unroll
+                        for (int u = 0; u < 8; ++u) {
+                            const int m = m0 + u * 32 + lane;
+                            kv[u] = (m < Mpad) ? __ldg(krow + m) : 0.0;
+                        }
+#pragma unroll
+                        for (int u = 0; u < 8; ++u) {
+                            const int m = m0 + u * 32 + lane;
+                            if (m < Mpad) {
+                                const double gk = Dt[n * ldb + m];
+                                const double out = -0.5 * gk * kv[u];
+                                sdv = fma(gk, kv[u], sdv);
+                                srs += out;
+                                Dt[n * ldb + m] = out;
+                            }
+                        }
+                    }
+                } else {
+                    for (int m = lane; m < Mpad; m += 32) Dt[n * ldb + m] = 0.0;
+                }
+                srs = warp_sum(srs);
+                sdv = warp_sum(sdv);
+                if (lane == 0) { rs[n] = srs; dv[n] = sdv * ivar; }
+            }
+        } else if (d.T == 1) {
             // fast path (one kernel for every row): cross term z.x on the tensor cores as in the forward pass, the
             // elementwise part in the accumulator layout (8 independent exp chains per thread); rs comes out of the T1
             // contraction below (ones column), and only the tile total of dv is needed (all rows share the task).
@@ -471,8 +543,8 @@ __global__ void __launch_bounds__(C::NTHREADS, 1) k_cond_bwd(const __grid_consta
         }
         consumer_sync<C>();
         PH(8);
-        // ---- row sums of Gr2 from the ones column (fast path; the general path computed them above)
-        if (d.T == 1) {
+        // ---- row sums of Gr2 from the ones column (fast path; the other paths computed them above)
+        if (d.T == 1 && !saved_k) {
             if (tid < C::NT) rs[tid] = rowq[tid * nq];
             consumer_sync<C>();
         }
@@ -745,7 +817,8 @@ __global__ void __launch_bounds__(GR_THREADS, 4) k_gram(GramArgs a) {
 using namespace dgp;
 
 extern "C" int dgp_cond_backward(const dgp_cond_desc* d, void* ws, const double* X, int64_t x_rows, int64_t n_rows,
-                                 const double* A_save, const double* U_save, const double* mean, const double* var,
+                                 const double* A_save, const double* U_save, const double* K_save, const double* mean,
+                                 const double* var,
                                  const double* F, int32_t ldf, const double* g_mean_in, const double* g_var_in,
                                  const double* g_F, int32_t ldgf, double* gX, int32_t accumulate_gX, int32_t mean_grad,
                                  void* stream) {
@@ -764,6 +837,7 @@ extern "C" int dgp_cond_backward(const dgp_cond_desc* d, void* ws, const double*
     a.LinvT = ws_ptr<double>(ws, w.LinvTTl); a.LqL = ws_ptr<double>(ws, w.LqTl); a.tl = w.tl;
     a.X = X; a.x_rows = x_rows; a.n_rows = n_rows;
     a.A_save = A_save; a.U_save = U_save; a.NG = usave_groups(n_rows);
+    a.K_save = K_save;
     a.mean = mean; a.var = var; a.F = F; a.ldf = ldf;
     a.g_mean_in = g_mean_in; a.g_var_in = g_var_in; a.g_F = g_F; a.ldgf = ldgf;
     a.gX = gX; a.accumulate_gX = accumulate_gX;

@@ -36,6 +36,7 @@ struct FwdArgs {
     long long rows_per_sample, sample_stride;
     double* mean; double* var; double* F; int ldf; double* A_save; double* scal;
     double* U_save; long long NG;     // saved U_r blocks (common.cuh usave_*), NG = groups of 8 rows; nullptr: not kept
+    double* K_save;                   // [n_rows][Mpad] Kuf per row (RBF: the backward pass reuses exp(-r2/2)); nullptr: not kept
     int ntiles;
 };
 
@@ -196,9 +197,21 @@ __global__ void __launch_bounds__(C::NTHREADS, 1) k_cond_fwd(const __grid_consta
         // (run_phase starts with a consumer barrier)
 
         PH(2);
+        // ---- Kuf tile -> HBM for the backward pass of an RBF kernel (k' = -k/2: no exp there), before phase T overwrites
+        //      the tile in place
+        if (a.K_save) {
+            consumer_sync<C>();
+            fence_async_smem();
+            if (tid < C::NT && n0 + tid < a.n_rows) {
+                bulk_s2g(a.K_save + (size_t)(n0 + tid) * Mpad, Bt + tid * ldb, (uint32_t)(Mpad * sizeof(double)));
+                bulk_commit();
+            }
+            // (the store drains while the first block row of phase T is multiplied; its epilogue waits for it)
+        }
         // ---- phase T: A = Linv * Kuf, in place
         {
             auto epi = [&](Acc<C>& acc, const Seg& sg) {
+                bulk_wait_read0();   // the Kuf store (if any) has finished reading the tile
                 consumer_sync<C>();  // all warps finished reading this block row's k-range of Bt
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
@@ -389,7 +402,7 @@ using namespace dgp;
 extern "C" int dgp_cond_forward(const dgp_cond_desc* d, const void* ws, const double* X, int64_t x_rows, int64_t n_rows,
                                 const double* eps, uint64_t seed, const uint64_t* seed_dev, uint64_t row_offset,
                                 int64_t rows_per_sample, int64_t sample_stride, double* mean, double* var, double* F,
-                                int32_t ldf, double* A_save, double* U_save, void* stream) {
+                                int32_t ldf, double* A_save, double* U_save, double* K_save, void* stream) {
     int rc = check_desc(d);
     if (rc != DGP_OK) return rc;
     if (!ws || !X || !mean || !var || x_rows < 1 || n_rows < 0) return DGP_ERR_ARG;
@@ -408,6 +421,7 @@ extern "C" int dgp_cond_forward(const dgp_cond_desc* d, const void* ws, const do
     a.sample_stride = sample_stride > 0 ? sample_stride : a.rows_per_sample;
     a.mean = mean; a.var = var; a.F = F; a.ldf = ldf; a.A_save = A_save;
     a.U_save = U_save; a.NG = usave_groups(n_rows);
+    a.K_save = K_save;
     a.scal = const_cast<double*>(ws_ptr<double>(ws, w.scal));
     cudaStream_t st = (cudaStream_t)stream;
     // row-tile width by inducing count (the A tile must fit in shared memory); ring depth 4, or 3 / 2 when the

@@ -236,7 +236,7 @@ class Engine:
         if buf is None:
             dev = self.device
             n = S * nb
-            buf = {"mean": [], "var": [], "F": [], "A": [], "U": [], "gX": []}
+            buf = {"mean": [], "var": [], "F": [], "A": [], "U": [], "K": [], "gX": []}
             for l, (layer, conds) in enumerate(zip(self.layers, self.conds)):
                 R = layer.output_dim
                 ldf = R + (1 if self.multitask else 0)
@@ -250,6 +250,9 @@ class Engine:
                     # U_r = tril(q_sqrt_r)^T A of every output, kept for the backward pass (the reference's LTA tensor)
                     buf["U"].append([torch.empty(_cabi.lib().dgp_usave_bytes(c.ref(), rows) // 8, dtype=_F64, device=dev)
                                      for c in conds])
+                    # Kuf of an RBF conditional: its backward pass then needs no exp (k' = -k / 2)
+                    buf["K"].append([torch.empty(rows, _cabi.mpad(layer.num_inducing), dtype=_F64, device=dev)
+                                     if (c.T == 1 and c.kinds[0] == _cabi.DGP_KIND_RBF) else None for c in conds])
                     buf["gX"].append(torch.empty(n, conds[0].desc.Dx, dtype=_F64, device=dev) if l > 0 else None)
             if save:
                 RL, R0 = self.layers[-1].output_dim, self.layers[0].output_dim
@@ -383,8 +386,8 @@ class Engine:
                     self._layer_seed(seed, l), self._seed_dev_ptr(), row_offset, nb, stride,
                     _cabi.ptr(buf["mean"][l]), _cabi.ptr(buf["var"][l]), _cabi.ptr(Fbuf) if fused_F else None,
                     Fbuf.shape[1] if fused_F else layer.output_dim,
-                    _cabi.ptr(buf["A"][l][ci]) if save else None, _cabi.ptr(buf["U"][l][ci]) if save else None, st),
-                    "dgp_cond_forward"))
+                    _cabi.ptr(buf["A"][l][ci]) if save else None, _cabi.ptr(buf["U"][l][ci]) if save else None,
+                    _cabi.ptr(buf["K"][l][ci]) if save else None, st), "dgp_cond_forward"))
             if l == 0 and want_F:
                 self._timed("sample.l0", lambda: _cabi.check(lib.dgp_sample_expand(
                     _cabi.ptr(buf["mean"][0]), _cabi.ptr(buf["var"][0]), _cabi.ptr(eps[0]) if eps is not None else None,
@@ -462,7 +465,7 @@ class Engine:
         for c in conds:
             A = torch.empty(N, _cabi.mpad(layer.num_inducing), dtype=_F64, device=dev)
             _cabi.check(lib.dgp_cond_forward(c.ref(), _cabi.ptr(c.ws), _cabi.ptr(X), N, N, None, 0, None, 0, 0, 0,
-                                             _cabi.ptr(mean), _cabi.ptr(var_diag), None, R, _cabi.ptr(A), None, st),
+                                             _cabi.ptr(mean), _cabi.ptr(var_diag), None, R, _cabi.ptr(A), None, None, st),
                         "dgp_cond_forward")
             nbytes = lib.dgp_cond_fullcov_ws_bytes(c.ref(), N)
             if nbytes == 0:
@@ -686,7 +689,8 @@ class Engine:
                     for ci, c in enumerate(conds):
                         self._timed(f"bwd.l{l}", lambda: _cabi.check(lib.dgp_cond_backward(
                             c.ref(), _cabi.ptr(c.ws), _cabi.ptr(inp), x_rows, rows, _cabi.ptr(buf["A"][l][ci]),
-                            _cabi.ptr(buf["U"][l][ci]), _cabi.ptr(buf["mean"][l]), _cabi.ptr(buf["var"][l]),
+                            _cabi.ptr(buf["U"][l][ci]), _cabi.ptr(buf["K"][l][ci]), _cabi.ptr(buf["mean"][l]),
+                            _cabi.ptr(buf["var"][l]),
                             _cabi.ptr(Fl) if Fl is not None else None, buf["F"][l].shape[1],
                             _cabi.ptr(g_mean_in) if g_mean_in is not None else None,
                             _cabi.ptr(g_var_in) if g_var_in is not None else None,

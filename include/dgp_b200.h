@@ -99,11 +99,13 @@ int dgp_cond_status_async(const void* ws, void* stream, int32_t* status_pinned);
  *   U_save  dgp_usave_bytes(d, n_rows) bytes: U_r = tril(q_sqrt_r)^T A for every output r, kept for the backward pass
  *           (the reference's [R, M, N'] LTA tensor of base_conditional, which TF keeps for its own reverse mode) in
  *           16 x 8 blocks [r][m / 16][n / 8][m % 16][n % 8]; NULL: not kept (prediction)
+ *   K_save  [n_rows, Mpad] Kuf = k(Z, x_n) per row (nullable): for an RBF kernel (T = 1) the backward pass then needs no
+ *           exp (k' = -k / 2); ignored there for other kernels, which recompute the covariance function
  */
 int dgp_cond_forward(const dgp_cond_desc* d, const void* ws, const double* X, int64_t x_rows, int64_t n_rows,
                      const double* eps, uint64_t seed, const uint64_t* seed_dev, uint64_t row_offset,
                      int64_t rows_per_sample, int64_t sample_stride, double* mean, double* var, double* F, int32_t ldf,
-                     double* A_save, double* U_save, void* stream);
+                     double* A_save, double* U_save, double* K_save, void* stream);
 /* bytes of the U_save buffer for n_rows rows of this conditional (R * Mpad * 8 * ceil(n_rows / 8) * 8) */
 size_t dgp_usave_bytes(const dgp_cond_desc* d, int64_t n_rows);
 
@@ -140,7 +142,7 @@ size_t dgp_lik_ws_bytes(int64_t n_rows, int32_t R);
  *   g_mean_in, g_var_in [n_rows, ldr]  direct gradients of mean / var (last layer: from the likelihood), or NULL
  *   g_F       [n_rows, ldgf] gradient of the sample F (from the next layer's gX), or NULL;  then
  *             g_mean = g_mean_in + g_F,  g_var = g_var_in + g_F * (F - mean) / (2 var)
- *   A_save, U_save  what dgp_cond_forward kept for these rows
+ *   A_save, U_save, K_save  what dgp_cond_forward kept for these rows (K_save may be NULL)
  *   gX        [n_rows, Dx] gradient w.r.t. the input rows (NULL for the data layer); accumulate != 0 adds to it
  *   mean_grad != 0: the Linear mean (d->mean_A, d->mean_b) is trainable -- an OutputLayer built with its own Linear mean,
  *             which dgplib/layers.py:211-218 does not freeze: also accumulate dA = X^T g_mean, db = sum_n g_mean
@@ -150,8 +152,8 @@ size_t dgp_lik_ws_bytes(int64_t n_rows, int32_t R);
  * may be pushed between one dgp_cond_prepare and dgp_cond_backward_params, which finishes them).
  */
 int dgp_cond_backward(const dgp_cond_desc* d, void* ws, const double* X, int64_t x_rows, int64_t n_rows,
-                      const double* A_save, const double* U_save, const double* mean, const double* var, const double* F,
-                      int32_t ldf, const double* g_mean_in, const double* g_var_in, const double* g_F, int32_t ldgf,
+                      const double* A_save, const double* U_save, const double* K_save, const double* mean,
+                      const double* var, const double* F, int32_t ldf, const double* g_mean_in, const double* g_var_in, const double* g_F, int32_t ldgf,
                       double* gX, int32_t accumulate_gX, int32_t mean_grad, void* stream);
 int dgp_cond_backward_gram(const dgp_cond_desc* d, void* ws, const double* A_save, int64_t n_rows, int32_t accumulate,
                            void* stream);   /* accumulate: 0 for the first row chunk after dgp_cond_prepare, 1 after */

@@ -51,7 +51,7 @@ def test_argument_validation_without_a_gpu():
     d = _cabi.CondDesc()
     d.M, d.D, d.Dx, d.R, d.ldr, d.col0, d.T = 2000, 8, 8, 8, 8, 0, 1     # M too large, null pointers
     assert lib.dgp_cond_prepare(ctypes.byref(d), None, 0, 0, None, None) < 0
-    assert lib.dgp_cond_forward(ctypes.byref(d), None, None, 1, 1, None, 0, None, 0, 0, 0, None, None, None, 8, None, None, None) < 0
+    assert lib.dgp_cond_forward(ctypes.byref(d), None, None, 1, 1, None, 0, None, 0, 0, 0, None, None, None, 8, None, None, None, None) < 0
     assert lib.dgp_lik_gaussian(None, None, None, 1, 1, 1, 1, None, 1, 1.0, None, None, None, None, None, 0, None) < 0
     assert lib.dgp_philox_normal(None, 1, 1, 1, 0, 0, 0, 0, None) < 0
 

@@ -78,9 +78,12 @@ def run_conditional(cuda, M, D, R, N, kind, S=1, white=1e-5, linear=True, backwa
     varo, F = torch.zeros_like(mean), torch.zeros_like(mean)
     Asave = torch.full((n, Mp), float("nan"), dtype=torch.float64, device=dev)
     Usave = torch.full((lib.dgp_usave_bytes(ctypes.byref(d), n) // 8,), float("nan"), dtype=torch.float64, device=dev)
+    # Kuf kept for the backward pass (used by RBF; every other seed exercises the recompute path of RBF as well)
+    Ksave = torch.full((n, Mp), float("nan"), dtype=torch.float64, device=dev) if (backward and seed % 2 == 0) else None
     # the S copies of X are addressed by index arithmetic (x_rows = N), never materialised
     C.check(lib.dgp_cond_forward(ctypes.byref(d), C.ptr(ws), C.ptr(Xd), N, n, C.ptr(epsd), 0, None, 0, 0, 0, C.ptr(mean),
-                                 C.ptr(varo), C.ptr(F), R, C.ptr(Asave), C.ptr(Usave) if backward else None, st), "forward")
+                                 C.ptr(varo), C.ptr(F), R, C.ptr(Asave), C.ptr(Usave) if backward else None, C.ptr(Ksave),
+                                 st), "forward")
     torch.cuda.synchronize()
     errs = {"kl": abs(kl.item() - kl_ref.item()) / max(abs(kl_ref.item()), 1e-12), "mean": rel(mean, m_ref),
             "var": rel(varo, v_ref), "F": rel(F, F_ref)}
@@ -93,7 +96,7 @@ def run_conditional(cuda, M, D, R, N, kind, S=1, white=1e-5, linear=True, backwa
         gX = torch.zeros(N * S, D, dtype=torch.float64, device=dev)
         Xrep = Xd.repeat(S, 1).contiguous()                  # d/dX per flattened row: give every row its own X row
         gmd, gvd, gFd = gm_in.to(dev), gv_in.to(dev), gF.to(dev)   # keep the device copies alive across the call
-        C.check(lib.dgp_cond_backward(ctypes.byref(d), C.ptr(ws), C.ptr(Xrep), n, n, C.ptr(Asave), C.ptr(Usave), C.ptr(mean),
+        C.check(lib.dgp_cond_backward(ctypes.byref(d), C.ptr(ws), C.ptr(Xrep), n, n, C.ptr(Asave), C.ptr(Usave), C.ptr(Ksave), C.ptr(mean),
                                       C.ptr(varo), C.ptr(F), R, C.ptr(gmd), C.ptr(gvd), C.ptr(gFd), R, C.ptr(gX), 0,
                                       1 if mean_grad else 0, st), "backward")
         C.check(lib.dgp_cond_backward_gram(ctypes.byref(d), C.ptr(ws), C.ptr(Asave), n, 0, st), "gram")
@@ -186,6 +189,16 @@ def test_every_tile_instantiation_matches_oracle(cuda, hooked_lib, fnt, bnt, M, 
     assert not bad, (bad, errs)
 
 
+def test_rbf_backward_with_and_without_saved_kuf(cuda):
+    """The RBF backward pass takes k' = -k / 2 from the Kuf tile the forward pass kept, or recomputes exp when no K_save was
+    given: both against the oracle (run_conditional keeps K_save on even seeds only)."""
+    for seed in (0, 1):
+        for (M, D, R, N) in [(256, 8, 8, 1500), (100, 3, 1, 333)]:
+            errs = run_conditional(cuda, M, D, R, N, "rbf", seed=seed)
+            bad = {k: v for k, v in errs.items() if not v < TOL}
+            assert not bad, (seed, bad, errs)
+
+
 def test_trainable_linear_mean_gradient(cuda):
     """A Linear mean left trainable (an OutputLayer built with its own Linear mean, dgplib/layers.py:211-218): dA = X^T g_mean,
     db = sum g_mean through the per-CTA partials, for a sample-tiled input and ragged tiles."""
@@ -274,18 +287,18 @@ def test_ragged_tiles_do_not_write_out_of_bounds(cuda):
     C.check(lib.dgp_cond_prepare(ctypes.byref(d), C.ptr(ws), wsb, 1, None, st), "prepare")
     Mp = C.mpad(M)
     full = lambda cols: torch.full((N + PAD, cols), SENT, dtype=torch.float64, device=cuda)
-    mean, var, F, A, gX = full(R), full(R), full(R), full(Mp), full(D)
+    mean, var, F, A, gX, Kk = full(R), full(R), full(R), full(Mp), full(D), full(Mp)
     nU = lib.dgp_usave_bytes(ctypes.byref(d), N) // 8
     U = torch.full((nU + 4096,), SENT, dtype=torch.float64, device=cuda)
     C.check(lib.dgp_cond_forward(ctypes.byref(d), C.ptr(ws), C.ptr(X), N, N, None, 5, None, 0, 0, 0, C.ptr(mean), C.ptr(var),
-                                 C.ptr(F), R, C.ptr(A), C.ptr(U), st), "forward")
+                                 C.ptr(F), R, C.ptr(A), C.ptr(U), C.ptr(Kk), st), "forward")
     gm, gv = t(rng.randn(N, R)), t(rng.randn(N, R))
-    C.check(lib.dgp_cond_backward(ctypes.byref(d), C.ptr(ws), C.ptr(X), N, N, C.ptr(A), C.ptr(U), C.ptr(mean), C.ptr(var), None, R,
+    C.check(lib.dgp_cond_backward(ctypes.byref(d), C.ptr(ws), C.ptr(X), N, N, C.ptr(A), C.ptr(U), C.ptr(Kk), C.ptr(mean), C.ptr(var), None, R,
                                   C.ptr(gm), C.ptr(gv), None, 0, C.ptr(gX), 0, 0, st), "backward")
     C.check(lib.dgp_cond_backward_gram(ctypes.byref(d), C.ptr(ws), C.ptr(A), N, 0, st), "gram")
     torch.cuda.synchronize()
     assert bool((U[nU:] == SENT).all()) and bool(torch.isfinite(U[:nU]).all()) and not bool((U[:nU] == SENT).any()), "U"
-    for name, buf in (("mean", mean), ("var", var), ("F", F), ("A", A), ("gX", gX)):
+    for name, buf in (("mean", mean), ("var", var), ("F", F), ("A", A), ("gX", gX), ("K", Kk)):
         assert bool((buf[N:] == SENT).all()), name
         assert bool(torch.isfinite(buf[:N]).all()) and not bool((buf[:N] == SENT).any()), name
 
@@ -304,13 +317,13 @@ def test_empty_and_unsupported_inputs(cuda):
     one = torch.zeros(8, 2, dtype=torch.float64, device=cuda)
     # zero rows: a no-op that succeeds
     assert lib.dgp_cond_forward(ctypes.byref(d), C.ptr(ws), C.ptr(one), 1, 0, None, 0, None, 0, 0, 0, C.ptr(one), C.ptr(one),
-                                None, 1, None, None, C.stream_ptr()) == 0
+                                None, 1, None, None, None, C.stream_ptr()) == 0
     assert lib.dgp_philox_normal(C.ptr(one), 0, 1, 1, 0, 0, 0, 0, C.stream_ptr()) == 0
     # too small a workspace is refused, not overrun
     assert lib.dgp_cond_prepare(ctypes.byref(d), C.ptr(ws), 1024, 0, None, C.stream_ptr()) == -3
     # inducing sets beyond 1024 points are refused by every entry point
     d.M = 1025
     assert lib.dgp_cond_ws_bytes(ctypes.byref(d), 8, 1) == 0
-    assert lib.dgp_cond_backward(ctypes.byref(d), C.ptr(ws), C.ptr(one), 1, 1, C.ptr(one), C.ptr(one), C.ptr(one), C.ptr(one), None, 1,
+    assert lib.dgp_cond_backward(ctypes.byref(d), C.ptr(ws), C.ptr(one), 1, 1, C.ptr(one), C.ptr(one), None, C.ptr(one), C.ptr(one), None, 1,
                                  C.ptr(one), C.ptr(one), None, 0, None, 0, 0, C.stream_ptr()) == -4
     torch.cuda.synchronize()

@@ -32,10 +32,11 @@ Mp = C.mpad(M)
 mean = torch.zeros(N, R, dtype=torch.float64, device=dev); var = torch.zeros_like(mean); F = torch.zeros_like(mean)
 A = torch.zeros(N, Mp, dtype=torch.float64, device=dev)
 U = torch.zeros(lib.dgp_usave_bytes(ctypes.byref(d), N) // 8, dtype=torch.float64, device=dev)
+Ks = torch.zeros(N, Mp, dtype=torch.float64, device=dev) if a.kind == "rbf" else None
 gm = t(rng.randn(N, R)); gv = t(rng.randn(N, R)); gF = t(rng.randn(N, R)); gX = torch.zeros(N, D, dtype=torch.float64, device=dev)
-def fwd(): C.check(lib.dgp_cond_forward(ctypes.byref(d), C.ptr(ws), C.ptr(X), N, N, None, 1, None, 0, 0, 0, C.ptr(mean), C.ptr(var), C.ptr(F), R, C.ptr(A), C.ptr(U), st), "fwd")
-def fwd_nosave(): C.check(lib.dgp_cond_forward(ctypes.byref(d), C.ptr(ws), C.ptr(X), N, N, None, 1, None, 0, 0, 0, C.ptr(mean), C.ptr(var), C.ptr(F), R, None, None, st), "fwd")
-def bwd(): C.check(lib.dgp_cond_backward(ctypes.byref(d), C.ptr(ws), C.ptr(X), N, N, C.ptr(A), C.ptr(U), C.ptr(mean), C.ptr(var), C.ptr(F), R, C.ptr(gm), C.ptr(gv), C.ptr(gF), R, C.ptr(gX), 0, 0, st), "bwd")
+def fwd(): C.check(lib.dgp_cond_forward(ctypes.byref(d), C.ptr(ws), C.ptr(X), N, N, None, 1, None, 0, 0, 0, C.ptr(mean), C.ptr(var), C.ptr(F), R, C.ptr(A), C.ptr(U), C.ptr(Ks), st), "fwd")
+def fwd_nosave(): C.check(lib.dgp_cond_forward(ctypes.byref(d), C.ptr(ws), C.ptr(X), N, N, None, 1, None, 0, 0, 0, C.ptr(mean), C.ptr(var), C.ptr(F), R, None, None, None, st), "fwd")
+def bwd(): C.check(lib.dgp_cond_backward(ctypes.byref(d), C.ptr(ws), C.ptr(X), N, N, C.ptr(A), C.ptr(U), C.ptr(Ks), C.ptr(mean), C.ptr(var), C.ptr(F), R, C.ptr(gm), C.ptr(gv), C.ptr(gF), R, C.ptr(gX), 0, 0, st), "bwd")
 def gram(): C.check(lib.dgp_cond_backward_gram(ctypes.byref(d), C.ptr(ws), C.ptr(A), N, 0, st), "gram")
 def prep(): C.check(lib.dgp_cond_prepare(ctypes.byref(d), C.ptr(ws), wsb, 1, None, st), "prepare")
 gZ = torch.zeros(M, D, dtype=torch.float64, device=dev); gth = torch.zeros(2 + D, dtype=torch.float64, device=dev)
@@ -59,4 +60,4 @@ if os.environ.get("DGP_PHASES"):
     fwd(); torch.cuda.synchronize()
     show("fwd phases (cycles of CTA 0, all its tiles):", ["top-sync", "setup", "K", "T", "E1", "U+E2"])
     bwd(); torch.cuda.synchronize()
-    show("bwd phases (cycles of CTA 0, all its tiles):", ["top-sync", "prologue", "-", "dA", "dK", "store+dqmu", "store-wait", "Gr2", "T1/T2z", "finish"])
+    show("bwd phases (cycles of CTA 0, all its tiles):", ["top-sync", "prologue", "-", "dA-loop", "dK", "store+dqmu", "store-wait", "Gr2", "T1/T2z", "finish", "dA-epilogue", "dA-entry-sync"])
