@@ -358,6 +358,13 @@ __global__ void __launch_bounds__(C::NTHREADS, 1) k_cond_bwd(const __grid_consta
             }
             for (int r0 = 0; r0 < R; r0 += 8) {
                 double c0[2] = {0.0, 0.0}, c1[2] = {0.0, 0.0};
+                // this CTA's running partial (global, L2): fetched before the DMMA chain so that its round trip is hidden
+                double pold[2];
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    const int m = m0 + g, r = r0 + 2 * t + e;
+                    pold[e] = (m < d.M && r < R) ? pqmu[m * R + r] : 0.0;
+                }
 #pragma unroll
                 for (int ks = 0; ks < C::NT / 4; ++ks) {
                     const int n = ks * 4 + t;
@@ -367,7 +374,7 @@ __global__ void __launch_bounds__(C::NTHREADS, 1) k_cond_bwd(const __grid_consta
 #pragma unroll
                 for (int e = 0; e < 2; ++e) {
                     const int m = m0 + g, r = r0 + 2 * t + e;
-                    if (m < d.M && r < R) pqmu[m * R + r] += c0[e] + c1[e];
+                    if (m < d.M && r < R) pqmu[m * R + r] = pold[e] + (c0[e] + c1[e]);
                 }
             }
         }
@@ -500,15 +507,15 @@ __global__ void __launch_bounds__(C::NTHREADS, 1) k_cond_bwd(const __grid_consta
             for (int d0 = 0; d0 < Dp + 1; d0 += 8) {
                 double c4[4][2] = {{0.0, 0.0}, {0.0, 0.0}, {0.0, 0.0}, {0.0, 0.0}};
                 const int kcol = d0 + g;
-                for (int m = 0; m < Mpad; m += 16) {          // Mpad is a multiple of 64
-                    double bv[4];
+                for (int m = 0; m < Mpad; m += 64) {          // Mpad is a multiple of 64; 16 global loads in flight
+                    double bv[16];
 #pragma unroll
-                    for (int u = 0; u < 4; ++u) {
+                    for (int u = 0; u < 16; ++u) {
                         const int mk = m + 4 * u + t;
-                        bv[u] = (kcol < Dp) ? a.Zs[(size_t)mk * Dp + kcol] : (kcol == Dp ? 1.0 : 0.0);
+                        bv[u] = (kcol < Dp) ? __ldg(a.Zs + (size_t)mk * Dp + kcol) : (kcol == Dp ? 1.0 : 0.0);
                     }
 #pragma unroll
-                    for (int u = 0; u < 4; ++u) dmma884(c4[u], Dt[(nt4 * 8 + g) * ldb + m + 4 * u + t], bv[u]);
+                    for (int u = 0; u < 16; ++u) dmma884(c4[u & 3], Dt[(nt4 * 8 + g) * ldb + m + 4 * u + t], bv[u]);
                 }
 #pragma unroll
                 for (int e = 0; e < 2; ++e) {
@@ -523,20 +530,26 @@ __global__ void __launch_bounds__(C::NTHREADS, 1) k_cond_bwd(const __grid_consta
         for (int mt = warp; mt < Mpad / 8; mt += C::NWARPS) {
             const int m0 = mt * 8;
             for (int d0 = 0; d0 < Dp + 1; d0 += 8) {
-                double c[2] = {0.0, 0.0};
+                double c[2] = {0.0, 0.0}, c2[2] = {0.0, 0.0};
                 const int kcol = d0 + g;
+                double pold[2];          // running partials of this CTA (global, L2): fetched ahead of the DMMA chain
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    const int m = m0 + g, k = d0 + 2 * t + e;
+                    pold[e] = (m < d.M && k <= Dp) ? (k < Dp ? pT2z[m * Dp + k] : pcs[m]) : 0.0;
+                }
 #pragma unroll
                 for (int ks = 0; ks < C::NT / 4; ++ks) {
                     const int n = ks * 4 + t;
                     const double bv = (kcol < Dp) ? xs[n * xld + kcol] : (kcol == Dp ? 1.0 : 0.0);
-                    dmma884(c, Dt[n * ldb + m0 + g], bv);
+                    if (ks & 1) dmma884(c2, Dt[n * ldb + m0 + g], bv); else dmma884(c, Dt[n * ldb + m0 + g], bv);
                 }
 #pragma unroll
                 for (int e = 0; e < 2; ++e) {
                     const int m = m0 + g, k = d0 + 2 * t + e;
                     if (m < d.M) {
-                        if (k < Dp) pT2z[m * Dp + k] += c[e];
-                        else if (k == Dp) pcs[m] += c[e];
+                        if (k < Dp) pT2z[m * Dp + k] = pold[e] + (c[e] + c2[e]);
+                        else if (k == Dp) pcs[m] = pold[e] + (c[e] + c2[e]);
                     }
                 }
             }

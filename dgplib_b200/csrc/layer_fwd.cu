@@ -248,15 +248,17 @@ __global__ void __launch_bounds__(C::NTHREADS, 1) k_cond_fwd(const __grid_consta
                 const bool rok = (r0 + g < d.R);
                 const double* qcol = d.q_mu + d.col0 + r0 + g;
                 const double* arow = Bt + (nt * 8 + g) * ldb + t;
-                for (int m = 0; m < Mpad; m += 16) {          // Mpad is a multiple of 64
-                    double bv[4];
+                // q_mu fragments come from global memory (L1 / L2): 16 loads are in flight before the DMMAs that use them
+                // (four at a time, behind the volatile DMMAs, exposed one round trip per 16 inducing points)
+                for (int m = 0; m < Mpad; m += 64) {          // Mpad is a multiple of 64
+                    double bv[16];
 #pragma unroll
-                    for (int u = 0; u < 4; ++u) {
+                    for (int u = 0; u < 16; ++u) {
                         const int mk = m + 4 * u + t;
-                        bv[u] = (rok && mk < d.M) ? qcol[(size_t)mk * d.ldr] : 0.0;
+                        bv[u] = (rok && mk < d.M) ? __ldg(qcol + (size_t)mk * d.ldr) : 0.0;
                     }
 #pragma unroll
-                    for (int u = 0; u < 4; ++u) dmma884(c4[u], arow[m + 4 * u], bv[u]);
+                    for (int u = 0; u < 16; ++u) dmma884(c4[u & 3], arow[m + 4 * u], bv[u]);
                 }
                 double c[2] = {(c4[0][0] + c4[1][0]) + (c4[2][0] + c4[3][0]), (c4[0][1] + c4[1][1]) + (c4[2][1] + c4[3][1])};
 #pragma unroll
