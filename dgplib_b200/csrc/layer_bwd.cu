@@ -46,7 +46,8 @@ struct BwdArgs {
     double* gX; int accumulate_gX;
     int mean_grad;       // != 0: also accumulate the gradient of a trainable Linear mean (A, b) in the per-CTA partials
     double* dKuf; double* gmv; double* part; int npart; double* scal;
-    long long row0;      // first row of this launch (a launch may cover a row range: tail tiles of another width)
+    long long row0;      // first row of this launch (a call may be split into a main and a tail launch of another width)
+    long long row_end;   // one past the last row of this launch
     int ntiles;
     int debug;           // test-hook builds only
 };
@@ -825,6 +826,37 @@ __global__ void __launch_bounds__(GR_THREADS, 4) k_gram(GramArgs a) {
             }
 }
 
+#ifdef DGP_TEST_HOOKS
+#define DGP_STAGE_OK(STG) (g_force_stages == 0 || g_force_stages == (STG))
+#else
+#define DGP_STAGE_OK(STG) true
+#endif
+
+// rows [row0, row_end) of the call with NT-row tiles (row0 a multiple of 8: the U blocks hold 8 rows)
+static int bwd_width(BwdArgs a, int nt, long long row0, long long row_end, cudaStream_t st) {
+    int rc = DGP_ERR_UNSUPPORTED;
+    a.row0 = row0;
+    a.row_end = row_end;
+#define DGP_TRY_BWD(WNV, NTV, STG)                                                        \
+    if (DGP_STAGE_OK(STG)) {                                                          \
+        using C = TileCfg<4, WNV, NTV, STG, true>;                                        \
+        a.ntiles = (int)((row_end - row0 + C::NT - 1) / C::NT);                       \
+        rc = launch_bwd<C>(a, st);                                                    \
+        if (rc != DGP_ERR_UNSUPPORTED) return rc;                                     \
+    }
+    switch (nt) {
+        case 72: DGP_TRY_BWD(3, 72, 2) break;
+        case 64: DGP_TRY_BWD(DGP_BWD_WN, 64, 3) DGP_TRY_BWD(DGP_BWD_WN, 64, 2) break;
+        case 40: DGP_TRY_BWD(5, 40, 4) DGP_TRY_BWD(5, 40, 3) break;
+        case 32: DGP_TRY_BWD(DGP_BWD_WN, 32, 4) DGP_TRY_BWD(DGP_BWD_WN, 32, 3) DGP_TRY_BWD(DGP_BWD_WN, 32, 2) break;
+        case 16: DGP_TRY_BWD(2, 16, 4) DGP_TRY_BWD(2, 16, 3) DGP_TRY_BWD(2, 16, 2) break;
+        case 8: DGP_TRY_BWD(1, 8, 3) DGP_TRY_BWD(1, 8, 2) break;
+        default: break;
+    }
+#undef DGP_TRY_BWD
+    return rc;
+}
+
 }  // namespace dgp
 
 using namespace dgp;
@@ -857,55 +889,44 @@ extern "C" int dgp_cond_backward(const dgp_cond_desc* d, void* ws, const double*
     a.mean_grad = (mean_grad && d->mean_A) ? 1 : 0;
     a.dKuf = ws_ptr<double>(ws, w.dKuf); a.gmv = ws_ptr<double>(ws, w.gmv);
     a.part = ws_ptr<double>(ws, w.part); a.npart = w.npart; a.scal = ws_ptr<double>(ws, w.scal);
-    a.row0 = 0;
 #ifdef DGP_TEST_HOOKS
     a.debug = g_debug_mode;
 #endif
+    int nt_force = 0;
 #ifdef DGP_TEST_HOOKS
-#define DGP_STAGE_OK(STG) (g_force_stages == 0 || g_force_stages == (STG))
-#else
-#define DGP_STAGE_OK(STG) true
+    nt_force = g_force_bwd_nt;      // parity tests pin every instantiation (tests/test_gpu_conditional.py)
 #endif
-#define DGP_TRY_BWD(WNV, NTV, STG)                                                        \
-    if (DGP_STAGE_OK(STG)) {                                                          \
-        using C = TileCfg<4, WNV, NTV, STG, true>;                                        \
-        a.ntiles = (int)((n_rows - a.row0 + C::NT - 1) / C::NT);                      \
-        rc = launch_bwd<C>(a, st);                                                    \
-        if (rc != DGP_ERR_UNSUPPORTED) return rc;                                     \
-    }
-#ifdef DGP_TEST_HOOKS
-    switch (g_force_bwd_nt) {      // parity tests pin every instantiation (tests/test_gpu_conditional.py)
-        case 72: DGP_TRY_BWD(3, 72, 2) return DGP_ERR_UNSUPPORTED;
-        case 64: DGP_TRY_BWD(DGP_BWD_WN, 64, 3) DGP_TRY_BWD(DGP_BWD_WN, 64, 2) return DGP_ERR_UNSUPPORTED;
-        case 32: DGP_TRY_BWD(DGP_BWD_WN, 32, 4) DGP_TRY_BWD(DGP_BWD_WN, 32, 3) DGP_TRY_BWD(DGP_BWD_WN, 32, 2) return DGP_ERR_UNSUPPORTED;
-        case 16: DGP_TRY_BWD(2, 16, 4) DGP_TRY_BWD(2, 16, 3) DGP_TRY_BWD(2, 16, 2) return DGP_ERR_UNSUPPORTED;
-        case 8: DGP_TRY_BWD(1, 8, 3) DGP_TRY_BWD(1, 8, 2) return DGP_ERR_UNSUPPORTED;
-        default: break;
-    }
-#endif
+    if (nt_force) return bwd_width(a, nt_force, 0, n_rows, st);
     if (w.Mpad <= 256) {
         // Only dA / dKuf is resident, so the row tile is as wide as the forward kernel's: 64 rows (4 x 4 consumer warps,
-        // two column tiles per warp, 3-slot ring), 72 rows (4 x 3 warps, three column tiles) when that saves a wave --
-        // 10 000 rows are one wave of 72-row tiles on 148 SMs -- and 32 rows when those fill the last wave much better.
-        const long long sms = device_sm_count();
-        const long long w64 = ((n_rows + 63) / 64 + sms - 1) / sms * 64;
-        const long long w32 = ((n_rows + 31) / 32 + sms - 1) / sms * 32;
-        const long long w72 = ((n_rows + 71) / 72 + sms - 1) / sms * 72;
-        if (w72 * 104 < w64 * 100 && w72 * 100 <= w32 * 108) { DGP_TRY_BWD(3, 72, 2) }
-        if (w32 * 108 < w64 * 100) { DGP_TRY_BWD(DGP_BWD_WN, 32, 4) DGP_TRY_BWD(DGP_BWD_WN, 32, 3) }
-        DGP_TRY_BWD(DGP_BWD_WN, 64, 3) DGP_TRY_BWD(DGP_BWD_WN, 64, 2)
-        DGP_TRY_BWD(DGP_BWD_WN, 32, 4) DGP_TRY_BWD(DGP_BWD_WN, 32, 3) DGP_TRY_BWD(DGP_BWD_WN, 32, 2)
-        DGP_TRY_BWD(2, 16, 3) DGP_TRY_BWD(2, 16, 2)
-    } else if (w.Mpad <= 512) {
-        DGP_TRY_BWD(DGP_BWD_WN, 32, 4) DGP_TRY_BWD(DGP_BWD_WN, 32, 3) DGP_TRY_BWD(DGP_BWD_WN, 32, 2)
-        DGP_TRY_BWD(2, 16, 4) DGP_TRY_BWD(2, 16, 3) DGP_TRY_BWD(2, 16, 2)
-    } else {
-        DGP_TRY_BWD(2, 16, 4) DGP_TRY_BWD(2, 16, 3) DGP_TRY_BWD(2, 16, 2)
-        DGP_TRY_BWD(1, 8, 3) DGP_TRY_BWD(1, 8, 2)   // very wide inputs / many outputs next to Mpad = 1024
+        // two column tiles per warp, 3-slot ring), 72 rows (4 x 3 warps, three column tiles, 2-slot ring) when that saves a
+        // wave -- 10 000 rows are one wave of 72-row tiles on 148 SMs -- or 64-row tiles for the full waves and one wave of
+        // 40- / 32- / 16-row tiles for the rest (common.cuh plan_tiles).
+        const TilePlan p = plan_tiles(n_rows, device_sm_count(), 1.15);
+        if (p.nt_tail) {
+            rc = bwd_width(a, p.nt_main, 0, p.rows_main, st);
+            if (rc == DGP_OK) {
+                rc = bwd_width(a, p.nt_tail, p.rows_main, n_rows, st);
+                if (rc == DGP_ERR_UNSUPPORTED) rc = bwd_width(a, 64, p.rows_main, n_rows, st);
+                if (rc == DGP_ERR_UNSUPPORTED) rc = bwd_width(a, 32, p.rows_main, n_rows, st);
+                if (rc == DGP_ERR_UNSUPPORTED) rc = bwd_width(a, 16, p.rows_main, n_rows, st);
+                return rc;
+            }
+            if (rc != DGP_ERR_UNSUPPORTED) return rc;
+        } else {
+            rc = bwd_width(a, p.nt_main, 0, n_rows, st);
+            if (rc != DGP_ERR_UNSUPPORTED) return rc;
+        }
+        rc = bwd_width(a, 64, 0, n_rows, st);
+        if (rc != DGP_ERR_UNSUPPORTED) return rc;
     }
-#undef DGP_TRY_BWD
-    rc = DGP_ERR_UNSUPPORTED;
-    return rc;
+    if (w.Mpad <= 512) {
+        rc = bwd_width(a, 32, 0, n_rows, st);
+        if (rc != DGP_ERR_UNSUPPORTED) return rc;
+    }
+    rc = bwd_width(a, 16, 0, n_rows, st);
+    if (rc != DGP_ERR_UNSUPPORTED) return rc;
+    return bwd_width(a, 8, 0, n_rows, st);       // very wide inputs / many outputs next to Mpad = 1024
 }
 
 extern "C" int dgp_cond_backward_gram(const dgp_cond_desc* d, void* ws, const double* A_save, int64_t n_rows,

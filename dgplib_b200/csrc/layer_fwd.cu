@@ -37,6 +37,7 @@ struct FwdArgs {
     double* mean; double* var; double* F; int ldf; double* A_save; double* scal;
     double* U_save; long long NG;     // saved U_r blocks (common.cuh usave_*), NG = groups of 8 rows; nullptr: not kept
     double* K_save;                   // [n_rows][Mpad] Kuf per row (RBF: the backward pass reuses exp(-r2/2)); nullptr: not kept
+    long long row0;                   // first row of this launch (a call may be split into a main and a tail launch)
     int ntiles;
 };
 
@@ -130,7 +131,7 @@ __global__ void __launch_bounds__(C::NTHREADS, 1) k_cond_fwd(const __grid_consta
     long long ph[12] = {0}; long long tlast = clock64();
 #endif
     for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
-        const long long n0 = (long long)tile * C::NT;
+        const long long n0 = a.row0 + (long long)tile * C::NT;
         // the previous tile's bulk store of Bt must have finished reading shared memory, and every warp must be done
         // with the previous tile, before Bt / xs are overwritten
         bulk_wait_read0();
@@ -397,6 +398,35 @@ static int launch_fwd(const FwdArgs& a, cudaStream_t st) {
     return cudaGetLastError() == cudaSuccess ? DGP_OK : DGP_ERR_LAUNCH;
 }
 
+#ifdef DGP_TEST_HOOKS
+#define DGP_STAGE_OK(STG) (g_force_stages == 0 || g_force_stages == (STG))
+#else
+#define DGP_STAGE_OK(STG) true
+#endif
+
+// rows [row0, row_end) of the call with NT-row tiles; the ring is as deep as the shared memory left by the tile allows
+static int fwd_width(FwdArgs a, int nt, long long row0, long long row_end, cudaStream_t st) {
+    int rc = DGP_ERR_UNSUPPORTED;
+    a.row0 = row0;
+#define DGP_TRY_FWD(WNV, NTV, STG)                                                        \
+    if (DGP_STAGE_OK(STG)) {                                                          \
+        using C = TileCfg<4, WNV, NTV, STG>;                                              \
+        a.ntiles = (int)((row_end - row0 + C::NT - 1) / C::NT);                       \
+        rc = launch_fwd<C>(a, st);                                                    \
+        if (rc != DGP_ERR_UNSUPPORTED) return rc;                                     \
+    }
+    switch (nt) {
+        case 72: DGP_TRY_FWD(3, 72, 3) DGP_TRY_FWD(3, 72, 2) break;
+        case 64: DGP_TRY_FWD(DGP_FWD_WN, 64, 4) DGP_TRY_FWD(DGP_FWD_WN, 64, 3) DGP_TRY_FWD(DGP_FWD_WN, 64, 2) break;
+        case 40: DGP_TRY_FWD(5, 40, 4) DGP_TRY_FWD(5, 40, 3) break;
+        case 32: DGP_TRY_FWD(DGP_FWD_WN, 32, 4) DGP_TRY_FWD(DGP_FWD_WN, 32, 3) DGP_TRY_FWD(DGP_FWD_WN, 32, 2) break;
+        case 16: DGP_TRY_FWD(2, 16, 4) DGP_TRY_FWD(2, 16, 3) DGP_TRY_FWD(2, 16, 2) break;
+        default: break;
+    }
+#undef DGP_TRY_FWD
+    return rc;
+}
+
 }  // namespace dgp
 
 using namespace dgp;
@@ -428,47 +458,33 @@ extern "C" int dgp_cond_forward(const dgp_cond_desc* d, const void* ws, const do
     cudaStream_t st = (cudaStream_t)stream;
     // row-tile width by inducing count (the A tile must fit in shared memory); ring depth 4, or 3 / 2 when the
     // per-row side buffers (large D) leave less room
+    int nt_force = 0;
 #ifdef DGP_TEST_HOOKS
-#define DGP_STAGE_OK(STG) (g_force_stages == 0 || g_force_stages == (STG))
-#else
-#define DGP_STAGE_OK(STG) true
+    nt_force = g_force_fwd_nt;      // parity tests pin every instantiation (tests/test_gpu_conditional.py)
 #endif
-#define DGP_TRY_FWD(WNV, NTV, STG)                                                        \
-    if (DGP_STAGE_OK(STG)) {                                                          \
-        using C = TileCfg<4, WNV, NTV, STG>;                                              \
-        a.ntiles = (int)((n_rows + C::NT - 1) / C::NT);                               \
-        rc = launch_fwd<C>(a, st);                                                    \
-        if (rc != DGP_ERR_UNSUPPORTED) return rc;                                     \
-    }
-#ifdef DGP_TEST_HOOKS
-    switch (g_force_fwd_nt) {      // parity tests pin every instantiation (tests/test_gpu_conditional.py)
-        case 72: DGP_TRY_FWD(3, 72, 3) DGP_TRY_FWD(3, 72, 2) return DGP_ERR_UNSUPPORTED;
-        case 64: DGP_TRY_FWD(DGP_FWD_WN, 64, 4) DGP_TRY_FWD(DGP_FWD_WN, 64, 3) DGP_TRY_FWD(DGP_FWD_WN, 64, 2) return DGP_ERR_UNSUPPORTED;
-        case 32: DGP_TRY_FWD(DGP_FWD_WN, 32, 4) DGP_TRY_FWD(DGP_FWD_WN, 32, 3) DGP_TRY_FWD(DGP_FWD_WN, 32, 2) return DGP_ERR_UNSUPPORTED;
-        case 16: DGP_TRY_FWD(2, 16, 4) DGP_TRY_FWD(2, 16, 3) DGP_TRY_FWD(2, 16, 2) return DGP_ERR_UNSUPPORTED;
-        default: break;
-    }
-#endif
+    if (nt_force) return fwd_width(a, nt_force, 0, n_rows, st);
     if (w.Mpad <= 256) {
-        // wave quantisation: a grid of ceil(n / 64) tiles that just spills into another wave (10 000 rows = 157 tiles on
-        // 148 SMs: two waves, the second almost empty) is cheaper as 32-row tiles, although those stream every operand
-        // chunk for half the rows (~8 % more time per row, measured)
-        const long long sms = device_sm_count();
-        const long long w64 = ((n_rows + 63) / 64 + sms - 1) / sms * 64;
-        const long long w32 = ((n_rows + 31) / 32 + sms - 1) / sms * 32;
-        const long long w72 = ((n_rows + 71) / 72 + sms - 1) / sms * 72;
-        // 72-row tiles (4 x 3 consumer warps, three column tiles per warp): one wave for the 10 000-row minibatch of the
-        // BASELINE configurations on 148 SMs, where 64-row tiles need two and 32-row tiles three
-        if (w72 * 104 < w64 * 100 && w72 * 100 <= w32 * 108) {
-            DGP_TRY_FWD(3, 72, 3) DGP_TRY_FWD(3, 72, 2)
+        // wave quantisation (common.cuh plan_tiles): one width, or 64-row tiles for the full waves + one narrower wave
+        const TilePlan p = plan_tiles(n_rows, device_sm_count(), 1.04);
+        if (p.nt_tail) {
+            rc = fwd_width(a, p.nt_main, 0, p.rows_main, st);
+            if (rc == DGP_OK) {
+                rc = fwd_width(a, p.nt_tail, p.rows_main, n_rows, st);
+                if (rc == DGP_ERR_UNSUPPORTED) rc = fwd_width(a, 64, p.rows_main, n_rows, st);
+                return rc;
+            }
+            if (rc != DGP_ERR_UNSUPPORTED) return rc;
+        } else {
+            rc = fwd_width(a, p.nt_main, 0, n_rows, st);
+            if (rc != DGP_ERR_UNSUPPORTED) return rc;
         }
-        if (w32 * 108 < w64 * 100) { DGP_TRY_FWD(DGP_FWD_WN, 32, 4) DGP_TRY_FWD(DGP_FWD_WN, 32, 3) }
-        DGP_TRY_FWD(DGP_FWD_WN, 64, 4) DGP_TRY_FWD(DGP_FWD_WN, 64, 3) DGP_TRY_FWD(DGP_FWD_WN, 64, 2)
-    } else if (w.Mpad <= 512) {
-        DGP_TRY_FWD(DGP_FWD_WN, 32, 4) DGP_TRY_FWD(DGP_FWD_WN, 32, 3) DGP_TRY_FWD(DGP_FWD_WN, 32, 2)
-    } else {
-        DGP_TRY_FWD(2, 16, 4) DGP_TRY_FWD(2, 16, 3) DGP_TRY_FWD(2, 16, 2)
+        rc = fwd_width(a, 64, 0, n_rows, st);
+        if (rc != DGP_ERR_UNSUPPORTED) return rc;
+        return fwd_width(a, 32, 0, n_rows, st);
     }
-#undef DGP_TRY_FWD
-    return DGP_ERR_UNSUPPORTED;
+    if (w.Mpad <= 512) {
+        rc = fwd_width(a, 32, 0, n_rows, st);
+        if (rc != DGP_ERR_UNSUPPORTED) return rc;
+    }
+    return fwd_width(a, 16, 0, n_rows, st);
 }

@@ -152,6 +152,7 @@ def test_conditional_forward_backward_parity(cuda, M, D, R, N, kind, S):
 # cases have the BASELINE row counts / shapes, so that the production variants -- not only the small-launch ones -- are
 # compared with the oracle (T hidden and output layers, configs[1] hidden layer, configs[2] hidden layer).
 PRODUCTION_CASES = [
+    (256, 8, 8, 100_000, "rbf", 1),      # T hidden layer in full: ten waves of 64-row tiles + one wave of 40-row tiles
     (256, 8, 8, 10_000, "rbf", 1),
     (256, 8, 1, 10_000, "rbf", 1),
     (128, 8, 8, 10_000, "rbf", 1),
@@ -173,6 +174,7 @@ FORCED = [
     (72, 72, 256, 8, 8, 700), (72, 72, 128, 8, 1, 333),
     (64, 64, 256, 8, 8, 700), (64, 64, 200, 5, 16, 130),
     (32, 32, 256, 8, 8, 700), (32, 32, 500, 16, 16, 200), (32, 32, 64, 3, 2, 100),
+    (40, 40, 256, 8, 8, 700), (40, 40, 100, 5, 1, 333),
     (16, 16, 1024, 8, 2, 100), (16, 16, 500, 16, 4, 90), (16, 16, 100, 4, 3, 50),
     (16, 8, 1024, 8, 8, 40), (32, 8, 300, 6, 5, 70),
 ]
