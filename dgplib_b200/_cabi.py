@@ -9,7 +9,16 @@ import os
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.environ.get("DGP_B200_LIB", os.path.join(_HERE, "libdgp_b200.so"))   # override: A/B builds only
+LIB_PATH = os.path.join(_HERE, "libdgp_b200.so")
+
+
+def use_library(path):
+    """Load another build of the library instead (tools/kbench.py: phase-counter and test-hook builds).  Must be called
+    before the first lib(); the product never calls it and reads no environment variable."""
+    global LIB_PATH
+    if _lib is not None:
+        raise DgpError("use_library() must be called before the library is loaded")
+    LIB_PATH = path
 
 DGP_OK, DGP_ERR_ARG, DGP_ERR_LAUNCH, DGP_ERR_WORKSPACE, DGP_ERR_UNSUPPORTED = 0, -1, -2, -3, -4
 DGP_KIND_RBF = 0

@@ -94,6 +94,7 @@ struct WsLayout {
     size_t LqTTl;      // [R] tiled copies of LqT_r (streamed by the forward kernel)
     size_t tl;         // doubles of one tiled matrix
     size_t klpart;     // [R][(Mpad/32)^2] per-tile partial sums of the KL term (written by k_lq_prep)
+    size_t cholws;     // scratch of the blocked Cholesky (Mpad > 512 only)
     // backward only
     size_t LinvT;      // [Mpad][Mpad]
     size_t Lq;         // [R][Mpad][Mpad] tril(q_sqrt_r) (lower), pad zero
@@ -144,6 +145,7 @@ static inline WsLayout ws_layout(const dgp_cond_desc& d, int64_t n_rows, int nee
     w.LinvTl = o; o += align256(w.tl * sizeof(double));
     w.LqTTl = o;  o += align256(w.tl * sizeof(double) * d.R);
     w.klpart = o; o += align256(size_t(d.R) * (w.Mpad / 32) * (w.Mpad / 32) * sizeof(double));
+    w.cholws = o; if (w.Mpad > 512) o += align256((2 * 256 * 256 + size_t(w.Mpad) * 256 + 64) * sizeof(double));
     if (need_bwd) {
         // split-K factor of the Gram kernel: enough CTAs to fill the machine ~3x (independent of n_rows so that every
         // offset except the two row-sized buffers at the end is a function of the descriptor only)
@@ -217,6 +219,11 @@ int cholesky_batched(double* K, int Mpad, int batch, int32_t* status, cudaStream
 // Linv = L^-1 for one lower-triangular Mpad x Mpad factor whose 32 x 32 diagonal-block inverses are already in Linv
 // (written by cholesky_batched); prep.cu
 int tri_inv_cols(const double* L, double* Linv, int Mpad, cudaStream_t st);
+// Blocked right-looking Cholesky over all SMs for np > 512 (np a multiple of 64; fullcov.cu): 256-wide diagonal blocks
+// through the one-CTA kernel, panel solves and trailing updates as GEMMs.  Lower factor in place (the strict upper
+// triangle outside the diagonal blocks keeps its input values); scratch: chol_blocked_scratch_doubles(np, batch).
+size_t chol_blocked_scratch_doubles(int np, int batch);
+int cholesky_blocked(double* K, int np, int batch, int32_t* status, double* scratch, cudaStream_t st);
 
 #ifdef __CUDACC__
 // ------------------------------------------------------------------------------------------------ PTX wrappers

@@ -95,11 +95,11 @@ __global__ void k_status_merge(const int32_t* __restrict__ blk, int j0, int batc
     if (b < batch && status[b] == 0 && blk[b] != 0) status[b] = j0 + blk[b];
 }
 
-static size_t chol_blocked_scratch_doubles(int np, int batch) {
+size_t chol_blocked_scratch_doubles(int np, int batch) {
     return (size_t)batch * (2 * CB * CB + (size_t)np * CB) + 64;        // D, Dinv, panel P (+ block status words)
 }
 
-static int cholesky_blocked(double* K, int np, int batch, int32_t* status, double* scratch, cudaStream_t st) {
+int cholesky_blocked(double* K, int np, int batch, int32_t* status, double* scratch, cudaStream_t st) {
     double* D = scratch;
     double* Dinv = D + (size_t)batch * CB * CB;
     double* P = Dinv + (size_t)batch * CB * CB;

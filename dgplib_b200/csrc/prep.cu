@@ -534,6 +534,12 @@ __global__ void k_diag_inv(const double* __restrict__ L, double* __restrict__ Li
     diag_block_inverse(sL, sInv, Linv + (size_t)b0 * Mpad + b0, Mpad, lane);
 }
 
+// strict upper triangle of an Mpad x Mpad matrix <- 0 (the blocked factorisation leaves the input there)
+__global__ void k_zero_upper(double* __restrict__ K, int Mpad) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x, i = blockIdx.y;
+    if (j < Mpad && j > i) K[(size_t)i * Mpad + j] = 0.0;
+}
+
 int cholesky_batched(double* K, int Mpad, int batch, int32_t* status, cudaStream_t st, double* Linv) {
     static DevOnceSize attr_set;
     const int dev = current_device();
@@ -737,7 +743,18 @@ extern "C" int dgp_cond_prepare(const dgp_cond_desc* d, void* ws, size_t ws_byte
     if (rc == DGP_OK) {
         k_prep_z<<<(Mpad + 127) / 128, 128, 0, st>>>(*d, Mpad, Dp, Zs, zn, ztask); DGP_COUNT_LAUNCH();
         k_kuu<<<dim3((Mpad + 127) / 128, Mpad), 128, 0, st>>>(*d, Mpad, Dp, Zs, zn, ztask, Lm); DGP_COUNT_LAUNCH();
-        rc = cholesky_batched(Lm, Mpad, 1, status, st, Linv);
+        if (Mpad > 512) {
+            // above the reach of the latency-tuned one-CTA kernel the single-CTA fallback took 11 ms at M = 1024: the
+            // blocked factorisation (256-wide diagonal blocks through that kernel, panel solves and trailing updates as
+            // GEMMs over all SMs) takes the serial chain down to four small factorisations
+            rc = cholesky_blocked(Lm, Mpad, 1, status, ws_ptr<double>(ws, w.cholws), st);
+            if (rc == DGP_OK) {
+                k_zero_upper<<<dim3((Mpad + 127) / 128, Mpad), 128, 0, st>>>(Lm, Mpad); DGP_COUNT_LAUNCH();
+                k_diag_inv<<<dim3(Mpad / 32, 1), 32, 0, st>>>(Lm, Linv, Mpad); DGP_COUNT_LAUNCH();
+            }
+        } else {
+            rc = cholesky_batched(Lm, Mpad, 1, status, st, Linv);
+        }
     }
     if (rc == DGP_OK) {
         rc = tri_inv_cols(Lm, Linv, Mpad, st);

@@ -4,6 +4,8 @@ import argparse, ctypes, os, sys
 import numpy as np, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from dgplib_b200 import _cabi as C
+if os.environ.get("DGP_B200_LIB"):          # A/B builds (make prof_lib / test_lib): a tool-side switch, not the product's
+    C.use_library(os.environ["DGP_B200_LIB"])
 
 ap = argparse.ArgumentParser()
 ap.add_argument("--M", type=int, default=256); ap.add_argument("--D", type=int, default=8)
