@@ -53,6 +53,10 @@ SIGNATURES = {
     "dgp_cond_forward": (ctypes.c_int, [_P, _vp, _vp, _i64, _i64, _vp, _u64, _vp, _u64, _i64, _i64, _vp, _vp, _vp, _i32,
                                         _vp, _vp, _vp, _vp]),
     "dgp_usave_bytes": (_sz, [_P, _i64]),
+    "dgp_cond_forward_group": (ctypes.c_int, [_i32, _vp, _vp, _vp, _i64, _i64, _vp, _u64, _vp, _u64, _i64, _i64, _vp, _vp,
+                                              _vp, _i32, _vp, _vp, _vp, _vp]),
+    "dgp_cond_backward_group": (ctypes.c_int, [_i32, _vp, _vp, _vp, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _vp,
+                                               _vp, _vp, _i32, _i32, _vp]),
     "dgp_sample_expand": (ctypes.c_int, [_vp, _vp, _vp, _u64, _vp, _u64, _i64, _i32, _i64, _i32, _i32, _vp, _i32, _vp,
                                          _i32, _vp]),
     "dgp_sample_reduce": (ctypes.c_int, [_vp, _i32, _vp, _i32, _vp, _vp, _i32, _i64, _i32, _i32, _vp, _vp, _vp]),

@@ -77,11 +77,25 @@ struct BwdSmem {
     }
 };
 
-template <class C>
-__global__ void __launch_bounds__(C::NTHREADS, 1) k_cond_bwd(const __grid_constant__ BwdArgs a) {
+// One launch over the (conditional, row tile) pairs of a MultikernelLayer (see layer_fwd.cu): members share the rows and
+// the shapes, differ in workspaces (operands, per-CTA partials, dKuf), descriptors and saved tensors.  Used when no input
+// gradient is wanted (a MultikernelInputLayer): gX is accumulated over the members and two of them in flight would race.
+constexpr int DGP_GROUP_MAX = 8;
+struct BwdGroup {
+    int n;
+    BwdArgs m[DGP_GROUP_MAX];
+};
+__device__ __forceinline__ const BwdArgs& bwd_member(const BwdArgs& p, int) { return p; }
+__device__ __forceinline__ const BwdArgs& bwd_member(const BwdGroup& p, int c) { return p.m[c]; }
+__device__ __forceinline__ int bwd_members(const BwdArgs&) { return 1; }
+__device__ __forceinline__ int bwd_members(const BwdGroup& p) { return p.n; }
+
+template <class C, class P>
+__global__ void __launch_bounds__(C::NTHREADS, 1) k_cond_bwd(const __grid_constant__ P p) {
     extern __shared__ __align__(128) double smem[];
-    const dgp_cond_desc& d = a.d;
-    const BwdSmem<C> L(a.Mpad, a.Dp, d.R);
+    const BwdArgs& a0 = bwd_member(p, 0);      // shapes, tile count and shared-memory layout are common to all members
+    const int ntiles = a0.ntiles, total_tiles = ntiles * bwd_members(p);
+    const BwdSmem<C> L(a0.Mpad, a0.Dp, a0.d.R);
     double* Dt = smem + L.Dt;
     double* Wst = smem + L.Wst;
     double* xs = smem + L.xs;
@@ -96,26 +110,18 @@ __global__ void __launch_bounds__(C::NTHREADS, 1) k_cond_bwd(const __grid_consta
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L.bars);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
-    const int Mpad = a.Mpad, Dp = a.Dp, ldb = L.ldb, xld = L.xld, R = d.R;
+    const int Mpad = a0.Mpad, Dp = a0.Dp, ldb = L.ldb, xld = L.xld, R = a0.d.R;
     const int nb = (Mpad + C::MB - 1) / C::MB;
     const int nkc = Mpad / C::KC;
-    const int thd = 2 + d.D;
     const int nq = 2 + Dp;
-
-    // this CTA's partial buffers (accumulated across tiles and across calls; zeroed by dgp_cond_prepare)
-    double* pT2z = a.part + (size_t)blockIdx.x * a.npart;   // [Mpad][Dp]
-    double* pcs = pT2z + (size_t)Mpad * Dp;                  // [Mpad]
-    double* pqmu = pcs + Mpad;                               // [Mpad][R]
-    double* pth = pqmu + (size_t)Mpad * R;                   // [T][2+Dp]
-    double* pmA = pth + (size_t)d.T * (2 + Dp);              // [Dx][R] Linear mean weights: X^T g_mean
-    double* pmb = pmA + (size_t)d.Dx * R;                    // [R]     Linear mean offset: sum_n g_mean
+    const BwdArgs* cur = &a0;       // member of the tile being produced / consumed (the segment lists read it)
 
     // segment lists of the two streamed phases (shared by the producer warp and the consumers)
     auto seg_dA = [&](int s) {      // dA block row i accumulates Lq_r (U_r . g_r) over all r: lower-triangular Lq_r
         Seg sg;
         sg.i = s / R;
         sg.r = s % R;
-        sg.W = a.LqL + (size_t)sg.r * a.tl;
+        sg.W = cur->LqL + (size_t)sg.r * cur->tl;
         sg.kc0 = 0;
         int kend = (sg.i + 1) * C::MB;
         if (kend > Mpad) kend = Mpad;
@@ -125,7 +131,7 @@ __global__ void __launch_bounds__(C::NTHREADS, 1) k_cond_bwd(const __grid_consta
     };
     auto seg_dK = [&](int s) {      // dKuf = LinvT * dA, block rows top-down, in place
         Seg sg;
-        sg.W = a.LinvT;
+        sg.W = cur->LinvT;
         sg.i = s;
         sg.kc0 = s * C::MB / C::KC;
         sg.kc1 = Mpad / C::KC;
@@ -148,7 +154,10 @@ __global__ void __launch_bounds__(C::NTHREADS, 1) k_cond_bwd(const __grid_consta
         // instructions by the idle lanes -- was measured slower both ways, 3.10 -> 3.31 / 3.25 ms at the T hidden-layer
         // shape: the ring's look-ahead already covers the HBM latency.)
         if (lane == 0) {
-            for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
+            for (int gt = blockIdx.x; gt < total_tiles; gt += gridDim.x) {
+                const BwdArgs& a = bwd_member(p, gt / ntiles);
+                cur = &a;
+                const int tile = gt % ntiles;
                 const long long n0 = a.row0 + (long long)tile * C::NT;
                 const long long left = a.n_rows - n0;
                 const int nvalid = (int)(left < C::NT ? left : C::NT);
@@ -181,7 +190,19 @@ __global__ void __launch_bounds__(C::NTHREADS, 1) k_cond_bwd(const __grid_consta
     long long ph[12] = {0}; long long tlast = clock64();
 #endif
 
-    for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
+    for (int gt = blockIdx.x; gt < total_tiles; gt += gridDim.x) {
+        const BwdArgs& a = bwd_member(p, gt / ntiles);
+        cur = &a;
+        const dgp_cond_desc& d = a.d;
+        const int thd = 2 + d.D;
+        const int tile = gt % ntiles;
+        // this CTA's partial buffers of this member (accumulated across tiles and across calls; zeroed by dgp_cond_prepare)
+        double* pT2z = a.part + (size_t)blockIdx.x * a.npart;   // [Mpad][Dp]
+        double* pcs = pT2z + (size_t)Mpad * Dp;                  // [Mpad]
+        double* pqmu = pcs + Mpad;                               // [Mpad][R]
+        double* pth = pqmu + (size_t)Mpad * R;                   // [T][2+Dp]
+        double* pmA = pth + (size_t)d.T * (2 + Dp);              // [Dx][R] Linear mean weights: X^T g_mean
+        double* pmb = pmA + (size_t)d.Dx * R;                    // [R]     Linear mean offset: sum_n g_mean
         const long long n0 = a.row0 + (long long)tile * C::NT;
         const int nvalid = (int)((a.n_rows - n0 < C::NT) ? (a.n_rows - n0) : C::NT);
         bulk_wait_read0();   // previous tile's dKuf store has finished reading Dt
@@ -627,7 +648,7 @@ __global__ void __launch_bounds__(C::NTHREADS, 1) k_cond_bwd(const __grid_consta
     }
     bulk_wait_read0();
 #ifdef DGP_PROFILE_PHASES
-    if (blockIdx.x == 0 && tid == 0) for (int i = 0; i < 12; ++i) a.scal[i] = (double)ph[i];
+    if (blockIdx.x == 0 && tid == 0) for (int i = 0; i < 12; ++i) a0.scal[i] = (double)ph[i];
 #endif
 }
 
@@ -639,11 +660,29 @@ static int launch_bwd(const BwdArgs& a, cudaStream_t st) {
     static DevOnceSize configured;
     const int dev = current_device();
     if (!configured.covers(dev, bytes)) {
-        if (cudaFuncSetAttribute(k_cond_bwd<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes) != cudaSuccess) return DGP_ERR_LAUNCH;
+        if (cudaFuncSetAttribute(k_cond_bwd<C, BwdArgs>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes) != cudaSuccess) return DGP_ERR_LAUNCH;
         configured.raise(dev, bytes);
     }
     const int grid = a.ntiles < device_sm_count() ? a.ntiles : device_sm_count();
-    k_cond_bwd<C><<<grid, C::NTHREADS, bytes, st>>>(a);
+    k_cond_bwd<C, BwdArgs><<<grid, C::NTHREADS, bytes, st>>>(a);
+    DGP_COUNT_LAUNCH();
+    return cudaGetLastError() == cudaSuccess ? DGP_OK : DGP_ERR_LAUNCH;
+}
+
+template <class C>
+static int launch_bwd_group(const BwdGroup& grp, cudaStream_t st) {
+    const BwdSmem<C> L(grp.m[0].Mpad, grp.m[0].Dp, grp.m[0].d.R);
+    const size_t bytes = (size_t)L.total_doubles * sizeof(double);
+    if (bytes > 227 * 1024) return DGP_ERR_UNSUPPORTED;
+    static DevOnceSize configured;
+    const int dev = current_device();
+    if (!configured.covers(dev, bytes)) {
+        if (cudaFuncSetAttribute(k_cond_bwd<C, BwdGroup>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes) != cudaSuccess) return DGP_ERR_LAUNCH;
+        configured.raise(dev, bytes);
+    }
+    const long long total = (long long)grp.m[0].ntiles * grp.n;
+    const int grid = (int)(total < device_sm_count() ? total : device_sm_count());
+    k_cond_bwd<C, BwdGroup><<<grid, C::NTHREADS, bytes, st>>>(grp);
     DGP_COUNT_LAUNCH();
     return cudaGetLastError() == cudaSuccess ? DGP_OK : DGP_ERR_LAUNCH;
 }
@@ -857,25 +896,46 @@ static int bwd_width(BwdArgs a, int nt, long long row0, long long row_end, cudaS
     return rc;
 }
 
+// the grouped launch with NT-row tiles (every member has the same tile count)
+static int bwd_group_width(BwdGroup grp, int nt, cudaStream_t st) {
+    int rc = DGP_ERR_UNSUPPORTED;
+#define DGP_TRY_BWDG(WNV, NTV, STG)                                                       \
+    if (DGP_STAGE_OK(STG)) {                                                          \
+        using C = TileCfg<4, WNV, NTV, STG, true>;                                        \
+        for (int c = 0; c < grp.n; ++c) {                                             \
+            grp.m[c].row0 = 0;                                                        \
+            grp.m[c].row_end = grp.m[c].n_rows;                                       \
+            grp.m[c].ntiles = (int)((grp.m[c].n_rows + C::NT - 1) / C::NT);           \
+        }                                                                             \
+        rc = launch_bwd_group<C>(grp, st);                                            \
+        if (rc != DGP_ERR_UNSUPPORTED) return rc;                                     \
+    }
+    switch (nt) {
+        case 72: DGP_TRY_BWDG(3, 72, 2) break;
+        case 64: DGP_TRY_BWDG(DGP_BWD_WN, 64, 3) DGP_TRY_BWDG(DGP_BWD_WN, 64, 2) break;
+        case 32: DGP_TRY_BWDG(DGP_BWD_WN, 32, 4) DGP_TRY_BWDG(DGP_BWD_WN, 32, 3) break;
+        case 16: DGP_TRY_BWDG(2, 16, 4) DGP_TRY_BWDG(2, 16, 3) break;
+        default: break;
+    }
+#undef DGP_TRY_BWDG
+    return rc;
+}
+
 }  // namespace dgp
 
 using namespace dgp;
 
-extern "C" int dgp_cond_backward(const dgp_cond_desc* d, void* ws, const double* X, int64_t x_rows, int64_t n_rows,
-                                 const double* A_save, const double* U_save, const double* K_save, const double* mean,
-                                 const double* var,
-                                 const double* F, int32_t ldf, const double* g_mean_in, const double* g_var_in,
-                                 const double* g_F, int32_t ldgf, double* gX, int32_t accumulate_gX, int32_t mean_grad,
-                                 void* stream) {
+static int fill_bwd_args(BwdArgs& a, const dgp_cond_desc* d, void* ws, const double* X, int64_t x_rows, int64_t n_rows,
+                         const double* A_save, const double* U_save, const double* K_save, const double* mean,
+                         const double* var, const double* F, int32_t ldf, const double* g_mean_in, const double* g_var_in,
+                         const double* g_F, int32_t ldgf, double* gX, int32_t accumulate_gX, int32_t mean_grad) {
     int rc = check_desc(d);
     if (rc != DGP_OK) return rc;
     if (!ws || !X || !A_save || !U_save || x_rows < 1 || n_rows < 0) return DGP_ERR_ARG;
     if (g_F && (!F || !mean || !var || ldgf < d->ldr || ldf < d->ldr)) return DGP_ERR_ARG;
     if (!g_F && !g_mean_in && !g_var_in) return DGP_ERR_ARG;
-    if (n_rows == 0) return DGP_OK;
     const WsLayout w = ws_layout(*d, n_rows, 1);
-    cudaStream_t st = (cudaStream_t)stream;
-    BwdArgs a{};
+    a = BwdArgs{};
     a.d = *d;
     a.Mpad = w.Mpad; a.Dp = w.Dp;
     a.Zs = ws_ptr<double>(ws, w.Zs); a.zn = ws_ptr<double>(ws, w.zn); a.ztask = ws_ptr<int32_t>(ws, w.ztask);
@@ -892,6 +952,71 @@ extern "C" int dgp_cond_backward(const dgp_cond_desc* d, void* ws, const double*
 #ifdef DGP_TEST_HOOKS
     a.debug = g_debug_mode;
 #endif
+    return DGP_OK;
+}
+
+// MultikernelLayer: the backward row kernels of the n conditionals of one layer in ONE launch over (conditional, row tile)
+// pairs.  Only without an input gradient (gX accumulates over the members); members must agree in M, D, Dx, R, T, n <= 8;
+// otherwise DGP_ERR_UNSUPPORTED (the caller launches them one by one).  dgp_cond_backward_gram / _params stay per member.
+extern "C" int dgp_cond_backward_group(int32_t n, const dgp_cond_desc* const* d, void* const* ws, const double* X,
+                                       int64_t x_rows, int64_t n_rows, const double* const* A_save,
+                                       const double* const* U_save, const double* const* K_save, const double* mean,
+                                       const double* var, const double* F, int32_t ldf, const double* g_mean_in,
+                                       const double* g_var_in, const double* g_F, int32_t ldgf, int32_t mean_grad,
+                                       void* stream) {
+    if (n < 1 || !d || !ws || !A_save || !U_save) return DGP_ERR_ARG;
+    if (n > DGP_GROUP_MAX) return DGP_ERR_UNSUPPORTED;
+    BwdGroup grp{};
+    grp.n = n;
+    for (int c = 0; c < n; ++c) {
+        if (!d[c]) return DGP_ERR_ARG;
+        if (d[c]->M != d[0]->M || d[c]->D != d[0]->D || d[c]->Dx != d[0]->Dx || d[c]->R != d[0]->R || d[c]->T != d[0]->T ||
+            d[c]->ldr != d[0]->ldr)
+            return DGP_ERR_UNSUPPORTED;
+    }
+    for (int c = 0; c < n; ++c) {
+        const int rc = fill_bwd_args(grp.m[c], d[c], ws[c], X, x_rows, n_rows, A_save[c], U_save[c],
+                                     K_save ? K_save[c] : nullptr, mean, var, F, ldf, g_mean_in, g_var_in, g_F, ldgf,
+                                     nullptr, 0, mean_grad);
+        if (rc != DGP_OK) return rc;
+    }
+    if (n_rows == 0) return DGP_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    const long long sms = device_sm_count();
+    const int Mpad = grp.m[0].Mpad;
+    const int cand[4] = {64, 72, 32, 16};
+    const double pen[4] = {1.0, 1.15, 1.08, 1.6};
+    int order[4] = {0, 1, 2, 3};
+    double cost[4];
+    for (int i = 0; i < 4; ++i) {
+        const long long tiles = ((n_rows + cand[i] - 1) / cand[i]) * n;
+        cost[i] = (double)((tiles + sms - 1) / sms) * cand[i] * pen[i];
+        if ((Mpad > 256 && cand[i] > 32) || (Mpad > 512 && cand[i] > 16)) cost[i] = 1e300;
+    }
+    for (int i = 0; i < 4; ++i)
+        for (int j = i + 1; j < 4; ++j)
+            if (cost[order[j]] < cost[order[i]]) { const int tmp = order[i]; order[i] = order[j]; order[j] = tmp; }
+    for (int i = 0; i < 4; ++i) {
+        if (cost[order[i]] >= 1e300) break;
+        const int rc = bwd_group_width(grp, cand[order[i]], st);
+        if (rc != DGP_ERR_UNSUPPORTED) return rc;
+    }
+    return DGP_ERR_UNSUPPORTED;
+}
+
+extern "C" int dgp_cond_backward(const dgp_cond_desc* d, void* ws, const double* X, int64_t x_rows, int64_t n_rows,
+                                 const double* A_save, const double* U_save, const double* K_save, const double* mean,
+                                 const double* var,
+                                 const double* F, int32_t ldf, const double* g_mean_in, const double* g_var_in,
+                                 const double* g_F, int32_t ldgf, double* gX, int32_t accumulate_gX, int32_t mean_grad,
+                                 void* stream) {
+    BwdArgs a{};
+    int rc = fill_bwd_args(a, d, ws, X, x_rows, n_rows, A_save, U_save, K_save, mean, var, F, ldf, g_mean_in, g_var_in,
+                           g_F, ldgf, gX, accumulate_gX, mean_grad);
+    if (rc != DGP_OK) return rc;
+    if (n_rows == 0) return DGP_OK;
+    const WsLayout w = ws_layout(*d, n_rows, 1);
+    cudaStream_t st = (cudaStream_t)stream;
     int nt_force = 0;
 #ifdef DGP_TEST_HOOKS
     nt_force = g_force_bwd_nt;      // parity tests pin every instantiation (tests/test_gpu_conditional.py)

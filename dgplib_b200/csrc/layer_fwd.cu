@@ -67,10 +67,26 @@ struct FwdSmem {
     }
 };
 
-template <class C>
-__global__ void __launch_bounds__(C::NTHREADS, 1) k_cond_fwd(const __grid_constant__ FwdArgs a) {
+// One launch over the (conditional, row tile) pairs of a MultikernelLayer (dgplib/multikernel_layers.py:74-85 builds one
+// conditional per kernel in a Python loop): the members share the input rows, the shapes (Mpad, Dp, R, row count) and the
+// tile plan, and differ in their workspaces, descriptors (kernel parameters, col0) and saved-tensor buffers.  The member
+// table travels as a __grid_constant__ kernel parameter (constant bank), indexed per tile.
+constexpr int DGP_GROUP_MAX = 8;
+struct FwdGroup {
+    int n;
+    FwdArgs m[DGP_GROUP_MAX];
+};
+__device__ __forceinline__ const FwdArgs& fwd_member(const FwdArgs& p, int) { return p; }
+__device__ __forceinline__ const FwdArgs& fwd_member(const FwdGroup& p, int c) { return p.m[c]; }
+__device__ __forceinline__ int fwd_members(const FwdArgs&) { return 1; }
+__device__ __forceinline__ int fwd_members(const FwdGroup& p) { return p.n; }
+
+template <class C, class P>
+__global__ void __launch_bounds__(C::NTHREADS, 1) k_cond_fwd(const __grid_constant__ P p) {
     extern __shared__ __align__(128) double smem[];
-    const FwdSmem<C> L(a.Mpad, a.Dp);
+    const FwdArgs& a0 = fwd_member(p, 0);      // shapes, tile count and shared-memory layout are common to all members
+    const int ntiles = a0.ntiles, total_tiles = ntiles * fwd_members(p);
+    const FwdSmem<C> L(a0.Mpad, a0.Dp);
     double* Bt = smem + L.Bt;
     double* Wst = smem + L.Wst;
     double* xs = smem + L.xs;
@@ -81,17 +97,16 @@ __global__ void __launch_bounds__(C::NTHREADS, 1) k_cond_fwd(const __grid_consta
     int32_t* xtask = reinterpret_cast<int32_t*>(smem + L.xtask);
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L.bars);
 
-    const dgp_cond_desc& d = a.d;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
     const int wm = warp / C::WN;
-    const int Mpad = a.Mpad, Dp = a.Dp, ldb = L.ldb, xld = L.xld;
+    const int Mpad = a0.Mpad, Dp = a0.Dp, ldb = L.ldb, xld = L.xld;
     const int nb = (Mpad + C::MB - 1) / C::MB;
-    const int thd = 2 + d.D;
+    const FwdArgs* cur = &a0;       // member of the tile being produced / consumed (the segment lists read it)
 
     // segment lists of the two streamed phases (shared by the producer warp and the consumers)
     auto seg_T = [&](int s) {       // A = Linv * Kuf, block rows bottom-up so the tile is updated in place
         Seg sg;
-        sg.W = a.Linv;
+        sg.W = cur->Linv;
         sg.i = nb - 1 - s;
         sg.kc0 = 0;
         int kend = (sg.i + 1) * C::MB;
@@ -105,7 +120,7 @@ __global__ void __launch_bounds__(C::NTHREADS, 1) k_cond_fwd(const __grid_consta
         Seg sg;
         sg.r = s / nb;
         sg.i = s % nb;
-        sg.W = a.LqT + (size_t)sg.r * a.tl;
+        sg.W = cur->LqT + (size_t)sg.r * cur->tl;
         sg.kc0 = sg.i * C::MB / C::KC;
         sg.kc1 = Mpad / C::KC;
         sg.flush = true;
@@ -119,9 +134,10 @@ __global__ void __launch_bounds__(C::NTHREADS, 1) k_cond_fwd(const __grid_consta
     if (warp == C::NWARPS) {
         // ---- producer warp: stream every W chunk of every tile of this CTA, in consumption order
         if (lane == 0) {
-            for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
+            for (int gt = blockIdx.x; gt < total_tiles; gt += gridDim.x) {
+                cur = &fwd_member(p, gt / ntiles);
                 produce_phase<C>(pipe, nb, seg_T, Mpad);
-                produce_phase<C>(pipe, nb * d.R, seg_U, Mpad);
+                produce_phase<C>(pipe, nb * cur->d.R, seg_U, Mpad);
             }
         }
         return;
@@ -130,7 +146,12 @@ __global__ void __launch_bounds__(C::NTHREADS, 1) k_cond_fwd(const __grid_consta
 #ifdef DGP_PROFILE_PHASES
     long long ph[12] = {0}; long long tlast = clock64();
 #endif
-    for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
+    for (int gt = blockIdx.x; gt < total_tiles; gt += gridDim.x) {
+        const FwdArgs& a = fwd_member(p, gt / ntiles);
+        cur = &a;
+        const dgp_cond_desc& d = a.d;
+        const int thd = 2 + d.D;
+        const int tile = gt % ntiles;
         const long long n0 = a.row0 + (long long)tile * C::NT;
         // the previous tile's bulk store of Bt must have finished reading shared memory, and every warp must be done
         // with the previous tile, before Bt / xs are overwritten
@@ -377,7 +398,7 @@ __global__ void __launch_bounds__(C::NTHREADS, 1) k_cond_fwd(const __grid_consta
     }
     bulk_wait_read0();
 #ifdef DGP_PROFILE_PHASES
-    if (blockIdx.x == 0 && tid == 0) for (int i = 0; i < 12; ++i) a.scal[i] = (double)ph[i];
+    if (blockIdx.x == 0 && tid == 0) for (int i = 0; i < 12; ++i) a0.scal[i] = (double)ph[i];
 #endif
 }
 
@@ -389,11 +410,29 @@ static int launch_fwd(const FwdArgs& a, cudaStream_t st) {
     static DevOnceSize configured;
     const int dev = current_device();
     if (!configured.covers(dev, bytes)) {
-        if (cudaFuncSetAttribute(k_cond_fwd<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes) != cudaSuccess) return DGP_ERR_LAUNCH;
+        if (cudaFuncSetAttribute(k_cond_fwd<C, FwdArgs>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes) != cudaSuccess) return DGP_ERR_LAUNCH;
         configured.raise(dev, bytes);
     }
     int grid = a.ntiles < device_sm_count() ? a.ntiles : device_sm_count();
-    k_cond_fwd<C><<<grid, C::NTHREADS, bytes, st>>>(a);
+    k_cond_fwd<C, FwdArgs><<<grid, C::NTHREADS, bytes, st>>>(a);
+    DGP_COUNT_LAUNCH();
+    return cudaGetLastError() == cudaSuccess ? DGP_OK : DGP_ERR_LAUNCH;
+}
+
+template <class C>
+static int launch_fwd_group(const FwdGroup& grp, cudaStream_t st) {
+    const FwdSmem<C> L(grp.m[0].Mpad, grp.m[0].Dp);
+    const size_t bytes = (size_t)L.total_doubles * sizeof(double);
+    if (bytes > 227 * 1024) return DGP_ERR_UNSUPPORTED;
+    static DevOnceSize configured;
+    const int dev = current_device();
+    if (!configured.covers(dev, bytes)) {
+        if (cudaFuncSetAttribute(k_cond_fwd<C, FwdGroup>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes) != cudaSuccess) return DGP_ERR_LAUNCH;
+        configured.raise(dev, bytes);
+    }
+    const long long total = (long long)grp.m[0].ntiles * grp.n;
+    const int grid = (int)(total < device_sm_count() ? total : device_sm_count());
+    k_cond_fwd<C, FwdGroup><<<grid, C::NTHREADS, bytes, st>>>(grp);
     DGP_COUNT_LAUNCH();
     return cudaGetLastError() == cudaSuccess ? DGP_OK : DGP_ERR_LAUNCH;
 }
@@ -427,21 +466,44 @@ static int fwd_width(FwdArgs a, int nt, long long row0, long long row_end, cudaS
     return rc;
 }
 
+// the grouped launch with NT-row tiles (every member has the same tile count)
+static int fwd_group_width(FwdGroup grp, int nt, cudaStream_t st) {
+    int rc = DGP_ERR_UNSUPPORTED;
+#define DGP_TRY_FWDG(WNV, NTV, STG)                                                       \
+    if (DGP_STAGE_OK(STG)) {                                                          \
+        using C = TileCfg<4, WNV, NTV, STG>;                                              \
+        for (int c = 0; c < grp.n; ++c) {                                             \
+            grp.m[c].row0 = 0;                                                        \
+            grp.m[c].ntiles = (int)((grp.m[c].n_rows + C::NT - 1) / C::NT);           \
+        }                                                                             \
+        rc = launch_fwd_group<C>(grp, st);                                            \
+        if (rc != DGP_ERR_UNSUPPORTED) return rc;                                     \
+    }
+    switch (nt) {
+        case 72: DGP_TRY_FWDG(3, 72, 3) DGP_TRY_FWDG(3, 72, 2) break;
+        case 64: DGP_TRY_FWDG(DGP_FWD_WN, 64, 4) DGP_TRY_FWDG(DGP_FWD_WN, 64, 3) break;
+        case 32: DGP_TRY_FWDG(DGP_FWD_WN, 32, 4) DGP_TRY_FWDG(DGP_FWD_WN, 32, 3) break;
+        case 16: DGP_TRY_FWDG(2, 16, 4) DGP_TRY_FWDG(2, 16, 3) break;
+        default: break;
+    }
+#undef DGP_TRY_FWDG
+    return rc;
+}
+
 }  // namespace dgp
 
 using namespace dgp;
 
-extern "C" int dgp_cond_forward(const dgp_cond_desc* d, const void* ws, const double* X, int64_t x_rows, int64_t n_rows,
-                                const double* eps, uint64_t seed, const uint64_t* seed_dev, uint64_t row_offset,
-                                int64_t rows_per_sample, int64_t sample_stride, double* mean, double* var, double* F,
-                                int32_t ldf, double* A_save, double* U_save, double* K_save, void* stream) {
+static int fill_fwd_args(FwdArgs& a, const dgp_cond_desc* d, const void* ws, const double* X, int64_t x_rows,
+                         int64_t n_rows, const double* eps, uint64_t seed, const uint64_t* seed_dev, uint64_t row_offset,
+                         int64_t rows_per_sample, int64_t sample_stride, double* mean, double* var, double* F, int32_t ldf,
+                         double* A_save, double* U_save, double* K_save) {
     int rc = check_desc(d);
     if (rc != DGP_OK) return rc;
     if (!ws || !X || !mean || !var || x_rows < 1 || n_rows < 0) return DGP_ERR_ARG;
     if (F && ldf < d->ldr) return DGP_ERR_ARG;
-    if (n_rows == 0) return DGP_OK;
     const WsLayout w = ws_layout(*d, 0, 0);
-    FwdArgs a{};
+    a = FwdArgs{};
     a.d = *d;
     a.Mpad = w.Mpad; a.Dp = w.Dp;
     a.Zs = ws_ptr<double>(ws, w.Zs); a.zn = ws_ptr<double>(ws, w.zn); a.ztask = ws_ptr<int32_t>(ws, w.ztask);
@@ -455,6 +517,68 @@ extern "C" int dgp_cond_forward(const dgp_cond_desc* d, const void* ws, const do
     a.U_save = U_save; a.NG = usave_groups(n_rows);
     a.K_save = K_save;
     a.scal = const_cast<double*>(ws_ptr<double>(ws, w.scal));
+    return DGP_OK;
+}
+
+// MultikernelLayer: the n conditionals of one layer on the same rows in ONE launch over (conditional, row tile) pairs.
+// Members must agree in M, D, Dx, R, T (the layer's kernels see the same input and own equal slices of the outputs,
+// dgplib/multikernel_layers.py:40, :74-85) and n <= 8; otherwise DGP_ERR_UNSUPPORTED (the caller launches them one by one).
+extern "C" int dgp_cond_forward_group(int32_t n, const dgp_cond_desc* const* d, const void* const* ws, const double* X,
+                                      int64_t x_rows, int64_t n_rows, const double* eps, uint64_t seed,
+                                      const uint64_t* seed_dev, uint64_t row_offset, int64_t rows_per_sample,
+                                      int64_t sample_stride, double* mean, double* var, double* F, int32_t ldf,
+                                      double* const* A_save, double* const* U_save, double* const* K_save, void* stream) {
+    if (n < 1 || !d || !ws) return DGP_ERR_ARG;
+    if (n > DGP_GROUP_MAX) return DGP_ERR_UNSUPPORTED;
+    FwdGroup grp{};
+    grp.n = n;
+    for (int c = 0; c < n; ++c) {
+        if (!d[c]) return DGP_ERR_ARG;
+        if (d[c]->M != d[0]->M || d[c]->D != d[0]->D || d[c]->Dx != d[0]->Dx || d[c]->R != d[0]->R || d[c]->T != d[0]->T ||
+            d[c]->ldr != d[0]->ldr || (d[c]->mean_A == nullptr) != (d[0]->mean_A == nullptr))
+            return DGP_ERR_UNSUPPORTED;
+    }
+    for (int c = 0; c < n; ++c) {
+        const int rc = fill_fwd_args(grp.m[c], d[c], ws[c], X, x_rows, n_rows, eps, seed, seed_dev, row_offset,
+                                     rows_per_sample, sample_stride, mean, var, F, ldf, A_save ? A_save[c] : nullptr,
+                                     U_save ? U_save[c] : nullptr, K_save ? K_save[c] : nullptr);
+        if (rc != DGP_OK) return rc;
+    }
+    if (n_rows == 0) return DGP_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    // one tile width for the whole launch: the one that needs the fewest row-waves over all (member, tile) pairs
+    const long long sms = device_sm_count();
+    const int Mpad = grp.m[0].Mpad;
+    const int cand[4] = {64, 72, 32, 16};
+    const double pen[4] = {1.0, 1.04, 1.08, 1.6};
+    int order[4] = {0, 1, 2, 3};
+    double cost[4];
+    for (int i = 0; i < 4; ++i) {
+        const long long tiles = ((n_rows + cand[i] - 1) / cand[i]) * n;
+        cost[i] = (double)((tiles + sms - 1) / sms) * cand[i] * pen[i];
+        if ((Mpad > 256 && cand[i] > 32) || (Mpad > 512 && cand[i] > 16)) cost[i] = 1e300;
+    }
+    for (int i = 0; i < 4; ++i)
+        for (int j = i + 1; j < 4; ++j)
+            if (cost[order[j]] < cost[order[i]]) { const int tmp = order[i]; order[i] = order[j]; order[j] = tmp; }
+    for (int i = 0; i < 4; ++i) {
+        if (cost[order[i]] >= 1e300) break;
+        const int rc = fwd_group_width(grp, cand[order[i]], st);
+        if (rc != DGP_ERR_UNSUPPORTED) return rc;
+    }
+    return DGP_ERR_UNSUPPORTED;
+}
+
+extern "C" int dgp_cond_forward(const dgp_cond_desc* d, const void* ws, const double* X, int64_t x_rows, int64_t n_rows,
+                                const double* eps, uint64_t seed, const uint64_t* seed_dev, uint64_t row_offset,
+                                int64_t rows_per_sample, int64_t sample_stride, double* mean, double* var, double* F,
+                                int32_t ldf, double* A_save, double* U_save, double* K_save, void* stream) {
+    FwdArgs a{};
+    int rc = fill_fwd_args(a, d, ws, X, x_rows, n_rows, eps, seed, seed_dev, row_offset, rows_per_sample, sample_stride,
+                           mean, var, F, ldf, A_save, U_save, K_save);
+    if (rc != DGP_OK) return rc;
+    if (n_rows == 0) return DGP_OK;
+    const WsLayout w = ws_layout(*d, 0, 0);
     cudaStream_t st = (cudaStream_t)stream;
     // row-tile width by inducing count (the A tile must fit in shared memory); ring depth 4, or 3 / 2 when the
     // per-row side buffers (large D) leave less room

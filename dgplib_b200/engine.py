@@ -266,6 +266,15 @@ class Engine:
             self._rows[key] = buf
         return buf
 
+    @staticmethod
+    def _groupable(conds):
+        """A MultikernelLayer whose conditionals can share one launch: 2..8 members of identical shape."""
+        if not (2 <= len(conds) <= 8):
+            return False
+        d0 = conds[0].desc
+        return all((c.desc.M, c.desc.D, c.desc.Dx, c.desc.R, c.desc.T, c.desc.ldr) ==
+                   (d0.M, d0.D, d0.Dx, d0.R, d0.T, d0.ldr) for c in conds)
+
     def _side_streams(self):
         """One side stream per conditional (parameter stages of different conditionals are independent)."""
         if getattr(self, "_streams", None) is None:
@@ -379,13 +388,29 @@ class Engine:
             Fbuf = buf["F"][l] if want_F else None
             rows = self._rows_of(l, S, nb)
             fused_F = want_F and l > 0        # layer 0 samples are drawn by dgp_sample_expand (S per data row)
-            for ci, c in enumerate(conds):
+            eps_ptr = _cabi.ptr(eps[l]) if (eps is not None and fused_F) else None
+            F_ptr = _cabi.ptr(Fbuf) if fused_F else None
+            ldf = Fbuf.shape[1] if fused_F else layer.output_dim
+            grouped = False
+            if self._groupable(conds):
+                # a MultikernelLayer's conditionals in ONE launch over (conditional, row tile) pairs
+                n_c = len(conds)
+                descs = (ctypes.POINTER(_cabi.CondDesc) * n_c)(*[ctypes.pointer(c.desc) for c in conds])
+                wss = (ctypes.c_void_p * n_c)(*[c.ws.data_ptr() for c in conds])
+                saves = [(ctypes.c_void_p * n_c)(*[(b.data_ptr() if b is not None else None) for b in buf[k][l]])
+                         if save else None for k in ("A", "U", "K")]
+                rc = self._timed(f"fwd.l{l}", lambda: lib.dgp_cond_forward_group(
+                    n_c, descs, wss, _cabi.ptr(inp), x_rows, rows, eps_ptr, self._layer_seed(seed, l), self._seed_dev_ptr(),
+                    row_offset, nb, stride, _cabi.ptr(buf["mean"][l]), _cabi.ptr(buf["var"][l]), F_ptr, ldf,
+                    saves[0], saves[1], saves[2], st))
+                if rc != _cabi.DGP_ERR_UNSUPPORTED:
+                    _cabi.check(rc, "dgp_cond_forward_group")
+                    grouped = True
+            for ci, c in enumerate(conds if not grouped else []):
                 self._timed(f"fwd.l{l}", lambda: _cabi.check(lib.dgp_cond_forward(
-                    c.ref(), _cabi.ptr(c.ws), _cabi.ptr(inp), x_rows, rows,
-                    _cabi.ptr(eps[l]) if (eps is not None and fused_F) else None,
+                    c.ref(), _cabi.ptr(c.ws), _cabi.ptr(inp), x_rows, rows, eps_ptr,
                     self._layer_seed(seed, l), self._seed_dev_ptr(), row_offset, nb, stride,
-                    _cabi.ptr(buf["mean"][l]), _cabi.ptr(buf["var"][l]), _cabi.ptr(Fbuf) if fused_F else None,
-                    Fbuf.shape[1] if fused_F else layer.output_dim,
+                    _cabi.ptr(buf["mean"][l]), _cabi.ptr(buf["var"][l]), F_ptr, ldf,
                     _cabi.ptr(buf["A"][l][ci]) if save else None, _cabi.ptr(buf["U"][l][ci]) if save else None,
                     _cabi.ptr(buf["K"][l][ci]) if save else None, st), "dgp_cond_forward"))
             if l == 0 and want_F:
@@ -686,17 +711,36 @@ class Engine:
                             layer.output_dim, _cabi.ptr(buf["g_mean0"]), _cabi.ptr(buf["g_var0"]), st),
                             "dgp_sample_reduce"))
                         g_mean_in, g_var_in, gF, Fl = buf["g_mean0"], buf["g_var0"], None, None
-                    for ci, c in enumerate(conds):
-                        self._timed(f"bwd.l{l}", lambda: _cabi.check(lib.dgp_cond_backward(
-                            c.ref(), _cabi.ptr(c.ws), _cabi.ptr(inp), x_rows, rows, _cabi.ptr(buf["A"][l][ci]),
-                            _cabi.ptr(buf["U"][l][ci]), _cabi.ptr(buf["K"][l][ci]), _cabi.ptr(buf["mean"][l]),
-                            _cabi.ptr(buf["var"][l]),
-                            _cabi.ptr(Fl) if Fl is not None else None, buf["F"][l].shape[1],
+                    grouped = False
+                    if l == 0 and self._groupable(conds):
+                        # no input gradient at the data layer: the members' backward row kernels share one launch
+                        n_c = len(conds)
+                        descs = (ctypes.POINTER(_cabi.CondDesc) * n_c)(*[ctypes.pointer(c.desc) for c in conds])
+                        wss = (ctypes.c_void_p * n_c)(*[c.ws.data_ptr() for c in conds])
+                        sv = [(ctypes.c_void_p * n_c)(*[(b.data_ptr() if b is not None else None) for b in buf[k][l]])
+                              for k in ("A", "U", "K")]
+                        rc = self._timed(f"bwd.l{l}", lambda: lib.dgp_cond_backward_group(
+                            n_c, descs, wss, _cabi.ptr(inp), x_rows, rows, sv[0], sv[1], sv[2], _cabi.ptr(buf["mean"][l]),
+                            _cabi.ptr(buf["var"][l]), _cabi.ptr(Fl) if Fl is not None else None, buf["F"][l].shape[1],
                             _cabi.ptr(g_mean_in) if g_mean_in is not None else None,
                             _cabi.ptr(g_var_in) if g_var_in is not None else None,
                             _cabi.ptr(gF) if gF is not None else None, gF.shape[1] if gF is not None else 0,
-                            _cabi.ptr(buf["gX"][l]) if l > 0 else None, 1 if ci > 0 else 0,
-                            1 if self.mean_trainable(layer) else 0, st), "dgp_cond_backward"))
+                            1 if self.mean_trainable(layer) else 0, st))
+                        if rc != _cabi.DGP_ERR_UNSUPPORTED:
+                            _cabi.check(rc, "dgp_cond_backward_group")
+                            grouped = True
+                    for ci, c in enumerate(conds):
+                        if not grouped:
+                            self._timed(f"bwd.l{l}", lambda: _cabi.check(lib.dgp_cond_backward(
+                                c.ref(), _cabi.ptr(c.ws), _cabi.ptr(inp), x_rows, rows, _cabi.ptr(buf["A"][l][ci]),
+                                _cabi.ptr(buf["U"][l][ci]), _cabi.ptr(buf["K"][l][ci]), _cabi.ptr(buf["mean"][l]),
+                                _cabi.ptr(buf["var"][l]),
+                                _cabi.ptr(Fl) if Fl is not None else None, buf["F"][l].shape[1],
+                                _cabi.ptr(g_mean_in) if g_mean_in is not None else None,
+                                _cabi.ptr(g_var_in) if g_var_in is not None else None,
+                                _cabi.ptr(gF) if gF is not None else None, gF.shape[1] if gF is not None else 0,
+                                _cabi.ptr(buf["gX"][l]) if l > 0 else None, 1 if ci > 0 else 0,
+                                1 if self.mean_trainable(layer) else 0, st), "dgp_cond_backward"))
                         if nchunks == 1 and l > 0 and self.gram_on_side_stream:
                             # the Gram reduction of this layer is not needed by the next layer's backward kernel: on the
                             # conditional's side stream it fills the SMs that kernel's last, partly empty wave leaves idle

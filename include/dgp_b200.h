@@ -106,6 +106,21 @@ int dgp_cond_forward(const dgp_cond_desc* d, const void* ws, const double* X, in
                      const double* eps, uint64_t seed, const uint64_t* seed_dev, uint64_t row_offset,
                      int64_t rows_per_sample, int64_t sample_stride, double* mean, double* var, double* F, int32_t ldf,
                      double* A_save, double* U_save, double* K_save, void* stream);
+/* MultikernelLayer (dgplib/multikernel_layers.py:74-85: one conditional per kernel, built in a Python loop): the n
+ * conditionals of one layer on the same rows in ONE launch over (conditional, row tile) pairs.  d / ws / A_save / U_save /
+ * K_save are host arrays of n pointers (the saved-tensor arrays may be NULL as a whole); everything else as in
+ * dgp_cond_forward.  Members must agree in M, D, Dx, R, T, ldr and n <= 8, otherwise DGP_ERR_UNSUPPORTED (launch them one
+ * by one).  dgp_cond_backward_group is the same for dgp_cond_backward when no input gradient is wanted (gX accumulates
+ * over the members); dgp_cond_backward_gram / dgp_cond_backward_params stay per member. */
+int dgp_cond_forward_group(int32_t n, const dgp_cond_desc* const* d, const void* const* ws, const double* X, int64_t x_rows,
+                           int64_t n_rows, const double* eps, uint64_t seed, const uint64_t* seed_dev, uint64_t row_offset,
+                           int64_t rows_per_sample, int64_t sample_stride, double* mean, double* var, double* F,
+                           int32_t ldf, double* const* A_save, double* const* U_save, double* const* K_save, void* stream);
+int dgp_cond_backward_group(int32_t n, const dgp_cond_desc* const* d, void* const* ws, const double* X, int64_t x_rows,
+                            int64_t n_rows, const double* const* A_save, const double* const* U_save,
+                            const double* const* K_save, const double* mean, const double* var, const double* F,
+                            int32_t ldf, const double* g_mean_in, const double* g_var_in, const double* g_F, int32_t ldgf,
+                            int32_t mean_grad, void* stream);
 /* bytes of the U_save buffer for n_rows rows of this conditional (R * Mpad * 8 * ceil(n_rows / 8) * 8) */
 size_t dgp_usave_bytes(const dgp_cond_desc* d, int64_t n_rows);
 

@@ -201,6 +201,124 @@ def test_rbf_backward_with_and_without_saved_kuf(cuda):
             assert not bad, (seed, bad, errs)
 
 
+@pytest.mark.parametrize("K,M,D,R,N,kind", [(3, 64, 3, 2, 333, "rbf"), (8, 256, 8, 1, 1500, "rbf"), (2, 100, 5, 3, 200, "matern52")])
+def test_grouped_launch_matches_per_member_launches(cuda, K, M, D, R, N, kind):
+    """MultikernelLayer: dgp_cond_forward_group / dgp_cond_backward_group (one launch over (member, row tile) pairs) against
+    K separate dgp_cond_forward / dgp_cond_backward launches on the same inputs (themselves checked against the oracle above)."""
+    lib, dev, st = C.lib(), cuda, C.stream_ptr()
+    rng = np.random.RandomState(K * 100 + M)
+    T = lambda a: torch.tensor(a, dtype=torch.float64, device=dev)
+    X, eps = T(rng.randn(N, D)), T(rng.randn(N, K * R))
+    A, b = T(rng.randn(D, K * R)), T(rng.randn(K * R))
+    q_mu = T(0.1 * rng.randn(M, K * R))
+    q_sqrt = T(np.eye(M)[None] + 0.1 * np.tril(rng.randn(K * R, M, M)))
+    gm, gv, gF = (T(rng.randn(N, K * R)) for _ in range(3))
+    Mp = C.mpad(M)
+    descs, keep, wss = [], [], []
+    for k in range(K):
+        d = C.CondDesc()
+        d.M, d.D, d.Dx, d.R, d.ldr, d.col0, d.T = M, D, D, R, K * R, k * R, 1
+        d.kind[0] = 0 if kind == "rbf" else 1
+        d.jitter = 1e-6
+        Z = T(rng.randn(M, D))
+        theta = T(np.concatenate([[1.0 + 0.2 * k, 1e-5], np.sqrt(D) * (0.8 + 0.4 * rng.rand(D))]))
+        keep += [Z, theta]
+        d.Z, d.theta, d.q_mu, d.q_sqrt = Z.data_ptr(), theta.data_ptr(), q_mu.data_ptr(), q_sqrt.data_ptr()
+        d.mean_A, d.mean_b = A.data_ptr(), b.data_ptr()
+        descs.append(d)
+
+    SENT, GUARD = -4321.5, 8192      # every buffer sits between sentinel-filled guard bands inside one arena
+
+    def run(grouped):
+        out = {}
+        ws_doubles = lib.dgp_cond_ws_bytes(ctypes.byref(descs[0]), N, 1) // 8 + GUARD + 64
+        arena = torch.full((K * ws_doubles + (32 << 20),), SENT, dtype=torch.float64, device=dev)
+        used, regions = [GUARD], []
+
+        def alloc(name, *shape):
+            n = int(np.prod(shape))
+            t = arena[used[0]:used[0] + n]
+            t.zero_()
+            regions.append((name, used[0], n))
+            used[0] += (n + GUARD + 63) // 64 * 64
+            return t.view(*shape)
+
+        wss = []
+        kl = alloc("kl", K)
+        for k, d in enumerate(descs):
+            wsb = lib.dgp_cond_ws_bytes(ctypes.byref(d), N, 1)
+            ws = alloc(f"ws{k}", (wsb + 7) // 8)
+            C.check(lib.dgp_cond_prepare(ctypes.byref(d), C.ptr(ws), wsb, 1, C.ptr(kl[k:]), st), "prepare")
+            wss.append(ws)
+        mean, var, F = alloc("mean", N, K * R), alloc("var", N, K * R), alloc("F", N, K * R)
+        As = [alloc(f"A{k}", N, Mp) for k in range(K)]
+        Us = [alloc(f"U{k}", lib.dgp_usave_bytes(ctypes.byref(d), N) // 8) for k, d in enumerate(descs)]
+        Ks = [alloc(f"K{k}", N, Mp) for k in range(K)]
+        arr = lambda ts: (ctypes.c_void_p * K)(*[t.data_ptr() for t in ts])
+        dp = (ctypes.POINTER(C.CondDesc) * K)(*[ctypes.pointer(d) for d in descs])
+        if grouped:
+            C.check(lib.dgp_cond_forward_group(K, dp, arr(wss), C.ptr(X), N, N, C.ptr(eps), 0, None, 0, 0, 0, C.ptr(mean),
+                                               C.ptr(var), C.ptr(F), K * R, arr(As), arr(Us), arr(Ks), st), "forward_group")
+            C.check(lib.dgp_cond_backward_group(K, dp, arr(wss), C.ptr(X), N, N, arr(As), arr(Us), arr(Ks), C.ptr(mean),
+                                                C.ptr(var), C.ptr(F), K * R, C.ptr(gm), C.ptr(gv), C.ptr(gF), K * R, 1, st),
+                    "backward_group")
+        else:
+            for k, d in enumerate(descs):
+                C.check(lib.dgp_cond_forward(ctypes.byref(d), C.ptr(wss[k]), C.ptr(X), N, N, C.ptr(eps), 0, None, 0, 0, 0,
+                                             C.ptr(mean), C.ptr(var), C.ptr(F), K * R, C.ptr(As[k]), C.ptr(Us[k]),
+                                             C.ptr(Ks[k]), st), "forward")
+            for k, d in enumerate(descs):
+                C.check(lib.dgp_cond_backward(ctypes.byref(d), C.ptr(wss[k]), C.ptr(X), N, N, C.ptr(As[k]), C.ptr(Us[k]),
+                                              C.ptr(Ks[k]), C.ptr(mean), C.ptr(var), C.ptr(F), K * R, C.ptr(gm), C.ptr(gv),
+                                              C.ptr(gF), K * R, None, 0, 1, st), "backward")
+        out.update(mean=mean, var=var, F=F, A=torch.stack(As), Kuf=torch.stack(Ks))
+        # the layer's gradient arrays: every member fills its own columns col0 .. col0+R-1
+        gqm, gqs = alloc("gqm", M, K * R), alloc("gqs", K * R, M, M)
+        gmA, gmb = alloc("gmA", D, K * R), alloc("gmb", K * R)
+        for k, d in enumerate(descs):
+            C.check(lib.dgp_cond_backward_gram(ctypes.byref(d), C.ptr(wss[k]), C.ptr(As[k]), N, 0, st), "gram")
+            gZ, gth = alloc(f"gZ{k}", M, D), alloc(f"gth{k}", 2 + D)
+            C.check(lib.dgp_cond_backward_params(ctypes.byref(d), C.ptr(wss[k]), 1.0, C.ptr(gZ), C.ptr(gth), C.ptr(gqm),
+                                                 C.ptr(gqs), C.ptr(gmA), C.ptr(gmb), st), "params")
+            out.update({f"gZ{k}": gZ, f"gth{k}": gth})
+        out.update(gqm=gqm, gqs=gqs, gmA=gmA, gmb=gmb)
+        torch.cuda.synchronize()
+        # nothing outside the buffers was written
+        prev_end, prev = 0, "arena start"
+        for name, start, n in regions + [("arena end", used[0], 0)]:
+            gap = arena[prev_end:start]
+            touched = (gap != SENT).nonzero()
+            assert touched.numel() == 0, (f"{'grouped' if grouped else 'single'}: {touched.shape[0]} doubles written between "
+                                          f"{prev} and {name}, first at +{int(touched[0])} of {gap.numel()}")
+            prev_end, prev = start + n, name
+        return out
+
+    one, grp = run(False), run(True)
+    # member 0 of both against the oracle's A = L^-1 Kuf
+    kern0 = {"kind": kind, "input_dim": D, "variance": keep[1][0].cpu(), "lengthscales": keep[1][2:].cpu(),
+             "white": keep[1][1].cpu()}
+    Kmm = O.kern_K(kern0, keep[0].cpu()) + 1e-6 * torch.eye(M, dtype=torch.float64)
+    A_ref = torch.linalg.solve_triangular(torch.linalg.cholesky(Kmm), O.kern_K(kern0, keep[0].cpu(), X.cpu()), upper=False).t()
+    assert rel(one["A"][0, :, :M], A_ref) < 1e-9, "per-member launch"
+    assert rel(grp["A"][0, :, :M], A_ref) < 1e-9, "grouped launch"
+    for name in one:
+        detail = ""
+        if name in ("A", "Kuf") and rel(grp[name], one[name].cpu()) >= 1e-11:
+            bad = ((grp[name] - one[name]).abs() > 1e-9).nonzero()
+            detail = f" members {sorted(set(bad[:, 0].tolist()))} rows {bad[:, 1].min().item()}..{bad[:, 1].max().item()} " \
+                     f"cols {bad[:, 2].min().item()}..{bad[:, 2].max().item()} count {bad.shape[0]} " \
+                     f"grp {grp[name][tuple(bad[0])].item()} one {one[name][tuple(bad[0])].item()} " \
+                     f"nan {int(torch.isnan(grp[name]).sum())}"
+        assert rel(grp[name], one[name].cpu()) < 1e-11, name + detail
+    # more than DGP_GROUP_MAX members or members of different shape: reported, not mis-launched
+    descs[1].M = M - 1
+    dp = (ctypes.POINTER(C.CondDesc) * K)(*[ctypes.pointer(d) for d in descs])
+    null = (ctypes.c_void_p * K)()
+    assert lib.dgp_cond_forward_group(K, dp, null, C.ptr(X), N, N, None, 0, None, 0, 0, 0, None, None, None, K * R,
+                                      null, null, null, st) == C.DGP_ERR_UNSUPPORTED
+    descs[1].M = M
+
+
 def test_trainable_linear_mean_gradient(cuda):
     """A Linear mean left trainable (an OutputLayer built with its own Linear mean, dgplib/layers.py:211-218): dA = X^T g_mean,
     db = sum g_mean through the per-CTA partials, for a sample-tiled input and ragged tiles."""
