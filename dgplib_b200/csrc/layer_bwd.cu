@@ -41,6 +41,7 @@ struct BwdArgs {
     const double* X; long long x_rows, n_rows;
     const double* A_save; const double* U_save; long long NG;
     const double* K_save;    // Kuf per row kept by the forward pass (nullptr: recompute the covariance function)
+    int k_rbf;               // K_save is given and every kernel of the conditional is an RBF: k'(r2) = -k / 2
     const double* mean; const double* var; const double* F; int ldf;
     const double* g_mean_in; const double* g_var_in; const double* g_F; int ldgf;
     double* gX; int accumulate_gX;
@@ -91,7 +92,7 @@ __device__ __forceinline__ int bwd_members(const BwdArgs&) { return 1; }
 __device__ __forceinline__ int bwd_members(const BwdGroup& p) { return p.n; }
 
 template <class C, class P>
-__global__ void __launch_bounds__(C::NTHREADS, 1) k_cond_bwd(const __grid_constant__ P p) {
+__global__ void __launch_bounds__(C::NTHREADS, C::CTAS) k_cond_bwd(const __grid_constant__ P p) {
     extern __shared__ __align__(128) double smem[];
     const BwdArgs& a0 = bwd_member(p, 0);      // shapes, tile count and shared-memory layout are common to all members
     const int ntiles = a0.ntiles, total_tiles = ntiles * bwd_members(p);
@@ -406,15 +407,17 @@ __global__ void __launch_bounds__(C::NTHREADS, 1) k_cond_bwd(const __grid_consta
         PH(6);
 
         // ---- Dt <- Gr2 = dKuf . variance . k'(r2);  per-row sums: rs = sum_m Gr2, dv = sum_m dKuf k(r2)/variance
-        const bool saved_k = (d.T == 1 && d.kind[0] == DGP_KIND_RBF && a.K_save != nullptr);
+        const bool saved_k = a.k_rbf != 0;
         if (saved_k) {
             // RBF with Kuf kept by the forward pass: k'(r2) = -k/2, so Gr2 = -dKuf Kuf / 2 and dv = sum dKuf Kuf / variance
             // need no exp, no cross term and no inducing inputs: one coalesced pass, a warp per row, 32 independent loads
             // per lane in flight.  (Recomputing exp(-r2/2) for the 16 k elements of a tile was 7 % of the kernel at R = 8
             // and 17 % at R = 1: latency-bound chains, five times the fp64-pipe time of the arithmetic.)
-            const double ivar = 1.0 / d.theta[0];
+            // (a SwitchedKernel of RBFs: Kuf is already zero where the tasks of row and inducing point differ)
             for (int n = warp; n < C::NT; n += C::NWARPS) {
                 double srs = 0.0, sdv = 0.0;
+                const int tx = xtask[n];
+                const double ivar = (tx >= 0) ? 1.0 / d.theta[(size_t)tx * thd] : 0.0;
                 if (n < nvalid) {
                     const double* krow = a.K_save + (size_t)(n0 + n) * Mpad;
                     for (int m0 = 0; m0 < Mpad; m0 += 256) {
@@ -525,8 +528,9 @@ __global__ void __launch_bounds__(C::NTHREADS, 1) k_cond_bwd(const __grid_consta
         // ---- T1[n][k] = sum_m Gr2[n][m] zs[m][k] on the tensor cores, one 8-row tile of the row tile per warp, four
         //      interleaved accumulators over the inducing index; parked in rowq[n][2 + k].  Column Dp of the product is a
         //      column of ones: the row sums of Gr2, parked in rowq[n][0].
+        const int t1_ones = (d.T == 1 && !saved_k) ? 1 : 0;     // the other paths have the row sums already
         for (int nt4 = warp; nt4 < C::NT / 8; nt4 += C::NWARPS) {
-            for (int d0 = 0; d0 < Dp + 1; d0 += 8) {
+            for (int d0 = 0; d0 < Dp + t1_ones; d0 += 8) {
                 double c4[4][2] = {{0.0, 0.0}, {0.0, 0.0}, {0.0, 0.0}, {0.0, 0.0}};
                 const int kcol = d0 + g;
                 for (int m = 0; m < Mpad; m += 64) {          // Mpad is a multiple of 64; 16 global loads in flight
@@ -548,31 +552,42 @@ __global__ void __launch_bounds__(C::NTHREADS, 1) k_cond_bwd(const __grid_consta
                 }
             }
         }
-        // ---- T2z[m][k] = sum_n Gr2[n][m] xs[n][k] and cs[m] = sum_n Gr2[n][m] (a column of ones appended to xs)
+        // ---- cs[m] = sum_n Gr2[n][m]: plain column sums, one thread per inducing point (as a ninth column of the T2z
+        //      product below it cost a whole extra pass of DMMAs whenever Dp is a multiple of 8)
+        for (int m = tid; m < Mpad; m += C::NCONS) {
+            const double pold = (m < d.M) ? pcs[m] : 0.0;
+            double s4[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll 4
+            for (int n = 0; n < C::NT; n += 4) {
+                s4[0] += Dt[n * ldb + m];
+                s4[1] += Dt[(n + 1) * ldb + m];
+                s4[2] += Dt[(n + 2) * ldb + m];
+                s4[3] += Dt[(n + 3) * ldb + m];
+            }
+            if (m < d.M) pcs[m] = pold + ((s4[0] + s4[1]) + (s4[2] + s4[3]));
+        }
+        // ---- T2z[m][k] = sum_n Gr2[n][m] xs[n][k]
         for (int mt = warp; mt < Mpad / 8; mt += C::NWARPS) {
             const int m0 = mt * 8;
-            for (int d0 = 0; d0 < Dp + 1; d0 += 8) {
+            for (int d0 = 0; d0 < Dp; d0 += 8) {
                 double c[2] = {0.0, 0.0}, c2[2] = {0.0, 0.0};
                 const int kcol = d0 + g;
                 double pold[2];          // running partials of this CTA (global, L2): fetched ahead of the DMMA chain
 #pragma unroll
                 for (int e = 0; e < 2; ++e) {
                     const int m = m0 + g, k = d0 + 2 * t + e;
-                    pold[e] = (m < d.M && k <= Dp) ? (k < Dp ? pT2z[m * Dp + k] : pcs[m]) : 0.0;
+                    pold[e] = (m < d.M && k < Dp) ? pT2z[m * Dp + k] : 0.0;
                 }
 #pragma unroll
                 for (int ks = 0; ks < C::NT / 4; ++ks) {
                     const int n = ks * 4 + t;
-                    const double bv = (kcol < Dp) ? xs[n * xld + kcol] : (kcol == Dp ? 1.0 : 0.0);
+                    const double bv = (kcol < Dp) ? xs[n * xld + kcol] : 0.0;
                     if (ks & 1) dmma884(c2, Dt[n * ldb + m0 + g], bv); else dmma884(c, Dt[n * ldb + m0 + g], bv);
                 }
 #pragma unroll
                 for (int e = 0; e < 2; ++e) {
                     const int m = m0 + g, k = d0 + 2 * t + e;
-                    if (m < d.M) {
-                        if (k < Dp) pT2z[m * Dp + k] = pold[e] + (c[e] + c2[e]);
-                        else if (k == Dp) pcs[m] = pold[e] + (c[e] + c2[e]);
-                    }
+                    if (m < d.M && k < Dp) pT2z[m * Dp + k] = pold[e] + (c[e] + c2[e]);
                 }
             }
         }
@@ -656,14 +671,16 @@ template <class C>
 static int launch_bwd(const BwdArgs& a, cudaStream_t st) {
     const BwdSmem<C> L(a.Mpad, a.Dp, a.d.R);
     const size_t bytes = (size_t)L.total_doubles * sizeof(double);
-    if (bytes > 227 * 1024) return DGP_ERR_UNSUPPORTED;
+    if (bytes > C::SMEM_LIMIT) return DGP_ERR_UNSUPPORTED;
     static DevOnceSize configured;
     const int dev = current_device();
     if (!configured.covers(dev, bytes)) {
         if (cudaFuncSetAttribute(k_cond_bwd<C, BwdArgs>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes) != cudaSuccess) return DGP_ERR_LAUNCH;
+        if (C::CTAS > 1) cudaFuncSetAttribute(k_cond_bwd<C, BwdArgs>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
         configured.raise(dev, bytes);
     }
-    const int grid = a.ntiles < device_sm_count() ? a.ntiles : device_sm_count();
+    const int slots = device_sm_count() * C::CTAS;
+    const int grid = a.ntiles < slots ? a.ntiles : slots;
     k_cond_bwd<C, BwdArgs><<<grid, C::NTHREADS, bytes, st>>>(a);
     DGP_COUNT_LAUNCH();
     return cudaGetLastError() == cudaSuccess ? DGP_OK : DGP_ERR_LAUNCH;
@@ -673,15 +690,17 @@ template <class C>
 static int launch_bwd_group(const BwdGroup& grp, cudaStream_t st) {
     const BwdSmem<C> L(grp.m[0].Mpad, grp.m[0].Dp, grp.m[0].d.R);
     const size_t bytes = (size_t)L.total_doubles * sizeof(double);
-    if (bytes > 227 * 1024) return DGP_ERR_UNSUPPORTED;
+    if (bytes > C::SMEM_LIMIT) return DGP_ERR_UNSUPPORTED;
     static DevOnceSize configured;
     const int dev = current_device();
     if (!configured.covers(dev, bytes)) {
         if (cudaFuncSetAttribute(k_cond_bwd<C, BwdGroup>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes) != cudaSuccess) return DGP_ERR_LAUNCH;
+        if (C::CTAS > 1) cudaFuncSetAttribute(k_cond_bwd<C, BwdGroup>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
         configured.raise(dev, bytes);
     }
     const long long total = (long long)grp.m[0].ntiles * grp.n;
-    const int grid = (int)(total < device_sm_count() ? total : device_sm_count());
+    const long long slots = (long long)device_sm_count() * C::CTAS;
+    const int grid = (int)(total < slots ? total : slots);
     k_cond_bwd<C, BwdGroup><<<grid, C::NTHREADS, bytes, st>>>(grp);
     DGP_COUNT_LAUNCH();
     return cudaGetLastError() == cudaSuccess ? DGP_OK : DGP_ERR_LAUNCH;
@@ -890,6 +909,7 @@ static int bwd_width(BwdArgs a, int nt, long long row0, long long row_end, cudaS
         case 32: DGP_TRY_BWD(DGP_BWD_WN, 32, 4) DGP_TRY_BWD(DGP_BWD_WN, 32, 3) DGP_TRY_BWD(DGP_BWD_WN, 32, 2) break;
         case 16: DGP_TRY_BWD(2, 16, 4) DGP_TRY_BWD(2, 16, 3) DGP_TRY_BWD(2, 16, 2) break;
         case 8: DGP_TRY_BWD(1, 8, 3) DGP_TRY_BWD(1, 8, 2) break;
+        case 33: DGP_TRY_BWD(2, 32, 3) DGP_TRY_BWD(2, 32, 2) break;       // 32-row tiles, two CTAs per SM
         default: break;
     }
 #undef DGP_TRY_BWD
@@ -943,6 +963,9 @@ static int fill_bwd_args(BwdArgs& a, const dgp_cond_desc* d, void* ws, const dou
     a.X = X; a.x_rows = x_rows; a.n_rows = n_rows;
     a.A_save = A_save; a.U_save = U_save; a.NG = usave_groups(n_rows);
     a.K_save = K_save;
+    a.k_rbf = K_save != nullptr;
+    for (int tk = 0; tk < d->T; ++tk)
+        if (d->kind[tk] != DGP_KIND_RBF) a.k_rbf = 0;
     a.mean = mean; a.var = var; a.F = F; a.ldf = ldf;
     a.g_mean_in = g_mean_in; a.g_var_in = g_var_in; a.g_F = g_F; a.ldgf = ldgf;
     a.gX = gX; a.accumulate_gX = accumulate_gX;

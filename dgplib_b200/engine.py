@@ -250,9 +250,10 @@ class Engine:
                     # U_r = tril(q_sqrt_r)^T A of every output, kept for the backward pass (the reference's LTA tensor)
                     buf["U"].append([torch.empty(_cabi.lib().dgp_usave_bytes(c.ref(), rows) // 8, dtype=_F64, device=dev)
                                      for c in conds])
-                    # Kuf of an RBF conditional: its backward pass then needs no exp (k' = -k / 2)
+                    # Kuf of an RBF conditional (or a SwitchedKernel of RBFs): its backward pass then needs no exp
+                    # (k' = -k / 2)
                     buf["K"].append([torch.empty(rows, _cabi.mpad(layer.num_inducing), dtype=_F64, device=dev)
-                                     if (c.T == 1 and c.kinds[0] == _cabi.DGP_KIND_RBF) else None for c in conds])
+                                     if all(k == _cabi.DGP_KIND_RBF for k in c.kinds[:c.T]) else None for c in conds])
                     buf["gX"].append(torch.empty(n, conds[0].desc.Dx, dtype=_F64, device=dev) if l > 0 else None)
             if save:
                 RL, R0 = self.layers[-1].output_dim, self.layers[0].output_dim

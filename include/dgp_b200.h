@@ -99,8 +99,9 @@ int dgp_cond_status_async(const void* ws, void* stream, int32_t* status_pinned);
  *   U_save  dgp_usave_bytes(d, n_rows) bytes: U_r = tril(q_sqrt_r)^T A for every output r, kept for the backward pass
  *           (the reference's [R, M, N'] LTA tensor of base_conditional, which TF keeps for its own reverse mode) in
  *           16 x 8 blocks [r][m / 16][n / 8][m % 16][n % 8]; NULL: not kept (prediction)
- *   K_save  [n_rows, Mpad] Kuf = k(Z, x_n) per row (nullable): for an RBF kernel (T = 1) the backward pass then needs no
- *           exp (k' = -k / 2); ignored there for other kernels, which recompute the covariance function
+ *   K_save  [n_rows, Mpad] Kuf = k(Z, x_n) per row (nullable): for an RBF kernel, or a SwitchedKernel whose T kernels are
+ *           all RBFs, the backward pass then needs no exp (k' = -k / 2); ignored there for other kernels, which recompute
+ *           the covariance function
  */
 int dgp_cond_forward(const dgp_cond_desc* d, const void* ws, const double* X, int64_t x_rows, int64_t n_rows,
                      const double* eps, uint64_t seed, const uint64_t* seed_dev, uint64_t row_offset,
