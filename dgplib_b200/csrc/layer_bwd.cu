@@ -162,7 +162,10 @@ __global__ void __launch_bounds__(C::NTHREADS, C::CTAS) k_cond_bwd(const __grid_
                 const long long n0 = a.row0 + (long long)tile * C::NT;
                 const long long left = a.n_rows - n0;
                 const int nvalid = (int)(left < C::NT ? left : C::NT);
-                // the A tile is only read elementwise (dA epilogue, d q_mu): pull it into L2 ahead of those reads
+                // the A tile is only read elementwise (dA epilogue, d q_mu): pull it into L2 ahead of those reads.
+                // (Also prefetching the saved Kuf tile and the next tile's row data -- upstream gradients, F, mean, var,
+                // inputs -- was measured: no gain when issued behind the previous tile's last chunk, a loss when issued
+                // here, where 2 x 131 KB per SM queue up in front of the prologue's own loads.)
                 bulk_prefetch_l2(a.A_save + (size_t)n0 * Mpad, (uint32_t)((size_t)nvalid * Mpad * sizeof(double)));
                 long long g0 = n0 / 8;
                 const long long gl = a.NG - g0;
@@ -529,6 +532,10 @@ __global__ void __launch_bounds__(C::NTHREADS, C::CTAS) k_cond_bwd(const __grid_
         //      interleaved accumulators over the inducing index; parked in rowq[n][2 + k].  Column Dp of the product is a
         //      column of ones: the row sums of Gr2, parked in rowq[n][0].
         const int t1_ones = (d.T == 1 && !saved_k) ? 1 : 0;     // the other paths have the row sums already
+        // (T1 has NT/8 units of Mpad/4 DMMAs each, T2z Mpad/8 units of NT/4: the first NT/8 warps take T1, the others
+        //  share the column sums and T2z, so that both finish at about the same time)
+        constexpr int T1W = (C::NT / 8 < C::NWARPS) ? C::NT / 8 : 0;      // warps that do T1 only (0: everyone does both)
+        constexpr int T2W = C::NWARPS - T1W;
         for (int nt4 = warp; nt4 < C::NT / 8; nt4 += C::NWARPS) {
             for (int d0 = 0; d0 < Dp + t1_ones; d0 += 8) {
                 double c4[4][2] = {{0.0, 0.0}, {0.0, 0.0}, {0.0, 0.0}, {0.0, 0.0}};
@@ -554,7 +561,8 @@ __global__ void __launch_bounds__(C::NTHREADS, C::CTAS) k_cond_bwd(const __grid_
         }
         // ---- cs[m] = sum_n Gr2[n][m]: plain column sums, one thread per inducing point (as a ninth column of the T2z
         //      product below it cost a whole extra pass of DMMAs whenever Dp is a multiple of 8)
-        for (int m = tid; m < Mpad; m += C::NCONS) {
+        for (int m = tid - T1W * 32; m < Mpad; m += T2W * 32) {
+            if (m < 0) break;                               // a T1 warp
             const double pold = (m < d.M) ? pcs[m] : 0.0;
             double s4[4] = {0.0, 0.0, 0.0, 0.0};
 #pragma unroll 4
@@ -567,7 +575,8 @@ __global__ void __launch_bounds__(C::NTHREADS, C::CTAS) k_cond_bwd(const __grid_
             if (m < d.M) pcs[m] = pold + ((s4[0] + s4[1]) + (s4[2] + s4[3]));
         }
         // ---- T2z[m][k] = sum_n Gr2[n][m] xs[n][k]
-        for (int mt = warp; mt < Mpad / 8; mt += C::NWARPS) {
+        for (int mt = warp - T1W; mt < Mpad / 8; mt += T2W) {
+            if (mt < 0) break;                              // a T1 warp
             const int m0 = mt * 8;
             for (int d0 = 0; d0 < Dp; d0 += 8) {
                 double c[2] = {0.0, 0.0}, c2[2] = {0.0, 0.0};
@@ -650,14 +659,16 @@ __global__ void __launch_bounds__(C::NTHREADS, C::CTAS) k_cond_bwd(const __grid_
             rowq[n * nq + 1] = s;
         }
         consumer_sync<C>();
-        // per-task hyper-parameter row terms, summed in row order by one thread per (task, column) (deterministic);
-        // the sum stays in a register so that the global partial sees one read-modify-write per tile
-        for (int idx = tid; idx < d.T * nq; idx += C::NCONS) {
+        // per-task hyper-parameter row terms: one warp per (task, column), lanes over the rows, fixed shuffle tree
+        // (deterministic); the global partial sees one read-modify-write per tile
+        for (int idx = warp; idx < d.T * nq; idx += C::NWARPS) {
             const int tk = idx / nq, c = idx % nq;
+            const double pold = (lane == 0) ? pth[idx] : 0.0;
             double s = 0.0;
-            for (int n = 0; n < nvalid; ++n)
+            for (int n = lane; n < nvalid; n += 32)
                 if (xtask[n] == tk) s += rowq[n * nq + c];
-            pth[idx] += s;
+            s = warp_sum(s);
+            if (lane == 0) pth[idx] = pold + s;
         }
         PH(9);
     }
