@@ -145,7 +145,15 @@ __device__ __forceinline__ void produce_phase(Pipe& p, int nseg, SegFn segfn, in
 __device__ __forceinline__ void dmul_inplace(double& x, double w) {
     asm volatile("mul.f64 %0, %0, %1;\n" : "+d"(x) : "d"(w));
 }
-template <class C, int QLO, int QHI, bool BSTAGE, bool WEIGHTED>
+// DIAG: the chunk starts exactly at the first row of one of the warp's 8-row tiles, which therefore meets only half of its
+// 16 columns: 1 = lower-triangular operand, tile QLO uses k-steps 0..1 (columns k0 .. k0+7 <= its last row);
+// 2 = upper-triangular operand whose tile QHI-1 starts 8 rows into the chunk and uses k-steps 2..3.  Resolved at compile
+// time in the unrolled loops: the skipped DMMAs (and their A fragments) are simply not there.
+template <int DIAG, int QLO, int QHI>
+__device__ __forceinline__ constexpr bool kstep_active(int q, int kk) {
+    return !((DIAG == 1 && q == QLO && kk >= 2) || (DIAG == 2 && q == QHI - 1 && kk < 2));
+}
+template <class C, int QLO, int QHI, bool BSTAGE, bool WEIGHTED, int DIAG = 0>
 __device__ __forceinline__ void chunk_mma(Acc<C>& acc, const double* __restrict__ Aw, const double* __restrict__ Bw,
                                           int ldb, const int (&ko)[4], const double (&wv)[C::NJ]) {
     // Software-pipelined over the four k-steps of the chunk: the fragments of step kk+1 are loaded (into their own
@@ -157,7 +165,8 @@ __device__ __forceinline__ void chunk_mma(Acc<C>& acc, const double* __restrict_
         for (int j = 0; j < C::NJ; ++j)
             bf[buf][j] = BSTAGE ? Bw[j * USAVE_BLOCK + kk * 32] : Bw[j * 8 * ldb + kk * 4];
 #pragma unroll
-        for (int q = QLO; q < QHI; ++q) af[buf][q] = Aw[q * C::WM * 8 * C::WLD + ko[kk]];
+        for (int q = QLO; q < QHI; ++q)
+            if (kstep_active<DIAG, QLO, QHI>(q, kk)) af[buf][q] = Aw[q * C::WM * 8 * C::WLD + ko[kk]];
     };
     auto scale = [&](int buf) {
 #pragma unroll
@@ -172,7 +181,8 @@ __device__ __forceinline__ void chunk_mma(Acc<C>& acc, const double* __restrict_
 #pragma unroll
         for (int q = QLO; q < QHI; ++q)
 #pragma unroll
-            for (int j = 0; j < C::NJ; ++j) dmma884(acc.v[q][j], af[kk & 1][q], bf[kk & 1][j]);
+            for (int j = 0; j < C::NJ; ++j)
+                if (kstep_active<DIAG, QLO, QHI>(q, kk)) dmma884(acc.v[q][j], af[kk & 1][q], bf[kk & 1][j]);
         if (WEIGHTED && kk + 1 < 4) scale((kk + 1) & 1);
     }
 }
@@ -233,8 +243,25 @@ __device__ __forceinline__ void run_phase(Pipe& p, int nseg, SegFn segfn, EpiFn 
                     const int h = ((k0 + 15 - rbase) >> 5) + 1;
                     qhi = h < qmax ? (h < 0 ? 0 : h) : qmax;
                 }
+                // the chunk that starts on a tile's own first row (lower) / 8 columns before it (upper): half of that
+                // tile's k-steps hit the zero triangle (3 % of all DMMAs of a 256-row operand)
+                // Only in the wide-tile configurations (Mpad <= 256): with 16- / 32-row tiles, i.e. 512 or 1024 operand rows,
+                // the share of diagonal chunks is small and the extra code measured slower (M = 1024 forward + 2.5 %).
+                constexpr bool use_diag = C::NT >= 40;
+                const bool diag_lo = use_diag && MASK == MASK_LOWER && qhi == 4 && qlo < 4 && rbase + 32 * qlo == k0;
+                const bool diag_up = use_diag && MASK == MASK_UPPER && qlo == 0 && qhi >= 1 && rbase + 32 * (qhi - 1) == k0 + 8;
                 mbar_wait(&p.full[p.stage], p.round & 1);
-                if (qlo == 0 && qhi == 4) {
+                if (diag_lo) switch (qlo) {
+                    case 0: chunk_mma<C, 0, 4, BSTAGE, WEIGHTED, 1>(acc, Aw, Bw, ldb, ko, wv); break;
+                    case 1: chunk_mma<C, 1, 4, BSTAGE, WEIGHTED, 1>(acc, Aw, Bw, ldb, ko, wv); break;
+                    case 2: chunk_mma<C, 2, 4, BSTAGE, WEIGHTED, 1>(acc, Aw, Bw, ldb, ko, wv); break;
+                    default: chunk_mma<C, 3, 4, BSTAGE, WEIGHTED, 1>(acc, Aw, Bw, ldb, ko, wv); break;
+                } else if (diag_up) switch (qhi) {
+                    case 1: chunk_mma<C, 0, 1, BSTAGE, WEIGHTED, 2>(acc, Aw, Bw, ldb, ko, wv); break;
+                    case 2: chunk_mma<C, 0, 2, BSTAGE, WEIGHTED, 2>(acc, Aw, Bw, ldb, ko, wv); break;
+                    case 3: chunk_mma<C, 0, 3, BSTAGE, WEIGHTED, 2>(acc, Aw, Bw, ldb, ko, wv); break;
+                    default: chunk_mma<C, 0, 4, BSTAGE, WEIGHTED, 2>(acc, Aw, Bw, ldb, ko, wv); break;
+                } else if (qlo == 0 && qhi == 4) {
                     chunk_mma<C, 0, 4, BSTAGE, WEIGHTED>(acc, Aw, Bw, ldb, ko, wv);
                 } else if (qlo < qhi) switch ((qlo << 3) | qhi) {
                     case (1 << 3) | 4: chunk_mma<C, 1, 4, BSTAGE, WEIGHTED>(acc, Aw, Bw, ldb, ko, wv); break;
