@@ -130,7 +130,7 @@ static inline WsLayout ws_layout(const dgp_cond_desc& d, int64_t n_rows, int nee
     WsLayout w{};
     w.Mpad = dgp_mpad(d.M);
     w.Dp = round_up(d.D, 4);
-    w.ncta = 2 * device_sm_count();      // row-kernel CTAs with a partial slot each: up to two per SM (TileCfg::CTAS)
+    w.ncta = device_sm_count();
     const size_t mm = size_t(w.Mpad) * w.Mpad * sizeof(double);
     size_t o = 0;
     w.status = o; o += align256(64 * sizeof(int32_t));
@@ -154,7 +154,7 @@ static inline WsLayout ws_layout(const dgp_cond_desc& d, int64_t n_rows, int nee
         // k_gram runs 4 CTAs per SM and its CTAs are uneven (diagonal tiles do 9/16 of the work): about five waves of
         // CTAs balance well (measured: 13 -> 32 splits took the T-shape Gram kernel from 2.33 to 2.09 ms); the partial
         // buffers are bounded to 512 MB
-        const int slots = 4 * device_sm_count();
+        const int slots = 4 * w.ncta;
         int ns = (5 * slots + tiles / 2) / tiles;
         const size_t per_split = mm * (d.R + 1);
         if ((size_t)ns * per_split > (size_t)512 << 20) ns = (int)(((size_t)512 << 20) / per_split);

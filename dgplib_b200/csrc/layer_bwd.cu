@@ -92,7 +92,7 @@ __device__ __forceinline__ int bwd_members(const BwdArgs&) { return 1; }
 __device__ __forceinline__ int bwd_members(const BwdGroup& p) { return p.n; }
 
 template <class C, class P>
-__global__ void __launch_bounds__(C::NTHREADS, C::CTAS) k_cond_bwd(const __grid_constant__ P p) {
+__global__ void __launch_bounds__(C::NTHREADS, 1) k_cond_bwd(const __grid_constant__ P p) {
     extern __shared__ __align__(128) double smem[];
     const BwdArgs& a0 = bwd_member(p, 0);      // shapes, tile count and shared-memory layout are common to all members
     const int ntiles = a0.ntiles, total_tiles = ntiles * bwd_members(p);
@@ -682,16 +682,14 @@ template <class C>
 static int launch_bwd(const BwdArgs& a, cudaStream_t st) {
     const BwdSmem<C> L(a.Mpad, a.Dp, a.d.R);
     const size_t bytes = (size_t)L.total_doubles * sizeof(double);
-    if (bytes > C::SMEM_LIMIT) return DGP_ERR_UNSUPPORTED;
+    if (bytes > 227 * 1024) return DGP_ERR_UNSUPPORTED;
     static DevOnceSize configured;
     const int dev = current_device();
     if (!configured.covers(dev, bytes)) {
         if (cudaFuncSetAttribute(k_cond_bwd<C, BwdArgs>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes) != cudaSuccess) return DGP_ERR_LAUNCH;
-        if (C::CTAS > 1) cudaFuncSetAttribute(k_cond_bwd<C, BwdArgs>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
         configured.raise(dev, bytes);
     }
-    const int slots = device_sm_count() * C::CTAS;
-    const int grid = a.ntiles < slots ? a.ntiles : slots;
+    const int grid = a.ntiles < device_sm_count() ? a.ntiles : device_sm_count();
     k_cond_bwd<C, BwdArgs><<<grid, C::NTHREADS, bytes, st>>>(a);
     DGP_COUNT_LAUNCH();
     return cudaGetLastError() == cudaSuccess ? DGP_OK : DGP_ERR_LAUNCH;
@@ -701,17 +699,15 @@ template <class C>
 static int launch_bwd_group(const BwdGroup& grp, cudaStream_t st) {
     const BwdSmem<C> L(grp.m[0].Mpad, grp.m[0].Dp, grp.m[0].d.R);
     const size_t bytes = (size_t)L.total_doubles * sizeof(double);
-    if (bytes > C::SMEM_LIMIT) return DGP_ERR_UNSUPPORTED;
+    if (bytes > 227 * 1024) return DGP_ERR_UNSUPPORTED;
     static DevOnceSize configured;
     const int dev = current_device();
     if (!configured.covers(dev, bytes)) {
         if (cudaFuncSetAttribute(k_cond_bwd<C, BwdGroup>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes) != cudaSuccess) return DGP_ERR_LAUNCH;
-        if (C::CTAS > 1) cudaFuncSetAttribute(k_cond_bwd<C, BwdGroup>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
         configured.raise(dev, bytes);
     }
     const long long total = (long long)grp.m[0].ntiles * grp.n;
-    const long long slots = (long long)device_sm_count() * C::CTAS;
-    const int grid = (int)(total < slots ? total : slots);
+    const int grid = (int)(total < device_sm_count() ? total : device_sm_count());
     k_cond_bwd<C, BwdGroup><<<grid, C::NTHREADS, bytes, st>>>(grp);
     DGP_COUNT_LAUNCH();
     return cudaGetLastError() == cudaSuccess ? DGP_OK : DGP_ERR_LAUNCH;
@@ -920,7 +916,6 @@ static int bwd_width(BwdArgs a, int nt, long long row0, long long row_end, cudaS
         case 32: DGP_TRY_BWD(DGP_BWD_WN, 32, 4) DGP_TRY_BWD(DGP_BWD_WN, 32, 3) DGP_TRY_BWD(DGP_BWD_WN, 32, 2) break;
         case 16: DGP_TRY_BWD(2, 16, 4) DGP_TRY_BWD(2, 16, 3) DGP_TRY_BWD(2, 16, 2) break;
         case 8: DGP_TRY_BWD(1, 8, 3) DGP_TRY_BWD(1, 8, 2) break;
-        case 33: DGP_TRY_BWD(2, 32, 3) DGP_TRY_BWD(2, 32, 2) break;       // 32-row tiles, two CTAs per SM
         default: break;
     }
 #undef DGP_TRY_BWD

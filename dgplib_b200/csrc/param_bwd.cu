@@ -47,9 +47,14 @@ __global__ void k_gq_sqrt(dgp_cond_desc d, int Mpad, const double* __restrict__ 
 __global__ void k_part_reduce(const double* __restrict__ part, int ncta, int npart, double* __restrict__ psum) {
     const int e = blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= npart) return;
-    double s = 0.0;
-    for (int c = 0; c < ncta; ++c) s += part[(size_t)c * npart + e];
-    psum[e] = s;
+    // eight interleaved partial sums (fixed association): the loads of a column are independent, only the adds chain
+    double s[8] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+    int c = 0;
+    for (; c + 8 <= ncta; c += 8)
+#pragma unroll
+        for (int u = 0; u < 8; ++u) s[u] += part[(size_t)(c + u) * npart + e];
+    for (; c < ncta; ++c) s[c & 7] += part[(size_t)c * npart + e];
+    psum[e] = ((s[0] + s[1]) + (s[2] + s[3])) + ((s[4] + s[5]) + (s[6] + s[7]));
 }
 
 // (c) d q_mu = row-summed partials - klw q_mu

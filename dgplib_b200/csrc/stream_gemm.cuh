@@ -38,11 +38,6 @@ struct TileCfg {
     static constexpr int MB = 32 * WM;                  // rows per block row
     static constexpr int NJ = NT / (8 * WN);            // 8-column tiles per warp
     static constexpr int KC = TILE_KC, WLD = TILE_WLD;
-    // 4 x 2 consumer warps on a 32-row tile: TWO such CTAs share an SM (registers: 2 x 288 threads x 112; shared memory:
-    // <= 113 KB each), so that the row-level phases of one tile (setup, covariance function, epilogues, parameter
-    // partials -- no tensor work) run under the streamed GEMM phases of the other CTA's tile
-    static constexpr int CTAS = (WN_ == 2 && NT_ == 32) ? 2 : 1;
-    static constexpr size_t SMEM_LIMIT = CTAS == 2 ? (size_t)113 * 1024 : (size_t)227 * 1024;
     static constexpr int UCH_DOUBLES = USTREAM ? NT * TILE_KC : 0;
     static constexpr int STAGE_DOUBLES = TILE_DOUBLES + UCH_DOUBLES;
     static_assert(MB == TILE_MB, "the tiled operand layout assumes 128-row block rows (WM = 4)");
