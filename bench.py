@@ -300,6 +300,7 @@ def run_predict(args, name, w, model, eng, rank, world, local_rank, dist, sync_a
     gc.collect(); gc.disable()
     eng.timers = {}
     l0 = _cabi.launch_count()
+    sync_all()               # all ranks enter the timed region together (rank 0 alone started the clock sampler)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for i in range(args.steps):
@@ -415,6 +416,8 @@ def run_elbo(args, name, w, rank, world, local_rank, dist, sync_all, with_cpu, w
     time.sleep(1.5)          # let nvidia-smi finish its NVML start-up before the timed region
     gc.collect()
     gc.disable()
+    sync_all()               # barrier + synchronize right in front of the timed region: rank 0 alone started the clock sampler,
+                             # and a rank that enters late makes the others wait inside their first collective
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     step_evs = []
