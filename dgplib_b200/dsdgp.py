@@ -101,8 +101,9 @@ class DSDGP(Parameterized):
         self._prefetched = None
         # Cholesky status words are read back every this many evaluations (0 = only on demand through
         # engine.check_status()).  The read is asynchronous: the copy into pinned memory is queued behind the evaluation and
-        # looked at when the NEXT evaluation is being queued (or by engine.poll_status()), so a failed factorisation raises
-        # one call later and the host never stalls the stream -- the reference surfaces it as TF's InvalidArgumentError
+        # looked at while a LATER evaluation is being queued -- the next one if the failed evaluation has finished by then,
+        # otherwise the one after -- or at once by engine.poll_status(): a failed factorisation raises one or two calls
+        # later and the host never waits for the device (the reference surfaces it as TF's InvalidArgumentError)
         self.check_status_every = 1
         # replay each evaluation of elbo_and_grad() as one CUDA graph (fixed minibatch shape; Philox noise only)
         self.use_cuda_graph = False
@@ -266,7 +267,7 @@ class DSDGP(Parameterized):
         """Arguments of Engine.elbo for the next minibatch taken from the model's own host data through the pinned,
         double-buffered staging path, plus a callback to run once the step's kernels are enqueued."""
         eng = self.engine
-        eng.poll_status()          # the previous evaluation's Cholesky status (posted asynchronously)
+        eng.poll_status(block=False)   # Cholesky status words of earlier evaluations that have arrived (posted asynchronously)
         staged = self._prefetched or self._stage_next()
         self._prefetched = None
         xd, yd, ready, lo, B, slot = staged

@@ -339,30 +339,40 @@ class Engine:
         the current stream, without waiting for it; `poll_status()` looks at the result once that work has finished."""
         lib, st = _cabi.lib(), _cabi.stream_ptr()
         n = sum(len(c) for c in self.conds)
-        if getattr(self, "_status_host", None) is None or self._status_host.numel() != n:
-            self._status_host = torch.zeros(n, dtype=torch.int32).pin_memory()
+        pend = self.__dict__.setdefault("_status_pending", [])
+        pool = self.__dict__.setdefault("_status_pool", [])
+        if len(pend) >= 3:                      # never more than three reads in flight (three pinned buffers)
+            self._check_status_entry(pend.pop(0), wait=True)
+        host = pool.pop() if pool and pool[-1].numel() == n else torch.zeros(n, dtype=torch.int32).pin_memory()
         i = 0
         for conds in self.conds:
             for c in conds:
-                _cabi.check(lib.dgp_cond_status_async(_cabi.ptr(c.ws), st,
-                                                      ctypes.c_void_p(self._status_host.data_ptr() + 4 * i)),
+                _cabi.check(lib.dgp_cond_status_async(_cabi.ptr(c.ws), st, ctypes.c_void_p(host.data_ptr() + 4 * i)),
                             "dgp_cond_status_async")
                 i += 1
-        self._status_event = torch.cuda.current_stream().record_event()
+        pend.append((torch.cuda.current_stream().record_event(), host))
 
-    def poll_status(self):
-        """Raises if the evaluation whose status was posted by post_status_read() had a failed Cholesky factorisation
-        (waits for that evaluation only -- normally long finished when the next one is being queued)."""
-        ev = getattr(self, "_status_event", None)
-        if ev is None:
-            return
-        ev.synchronize()
-        self._status_event = None
-        bad = self._status_host.nonzero()
-        if bad.numel():
-            i = int(bad[0])
-            raise _cabi.DgpError(f"Cholesky of Kuu failed in conditional {i} at pivot {int(self._status_host[i]) - 1}: "
+    def _check_status_entry(self, entry, wait):
+        ev, host = entry
+        if wait:
+            ev.synchronize()
+        bad = host.nonzero()
+        info = (int(bad[0]), int(host[int(bad[0])]) - 1) if bad.numel() else None
+        self._status_pool.append(host)
+        if info is not None:
+            raise _cabi.DgpError(f"Cholesky of Kuu failed in conditional {info[0]} at pivot {info[1]}: "
                                  "Kuu + jitter is not positive definite")
+
+    def poll_status(self, block=True):
+        """Raises if an evaluation whose status was posted by post_status_read() had a failed Cholesky factorisation.
+        block=True waits for every posted read; block=False (what DSDGP does while queueing the next evaluation) looks only
+        at the reads that have already arrived, so the host never waits for the evaluation that is still running -- the
+        device always has the next step queued behind the current one."""
+        pend = getattr(self, "_status_pending", None)
+        while pend:
+            if not block and not pend[0][0].query():
+                break
+            self._check_status_entry(pend.pop(0), wait=True)
 
     # ------------------------------------------------------------------------------------------ forward
     def _seed_dev_ptr(self):

@@ -689,13 +689,15 @@ def test_prediction_cache_sees_parameter_changes(cuda):
 
 def test_cholesky_failure_surfaces_through_the_model(cuda, monkeypatch):
     """Numerical failure convention at the model level: the status words are read back asynchronously, so an indefinite
-    Kuu + jitter raises when the next evaluation is queued, or at once through engine.poll_status() / check_status()."""
+    Kuu + jitter raises when a later evaluation is queued (the next one once the failed one has finished), or at once through
+    engine.poll_status() / check_status()."""
     from dgplib_b200 import settings
     from dgplib_b200._cabi import DgpError
     monkeypatch.setattr(settings, "jitter_level", -3.0)
     model, X, Y = build_dsdgp(L=2, M=12, D=2, N=40, S=2, minibatch=20)
     model.compile()
     model.elbo_and_grad()                      # queued; the failure is found behind it
+    torch.cuda.synchronize()                   # (a status read that has not arrived yet is looked at one call later)
     with pytest.raises(DgpError, match="not positive definite"):
         model.elbo_and_grad()
     model.elbo_and_grad()
