@@ -213,8 +213,10 @@ __global__ void __launch_bounds__(C::NTHREADS, 1) k_cond_bwd(const __grid_consta
         consumer_sync<C>();  // every warp is done with the previous tile
         PH(0);
 
-        // ---- per-row setup: scaled inputs, combined upstream gradients
-        for (int n = tid; n < C::NT; n += C::NCONS) {
+        // ---- per-row setup: scaled inputs (one thread per (row, input column): the fp64 divisions of a row do not queue up
+        //      behind each other in one thread), combined upstream gradients
+        for (int idx = tid; idx < C::NT * Dp; idx += C::NCONS) {
+            const int n = idx / Dp, k = idx - n * Dp;
             long long gn = n0 + n;
             if (gn >= a.n_rows) gn = a.n_rows - 1;
             const double* xr = a.X + (size_t)(gn % a.x_rows) * d.Dx;
@@ -223,16 +225,9 @@ __global__ void __launch_bounds__(C::NTHREADS, 1) k_cond_bwd(const __grid_consta
                 tk = (int)xr[d.Dx - 1];
                 if (tk < 0 || tk >= d.T) tk = -1;
             }
-            xtask[n] = tk;
+            if (k == 0) xtask[n] = tk;
             const double* th = d.theta + (size_t)(tk < 0 ? 0 : tk) * thd;
-            double s = 0.0;
-            for (int k = 0; k < Dp; ++k) {
-                double v = 0.0;
-                if (k < d.D) v = xr[k] / th[2 + k];
-                xs[n * xld + k] = v;
-                s = fma(v, v, s);
-            }
-            xn[n] = s;
+            xs[n * xld + k] = (k < d.D) ? xr[k] / th[2 + k] : 0.0;
         }
         for (int idx = tid; idx < C::NT * R; idx += C::NCONS) {
             const int n = idx / R, r = idx % R;
@@ -258,6 +253,9 @@ __global__ void __launch_bounds__(C::NTHREADS, 1) k_cond_bwd(const __grid_consta
             double s = 0.0;
             for (int r = 0; r < R; ++r) s += gv[n * R + r];
             gs[n] = s;
+            double s2 = 0.0;                                // squared norm of the scaled input row
+            for (int k = 0; k < Dp; ++k) s2 = fma(xs[n * xld + k], xs[n * xld + k], s2);
+            xn[n] = s2;
         }
         // ---- Dt <- q_mu g_mean^T (the mean path of dA) on the tensor cores, K = R: the dA tile is free until the epilogue
         //      of the streamed phase adds the variance path to it.  (As a scalar loop in that epilogue -- q_mu rows from

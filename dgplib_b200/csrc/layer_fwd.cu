@@ -159,8 +159,10 @@ __global__ void __launch_bounds__(C::NTHREADS, 1) k_cond_fwd(const __grid_consta
         consumer_sync<C>();
         PH(0);
 
-        // ---- tile setup: scaled inputs, norms, task ids, Kdiag
-        for (int n = tid; n < C::NT; n += C::NCONS) {
+        // ---- tile setup: scaled inputs (one thread per (row, input column): the fp64 divisions of a row do not queue up
+        //      behind each other in one thread), task ids; then norms and Kdiag per row
+        for (int idx = tid; idx < C::NT * Dp; idx += C::NCONS) {
+            const int n = idx / Dp, k = idx - n * Dp;
             long long gn = n0 + n;
             if (gn >= a.n_rows) gn = a.n_rows - 1;  // ragged last tile: compute on a valid row, never store it
             const double* xr = a.X + (size_t)(gn % a.x_rows) * d.Dx;
@@ -169,15 +171,16 @@ __global__ void __launch_bounds__(C::NTHREADS, 1) k_cond_fwd(const __grid_consta
                 tk = (int)xr[d.Dx - 1];
                 if (tk < 0 || tk >= d.T) tk = -1;
             }
-            xtask[n] = tk;
+            if (k == 0) xtask[n] = tk;
+            const double* th = d.theta + (size_t)(tk < 0 ? 0 : tk) * thd;
+            xs[n * xld + k] = (k < d.D) ? xr[k] / th[2 + k] : 0.0;
+        }
+        consumer_sync<C>();
+        for (int n = tid; n < C::NT; n += C::NCONS) {
+            const int tk = xtask[n];
             const double* th = d.theta + (size_t)(tk < 0 ? 0 : tk) * thd;
             double s = 0.0;
-            for (int k = 0; k < Dp; ++k) {
-                double v = 0.0;
-                if (k < d.D) v = xr[k] / th[2 + k];
-                xs[n * xld + k] = v;
-                s = fma(v, v, s);
-            }
+            for (int k = 0; k < Dp; ++k) s = fma(xs[n * xld + k], xs[n * xld + k], s);
             xn[n] = s;
             kd[n] = (tk < 0) ? 0.0 : th[0] + th[1];  // Stationary.Kdiag + White.Kdiag
         }
