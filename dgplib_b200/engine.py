@@ -152,12 +152,19 @@ class Engine:
 
     def raw_parameters(self):
         """The unconstrained torch Parameters behind params() (every Param of the layers and the likelihood)."""
-        out = []
-        for layer in self.layers:
-            out.extend(layer.parameters())
-        if self.likelihood is not None:
-            out.extend(self.likelihood.parameters())
-        return out
+        from . import params as _params
+        epoch = _params.structure_epoch()
+        cached = self.__dict__.get("_raw_params")
+        if cached is None or cached[0] != epoch:
+            # the walk over the module tree costs ~10 us per layer and used to run a dozen times per evaluation: kept until
+            # the set of Parameters can have changed (params.structure_epoch)
+            out = []
+            for layer in self.layers:
+                out.extend(layer.parameters())
+            if self.likelihood is not None:
+                out.extend(self.likelihood.parameters())
+            cached = self._raw_params = (epoch, out)
+        return cached[1]
 
     @staticmethod
     def mean_trainable(layer):

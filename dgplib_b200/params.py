@@ -7,6 +7,20 @@ import torch
 from . import settings
 
 
+# Bumped whenever the SET of torch Parameters of any model can have changed (a Param created or its `raw` replaced, a
+# sub-module attached or replaced, a ParamList edited).  The engine caches its walk over the module tree on it; storage
+# addresses and trainable flags are still compared on every evaluation (flatparams.FlatParams.storage_key).
+_structure_epoch = [0]
+
+
+def structure_epoch():
+    return _structure_epoch[0]
+
+
+def _structure_changed():
+    _structure_epoch[0] += 1
+
+
 def _to_tensor(value):
     if isinstance(value, torch.Tensor):
         return value.detach().to(settings.float_type).clone()
@@ -20,6 +34,11 @@ class Param(torch.nn.Module):
         super().__init__()
         self.positive = bool(positive)
         self.raw = torch.nn.Parameter(self._backward(_to_tensor(value)), requires_grad=bool(trainable))
+
+    def __setattr__(self, name, value):
+        if isinstance(value, (torch.nn.Parameter, torch.nn.Module)):
+            _structure_changed()
+        super().__setattr__(name, value)
 
     def _backward(self, y):
         if not self.positive:
@@ -70,6 +89,15 @@ class Parameterized(torch.nn.Module):
         super().__init__()
         self.name = name or type(self).__name__
 
+    def __setattr__(self, name, value):
+        if isinstance(value, (torch.nn.Parameter, torch.nn.Module)):
+            _structure_changed()
+        super().__setattr__(name, value)
+
+    def __delattr__(self, name):
+        _structure_changed()
+        super().__delattr__(name)
+
     def set_trainable(self, flag):
         for p in self.parameters():
             p.requires_grad_(bool(flag))
@@ -83,3 +111,23 @@ class ParamList(torch.nn.ModuleList):
 
     def __bool__(self):
         return len(self) > 0
+
+    def __setitem__(self, idx, module):
+        _structure_changed()
+        return super().__setitem__(idx, module)
+
+    def __delitem__(self, idx):
+        _structure_changed()
+        return super().__delitem__(idx)
+
+    def append(self, module):
+        _structure_changed()
+        return super().append(module)
+
+    def extend(self, modules):
+        _structure_changed()
+        return super().extend(modules)
+
+    def insert(self, index, module):
+        _structure_changed()
+        return super().insert(index, module)
