@@ -684,7 +684,16 @@ def test_prediction_cache_sees_parameter_changes(cuda):
     opt = torch.optim.SGD(model.trainable_parameters(), lr=1e-4)
     (-model._build_likelihood()).backward()
     opt.step()
-    assert not np.allclose(d, check())
+    e = check()
+    assert not np.allclose(d, e)
+    # a parameter OBJECT replaced after compile (ARD lengthscales: the shape changes, Param.assign swaps `raw`) and a whole
+    # kernel replaced: the engine's cached parameter list (params.structure_epoch) and the flat buffer follow
+    from dgplib_b200.kernels import RBF, White
+    model.layers.layers[0].kernel.kernels[0].lengthscales.assign(np.array([1.5, 3.0]))
+    f = check()
+    assert not np.allclose(e, f)
+    v, _ = model.elbo_and_grad()
+    assert np.isfinite(float(v))
 
 
 def test_cholesky_failure_surfaces_through_the_model(cuda, monkeypatch):

@@ -2,6 +2,7 @@
 Sequential validation rules, MultikernelLayer construction, DSDGP constructor checks, minibatch iterator."""
 import numpy as np
 import pytest
+import torch
 
 import dgplib_b200 as dg
 from dgplib_b200.cascade import Sequential, MultitaskSequential
@@ -209,3 +210,28 @@ def test_compute_paths_fail_loudly_without_cuda():
                  lambda: model.elbo_and_grad()):
         with pytest.raises(DgpError):
             call()
+
+
+def test_structure_epoch_tracks_every_change_of_the_parameter_set():
+    """The engine caches its walk over the module tree on params.structure_epoch(): every way the SET of torch Parameters
+    of a model can change has to bump it (in-place value updates must not)."""
+    from dgplib_b200 import params as P
+    from dgplib_b200.kernels import RBF, White
+
+    def bumped(fn):
+        e0 = P.structure_epoch()
+        fn()
+        return P.structure_epoch() > e0
+
+    k = RBF(2)
+    assert bumped(lambda: RBF(2))                                         # new Params
+    assert not bumped(lambda: k.variance.assign(2.0))                     # in place
+    assert bumped(lambda: k.lengthscales.assign(np.ones(2)))              # shape change: `raw` is replaced
+    assert bumped(lambda: setattr(k, "variance", P.Param(1.5, positive=True)))   # a sub-module replaced
+    assert bumped(lambda: setattr(k.variance, "raw", torch.nn.Parameter(torch.zeros((), dtype=torch.float64))))
+    s = k + White(2)
+    assert bumped(lambda: s.kernels.append(White(2)))                     # ParamList edited
+    assert bumped(lambda: s.kernels.__setitem__(0, RBF(2)))
+    layer = InputLayer(2, 2, 5, RBF(2))
+    assert bumped(lambda: setattr(layer, "kernel", RBF(2)))
+    assert not bumped(lambda: layer.q_mu.assign(np.ones((5, 2))))
