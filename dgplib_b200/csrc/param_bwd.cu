@@ -9,6 +9,22 @@
 
 namespace dgp {
 
+// sum of n values `stride` apart in four interleaved partial sums (fixed association): the loads are independent, only the
+// adds chain -- these reductions sit on the latency path of the parameter tail
+__device__ __forceinline__ double split_sum(const double* __restrict__ p, int n, size_t stride) {
+    double s[4] = {0.0, 0.0, 0.0, 0.0};
+    int c = 0;
+    for (; c + 8 <= n; c += 8) {
+        double v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) v[u] = p[(size_t)(c + u) * stride];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) s[u & 3] += v[u];
+    }
+    for (; c < n; ++c) s[c & 3] += p[(size_t)c * stride];
+    return (s[0] + s[1]) + (s[2] + s[3]);
+}
+
 // (a) reduce the split-K Gram partials.  mat < R: full symmetric G (lower tiles mirrored); mat == R: Lbar = -tril(P).
 //     blockIdx.z + mat0 = matrix index, so that the G_r and the Lbar parts can be launched separately.
 __global__ void k_gram_reduce(const double* __restrict__ gram, int nsplit, int R, int Mpad, int mat0,
@@ -19,13 +35,10 @@ __global__ void k_gram_reduce(const double* __restrict__ gram, int nsplit, int R
     if (mat < R) {
         const bool lower = (i / 8) >= (j / 8);     // k_gram fills the 8x8 tiles on and below the tile diagonal
         const size_t off = lower ? (size_t)i * Mpad + j : (size_t)j * Mpad + i;
-        double s = 0.0;
-        for (int sp = 0; sp < nsplit; ++sp) s += gram[((size_t)sp * (R + 1) + mat) * mm + off];
-        Gfull[(size_t)mat * mm + (size_t)i * Mpad + j] = s;
+        Gfull[(size_t)mat * mm + (size_t)i * Mpad + j] = split_sum(gram + (size_t)mat * mm + off, nsplit, (size_t)(R + 1) * mm);
     } else {
         double s = 0.0;
-        if (j <= i)
-            for (int sp = 0; sp < nsplit; ++sp) s += gram[((size_t)sp * (R + 1) + R) * mm + (size_t)i * Mpad + j];
+        if (j <= i) s = split_sum(gram + (size_t)R * mm + (size_t)i * Mpad + j, nsplit, (size_t)(R + 1) * mm);
         Lbar[(size_t)i * Mpad + j] = -s;
     }
 }
@@ -47,14 +60,7 @@ __global__ void k_gq_sqrt(dgp_cond_desc d, int Mpad, const double* __restrict__ 
 __global__ void k_part_reduce(const double* __restrict__ part, int ncta, int npart, double* __restrict__ psum) {
     const int e = blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= npart) return;
-    // eight interleaved partial sums (fixed association): the loads of a column are independent, only the adds chain
-    double s[8] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
-    int c = 0;
-    for (; c + 8 <= ncta; c += 8)
-#pragma unroll
-        for (int u = 0; u < 8; ++u) s[u] += part[(size_t)(c + u) * npart + e];
-    for (; c < ncta; ++c) s[c & 7] += part[(size_t)c * npart + e];
-    psum[e] = ((s[0] + s[1]) + (s[2] + s[3])) + ((s[4] + s[5]) + (s[6] + s[7]));
+    psum[e] = split_sum(part + e, ncta, (size_t)npart);
 }
 
 // (c) d q_mu = row-summed partials - klw q_mu
