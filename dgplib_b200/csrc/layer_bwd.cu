@@ -295,7 +295,7 @@ __global__ void __launch_bounds__(C::NTHREADS, 1) k_cond_bwd(const __grid_consta
             // of a 17-warp CTA for the software pipeline of the streamed loop (ptxas put every LDS right in front of its
             // DMMA: DMMA pipe 59 % active); accumulating that sum in the shared-memory tile was slower still.
             // Columns beyond the last valid row get weight 0; their ring bytes are stale but finite (zeroed at start).
-            auto epi = [&](Acc<C>& acc, const Seg& sg) {
+            auto epi = [&](auto& acc, const Seg& sg) {
                 PH(3);
                 // A[n][row] for every element this thread owns, straight from L2 (prefetched by the producer warp): all
                 // 8 NJ loads are issued before the first use, one exposed round trip per block row
@@ -342,7 +342,7 @@ __global__ void __launch_bounds__(C::NTHREADS, 1) k_cond_bwd(const __grid_consta
 
         // ---- phase dK: Dt <- Lm^-T Dt, block rows top-down, in place
         {
-            auto epi = [&](Acc<C>& acc, const Seg& sg) {
+            auto epi = [&](auto& acc, const Seg& sg) {
                 consumer_sync<C>();
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {

@@ -235,7 +235,7 @@ __global__ void __launch_bounds__(C::NTHREADS, 1) k_cond_fwd(const __grid_consta
         }
         // ---- phase T: A = Linv * Kuf, in place
         {
-            auto epi = [&](Acc<C>& acc, const Seg& sg) {
+            auto epi = [&](auto& acc, const Seg& sg) {
                 bulk_wait_read0();   // the Kuf store (if any) has finished reading the tile
                 consumer_sync<C>();  // all warps finished reading this block row's k-range of Bt
 #pragma unroll
@@ -320,7 +320,7 @@ __global__ void __launch_bounds__(C::NTHREADS, 1) k_cond_fwd(const __grid_consta
             for (int j = 0; j < C::NJ; ++j) { colsq[j][0] = 0.0; colsq[j][1] = 0.0; }
             const int wn = warp % C::WN;
             const int nkc = Mpad / C::KC;
-            auto epi = [&](Acc<C>& acc, const Seg& sg) {
+            auto epi = [&](auto& acc, const Seg& sg) {
 #pragma unroll
                 for (int q = 0; q < 4; ++q)
 #pragma unroll

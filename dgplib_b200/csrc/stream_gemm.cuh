@@ -52,14 +52,36 @@ struct Seg {
     bool flush;       // run the epilogue (and clear the accumulators) after this segment
 };
 
+// Accumulators of one warp: 4 row tiles x NJ column tiles.  With a single column tile per warp (NJ = 1: the 16- and 32-row
+// configurations of Mpad > 256) the same four accumulators would be hit again every fourth DMMA; there the odd k-steps
+// go to a second set (SPLIT), which doubles the distance between dependent DMMAs, and fold() adds the two sets before the
+// epilogue reads v.  (Used where the B operand is the resident tile: M = 1024 forward -3 % with the saved tensors, -5 % without;
+// with the streamed, weighted B operand of the backward dA phase it measured 2 % slower and is left off.)
+template <class C, bool SPLIT_>
+struct AccSecond { double w[4][C::NJ][2]; };
 template <class C>
-struct Acc {
+struct AccSecond<C, false> {};
+
+template <class C, bool SPLIT_ = false>
+struct Acc : AccSecond<C, SPLIT_> {
+    static constexpr bool SPLIT = SPLIT_;
     double v[4][C::NJ][2];
     __device__ __forceinline__ void clear() {
 #pragma unroll
         for (int q = 0; q < 4; ++q)
 #pragma unroll
-            for (int j = 0; j < C::NJ; ++j) { v[q][j][0] = 0.0; v[q][j][1] = 0.0; }
+            for (int j = 0; j < C::NJ; ++j) {
+                v[q][j][0] = 0.0; v[q][j][1] = 0.0;
+                if constexpr (SPLIT_) { this->w[q][j][0] = 0.0; this->w[q][j][1] = 0.0; }
+            }
+    }
+    __device__ __forceinline__ void fold() {
+        if constexpr (SPLIT_) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+#pragma unroll
+                for (int j = 0; j < C::NJ; ++j) { v[q][j][0] += this->w[q][j][0]; v[q][j][1] += this->w[q][j][1]; }
+        }
     }
 };
 
@@ -148,8 +170,8 @@ template <int DIAG, int QLO, int QHI>
 __device__ __forceinline__ constexpr bool kstep_active(int q, int kk) {
     return !((DIAG == 1 && q == QLO && kk >= 2) || (DIAG == 2 && q == QHI - 1 && kk < 2));
 }
-template <class C, int QLO, int QHI, bool BSTAGE, bool WEIGHTED, int DIAG = 0>
-__device__ __forceinline__ void chunk_mma(Acc<C>& acc, const double* __restrict__ Aw, const double* __restrict__ Bw,
+template <class C, int QLO, int QHI, bool BSTAGE, bool WEIGHTED, int DIAG = 0, class AccT>
+__device__ __forceinline__ void chunk_mma(AccT& acc, const double* __restrict__ Aw, const double* __restrict__ Bw,
                                           int ldb, const int (&ko)[4], const double (&wv)[C::NJ]) {
     // Software-pipelined over the four k-steps of the chunk: the fragments of step kk+1 are loaded (into their own
     // registers) before the DMMAs of step kk are issued.  Left to itself ptxas reused one register pair for every A
@@ -177,7 +199,14 @@ __device__ __forceinline__ void chunk_mma(Acc<C>& acc, const double* __restrict_
         for (int q = QLO; q < QHI; ++q)
 #pragma unroll
             for (int j = 0; j < C::NJ; ++j)
-                if (kstep_active<DIAG, QLO, QHI>(q, kk)) dmma884(acc.v[q][j], af[kk & 1][q], bf[kk & 1][j]);
+                if (kstep_active<DIAG, QLO, QHI>(q, kk)) {
+                    if constexpr (AccT::SPLIT) {
+                        if (kk & 1) dmma884(acc.w[q][j], af[kk & 1][q], bf[kk & 1][j]);
+                        else dmma884(acc.v[q][j], af[kk & 1][q], bf[kk & 1][j]);
+                    } else {
+                        dmma884(acc.v[q][j], af[kk & 1][q], bf[kk & 1][j]);
+                    }
+                }
         if (WEIGHTED && kk + 1 < 4) scale((kk + 1) & 1);
     }
 }
@@ -195,7 +224,7 @@ __device__ __forceinline__ void run_phase(Pipe& p, int nseg, SegFn segfn, EpiFn 
     const int wm = warp / C::WN, wn = warp % C::WN;
     const int ko[4] = {((0 ^ (g & 3)) << 2), ((1 ^ (g & 3)) << 2), ((2 ^ (g & 3)) << 2), ((3 ^ (g & 3)) << 2)};
 
-    Acc<C> acc;
+    Acc<C, (C::NJ == 1 && !BSTAGE)> acc;
     acc.clear();
     consumer_sync<C>();
 
@@ -276,6 +305,7 @@ __device__ __forceinline__ void run_phase(Pipe& p, int nseg, SegFn segfn, EpiFn 
             pipe_advance<C>(p);
         }
         if (seg.flush) {
+            acc.fold();
             epi(acc, seg);
             acc.clear();
         }
