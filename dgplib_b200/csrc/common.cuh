@@ -282,6 +282,10 @@ __device__ __forceinline__ void bulk_s2g(void* gdst, const void* smem_src, uint3
     asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;\n"
                  :: "l"(gdst), "r"(smem_u32(smem_src)), "r"(bytes) : "memory");
 }
+__device__ __forceinline__ void bulk_s2g_hint(void* gdst, const void* smem_src, uint32_t bytes, uint64_t policy) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group.L2::cache_hint [%0], [%1], %2, %3;\n"
+                 :: "l"(gdst), "r"(smem_u32(smem_src)), "r"(bytes), "l"(policy) : "memory");
+}
 // L2 prefetch of a contiguous global range (no shared-memory destination, no completion tracking)
 __device__ __forceinline__ void bulk_prefetch_l2(const void* gsrc, uint32_t bytes) {
     asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;\n" :: "l"(gsrc), "r"(bytes) : "memory");

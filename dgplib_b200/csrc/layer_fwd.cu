@@ -228,7 +228,7 @@ __global__ void __launch_bounds__(C::NTHREADS, 1) k_cond_fwd(const __grid_consta
             consumer_sync<C>();
             fence_async_smem();
             if (tid < C::NT && n0 + tid < a.n_rows) {
-                bulk_s2g(a.K_save + (size_t)(n0 + tid) * Mpad, Bt + tid * ldb, (uint32_t)(Mpad * sizeof(double)));
+                bulk_s2g_hint(a.K_save + (size_t)(n0 + tid) * Mpad, Bt + tid * ldb, (uint32_t)(Mpad * sizeof(double)), l2_policy(false));
                 bulk_commit();
             }
             // (the store drains while the first block row of phase T is multiplied; its epilogue waits for it)
@@ -259,7 +259,7 @@ __global__ void __launch_bounds__(C::NTHREADS, 1) k_cond_fwd(const __grid_consta
         if (a.A_save) {
             fence_async_smem();
             if (tid < C::NT && n0 + tid < a.n_rows) {
-                bulk_s2g(a.A_save + (size_t)(n0 + tid) * Mpad, Bt + tid * ldb, (uint32_t)(Mpad * sizeof(double)));
+                bulk_s2g_hint(a.A_save + (size_t)(n0 + tid) * Mpad, Bt + tid * ldb, (uint32_t)(Mpad * sizeof(double)), l2_policy(false));
                 bulk_commit();
             }
         }
@@ -341,8 +341,8 @@ __global__ void __launch_bounds__(C::NTHREADS, 1) k_cond_fwd(const __grid_consta
 #pragma unroll
                             for (int j = 0; j < C::NJ; ++j)
                                 if (grp0 + j < a.NG)
-                                    *reinterpret_cast<double2*>(ub + (size_t)(grp0 + j) * USAVE_BLOCK) =
-                                        make_double2(acc.v[q][j][0], acc.v[q][j][1]);
+                                    __stcs(reinterpret_cast<double2*>(ub + (size_t)(grp0 + j) * USAVE_BLOCK),
+                                           make_double2(acc.v[q][j][0], acc.v[q][j][1]));
                         }
                     }
                 }
