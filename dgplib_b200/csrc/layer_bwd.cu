@@ -426,7 +426,7 @@ __global__ void __launch_bounds__(C::NTHREADS, 1) k_cond_bwd(const __grid_consta
 #pragma unroll
                         for (int u = 0; u < 8; ++u) {
                             const int m = m0 + u * 32 + lane;
-                            kv[u] = (m < Mpad) ? __ldg(krow + m) : 0.0;
+                            kv[u] = (m < Mpad) ? __ldcs(krow + m) : 0.0;      // read once: streaming load
                         }
 #pragma unroll
                         for (int u = 0; u < 8; ++u) {
