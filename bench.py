@@ -636,7 +636,9 @@ def main():
     dist = None
     if world > 1:
         import torch.distributed as dist
-        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local_rank}"))
+        from dgplib_b200.parallel import nccl_options
+        # few NCCL CTAs: the gradient buckets overlap the persistent backward kernels, which hold every SM (parallel.py)
+        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local_rank}"), pg_options=nccl_options())
 
     def sync_all():
         torch.cuda.synchronize()

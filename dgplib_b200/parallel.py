@@ -20,6 +20,22 @@ def philox_row_id(row_offset, sample, local_row, sample_stride):
     return row_offset + sample * sample_stride + local_row
 
 
+def nccl_options(max_ctas=4):
+    """ProcessGroupNCCL options for the process group handed to DSDGP.distribute(): at most `max_ctas` CTAs per collective.
+    The per-layer gradient buckets (a few MB) are all-reduced on a communication stream WHILE the persistent row kernels of
+    the earlier layers hold every SM with one 220 KB CTA each; NCCL's default CTA count made every other T step 0.4 ms slower
+    on 2, 4 and 8 GPUs (9.8 / 10.2 ms bimodal), because the row-kernel CTAs of the SMs NCCL reached first had to wait for it.
+    Four CTAs move these buckets over NVLink just as fast and leave the step at its single-GPU time."""
+    import torch.distributed as dist
+    opts = dist.ProcessGroupNCCL.Options()
+    try:
+        opts.config.max_ctas = int(max_ctas)
+        opts.config.min_ctas = 1
+    except AttributeError:        # a torch without ncclConfig_t in its bindings: NCCL's defaults
+        pass
+    return opts
+
+
 class BucketReducer:
     """Sum-all-reduce of the flat [elbo | gradients] buffer in per-layer buckets, each issued as soon as that layer's
     gradients are final (last layer first), so that the collectives run on NCCL's stream beside the backward kernels of
