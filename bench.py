@@ -637,8 +637,9 @@ def main():
     if world > 1:
         import torch.distributed as dist
         from dgplib_b200.parallel import nccl_options
-        # few NCCL CTAs: the gradient buckets overlap the persistent backward kernels, which hold every SM (parallel.py)
-        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local_rank}"), pg_options=nccl_options())
+        # NCCL CTA budget by world size: the gradient buckets overlap the persistent backward kernels, which hold every SM
+        # (measurements in parallel.nccl_options)
+        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local_rank}"), pg_options=nccl_options(world))
 
     def sync_all():
         torch.cuda.synchronize()

@@ -20,19 +20,25 @@ def philox_row_id(row_offset, sample, local_row, sample_stride):
     return row_offset + sample * sample_stride + local_row
 
 
-def nccl_options(max_ctas=4):
-    """ProcessGroupNCCL options for the process group handed to DSDGP.distribute(): at most `max_ctas` CTAs per collective.
+def nccl_options(world_size=None, max_ctas=None):
+    """ProcessGroupNCCL options for the process group handed to DSDGP.distribute().
+
     The per-layer gradient buckets (a few MB) are all-reduced on a communication stream WHILE the persistent row kernels of
-    the earlier layers hold every SM with one 220 KB CTA each; NCCL's default CTA count made every other T step 0.4 ms slower
-    on 2, 4 and 8 GPUs (9.8 / 10.2 ms bimodal), because the row-kernel CTAs of the SMs NCCL reached first had to wait for it.
-    Four CTAs move these buckets over NVLink just as fast and leave the step at its single-GPU time."""
+    the earlier layers hold every SM with one 220 KB CTA each, so the number of CTAs NCCL may use is a trade: few CTAs leave
+    the row kernels alone, many finish the (partly exposed) last bucket sooner.  Measured on T (10 k rows per GPU):
+    2 ranks, NCCL default: steps bimodal 9.8 / 10.2 ms, mean 10.02; max_ctas = 4: every step 9.85-9.97 ms, mean 9.90.
+    4 ranks, default: 10.16 ms; max_ctas = 4: 10.32 ms (the ring over four GPUs needs more than four CTAs to hide).
+    Hence: four CTAs for two ranks, NCCL's own choice otherwise, unless `max_ctas` says so."""
     import torch.distributed as dist
     opts = dist.ProcessGroupNCCL.Options()
-    try:
-        opts.config.max_ctas = int(max_ctas)
-        opts.config.min_ctas = 1
-    except AttributeError:        # a torch without ncclConfig_t in its bindings: NCCL's defaults
-        pass
+    if max_ctas is None and world_size == 2:
+        max_ctas = 4
+    if max_ctas is not None:
+        try:
+            opts.config.max_ctas = int(max_ctas)
+            opts.config.min_ctas = 1
+        except AttributeError:        # a torch without ncclConfig_t in its bindings: NCCL's defaults
+            pass
     return opts
 
 

@@ -23,7 +23,7 @@ def _worker(rank, world, port, out, graph, overlap=True):
     os.environ["MASTER_PORT"] = str(port)
     torch.cuda.set_device(rank)
     from dgplib_b200.parallel import nccl_options
-    dist.init_process_group("nccl", rank=rank, world_size=world, pg_options=nccl_options())
+    dist.init_process_group("nccl", rank=rank, world_size=world, pg_options=nccl_options(world))
     model, X, Y = _model()
     model.compile(f"cuda:{rank}")
     model.use_cuda_graph = graph
@@ -73,7 +73,7 @@ def _train_worker(rank, world, port, out, graph):
     os.environ["MASTER_PORT"] = str(port)
     torch.cuda.set_device(rank)
     from dgplib_b200.parallel import nccl_options
-    dist.init_process_group("nccl", rank=rank, world_size=world, pg_options=nccl_options())
+    dist.init_process_group("nccl", rank=rank, world_size=world, pg_options=nccl_options(world))
     from dgplib_b200.training import AdamOptimizer
     model, X, Y = _model()
     model.compile(f"cuda:{rank}")
