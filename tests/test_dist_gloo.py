@@ -121,3 +121,17 @@ def test_shard_helpers():
             for s in range(3):
                 for b in range(lo, hi):
                     assert philox_row_id(lo, s, b - lo, B) == full[(s, b)]
+
+
+def test_nccl_options_cta_budget_by_world_size():
+    """parallel.nccl_options: four CTAs per collective for two-rank groups (measured), NCCL's own choice otherwise, an
+    explicit request always honoured."""
+    import torch.distributed as dist
+    from dgplib_b200.parallel import nccl_options
+    if not hasattr(dist, "ProcessGroupNCCL"):
+        pytest.skip("torch built without NCCL")
+    default = dist.ProcessGroupNCCL.Options().config.max_ctas
+    assert nccl_options(2).config.max_ctas == 4 and nccl_options(2).config.min_ctas == 1
+    assert nccl_options(4).config.max_ctas == default and nccl_options(8).config.max_ctas == default
+    assert nccl_options(8, max_ctas=16).config.max_ctas == 16
+    assert nccl_options().config.max_ctas == default
